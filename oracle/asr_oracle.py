@@ -1,0 +1,413 @@
+"""Plain-PyTorch fp32 restatement of the reference ASR inference path.
+
+TEST INFRASTRUCTURE (see oracle/__init__.py). Every function cites the reference
+file:line it follows (paths relative to /root/reference/speechbrain/).
+
+All model functions take ``sd``: a flat ``{key: tensor}`` dict using the
+reference's own ``state_dict`` key names, and a small config dict.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+# --------------------------------------------------------------------------
+# Frontend: STFT -> power -> mel filterbank -> dB (+ top_db clip)
+# --------------------------------------------------------------------------
+
+
+def stft_power(wav, n_fft=400, win_length_ms=25, hop_length_ms=10, sample_rate=16000):
+    """processing/features.py:109-188 (STFT) + :341-378 (spectral_magnitude, power=1).
+
+    torch.stft(center=True, pad_mode="constant", periodic hamming window,
+    onesided) followed by re^2 + im^2.  Returns (B, T_f, n_fft//2+1).
+    """
+    win = int(round(sample_rate / 1000.0 * win_length_ms))
+    hop = int(round(sample_rate / 1000.0 * hop_length_ms))
+    window = torch.hamming_window(win)
+    if win < n_fft:  # torch.stft centres a short window inside n_fft
+        left = (n_fft - win) // 2
+        window = F.pad(window, (left, n_fft - win - left))
+    x = F.pad(wav.float(), (n_fft // 2, n_fft // 2))  # zeros ("constant")
+    frames = x.unfold(1, n_fft, hop) * window
+    spec = torch.fft.rfft(frames, dim=-1)
+    return spec.real.pow(2) + spec.imag.pow(2)
+
+
+def mel_matrix(n_mels=40, n_fft=400, sample_rate=16000, f_min=0, f_max=None):
+    """processing/features.py:487-507 (band edges) + :620-650 (triangular filters).
+
+    Returns the (n_fft//2+1, n_mels) matrix the reference rebuilds every call.
+    """
+    if f_max is None:
+        f_max = sample_rate // 2
+    n_stft = n_fft // 2 + 1
+    to_mel = lambda hz: 2595 * math.log10(1 + hz / 700)
+    mel = torch.linspace(to_mel(f_min), to_mel(f_max), n_mels + 2)
+    hz = 700 * (10 ** (mel / 2595) - 1)
+    band = (hz[1:] - hz[:-1])[:-1]
+    f_central = hz[1:-1]
+    all_freqs = torch.linspace(0, sample_rate // 2, n_stft)
+    all_freqs_mat = all_freqs.repeat(f_central.shape[0], 1)
+    f_central_mat = f_central.repeat(all_freqs_mat.shape[1], 1).transpose(0, 1)
+    band_mat = band.repeat(all_freqs_mat.shape[1], 1).transpose(0, 1)
+    slope = (all_freqs_mat - f_central_mat) / band_mat
+    left_side = slope + 1.0
+    right_side = -slope + 1.0
+    zero = torch.zeros(1)
+    return torch.max(zero, torch.min(left_side, right_side)).transpose(0, 1)
+
+
+def fbank(wav, n_fft=400, n_mels=40, win_length_ms=25, hop_length_ms=10,
+          sample_rate=16000, f_min=0, f_max=None, amin=1e-10, top_db=80.0):
+    """lobes/features.py:147-169 (Fbank.forward, deltas=False, context=False) with
+    processing/features.py:512-586 (Filterbank.forward) and :736-759 (_amplitude_to_DB).
+    """
+    power = stft_power(wav, n_fft, win_length_ms, hop_length_ms, sample_rate)
+    fb = torch.matmul(power, mel_matrix(n_mels, n_fft, sample_rate, f_min, f_max))
+    x_db = 10.0 * torch.log10(torch.clamp(fb, min=amin))
+    # db_multiplier = log10(max(amin, ref_value=1)) = 0
+    new_max = x_db.amax(dim=(-2, -1)) - top_db  # per sequence, incl. padding
+    return torch.max(x_db, new_max.view(-1, 1, 1))
+
+
+def padding_mask(T, lengths, eps=1e-6):
+    """processing/features.py:1554-1615 make_padding_mask -> (B, T) bool, True = valid."""
+    abs_lengths = (lengths * T - eps).unsqueeze(1)
+    return torch.arange(T).unsqueeze(0) < abs_lengths
+
+
+def input_norm(x, lengths=None, norm_type="global", glob_mean=None, glob_std=None,
+               std_norm=True, avoid_padding_norm=False, epsilon=1e-10):
+    """processing/features.py:1404-1455 InputNormalization.forward in eval mode
+    ("global": fixed stats; "sentence": masked per-utterance stats :1478-1486)."""
+    B, T, _ = x.shape
+    if lengths is None:
+        lengths = torch.ones(B)
+    mask = padding_mask(T, lengths).unsqueeze(-1)
+    if norm_type == "global":
+        mean, std = glob_mean.unsqueeze(0), glob_std.unsqueeze(0)
+    elif norm_type == "sentence":
+        n = mask.sum(1, keepdim=True)
+        mean = (x * mask).sum(1, keepdim=True) / n
+        var = ((x - mean) * mask).square().sum(1, keepdim=True) / n
+        mean, std = mean.squeeze(1), var.squeeze(1).sqrt()
+    else:
+        raise ValueError(norm_type)
+    if not std_norm:
+        std = torch.ones_like(mean)
+    mean, std = mean.unsqueeze(1), std.unsqueeze(1)
+    if avoid_padding_norm:
+        mean = mean.masked_fill(~mask, 0.0)
+        std = std.masked_fill(~mask, 1.0)
+    return (x - mean) / std.clamp(min=epsilon)
+
+
+def cnn_frontend(x, sd, prefix="", num_blocks=2):
+    """lobes/models/convolution.py:116-320 (ConvolutionFrontEnd/ConvBlock, one conv
+    per block, stride 2, no residual) + nnet/CNN.py:654-751 (Conv2d: channels-last
+    API, reflect "same" padding k//2 when stride>1) + nnet/normalization.py:185-242
+    (LayerNorm over the last two dims) + LeakyReLU(0.01).
+
+    x: (B, T, F) -> (B, T', F', C).
+    """
+    x = x.transpose(1, -1).unsqueeze(1)  # (B, 1, F, T)
+    for i in range(num_blocks):
+        p = f"{prefix}convblock_{i}.convs."
+        w, b = sd[p + "conv_0.conv.weight"], sd[p + "conv_0.conv.bias"]
+        x = F.pad(x, (1, 1, 1, 1), mode="reflect")
+        x = F.conv2d(x, w, b, stride=2)  # (B, C, F', T')
+        x = x.transpose(1, -1)  # (B, T', F', C)
+        g, be = sd[p + "norm_0.norm.weight"], sd[p + "norm_0.norm.bias"]
+        x = F.layer_norm(x, g.shape, g, be, 1e-5)
+        x = F.leaky_relu(x, 0.01)
+        if i + 1 < num_blocks:
+            x = x.transpose(1, -1)  # back to (B, C, F', T')
+    return x
+
+
+# --------------------------------------------------------------------------
+# Conformer encoder
+# --------------------------------------------------------------------------
+
+
+def length_to_mask(length, max_len=None):
+    """dataio/dataio.py:803-848."""
+    if max_len is None:
+        max_len = int(length.max().long().item())
+    return torch.arange(max_len, dtype=length.dtype).expand(len(length), max_len) < length.unsqueeze(1)
+
+
+def rope_tables(T, head_dim):
+    """nnet/attention.py:1012-1055 PrecomputedRoPESinusoids: (cos, signed sin), (T, head_dim)."""
+    angles = torch.exp(torch.arange(0, head_dim, 2, dtype=torch.float32) * -(math.log(10000.0) / head_dim))
+    times = torch.arange(0, T, dtype=torch.float32)
+    ta = torch.outer(times, angles)
+    cos = torch.stack([torch.cos(ta)] * 2, dim=-1).reshape(T, head_dim)
+    uns = torch.stack([torch.sin(ta)] * 2, dim=-1).reshape(T, head_dim)
+    sin = ((-1) ** torch.arange(head_dim, dtype=torch.float32)) * -uns
+    return cos, sin
+
+
+def rope_rotate(x):
+    """nnet/attention.py:1161-1188 _rope_rotate; x: (B, L, H, d_h).
+
+    The reference memoises tables of length 2**ceil(log2(L)) and slices [:L]; the
+    values for t < L are identical, so we build exactly L rows."""
+    _, L, _, dh = x.shape
+    cos, sin = rope_tables(L, dh)
+    idx = torch.arange(dh).view(-1, 2).flip(1).reshape(-1)
+    return x * cos.unsqueeze(1) + x[..., idx] * sin.unsqueeze(1)
+
+
+def relpos_table(T, d):
+    """nnet/attention.py:360-408 RelPosEncXL.make_pe -> (1, 2T-1, d)."""
+    inv_freq = torch.exp(torch.arange(0, d, 2, dtype=torch.float32) * -(math.log(10000.0) / d))
+    tot = torch.empty((2, T, d))
+    pos = torch.arange(0, T, dtype=torch.float32).unsqueeze(-1)
+    sinus = torch.sin(pos * inv_freq)
+    tot[0][:, 0::2] = sinus
+    tot[0][:, 1::2] = torch.cos(pos * inv_freq)
+    tot[1][:, 0::2] = sinus
+    tot[1][:, 1::2] = torch.cos(-pos * inv_freq)
+    past = torch.flip(tot[0], (0,)).unsqueeze(0)
+    future = tot[1][1:].unsqueeze(0)
+    return torch.cat([past, future], dim=1)
+
+
+def _mm(x, w, b=None, q=None):
+    """x @ w.T (+b). ``q`` optionally rounds both operands (used only to *predict*
+    the error of reduced-precision tensor-core operands; q=None is the oracle)."""
+    if q is not None:
+        x, w = q(x), q(w)
+    return F.linear(x, w, b)
+
+
+def rope_mha(x, sd, p, nhead, key_padding_mask, q=None):
+    """nnet/attention.py:1284-1399 RoPEMHA.forward (self-attention branch) with
+    masks_union :1402-1440 and SDPA(scale=1/sqrt(embed_dim) :1272)."""
+    B, T, d = x.shape
+    dh = d // nhead
+    qkv = _mm(x, sd[p + "in_proj_weight"], None, q).view(B, T, nhead, 3 * dh)
+    qh, kh, vh = qkv.chunk(3, dim=-1)
+    qh, kh = rope_rotate(qh), rope_rotate(kh)
+    scale = 1.0 / math.sqrt(d)
+    s = torch.einsum("bihd,bjhd->bhij", qh, kh) * scale
+    if key_padding_mask is not None:
+        s = s.masked_fill(key_padding_mask.view(B, 1, 1, T), float("-inf"))
+    a = torch.softmax(s, dim=-1)
+    o = torch.einsum("bhij,bjhd->bihd", a, vh).reshape(B, T, d)
+    return _mm(o, sd[p + "out_proj.weight"], sd[p + "out_proj.bias"], q)
+
+
+def relpos_mha(x, pos_embs, sd, p, nhead, key_padding_mask, q=None):
+    """nnet/attention.py:555-742 RelPosMHAXL.forward + rel_shift :537-553.
+
+    Quirks kept: scale 1/sqrt(embed_dim); pos_bias_{u,v} stored (d_h, H) but
+    *viewed* (H, d_h); interleaved per-head QKV rows."""
+    B, T, d = x.shape
+    dh = d // nhead
+    qkv = _mm(x, sd[p + "in_proj_weight"], None, q).view(B, T, nhead, 3 * dh)
+    qh, kh, vh = qkv.chunk(3, dim=-1)
+    p_k = _mm(pos_embs, sd[p + "linear_pos.weight"], None, q).view(1, -1, nhead, dh)
+    u = sd[p + "pos_bias_u"].reshape(1, 1, nhead, dh)
+    v = sd[p + "pos_bias_v"].reshape(1, 1, nhead, dh)
+    scale = 1.0 / math.sqrt(d)
+    q_u = (qh + u).transpose(1, 2) * scale
+    q_v = (qh + v).transpose(1, 2) * scale
+    ac = torch.matmul(q_u, kh.permute(0, 2, 3, 1))
+    bd = torch.matmul(q_v, p_k.permute(0, 2, 3, 1))  # (B,H,T,2T-1)
+    b_, h_, ql, pl = bd.shape
+    bd = F.pad(bd, (1, 0)).view(b_, h_, -1, ql)[:, :, 1:].reshape(b_, h_, ql, pl)[..., : pl // 2 + 1]
+    s = ac + bd
+    if key_padding_mask is not None:
+        s = s.masked_fill(key_padding_mask.view(B, 1, 1, T), float("-inf"))
+    a = torch.softmax(s, dim=-1)
+    if key_padding_mask is not None:
+        a = a.masked_fill(key_padding_mask.view(B, 1, 1, T), 0.0)
+    o = torch.matmul(a, vh.transpose(1, 2)).transpose(1, 2).reshape(B, T, d)
+    return _mm(o, sd[p + "out_proj.weight"], sd[p + "out_proj.bias"], q)
+
+
+def _ln(x, sd, p, eps):
+    return F.layer_norm(x, (x.shape[-1],), sd[p + "weight"], sd[p + "bias"], eps)
+
+
+def conformer_ffn(x, sd, p, q=None):
+    """Conformer.py:425-445 ffn_module{1,2}: LN(1e-5) -> Linear -> Swish -> Linear
+    (nnet/attention.py:889-947 PositionalwiseFeedForward)."""
+    h = _ln(x, sd, p + "0.", 1e-5)
+    h = F.silu(_mm(h, sd[p + "1.ffn.0.weight"], sd[p + "1.ffn.0.bias"], q))
+    return _mm(h, sd[p + "1.ffn.3.weight"], sd[p + "1.ffn.3.bias"], q)
+
+
+def conv_module(x, sd, p, conv_mask, q=None):
+    """Conformer.py:314-330 ConvolutionModule.forward (non-chunked branch)."""
+    d = x.shape[-1]
+    h = _ln(x, sd, p + "layer_norm.", 1e-5)
+    w = sd[p + "bottleneck.0.weight"]
+    h = _mm(h, w[:, :, 0], sd[p + "bottleneck.0.bias"], q)  # Conv1d k=1
+    h = F.glu(h, dim=-1)
+    wdw = sd[p + "conv.weight"]
+    K = wdw.shape[-1]
+    h = F.conv1d(h.transpose(1, 2), wdw, sd[p + "conv.bias"], padding=(K - 1) // 2, groups=d).transpose(1, 2)
+    h = F.silu(_ln(h, sd, p + "after_conv.0.", 1e-5))
+    h = _mm(h, sd[p + "after_conv.2.weight"], sd[p + "after_conv.2.bias"], q)
+    if conv_mask is not None:
+        h = h.masked_fill(conv_mask, 0.0)
+    return h
+
+
+def conformer_layer(x, sd, p, nhead, attention_type, key_padding_mask, pos_embs, q=None):
+    """Conformer.py:451-499 ConformerEncoderLayer.forward."""
+    conv_mask = key_padding_mask.unsqueeze(-1) if key_padding_mask is not None else None
+    x = x + 0.5 * conformer_ffn(x, sd, p + "ffn_module1.", q)
+    skip = x
+    h = _ln(x, sd, p + "norm1.norm.", 1e-5)
+    if attention_type == "RoPEMHA":
+        h = rope_mha(h, sd, p + "mha_layer.", nhead, key_padding_mask, q)
+    elif attention_type == "RelPosMHAXL":
+        h = relpos_mha(h, pos_embs, sd, p + "mha_layer.", nhead, key_padding_mask, q)
+    else:
+        raise ValueError(attention_type)
+    x = h + skip
+    x = x + conv_module(x, sd, p + "convolution_module.", conv_mask, q)
+    return _ln(x + 0.5 * conformer_ffn(x, sd, p + "ffn_module2.", q), sd, p + "norm2.norm.", 1e-5)
+
+
+def encode(src, wav_len, sd, cfg, prefix="", q=None, return_layers=False):
+    """TransformerASR.py:475-544 TransformerASR.encode (+ :106-164 masks,
+    Conformer.py:705-778 ConformerEncoder.forward incl. final LayerNorm(eps=1e-6))."""
+    if src.dim() == 4:
+        bz, t, c1, c2 = src.shape
+        src = src.reshape(bz, t, c1 * c2)
+    B, T, _ = src.shape
+    kpm = None
+    if wav_len is not None:
+        abs_len = torch.round(wav_len * T)
+        kpm = ~length_to_mask(abs_len)
+        if kpm.shape[1] != T:
+            raise ValueError("longest relative length must be 1.0")
+    x = _mm(src, sd[prefix + "custom_src_module.layers.0.w.weight"],
+            sd[prefix + "custom_src_module.layers.0.w.bias"], q)
+    pos = relpos_table(T, x.shape[-1]) if cfg["attention_type"] == "RelPosMHAXL" else None
+    layers = []
+    for i in range(cfg["num_encoder_layers"]):
+        x = conformer_layer(x, sd, f"{prefix}encoder.layers.{i}.", cfg["nhead"],
+                            cfg["attention_type"], kpm, pos, q)
+        layers.append(x)
+    x = _ln(x, sd, prefix + "encoder.norm.norm.", 1e-6)
+    return (x, layers) if return_layers else x
+
+
+# --------------------------------------------------------------------------
+# Transformer decoder (no KV cache -- exactly like the reference) and searchers
+# --------------------------------------------------------------------------
+
+
+def sine_pe(n, d):
+    """Transformer.py:252-303 PositionalEncoding table rows [0, n)."""
+    pe = torch.zeros(n, d)
+    pos = torch.arange(0, n).unsqueeze(1).float()
+    den = torch.exp(torch.arange(0, d, 2).float() * -(math.log(10000.0) / d))
+    pe[:, 0::2] = torch.sin(pos * den)
+    pe[:, 1::2] = torch.cos(pos * den)
+    return pe
+
+
+def _mha_regular(qx, kx, sd, p, nhead, attn_mask=None, key_padding_mask=None):
+    """nnet/attention.py:802-886 -> torch.nn.MultiheadAttention (in_proj [Wq;Wk;Wv]
+    with bias, scale 1/sqrt(d_h))."""
+    n, s, d = qx.shape
+    dh = d // nhead
+    W, b = sd[p + "att.in_proj_weight"], sd[p + "att.in_proj_bias"]
+    qh = F.linear(qx, W[:d], b[:d]).view(n, s, nhead, dh).transpose(1, 2)
+    kh = F.linear(kx, W[d:2 * d], b[d:2 * d]).view(n, -1, nhead, dh).transpose(1, 2)
+    vh = F.linear(kx, W[2 * d:], b[2 * d:]).view(n, -1, nhead, dh).transpose(1, 2)
+    sc = torch.matmul(qh, kh.transpose(-1, -2)) / math.sqrt(dh)
+    if attn_mask is not None:
+        sc = sc + attn_mask
+    if key_padding_mask is not None:
+        sc = sc.masked_fill(key_padding_mask.view(n, 1, 1, -1), float("-inf"))
+    a = torch.softmax(sc, dim=-1)
+    o = torch.matmul(a, vh).transpose(1, 2).reshape(n, s, d)
+    return F.linear(o, sd[p + "att.out_proj.weight"], sd[p + "att.out_proj.bias"]), a.mean(1)
+
+
+def decode(tgt, enc_out, enc_len, sd, cfg, prefix=""):
+    """TransformerASR.py:426-473 TransformerASR.decode + Transformer.py:751-834,
+    :915-963 (pre-norm decoder layers, eps 1e-6, GELU FFN) -- whole prefix each call."""
+    n, s = tgt.shape
+    d = cfg["d_model"]
+    tgt_mask = torch.triu(torch.full((s, s), float("-inf")), diagonal=1)  # Transformer.py:1037-1068
+    mem_kpm = None
+    if enc_len is not None:
+        mem_kpm = ~length_to_mask(enc_len.float())
+    x = F.embedding(tgt.long(), sd[prefix + "custom_tgt_module.layers.0.emb.Embedding.weight"]) * math.sqrt(d)
+    x = x + sine_pe(s, d).unsqueeze(0)
+    attn = None
+    act = F.gelu if cfg.get("decoder_activation", "gelu") == "gelu" else F.relu
+    for j in range(cfg["num_decoder_layers"]):
+        p = f"{prefix}decoder.layers.{j}."
+        h = _ln(x, sd, p + "norm1.norm.", 1e-6)
+        h, _ = _mha_regular(h, h, sd, p + "self_attn.", cfg["nhead"], attn_mask=tgt_mask)
+        x = x + h
+        h = _ln(x, sd, p + "norm2.norm.", 1e-6)
+        h, attn = _mha_regular(h, enc_out, sd, p + "multihead_attn.", cfg["nhead"], key_padding_mask=mem_kpm)
+        x = x + h
+        h = _ln(x, sd, p + "norm3.norm.", 1e-6)
+        h = F.linear(act(F.linear(h, sd[p + "pos_ffn.ffn.0.weight"], sd[p + "pos_ffn.ffn.0.bias"])),
+                     sd[p + "pos_ffn.ffn.3.weight"], sd[p + "pos_ffn.ffn.3.bias"])
+        x = x + h
+    return _ln(x, sd, prefix + "decoder.norm.norm.", 1e-6), attn
+
+
+def greedy_search(enc_states, wav_len, sd, cfg, seq_lin_w, seq_lin_b, bos_index=1, eos_index=2,
+                  min_decode_ratio=0.0, max_decode_ratio=1.0, prefix="", return_logits=False):
+    """decoders/seq2seq.py:181-276 S2SGreedySearcher.forward (temperature 0) with
+    S2STransformerGreedySearcher.forward_step :360-367.
+
+    Returns (hyps list[list[int]], top_lengths (B,1), top_scores (B,1,L), top_log_probs (B,1,L,V))."""
+    B, T, _ = enc_states.shape
+    enc_lens = torch.round(T * wav_len).int()
+    memory = None
+    inp = torch.full((B,), bos_index, dtype=torch.long)
+    lp_list, logit_list = [], []
+    has_ended = torch.zeros(B, dtype=torch.bool)
+    for _ in range(int(T * min_decode_ratio), int(T * max_decode_ratio)):
+        memory = inp.unsqueeze(1) if memory is None else torch.cat([memory, inp.unsqueeze(1)], dim=-1)
+        pred, _ = decode(memory, enc_states, enc_lens, sd, cfg, prefix)
+        logits = F.linear(pred, seq_lin_w, seq_lin_b)[:, -1, :]
+        logit_list.append(logits)
+        inp = logits.argmax(dim=-1)
+        lp = F.log_softmax(logits.float(), dim=-1)
+        lp_list.append(lp)
+        has_ended = has_ended | (inp == eos_index)
+        lp[has_ended] = -torch.inf
+        inp[has_ended] = eos_index
+        if has_ended.all():
+            break
+    log_probs = torch.stack(lp_list, dim=1)
+    scores, preds = log_probs.max(dim=-1)
+    m = scores == -torch.inf
+    scores[m] = 0
+    preds[m] = eos_index
+    L = preds.shape[1]
+    lens = []
+    for b in range(B):
+        nz = (preds[b] == eos_index).nonzero()
+        lens.append(int(nz[0]) if len(nz) > 0 else L)
+    hyps = [preds[b, : lens[b]].tolist() for b in range(B)]
+    top_lengths = torch.tensor(lens, dtype=torch.float) / L
+    out = (hyps, top_lengths.unsqueeze(1), scores.unsqueeze(1), log_probs.unsqueeze(1))
+    if return_logits:
+        return out + (torch.stack(logit_list, dim=1),)
+    return out
+
+
+def full_pipeline_features(wav, wav_lens, sd, cfg):
+    """inference/ASR.py:100-128 encode_batch up to the encoder input: Fbank ->
+    InputNormalization(global) -> ConvolutionFrontEnd."""
+    f = fbank(wav, n_fft=cfg["n_fft"], n_mels=cfg["n_mels"], win_length_ms=cfg["win_length"])
+    f = input_norm(f, wav_lens, "global", sd["normalize.glob_mean"], sd["normalize.glob_std"])
+    return cnn_frontend(f, sd, "CNN.")

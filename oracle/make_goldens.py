@@ -1,0 +1,181 @@
+"""Generate tests/golden/*.pt by RUNNING THE REFERENCE (build container only).
+
+TEST INFRASTRUCTURE. Usage (needs /root/reference and a 2-function hyperpyyaml stub):
+
+    mkdir -p /tmp/stub && printf 'def resolve_references(*a,**k): raise RuntimeError\\n'\\
+        'def load_hyperpyyaml(*a,**k): raise RuntimeError\\n' > /tmp/stub/hyperpyyaml.py
+    PYTHONPATH=/tmp/stub:/root/reference:/root/repo python oracle/make_goldens.py
+
+For every case it (1) builds the reference modules with the recipe's kwargs
+(recipes/LibriSpeech/ASR/transformer/hparams/conformer_{large,small}.yaml), (2) loads
+seeded weights (speechbrain_b200.utils.seeded_init -- regenerated, not stored),
+(3) runs the reference on seeded inputs, (4) checks oracle/asr_oracle.py against
+it, and (5) stores inputs + reference outputs as small fixtures.
+"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from oracle import asr_oracle as O  # noqa: E402
+from speechbrain_b200.utils.seeded_init import seeded_state_dict  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+CFG_L = dict(name="conformer_large", d_model=512, nhead=8, num_encoder_layers=12, num_decoder_layers=6,
+             d_ffn=2048, vocab=5000, n_fft=512, win_length=32, n_mels=80, kernel_size=31,
+             cnn_channels=(64, 32), input_size=640)
+CFG_S = dict(name="conformer_small", d_model=144, nhead=4, num_encoder_layers=12, num_decoder_layers=4,
+             d_ffn=1024, vocab=5000, n_fft=400, win_length=25, n_mels=80, kernel_size=31,
+             cnn_channels=(64, 32), input_size=640)
+
+
+def rel(a, b):
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def build_reference(cfg, attention_type):
+    import speechbrain  # noqa: F401
+    from speechbrain.lobes.features import Fbank
+    from speechbrain.lobes.models.convolution import ConvolutionFrontEnd
+    from speechbrain.lobes.models.transformer.TransformerASR import TransformerASR
+    from speechbrain.nnet.linear import Linear
+    from speechbrain.processing.features import InputNormalization
+
+    fb = Fbank(n_fft=cfg["n_fft"], n_mels=cfg["n_mels"], win_length=cfg["win_length"])
+    norm = InputNormalization(norm_type="global", update_until_epoch=4)
+    cnn = ConvolutionFrontEnd(input_shape=(8, 10, 80), num_blocks=2, num_layers_per_block=1,
+                              out_channels=cfg["cnn_channels"], kernel_sizes=(3, 3), strides=(2, 2),
+                              residuals=(False, False))
+    tr = TransformerASR(input_size=cfg["input_size"], tgt_vocab=cfg["vocab"], d_model=cfg["d_model"],
+                        nhead=cfg["nhead"], num_encoder_layers=cfg["num_encoder_layers"],
+                        num_decoder_layers=cfg["num_decoder_layers"], d_ffn=cfg["d_ffn"], dropout=0.1,
+                        activation=torch.nn.GELU, encoder_module="conformer", attention_type=attention_type,
+                        normalize_before=True, causal=False)
+    seq_lin = Linear(input_size=cfg["d_model"], n_neurons=cfg["vocab"])
+    ctc_lin = Linear(input_size=cfg["d_model"], n_neurons=cfg["vocab"])
+    mods = torch.nn.ModuleDict(dict(CNN=cnn, Transformer=tr, seq_lin=seq_lin, ctc_lin=ctc_lin))
+    sd = seeded_state_dict(mods, seed=0)
+    mods.load_state_dict(sd)
+    mods.eval()
+    from speechbrain_b200.utils.seeded_init import seeded_tensor
+    norm.glob_mean = seeded_tensor(0, "normalize.glob_mean", (cfg["n_mels"],)) * 3.0 - 20.0
+    norm.glob_std = seeded_tensor(0, "normalize.glob_std", (cfg["n_mels"],)) * 8.0
+    norm.count = 1
+    norm.eval()
+    sd["normalize.glob_mean"], sd["normalize.glob_std"] = norm.glob_mean, norm.glob_std
+    return fb, norm, mods, sd
+
+
+def fbank_cases():
+    from speechbrain.lobes.features import Fbank
+    g = torch.Generator().manual_seed(1234)
+    out = {}
+    for name, kw, B, L in [("cfg1_nfft400", dict(n_fft=400, n_mels=80), 1, 16000),
+                           ("nfft400_b3_ragged", dict(n_fft=400, n_mels=80), 3, 12345),
+                           ("nfft512_win32", dict(n_fft=512, n_mels=80, win_length=32), 2, 24000),
+                           ("default_nmels40", dict(), 2, 8000),
+                           ("nfft512_win25", dict(n_fft=512, n_mels=40), 1, 4800)]:
+        wav = torch.randn(B, L, generator=g) * (0.1 if "ragged" in name else 1.0)
+        if "ragged" in name:
+            wav[1, 9000:] = 0
+            wav[2, 5000:] = 0
+        ref = Fbank(**kw)(wav)
+        okw = dict(n_fft=kw.get("n_fft", 400), n_mels=kw.get("n_mels", 40), win_length_ms=kw.get("win_length", 25))
+        ora = O.fbank(wav, **okw)
+        err = (ora - ref).abs().max().item()
+        print(f"fbank {name}: ref {tuple(ref.shape)} oracle max-abs err {err:.3e}")
+        assert err < 1e-3
+        out[name] = dict(kwargs=kw, wav=wav, out=ref)
+    # all-zero utterance: amin clamp + top_db
+    wav = torch.zeros(1, 1600)
+    out["zeros"] = dict(kwargs=dict(n_fft=400, n_mels=80), wav=wav, out=Fbank(n_fft=400, n_mels=80)(wav))
+    torch.save(out, os.path.join(OUT, "fbank.pt"))
+
+
+def norm_cases():
+    from speechbrain.processing.features import InputNormalization
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(3, 50, 80, generator=g) * 5 - 10
+    lens = torch.tensor([1.0, 0.62, 0.3])
+    out = {"x": x, "lens": lens}
+    n = InputNormalization(norm_type="global")
+    n.glob_mean = torch.randn(80, generator=g)
+    n.glob_std = torch.rand(80, generator=g) + 0.5
+    n.count = 1
+    n.eval()
+    out["glob_mean"], out["glob_std"] = n.glob_mean, n.glob_std
+    out["global"] = n(x, lens)
+    assert torch.equal(O.input_norm(x, lens, "global", n.glob_mean, n.glob_std), out["global"])
+    n = InputNormalization(norm_type="sentence").eval()
+    out["sentence"] = n(x, lens)
+    print("norm sentence err", (O.input_norm(x, lens, "sentence") - out["sentence"]).abs().max().item())
+    n = InputNormalization(norm_type="sentence", avoid_padding_norm=True).eval()
+    out["sentence_avoid_pad"] = n(x, lens)
+    assert (O.input_norm(x, lens, "sentence", avoid_padding_norm=True) - out["sentence_avoid_pad"]).abs().max() < 1e-5
+    # KAT from tests/unittests/test_features.py:112-118
+    kat = InputNormalization(norm_type="sentence").eval()(torch.tensor([[[1.0], [3.0], [0.0], [0.0], [0.0]]]),
+                                                            torch.tensor([0.4]))
+    out["kat"] = kat
+    torch.save(out, os.path.join(OUT, "input_norm.pt"))
+
+
+def model_case(cfg, attention_type, B, L, lens, n_steps, tag):
+    from speechbrain.decoders.seq2seq import S2STransformerGreedySearcher
+    fb, norm, mods, sd = build_reference(cfg, attention_type)
+    g = torch.Generator().manual_seed(1234)
+    wav = torch.randn(B, L, generator=g)
+    wav_lens = torch.tensor(lens)
+    for b in range(B):
+        wav[b, int(round(lens[b] * L)):] = 0
+    ocfg = dict(cfg, attention_type=attention_type)
+    with torch.no_grad():
+        f = fb(wav)
+        fn = norm(f, wav_lens)
+        c = mods["CNN"](fn)
+        enc = mods["Transformer"].encode(c, wav_lens)
+        T = enc.shape[1]
+        gs = S2STransformerGreedySearcher(modules=[mods["Transformer"], mods["seq_lin"]], bos_index=1, eos_index=2,
+                                          min_decode_ratio=0.0, max_decode_ratio=(n_steps + 0.5) / T)
+        hyps, top_len, top_scores, top_lp = gs(enc, wav_lens)
+        ctc_logits = mods["ctc_lin"](enc)
+        # oracle checks
+        of = O.fbank(wav, n_fft=cfg["n_fft"], n_mels=cfg["n_mels"], win_length_ms=cfg["win_length"])
+        ofn = O.input_norm(of, wav_lens, "global", sd["normalize.glob_mean"], sd["normalize.glob_std"])
+        oc = O.cnn_frontend(fn, sd, "CNN.")
+        oenc, olayers = O.encode(c, wav_lens, sd, ocfg, "Transformer.", return_layers=True)
+        ohyps, olen, oscores, olp, ologits = O.greedy_search(
+            enc, wav_lens, sd, ocfg, sd["seq_lin.w.weight"], sd["seq_lin.w.bias"], 1, 2, 0.0,
+            (n_steps + 0.5) / T, "Transformer.", return_logits=True)
+    print(f"[{tag}] fbank err {(of - f).abs().max():.2e}  norm err {(ofn - fn).abs().max():.2e} "
+          f"cnn err {(oc - c).abs().max():.2e}  enc rel {rel(oenc, enc):.2e}  "
+          f"greedy equal {ohyps == hyps} lp err {(olp - top_lp).abs().max():.2e}")
+    assert (oc - c).abs().max() < 1e-4 and rel(oenc, enc) < 1e-5 and ohyps == hyps
+    logits = ologits
+    top2 = logits.topk(2, dim=-1).values
+    print(f"   T={T} steps={logits.shape[1]} min top1-top2 margin {float((top2[..., 0] - top2[..., 1]).min()):.4f}")
+    gold = dict(cfg=ocfg, wav=wav, wav_lens=wav_lens, fbank=f, cnn_out=c, enc_out=enc,
+                enc_layer0=olayers[0], enc_layer5=olayers[5], hyps=hyps, greedy_logits=logits,
+                ctc_logits_head=ctc_logits[:, :, :64].clone(),
+                weight_checksum=float(sum(v.double().abs().sum() for v in sd.values() if v.is_floating_point())))
+    torch.save(gold, os.path.join(OUT, f"{tag}.pt"))
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    torch.manual_seed(0)
+    which = sys.argv[1:] or ["fbank", "norm", "L_rope", "L_relpos", "S_relpos"]
+    if "fbank" in which:
+        fbank_cases()
+    if "norm" in which:
+        norm_cases()
+    if "L_rope" in which:
+        model_case(CFG_L, "RoPEMHA", 2, 32000, [1.0, 0.7], 6, "conformer_large_rope")
+    if "L_relpos" in which:
+        model_case(CFG_L, "RelPosMHAXL", 2, 32000, [1.0, 0.7], 6, "conformer_large_relpos")
+    if "S_relpos" in which:
+        model_case(CFG_S, "RelPosMHAXL", 2, 24000, [0.8, 1.0], 6, "conformer_small_relpos")
+    for fn in sorted(os.listdir(OUT)):
+        print(fn, os.path.getsize(os.path.join(OUT, fn)))
