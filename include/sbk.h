@@ -1,0 +1,97 @@
+/* sbk.h -- C ABI of libsbk.so: the B200-native (sm_100a) ASR inference hot path behind SpeechBrain's
+ * module API.  Plain C: raw pointers + sizes, int error codes (0 = ok, <0 = error; text via
+ * sbk_last_error()), an opaque CUDA stream (cudaStream_t passed as void*).  No torch types.
+ *
+ * The reference (speechbrain v1.1.0) has no FFI for this path -- its seam is nn.Module call
+ * signatures.  Each entry point below names the reference call it replaces
+ * (file:line relative to /root/reference/speechbrain/).  Device pointers are caller-owned
+ * (torch tensors); the library owns only repacked weights and its workspace.
+ */
+#ifndef SBK_H_
+#define SBK_H_
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sbk_fbank sbk_fbank; /* opaque */
+typedef struct sbk_asr sbk_asr;     /* opaque */
+
+enum { SBK_ATT_ROPE = 0, SBK_ATT_RELPOS = 1 };
+enum { SBK_ACT_RELU = 0, SBK_ACT_GELU = 1 };
+
+typedef struct {
+    const char* name;  /* reference state_dict key with recipe prefix, e.g. "Transformer.encoder.layers.0.norm1.norm.weight" */
+    const float* data; /* HOST fp32, contiguous, reference layout */
+    int64_t numel;
+} sbk_tensor;
+
+typedef struct {
+    /* Fbank (lobes/features.py:98-145) -- sizes in samples */
+    int n_fft, hop, n_mels;
+    /* ConvolutionFrontEnd (lobes/models/convolution.py:162-203): 2 blocks, 3x3, stride 2 */
+    int cnn_c1, cnn_c2;
+    /* TransformerASR (lobes/models/transformer/TransformerASR.py:247-325) */
+    int input_size, d_model, nhead, num_encoder_layers, num_decoder_layers, d_ffn, vocab, kernel_size;
+    int attention_type;     /* SBK_ATT_ROPE (RoPEMHA) | SBK_ATT_RELPOS (RelPosMHAXL) */
+    int decoder_activation; /* SBK_ACT_RELU | SBK_ACT_GELU (the `activation` ctor kwarg) */
+    int max_len;            /* positional tables (ctor kwarg max_length, default 2500) */
+} sbk_asr_config;
+
+const char* sbk_last_error(void); /* thread-local message of the last failing call */
+int sbk_version(void);
+
+/* ---- Fbank.forward (lobes/features.py:147-169 = STFT processing/features.py:141-188 + spectral_magnitude
+ *      :341-378 + Filterbank.forward :512-586 + _amplitude_to_DB :736-759).  window_host[n_fft] is the (centre-
+ *      padded) analysis window and mel_matrix_host[(n_fft/2+1) * n_mels] the dense triangular matrix, both
+ *      computed by the caller exactly as the reference does (torch ops), so filter values are bit-identical. */
+int sbk_fbank_create(int n_fft, int hop, int n_mels, const float* window_host, const float* mel_matrix_host,
+                     float amin, float top_db, sbk_fbank** out);
+void sbk_fbank_destroy(sbk_fbank* fb);
+int sbk_fbank_num_frames(const sbk_fbank* fb, int n_samples);
+/* wav_dev [B, L] fp32 -> out_dev [B, 1 + L/hop, n_mels] fp32; utt_max_scratch_dev: B ints */
+int sbk_fbank_forward(const sbk_fbank* fb, const float* wav_dev, int B, int L, float* out_dev,
+                      int* utt_max_scratch_dev, void* stream);
+
+/* ---- InputNormalization.forward, eval mode (processing/features.py:1404-1455) */
+int sbk_input_norm_global(const float* x_dev, float* out_dev, int B, int T, int F, const float* mean_dev,
+                          const float* std_dev, float eps, void* stream);
+int sbk_input_norm_sentence(const float* x_dev, float* out_dev, const float* rel_len_dev, int B, int T, int F,
+                            int std_norm, int avoid_padding_norm, float eps, void* stream);
+
+/* ---- tcgen05 GEMM self-test hook: out[M,N] = act(A[M,K] W[N,K]^T + bias) (fp16 in, fp32 accumulate) */
+int sbk_gemm_f16_test(const void* A_dev, const void* W_dev, const float* bias_dev, void* out_dev, int out_is_f32,
+                      int act, int M, int N, int K, void* stream);
+
+/* ---- model handle: repacks the reference state_dict once */
+int sbk_asr_create(const sbk_asr_config* cfg, const sbk_tensor* weights, int n_weights, sbk_asr** out);
+void sbk_asr_destroy(sbk_asr* m);
+int sbk_asr_num_frames(const sbk_asr* m, int n_samples, int* T_feat, int* T_enc);
+
+/* ConvolutionFrontEnd.forward (lobes/models/convolution.py:116-320): feats [B,T0,n_mels] -> out [B,T2,F2*C2] fp32 */
+int sbk_asr_cnn_forward(sbk_asr* m, const float* feats_dev, int B, int T0, float* out_dev, void* stream);
+/* TransformerASR.encode (TransformerASR.py:475-544): src [B,T,input_size] fp32 -> enc_out [B,T,d_model] fp32.
+ * rel_len_dev: relative lengths (wav_len) or NULL. */
+int sbk_asr_encode_from_cnn(sbk_asr* m, const float* src_dev, const float* rel_len_dev, int B, int T,
+                            float* enc_out_dev, void* stream);
+/* normalised feats [B,T0,n_mels] -> CNN -> encode in one call (inference/ASR.py:100-128 encode_batch, minus Fbank) */
+int sbk_asr_encode_feats(sbk_asr* m, const float* feats_dev, const float* rel_len_dev, int B, int T0,
+                         float* cnn_out_dev, float* enc_out_dev, void* stream);
+/* S2STransformerGreedySearcher.forward (decoders/seq2seq.py:181-276,360-367), KV-cached.
+ * pred_dev/score_dev [B, max_steps]; log_probs_dev [B, max_steps, vocab] or NULL; *steps_done = executed steps. */
+int sbk_asr_greedy_from_enc(sbk_asr* m, const float* enc_dev, const float* rel_len_dev, int B, int T, int max_steps,
+                            int bos, int eos, int* pred_dev, float* score_dev, float* log_probs_dev, int* steps_done,
+                            void* stream);
+/* EncoderDecoderASR.transcribe_batch minus the tokenizer (inference/ASR.py:131-169): wav -> token ids.
+ * _dev: wav already on the device; _host: HOST buffers, H2D/D2H inside the call (synchronises the stream). */
+int sbk_asr_transcribe_greedy_dev(sbk_asr* m, const float* wav_dev, const float* rel_len_dev, int B, int L,
+                                  int max_steps, int bos, int eos, float* enc_out_dev, int* pred_dev,
+                                  float* score_dev, float* log_probs_dev, int* steps_done, void* stream);
+int sbk_asr_transcribe_greedy_host(sbk_asr* m, const float* wav_host, const float* rel_len_host, int B, int L,
+                                   int max_steps, int bos, int eos, int* pred_host, float* score_host,
+                                   int* steps_done, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SBK_H_ */

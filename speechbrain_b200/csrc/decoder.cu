@@ -1,0 +1,291 @@
+// KV-cached Transformer decoder step + greedy bookkeeping for S2STransformer{Greedy,Beam}Searcher.
+//
+// The reference (decoders/seq2seq.py:360-367,1929-1934 -> TransformerASR.decode
+// lobes/models/transformer/TransformerASR.py:426-473 -> Transformer.py:751-834,915-963) re-embeds and
+// re-runs all decoder layers over the WHOLE prefix every step and re-projects the encoder memory to K/V in
+// every layer every step. Here: cross-attention K/V are projected once per utterance (one tcgen05 GEMM
+// over all layers), self-attention K/V are appended to a cache, and one step touches only the newest token.
+// Numerically the step computes exactly the reference's last-position output.
+//
+// All step kernels read the current step index from device memory so that a single captured CUDA graph
+// can be replayed for every step.
+#include <algorithm>
+
+#include "common.cuh"
+#include "sbk_internal.h"
+
+namespace sbk {
+
+__device__ __forceinline__ void mma16816_d(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// --------------------------------------------------------------------------- embedding + positional encoding
+// x[r] = emb[tok[r]] * sqrt(d) + pe[step]   (Transformer.py:966-995 NormalizedEmbedding, :252-303 PositionalEncoding)
+__global__ void dec_embed_kernel(const int* __restrict__ tokens, int tok_stride, const int* __restrict__ step_ptr,
+                                 const float* __restrict__ emb, const float* __restrict__ pe, int d, float sqrt_d,
+                                 float* __restrict__ x) {
+    const int r = blockIdx.x, step = *step_ptr;
+    const int tok = tokens[static_cast<size_t>(r) * tok_stride + step];
+    const float* e = emb + static_cast<size_t>(tok) * d;
+    const float* p = pe + static_cast<size_t>(step) * d;
+    for (int i = threadIdx.x; i < d; i += blockDim.x) x[static_cast<size_t>(r) * d + i] = e[i] * sqrt_d + p[i];
+}
+
+// --------------------------------------------------------------------------- skinny GEMM (weight streaming)
+// y[n_rows, N] = epi( A[n_rows, K] (fp16) x W[N, K]^T (fp16) + bias ).  n_rows is the number of live
+// hypotheses (32..320): the cost is streaming W once, so one CTA owns 8 output columns for up to 128 rows,
+// its 4 warps split K (deterministic in-CTA reduction through shared memory).
+constexpr int SK_ROWS = 128;
+
+__global__ void __launch_bounds__(128) skinny_gemm_kernel(const SkinnyArgs a) {
+    __shared__ float red[4][SK_ROWS][9];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
+    const int n0 = blockIdx.x * 8;
+    const int row0 = blockIdx.y * SK_ROWS;
+    const int rows = min(SK_ROWS, a.n_rows - row0);
+    const int m_tiles = (rows + 15) >> 4;
+    const int k_per_warp = ((a.K / 16 + 3) / 4) * 16;
+    const int k_begin = warp * k_per_warp, k_end = min(a.K, k_begin + k_per_warp);
+
+    float acc[SK_ROWS / 16][4];
+#pragma unroll
+    for (int i = 0; i < SK_ROWS / 16; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0f;
+    const int wn = min(n0 + g, a.N - 1);  // clamp for the N tail (results discarded)
+    const __half* wrow = a.W + static_cast<size_t>(wn) * a.ldw + 2 * c;
+    for (int k0 = k_begin; k0 < k_end; k0 += 16) {
+        const uint32_t b0 = __ldg(reinterpret_cast<const uint32_t*>(wrow + k0));
+        const uint32_t b1 = __ldg(reinterpret_cast<const uint32_t*>(wrow + k0 + 8));
+#pragma unroll
+        for (int mt = 0; mt < SK_ROWS / 16; ++mt) {
+            if (mt < m_tiles) {
+                const int r0 = min(row0 + mt * 16 + g, a.n_rows - 1), r1 = min(row0 + mt * 16 + g + 8, a.n_rows - 1);
+                const __half* a0 = a.A + static_cast<size_t>(r0) * a.lda + k0 + 2 * c;
+                const __half* a1 = a.A + static_cast<size_t>(r1) * a.lda + k0 + 2 * c;
+                uint32_t af[4];
+                af[0] = *reinterpret_cast<const uint32_t*>(a0);
+                af[1] = *reinterpret_cast<const uint32_t*>(a1);
+                af[2] = *reinterpret_cast<const uint32_t*>(a0 + 8);
+                af[3] = *reinterpret_cast<const uint32_t*>(a1 + 8);
+                mma16816_d(acc[mt], af, b0, b1);
+            }
+        }
+    }
+#pragma unroll
+    for (int mt = 0; mt < SK_ROWS / 16; ++mt) {
+        if (mt < m_tiles) {
+            red[warp][mt * 16 + g][2 * c] = acc[mt][0];
+            red[warp][mt * 16 + g][2 * c + 1] = acc[mt][1];
+            red[warp][mt * 16 + g + 8][2 * c] = acc[mt][2];
+            red[warp][mt * 16 + g + 8][2 * c + 1] = acc[mt][3];
+        }
+    }
+    __syncthreads();
+    const int step = a.step_ptr ? *a.step_ptr : 0;
+    for (int i = threadIdx.x; i < rows * 8; i += blockDim.x) {
+        const int r = i >> 3, j = i & 7;
+        const int col = n0 + j;
+        if (col >= a.N) continue;
+        float v = red[0][r][j] + red[1][r][j] + red[2][r][j] + red[3][r][j];
+        if (a.bias) v += __ldg(a.bias + col);
+        const int row = row0 + r;
+        switch (a.epi) {
+            case SK_F16: reinterpret_cast<__half*>(a.out)[static_cast<size_t>(row) * a.ldo + col] = __float2half_rn(v); break;
+            case SK_F16_RELU:
+                reinterpret_cast<__half*>(a.out)[static_cast<size_t>(row) * a.ldo + col] = __float2half_rn(fmaxf(v, 0.0f));
+                break;
+            case SK_F16_GELU:
+                reinterpret_cast<__half*>(a.out)[static_cast<size_t>(row) * a.ldo + col] = __float2half_rn(gelu_erf_f(v));
+                break;
+            case SK_F32: reinterpret_cast<float*>(a.out)[static_cast<size_t>(row) * a.ldo + col] = v; break;
+            case SK_RESID: reinterpret_cast<float*>(a.out)[static_cast<size_t>(row) * a.ldo + col] += v; break;
+            case SK_QKV_CACHE: {
+                if (col < a.d) {
+                    reinterpret_cast<__half*>(a.out)[static_cast<size_t>(row) * a.ldo + col] = __float2half_rn(v * a.q_scale);
+                } else if (col < 2 * a.d) {
+                    a.kcache[(static_cast<size_t>(row) * a.S_max + step) * a.d + (col - a.d)] = __float2half_rn(v);
+                } else {
+                    a.vcache[(static_cast<size_t>(row) * a.S_max + step) * a.d + (col - 2 * a.d)] = __float2half_rn(v);
+                }
+                break;
+            }
+        }
+    }
+}
+
+int skinny_gemm(const SkinnyArgs& a, cudaStream_t stream) {
+    SBK_REQUIRE(a.K % 16 == 0 && a.lda % 2 == 0 && a.ldw % 2 == 0, "skinny_gemm: K %% 16 required (K=%d)", a.K);
+    if (a.n_rows == 0) return SBK_OK;
+    dim3 grid(ceil_div(a.N, 8), ceil_div(a.n_rows, SK_ROWS));
+    skinny_gemm_kernel<<<grid, 128, 0, stream>>>(a);
+    SBK_LAUNCH_CHECK();
+    return SBK_OK;
+}
+
+// --------------------------------------------------------------------------- decode-time attention (1 query / row)
+// One warp per (row, head): lanes parallel over keys for q.k, warp softmax, lanes parallel over dims for p.V.
+// Self-attention: keys = cache positions [0, step]; cross-attention: keys = encoder frames [0, enc_len[utt]).
+// (nn.MultiheadAttention semantics, scale 1/sqrt(d_h) already folded into q.)
+__global__ void __launch_bounds__(256) dec_attention_kernel(const DecAttnArgs a) {
+    extern __shared__ float da_smem[];  // [warps][max_keys]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+    const int r = blockIdx.x;
+    const int blk = r / a.rows_per_block;
+    int n_keys;
+    if (a.n_keys_ptr) {
+        n_keys = *a.n_keys_ptr + 1;
+    } else {
+        n_keys = a.enc_len ? min(a.enc_len[blk], a.n_keys_fixed) : a.n_keys_fixed;
+    }
+    float* sc = da_smem + static_cast<size_t>(warp) * a.n_keys_fixed;
+    for (int h = warp; h < a.H; h += n_warps) {
+        const __half* q = a.q + static_cast<size_t>(r) * a.ldq + h * a.dh;
+        const __half* kb = a.kbase + static_cast<size_t>(blk) * a.row_stride + h * a.dh;
+        const __half* vb = a.vbase + static_cast<size_t>(blk) * a.row_stride + h * a.dh;
+        // q in registers (dh <= 128): every lane holds the full query vector as half2 pairs
+        float mx = -INFINITY;
+        for (int j = lane; j < n_keys; j += 32) {
+            const __half* kr = kb + static_cast<size_t>(j) * a.key_stride;
+            float dot = 0.0f;
+            for (int e = 0; e < a.dh; e += 8) {
+                const uint4 kv = *reinterpret_cast<const uint4*>(kr + e);
+                const uint4 qv = *reinterpret_cast<const uint4*>(q + e);
+                const __half2* k2 = reinterpret_cast<const __half2*>(&kv);
+                const __half2* q2 = reinterpret_cast<const __half2*>(&qv);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const float2 kf = __half22float2(k2[t]), qf = __half22float2(q2[t]);
+                    dot = fmaf(kf.x, qf.x, dot);
+                    dot = fmaf(kf.y, qf.y, dot);
+                }
+            }
+            sc[j] = dot;
+            mx = fmaxf(mx, dot);
+        }
+        mx = warp_max(mx);
+        float sum = 0.0f;
+        for (int j = lane; j < n_keys; j += 32) {
+            const float p = __expf(sc[j] - mx);
+            sc[j] = p;
+            sum += p;
+        }
+        sum = warp_sum(sum);
+        __syncwarp();
+        const float inv = 1.0f / sum;
+        // p.V : lane owns dims [2*lane, 2*lane+1] (+64 per extra pass)
+        for (int d0 = 2 * lane; d0 < a.dh; d0 += 64) {
+            float o0 = 0.0f, o1 = 0.0f;
+            for (int j = 0; j < n_keys; ++j) {
+                const float p = sc[j];
+                const float2 vf = __half22float2(*reinterpret_cast<const __half2*>(vb + static_cast<size_t>(j) * a.key_stride + d0));
+                o0 = fmaf(p, vf.x, o0);
+                o1 = fmaf(p, vf.y, o1);
+            }
+            *reinterpret_cast<__half2*>(a.out + static_cast<size_t>(r) * a.ldo + h * a.dh + d0) =
+                __floats2half2_rn(o0 * inv, o1 * inv);
+        }
+        __syncwarp();
+    }
+}
+
+int dec_attention(const DecAttnArgs& a, int n_rows, int max_keys, cudaStream_t stream) {
+    SBK_REQUIRE(a.dh % 8 == 0 && a.dh <= 128, "dec_attention: head_dim=%d unsupported", a.dh);
+    if (n_rows == 0) return SBK_OK;
+    const int warps = std::min(8, a.H);
+    const size_t smem = static_cast<size_t>(warps) * max_keys * sizeof(float);
+    SBK_REQUIRE(smem <= 160 * 1024, "dec_attention: too many keys (%d)", max_keys);
+    if (smem > 48 * 1024)
+        SBK_CUDA_CHECK(cudaFuncSetAttribute(dec_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DecAttnArgs b = a;
+    b.n_keys_fixed = max_keys;
+    dec_attention_kernel<<<n_rows, warps * 32, smem, stream>>>(b);
+    SBK_LAUNCH_CHECK();
+    return SBK_OK;
+}
+
+// --------------------------------------------------------------------------- greedy step bookkeeping
+// decoders/seq2seq.py:226-257: argmax, fp32 log_softmax, has_ended |= (tok == eos); ended rows get
+// log_probs = -inf (=> prediction eos, score 0 after :259-263) and keep feeding eos.
+// One CTA per row. Writes tokens[r][step+1], pred[r][step], score[r][step], optional log-prob row.
+__global__ void __launch_bounds__(256)
+greedy_select_kernel(const float* __restrict__ logits, int V, const int* __restrict__ step_ptr, int eos, int* tokens,
+                     int tok_stride, int* has_ended, int* ended_count, int* pred, float* score, int out_stride,
+                     float* log_probs /* [n, L, V] or null */, int L) {
+    __shared__ float s_val[8];
+    __shared__ int s_idx[8];
+    __shared__ float s_sum[8];
+    const int r = blockIdx.x, step = *step_ptr;
+    const float* lg = logits + static_cast<size_t>(r) * V;
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = threadIdx.x; i < V; i += blockDim.x) {
+        const float v = lg[i];
+        if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { s_val[threadIdx.x >> 5] = best; s_idx[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    best = s_val[0]; bi = s_idx[0];
+    for (int w = 1; w < 8; ++w)
+        if (s_val[w] > best || (s_val[w] == best && s_idx[w] < bi)) { best = s_val[w]; bi = s_idx[w]; }
+    float sum = 0.0f;
+    for (int i = threadIdx.x; i < V; i += blockDim.x) sum += expf(lg[i] - best);
+    sum = warp_sum(sum);
+    if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    sum = 0.0f;
+    for (int w = 0; w < 8; ++w) sum += s_sum[w];
+    const float lse = best + logf(sum);
+    const int was_ended = has_ended[r];
+    const int ended = was_ended | (bi == eos ? 1 : 0);
+    if (log_probs) {
+        float* lp = log_probs + (static_cast<size_t>(r) * L + step) * V;
+        for (int i = threadIdx.x; i < V; i += blockDim.x) lp[i] = ended ? -INFINITY : lg[i] - lse;
+    }
+    if (threadIdx.x == 0) {
+        const int tok = ended ? eos : bi;
+        tokens[static_cast<size_t>(r) * tok_stride + step + 1] = tok;
+        pred[static_cast<size_t>(r) * out_stride + step] = tok;
+        score[static_cast<size_t>(r) * out_stride + step] = ended ? 0.0f : best - lse;
+        if (ended && !was_ended) {
+            has_ended[r] = 1;
+            atomicAdd(ended_count, 1);
+        }
+    }
+}
+
+__global__ void advance_step_kernel(int* step_ptr) { *step_ptr += 1; }
+
+int dec_embed(const int* tokens, int tok_stride, const int* step_ptr, const float* emb, const float* pe, int d,
+              int n_rows, float* x, cudaStream_t stream) {
+    if (n_rows == 0) return SBK_OK;
+    dec_embed_kernel<<<n_rows, 128, 0, stream>>>(tokens, tok_stride, step_ptr, emb, pe, d, sqrtf(static_cast<float>(d)), x);
+    SBK_LAUNCH_CHECK();
+    return SBK_OK;
+}
+
+int greedy_select(const float* logits, int n_rows, int V, const int* step_ptr, int eos, int* tokens, int tok_stride,
+                  int* has_ended, int* ended_count, int* pred, float* score, int out_stride, float* log_probs, int L,
+                  cudaStream_t stream) {
+    if (n_rows == 0) return SBK_OK;
+    greedy_select_kernel<<<n_rows, 256, 0, stream>>>(logits, V, step_ptr, eos, tokens, tok_stride, has_ended, ended_count,
+                                                     pred, score, out_stride, log_probs, L);
+    SBK_LAUNCH_CHECK();
+    return SBK_OK;
+}
+
+int advance_step(int* step_ptr, cudaStream_t stream) {
+    advance_step_kernel<<<1, 1, 0, stream>>>(step_ptr);
+    SBK_LAUNCH_CHECK();
+    return SBK_OK;
+}
+
+}  // namespace sbk

@@ -1,0 +1,459 @@
+// Non-GEMM pieces of the Conformer encoder layer:
+//   * row LayerNorm fp32 -> fp16 (GEMM A operand) or fp32 in place        (nn.LayerNorm call sites in
+//     Conformer.py:425-445 ffn LN, :146-157 conv LN, nnet/normalization.py:242 norm1/norm2, final norm :700)
+//   * depthwise Conv1d(k=31) + bias + LayerNorm + Swish                   (Conformer.py:136-157,318-325)
+//   * self-attention, flash style on mma.sync tensor cores, RoPE or Transformer-XL relative
+//     position bias                                                       (nnet/attention.py:555-742, :1284-1399)
+#include <algorithm>
+
+#include "common.cuh"
+#include "sbk_internal.h"
+
+namespace sbk {
+
+// --------------------------------------------------------------------------- LayerNorm
+// One warp per row, two-pass statistics in registers. D <= 32 * LN_MAX_PER_LANE.
+constexpr int LN_MAX_PER_LANE = 32;
+
+template <bool OUT_HALF>
+__global__ void __launch_bounds__(256)
+layernorm_rows_kernel(const float* __restrict__ x, void* __restrict__ out, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, int M, int D, float eps, int act_silu) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const int lane = threadIdx.x & 31;
+    const float* xr = x + static_cast<size_t>(row) * D;
+    float v[LN_MAX_PER_LANE];
+    float s = 0.0f;
+    const int nv = D >> 2;  // float4 vectors per row (D % 4 == 0)
+#pragma unroll
+    for (int i = 0; i < LN_MAX_PER_LANE / 4; ++i) {
+        const int vi = lane + i * 32;
+        if (vi < nv) {
+            const float4 t = *reinterpret_cast<const float4*>(xr + vi * 4);
+            v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+            s += (t.x + t.y) + (t.z + t.w);
+        } else {
+            v[4 * i] = v[4 * i + 1] = v[4 * i + 2] = v[4 * i + 3] = 0.0f;
+        }
+    }
+    const float mean = warp_sum(s) / D;
+    float q = 0.0f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_PER_LANE / 4; ++i) {
+        const int vi = lane + i * 32;
+        if (vi < nv) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float d = v[4 * i + j] - mean;
+                q += d * d;
+            }
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / D + eps);
+#pragma unroll
+    for (int i = 0; i < LN_MAX_PER_LANE / 4; ++i) {
+        const int vi = lane + i * 32;
+        if (vi < nv) {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + vi * 4));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(beta + vi * 4));
+            float y0 = (v[4 * i] - mean) * rstd * g.x + b.x;
+            float y1 = (v[4 * i + 1] - mean) * rstd * g.y + b.y;
+            float y2 = (v[4 * i + 2] - mean) * rstd * g.z + b.z;
+            float y3 = (v[4 * i + 3] - mean) * rstd * g.w + b.w;
+            if (act_silu) { y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3); }
+            if constexpr (OUT_HALF) {
+                __half2 h0 = __floats2half2_rn(y0, y1), h1 = __floats2half2_rn(y2, y3);
+                uint2 u;
+                u.x = *reinterpret_cast<uint32_t*>(&h0);
+                u.y = *reinterpret_cast<uint32_t*>(&h1);
+                *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(out) + static_cast<size_t>(row) * D + vi * 4) = u;
+            } else {
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + static_cast<size_t>(row) * D + vi * 4) =
+                    make_float4(y0, y1, y2, y3);
+            }
+        }
+    }
+}
+
+int layernorm_rows(const float* x, void* out, bool out_half, const float* gamma, const float* beta, int M, int D,
+                   float eps, bool act_silu, cudaStream_t stream) {
+    SBK_REQUIRE(D % 4 == 0 && D <= 32 * LN_MAX_PER_LANE, "layernorm_rows: D=%d unsupported", D);
+    if (M == 0) return SBK_OK;
+    const int rows_per_cta = 8;
+    if (out_half)
+        layernorm_rows_kernel<true><<<ceil_div(M, rows_per_cta), rows_per_cta * 32, 0, stream>>>(x, out, gamma, beta, M, D,
+                                                                                              eps, act_silu);
+    else
+        layernorm_rows_kernel<false><<<ceil_div(M, rows_per_cta), rows_per_cta * 32, 0, stream>>>(x, out, gamma, beta, M,
+                                                                                               D, eps, act_silu);
+    SBK_LAUNCH_CHECK();
+    return SBK_OK;
+}
+
+// fp32 -> fp16 cast (used for goldens-driven tests and the decoder memory)
+__global__ void cast_f32_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, size_t n) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x)
+        out[i] = __float2half_rn(in[i]);
+}
+int cast_f32_f16(const float* in, __half* out, size_t n, cudaStream_t stream) {
+    if (n == 0) return SBK_OK;
+    const int blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, 148 * 16));
+    cast_f32_f16_kernel<<<blocks, 256, 0, stream>>>(in, out, n);
+    SBK_LAUNCH_CHECK();
+    return SBK_OK;
+}
+
+// --------------------------------------------------------------------------- depthwise conv + LN + Swish
+// glu [B*T, D] fp32 (GLU output) -> out [B*T, D] fp16 = Swish(LN(dwconv(glu) + bias)).
+// Zero padding at utterance edges only: padded frames inside T are real inputs (Conformer.py:318-325
+// runs the conv before masking). One CTA per (utterance, tile of DW_TT frames); the (DW_TT + K - 1) x D
+// input slab is staged in shared memory once.
+constexpr int DW_TT = 16;
+
+template <int KT>  // KT > 0: compile-time kernel size (taps held in registers); KT == 0: runtime K
+__global__ void __launch_bounds__(256)
+dwconv_ln_swish_kernel(const float* __restrict__ glu, int T, int D, int K, const float* __restrict__ wdw /*[D,K]*/,
+                       const float* __restrict__ bdw, const float* __restrict__ gamma, const float* __restrict__ beta,
+                       float eps, __half* __restrict__ out) {
+    extern __shared__ float dw_smem[];
+    const int halo = (K - 1) / 2;
+    const int rows_in = DW_TT + K - 1;
+    float* slab = dw_smem;                 // [rows_in][D]
+    float* conv = slab + rows_in * D;      // [DW_TT][D]
+    const int b = blockIdx.y, t0 = blockIdx.x * DW_TT;
+    const float* src = glu + static_cast<size_t>(b) * T * D;
+    const int nv = D >> 2;
+    for (int i = threadIdx.x; i < rows_in * nv; i += blockDim.x) {
+        const int r = i / nv, vi = i - r * nv;
+        const int t = t0 - halo + r;
+        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t >= 0 && t < T) val = *reinterpret_cast<const float4*>(src + static_cast<size_t>(t) * D + vi * 4);
+        *reinterpret_cast<float4*>(slab + r * D + vi * 4) = val;
+    }
+    __syncthreads();
+    for (int ch = threadIdx.x; ch < D; ch += blockDim.x) {
+        float acc[DW_TT];
+        const float bz = __ldg(bdw + ch);
+#pragma unroll
+        for (int i = 0; i < DW_TT; ++i) acc[i] = bz;
+        const float* w = wdw + static_cast<size_t>(ch) * K;
+        // sliding window: each input row contributes to up to DW_TT outputs
+        if constexpr (KT > 0) {
+            float wr[KT];
+#pragma unroll
+            for (int k = 0; k < KT; ++k) wr[k] = __ldg(w + k);
+#pragma unroll
+            for (int r = 0; r < DW_TT + KT - 1; ++r) {
+                const float xv = slab[r * D + ch];
+#pragma unroll
+                for (int i = 0; i < DW_TT; ++i)
+                    if (r - i >= 0 && r - i < KT) acc[i] = fmaf(xv, wr[r - i], acc[i]);
+            }
+        } else {
+            for (int r = 0; r < rows_in; ++r) {
+                const float xv = slab[r * D + ch];
+#pragma unroll
+                for (int i = 0; i < DW_TT; ++i) {
+                    const int k = r - i;  // tap index for output i
+                    if (k >= 0 && k < K) acc[i] = fmaf(xv, __ldg(w + k), acc[i]);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < DW_TT; ++i) conv[i * D + ch] = acc[i];
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = warp; i < DW_TT; i += (blockDim.x >> 5)) {
+        const int t = t0 + i;
+        if (t >= T) continue;
+        const float* c = conv + i * D;
+        float s = 0.0f;
+        for (int j = lane; j < D; j += 32) s += c[j];
+        const float mean = warp_sum(s) / D;
+        float q = 0.0f;
+        for (int j = lane; j < D; j += 32) {
+            const float d = c[j] - mean;
+            q += d * d;
+        }
+        const float rstd = rsqrtf(warp_sum(q) / D + eps);
+        __half* o = out + (static_cast<size_t>(b) * T + t) * D;
+        for (int j = lane; j < D; j += 32)
+            o[j] = __float2half_rn(silu_f((c[j] - mean) * rstd * __ldg(gamma + j) + __ldg(beta + j)));
+    }
+}
+
+int dwconv_ln_swish(const float* glu, int B, int T, int D, int K, const float* wdw, const float* bdw,
+                    const float* gamma, const float* beta, float eps, __half* out, cudaStream_t stream) {
+    SBK_REQUIRE(D % 4 == 0 && (K & 1) == 1, "dwconv_ln_swish: D %% 4 and odd K required (D=%d K=%d)", D, K);
+    const size_t smem = static_cast<size_t>(DW_TT + K - 1 + DW_TT) * D * sizeof(float);
+    SBK_REQUIRE(smem <= 200 * 1024, "dwconv_ln_swish: tile too large for shared memory (D=%d K=%d)", D, K);
+    auto kern = (K == 31) ? dwconv_ln_swish_kernel<31> : dwconv_ln_swish_kernel<0>;
+    SBK_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<dim3(ceil_div(T, DW_TT), B), 256, smem, stream>>>(glu, T, D, K, wdw, bdw, gamma, beta, eps, out);
+    SBK_LAUNCH_CHECK();
+    return SBK_OK;
+}
+
+
+
+// =========================================================================== self-attention
+// Flash-style attention for the Conformer encoder on mma.sync.m16n8k16 (fp16 operands, fp32
+// accumulate, fp32 online softmax).  One CTA = (utterance b, head h, 64 query rows), 4 warps x 16 rows.
+//
+//  RoPE  (nnet/attention.py:1284-1399): q,k arrive already rotated (and q pre-scaled by 1/sqrt(d_model))
+//        from the QKV GEMM epilogue; scores = q.k ; keys >= len_b are masked (masks_union :1402-1440).
+//  RelPos(nnet/attention.py:555-742):   scores = (q+u)s.k + (q+v)s.p_{|i-j|}.  The reference builds a
+//        (2T-1)-row table and rel_shifts it (:537-553); row r of the table depends only on |r| (RelPosEncXL
+//        :360-408 uses +sin for both halves), so BD[i,j] = (q_i+v).P[|i-j|] with P = linear_pos(pe[0..T-1]).
+//        Per key block each warp computes the 16 x 80 band G = Qv.Pband^T on tensor cores, parks it in
+//        shared memory and re-reads it diagonally shifted.
+//  Padded *query* rows are computed like any other row (the reference does; they leak into valid frames
+//  through the depthwise conv), only padded *keys* are masked.
+constexpr int ATT_BQ = 64;
+constexpr int ATT_BK = 64;
+
+__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, const void* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int DH, bool RELPOS>
+__global__ void __launch_bounds__(128)
+encoder_attention_kernel(const __half* __restrict__ qkv, int ld, int T, const int* __restrict__ lens,
+                         const float* __restrict__ pos_u, const float* __restrict__ pos_v,
+                         const __half* __restrict__ P, int ldp, float scale, __half* __restrict__ out, int ldo) {
+    constexpr int STR = DH + 8;  // padded row stride (halfs): conflict-free fragment loads
+    constexpr int KS = DH / 16;
+    constexpr int GW = 80;       // relpos band width (16 + 64 - 1 rounded to 8)
+    extern __shared__ __align__(16) uint8_t att_smem[];
+    __half* Qs = reinterpret_cast<__half*>(att_smem);  // [64][STR]   (RELPOS: Qu)
+    __half* Ks = Qs + ATT_BQ * STR;                    // [64][STR]
+    __half* Vs = Ks + ATT_BK * STR;                    // [64][STR]
+    __half* Qv = Vs + ATT_BK * STR;                    // RELPOS: [64][STR]
+    __half* Ps = Qv + ATT_BQ * STR;                    // RELPOS: [T][STR]
+    float* Gs = reinterpret_cast<float*>(Ps + (RELPOS ? T : 0) * STR);  // RELPOS: [4 warps][16][GW+1]
+
+    const int b = blockIdx.z, h = blockIdx.y, i0 = blockIdx.x * ATT_BQ;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
+    const int len = lens ? min(lens[b], T) : T;
+    const __half* base = qkv + static_cast<size_t>(b) * T * ld + h * 3 * DH;
+    constexpr int VPR = DH / 8;  // 16-byte vectors per row
+
+    // ---- stage Q (and RELPOS: Qu/Qv, P_h)
+    for (int i = threadIdx.x; i < ATT_BQ * VPR; i += blockDim.x) {
+        const int r = i / VPR, v8 = i - r * VPR;
+        uint4 val = make_uint4(0, 0, 0, 0);
+        if (i0 + r < T) val = *reinterpret_cast<const uint4*>(base + static_cast<size_t>(i0 + r) * ld + v8 * 8);
+        if constexpr (RELPOS) {
+            const __half* hv = reinterpret_cast<const __half*>(&val);
+            __half qu[8], qv[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float q = __half2float(hv[e]);
+                qu[e] = __float2half_rn((q + __ldg(pos_u + h * DH + v8 * 8 + e)) * scale);
+                qv[e] = __float2half_rn((q + __ldg(pos_v + h * DH + v8 * 8 + e)) * scale);
+            }
+            *reinterpret_cast<uint4*>(Qs + r * STR + v8 * 8) = *reinterpret_cast<uint4*>(qu);
+            *reinterpret_cast<uint4*>(Qv + r * STR + v8 * 8) = *reinterpret_cast<uint4*>(qv);
+        } else {
+            *reinterpret_cast<uint4*>(Qs + r * STR + v8 * 8) = val;
+        }
+    }
+    if constexpr (RELPOS) {
+        for (int i = threadIdx.x; i < T * VPR; i += blockDim.x) {
+            const int r = i / VPR, v8 = i - r * VPR;
+            *reinterpret_cast<uint4*>(Ps + r * STR + v8 * 8) =
+                *reinterpret_cast<const uint4*>(P + static_cast<size_t>(r) * ldp + h * DH + v8 * 8);
+        }
+    }
+    __syncthreads();
+
+    uint32_t qa[KS][4];
+    uint32_t qva[RELPOS ? KS : 1][4];
+    {
+        const __half* q0 = Qs + (warp * 16 + g) * STR + 2 * c;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            qa[ks][0] = *reinterpret_cast<const uint32_t*>(q0 + ks * 16);
+            qa[ks][1] = *reinterpret_cast<const uint32_t*>(q0 + 8 * STR + ks * 16);
+            qa[ks][2] = *reinterpret_cast<const uint32_t*>(q0 + ks * 16 + 8);
+            qa[ks][3] = *reinterpret_cast<const uint32_t*>(q0 + 8 * STR + ks * 16 + 8);
+        }
+        if constexpr (RELPOS) {
+            const __half* v0 = Qv + (warp * 16 + g) * STR + 2 * c;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                qva[ks][0] = *reinterpret_cast<const uint32_t*>(v0 + ks * 16);
+                qva[ks][1] = *reinterpret_cast<const uint32_t*>(v0 + 8 * STR + ks * 16);
+                qva[ks][2] = *reinterpret_cast<const uint32_t*>(v0 + ks * 16 + 8);
+                qva[ks][3] = *reinterpret_cast<const uint32_t*>(v0 + 8 * STR + ks * 16 + 8);
+            }
+        }
+    }
+
+    float o[DH / 8][4];
+#pragma unroll
+    for (int i = 0; i < DH / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.0f;
+    float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.0f, 0.0f};
+    const float LOG2E = 1.4426950408889634f;
+    const int n_blk = (len + ATT_BK - 1) / ATT_BK;
+
+    for (int jb = 0; jb < n_blk; ++jb) {
+        const int j0 = jb * ATT_BK;
+        __syncthreads();  // previous block's K/V fully consumed
+        for (int i = threadIdx.x; i < ATT_BK * VPR; i += blockDim.x) {
+            const int r = i / VPR, v8 = i - r * VPR;
+            uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+            if (j0 + r < T) {
+                const __half* rowp = base + static_cast<size_t>(j0 + r) * ld + v8 * 8;
+                kv = *reinterpret_cast<const uint4*>(rowp + DH);
+                vv = *reinterpret_cast<const uint4*>(rowp + 2 * DH);
+            }
+            *reinterpret_cast<uint4*>(Ks + r * STR + v8 * 8) = kv;
+            *reinterpret_cast<uint4*>(Vs + r * STR + v8 * 8) = vv;
+        }
+        __syncthreads();
+
+        float s[ATT_BK / 8][4];
+#pragma unroll
+        for (int nt = 0; nt < ATT_BK / 8; ++nt) {
+            s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.0f;
+            const __half* kp = Ks + (nt * 8 + g) * STR + 2 * c;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks)
+                mma16816(s[nt], qa[ks], *reinterpret_cast<const uint32_t*>(kp + ks * 16),
+                         *reinterpret_cast<const uint32_t*>(kp + ks * 16 + 8));
+        }
+        if constexpr (RELPOS) {
+            // band G[li][rr] = Qv[li] . P[|rmin + rr|], rr in [0, 80): rmin = iw - j0 - 63
+            float* Gw = Gs + warp * 16 * (GW + 1);
+            const int rmin = (i0 + warp * 16) - j0 - (ATT_BK - 1);
+#pragma unroll 1
+            for (int nt = 0; nt < GW / 8; ++nt) {
+                float gacc[4] = {0.f, 0.f, 0.f, 0.f};
+                int pr = rmin + nt * 8 + g;
+                pr = pr < 0 ? -pr : pr;
+                pr = min(pr, T - 1);  // columns outside the band that are never read back
+                const __half* pp = Ps + pr * STR + 2 * c;
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks)
+                    mma16816(gacc, qva[ks], *reinterpret_cast<const uint32_t*>(pp + ks * 16),
+                             *reinterpret_cast<const uint32_t*>(pp + ks * 16 + 8));
+                const int col = nt * 8 + 2 * c;
+                Gw[g * (GW + 1) + col] = gacc[0];
+                Gw[g * (GW + 1) + col + 1] = gacc[1];
+                Gw[(g + 8) * (GW + 1) + col] = gacc[2];
+                Gw[(g + 8) * (GW + 1) + col + 1] = gacc[3];
+            }
+            __syncwarp();
+#pragma unroll
+            for (int nt = 0; nt < ATT_BK / 8; ++nt) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int li = g + (e >> 1) * 8, lj = nt * 8 + 2 * c + (e & 1);
+                    s[nt][e] += Gw[li * (GW + 1) + (li - lj + ATT_BK - 1)];
+                }
+            }
+            __syncwarp();
+        }
+        // ---- key padding mask + online softmax (rows g and g+8 of this warp's 16)
+        float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+        for (int nt = 0; nt < ATT_BK / 8; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int j = j0 + nt * 8 + 2 * c + (e & 1);
+                if (j >= len) s[nt][e] = -INFINITY;
+                mx[e >> 1] = fmaxf(mx[e >> 1], s[nt][e]);
+            }
+        float alpha[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+            const float m_new = fmaxf(m_run[r], mx[r]);
+            alpha[r] = exp2f((m_run[r] - m_new) * LOG2E);
+            m_run[r] = m_new;
+        }
+        float rs[2] = {0.0f, 0.0f};
+        uint32_t pa[ATT_BK / 16][4];
+#pragma unroll
+        for (int nt = 0; nt < ATT_BK / 8; ++nt) {
+            const float p0 = exp2f((s[nt][0] - m_run[0]) * LOG2E), p1 = exp2f((s[nt][1] - m_run[0]) * LOG2E);
+            const float p2 = exp2f((s[nt][2] - m_run[1]) * LOG2E), p3 = exp2f((s[nt][3] - m_run[1]) * LOG2E);
+            rs[0] += p0 + p1;
+            rs[1] += p2 + p3;
+            pa[nt >> 1][(nt & 1) * 2 + 0] = pack_half2(p0, p1);
+            pa[nt >> 1][(nt & 1) * 2 + 1] = pack_half2(p2, p3);
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 1);
+            rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 2);
+            l_run[r] = l_run[r] * alpha[r] + rs[r];
+        }
+#pragma unroll
+        for (int nt = 0; nt < DH / 8; ++nt) {
+            o[nt][0] *= alpha[0]; o[nt][1] *= alpha[0];
+            o[nt][2] *= alpha[1]; o[nt][3] *= alpha[1];
+        }
+        // ---- O += P V : B fragments of V[key][dim] via ldmatrix.trans
+#pragma unroll
+        for (int kk = 0; kk < ATT_BK / 16; ++kk) {
+#pragma unroll
+            for (int nt = 0; nt < DH / 8; ++nt) {
+                uint32_t b0, b1;
+                ldmatrix_x2_trans(b0, b1, Vs + (kk * 16 + (lane & 15)) * STR + nt * 8);
+                mma16816(o[nt], pa[kk], b0, b1);
+            }
+        }
+    }
+    // ---- normalise and store
+    const int r0 = i0 + warp * 16 + g, r1 = r0 + 8;
+    const float inv0 = 1.0f / l_run[0], inv1 = 1.0f / l_run[1];
+    __half* ob = out + static_cast<size_t>(b) * T * ldo + h * DH;
+#pragma unroll
+    for (int nt = 0; nt < DH / 8; ++nt) {
+        const int col = nt * 8 + 2 * c;
+        if (r0 < T) *reinterpret_cast<uint32_t*>(ob + static_cast<size_t>(r0) * ldo + col) = pack_half2(o[nt][0] * inv0, o[nt][1] * inv0);
+        if (r1 < T) *reinterpret_cast<uint32_t*>(ob + static_cast<size_t>(r1) * ldo + col) = pack_half2(o[nt][2] * inv1, o[nt][3] * inv1);
+    }
+}
+
+// qkv [B*T, ld] fp16 with per-head [q | k | v] blocks of head_dim; out [B*T, ldo] fp16.
+int encoder_attention(const __half* qkv, int ld, int B, int T, int H, int head_dim, const int* lens, bool relpos,
+                      const float* pos_u, const float* pos_v, const __half* P, int ldp, float scale, __half* out,
+                      int ldo, cudaStream_t stream) {
+    SBK_REQUIRE(head_dim == 64, "encoder_attention: head_dim=%d not built (64 only)", head_dim);
+    SBK_REQUIRE(ld % 8 == 0 && ldo % 2 == 0, "encoder_attention: bad leading dims");
+    constexpr int DH = 64, STR = DH + 8;
+    dim3 grid(ceil_div(T, ATT_BQ), H, B);
+    if (!relpos) {
+        const size_t smem = 3ull * ATT_BQ * STR * 2;
+        encoder_attention_kernel<DH, false><<<grid, 128, smem, stream>>>(qkv, ld, T, lens, nullptr, nullptr, nullptr, 0,
+                                                                         scale, out, ldo);
+    } else {
+        SBK_REQUIRE(ldp % 8 == 0, "encoder_attention: bad ldp");
+        const size_t smem = 4ull * ATT_BQ * STR * 2 + static_cast<size_t>(T) * STR * 2 + 4ull * 16 * 81 * 4;
+        SBK_REQUIRE(smem <= 220 * 1024, "encoder_attention(RelPos): T=%d too long for the shared-memory table", T);
+        auto kern = encoder_attention_kernel<DH, true>;
+        SBK_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, 128, smem, stream>>>(qkv, ld, T, lens, pos_u, pos_v, P, ldp, scale, out, ldo);
+    }
+    SBK_LAUNCH_CHECK();
+    return SBK_OK;
+}
+
+}  // namespace sbk

@@ -1,0 +1,807 @@
+// Model engine: weight repacking, workspace, the encode pipeline (CNN front-end -> Conformer encoder)
+// and the KV-cached greedy decode loop.  Host-side orchestration only; all math is in the kernels.
+//
+// Weights arrive as HOST fp32 arrays named exactly like the reference state_dict with
+// the recipe's module prefixes:  "CNN.", "Transformer.", "seq_lin.", plus "normalize.glob_mean/std"
+// and "fbank.window" / "fbank.mel_matrix".  They are repacked once (fp16 GEMM operands, interleaved GLU
+// rows, concatenated cross-attention K/V projections, pre-scaled decoder queries) into one device arena.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "sbk_internal.h"
+#include "../../include/sbk.h"
+
+namespace sbk {
+
+struct EncLayerW {
+    const float *ffn1_ln_g, *ffn1_ln_b, *ffn1_b1, *ffn1_b2;
+    const __half *ffn1_w1, *ffn1_w2;
+    const float *norm1_g, *norm1_b;
+    const __half *wqkv, *wo;
+    const float* bo;
+    const __half* wpos;               // RelPos linear_pos
+    const float *pos_u, *pos_v;       // RelPos biases, raw (d_h, H) buffer viewed (H, d_h)
+    const float *conv_ln_g, *conv_ln_b;
+    const __half* wpw1;               // [2d, d] rows interleaved 16 value / 16 gate
+    const float* bpw1;                // interleaved the same way
+    const float *wdw, *bdw;           // [d, K], [d]
+    const float *aconv_ln_g, *aconv_ln_b;
+    const __half* wpw2;
+    const float* bpw2;
+    const float *ffn2_ln_g, *ffn2_ln_b, *ffn2_b1, *ffn2_b2;
+    const __half *ffn2_w1, *ffn2_w2;
+    const float *norm2_g, *norm2_b;
+};
+
+struct DecLayerW {
+    const float *n1g, *n1b, *n2g, *n2b, *n3g, *n3b;
+    const __half *w_self_in, *w_self_out, *w_cross_q, *w_cross_out, *w_ffn1, *w_ffn2;
+    const float *b_self_in, *b_self_out, *b_cross_q, *b_cross_out, *b_ffn1, *b_ffn2;
+};
+
+struct Arena {
+    uint8_t* base = nullptr;
+    size_t cap = 0, used = 0;
+    void* take(size_t bytes) {
+        const size_t off = (used + 255) & ~size_t(255);
+        if (off + bytes > cap) return nullptr;
+        used = off + bytes;
+        return base + off;
+    }
+};
+
+struct AsrModel {
+    sbk_asr_config cfg;
+    Fbank* fbank = nullptr;
+    Arena warena;  // weights
+    Arena ws;      // workspace (re-carved per shape)
+    // frontend
+    const float *glob_mean = nullptr, *glob_std = nullptr;
+    const float *c1_w, *c1_b, *c1_g, *c1_be, *c2_b, *c2_g, *c2_be;
+    const __half* c2_w;
+    // encoder
+    const __half* w_in; const float* b_in;
+    std::vector<EncLayerW> enc;
+    const float *enc_norm_g, *enc_norm_b;
+    const float *rope_cos = nullptr, *rope_sin = nullptr;  // [max_len, dh/2]
+    const __half* relpos_pe = nullptr;                     // [max_len, d] rows = |r|
+    int pos_len = 0;
+    // decoder
+    const float* emb; const float* dec_pe;
+    std::vector<DecLayerW> dec;
+    const __half* w_ckv; const float* b_ckv;  // [L*2d, d]
+    const float *dec_norm_g, *dec_norm_b;
+    const __half* w_lin; const float* b_lin;
+    const __half* w_ctc = nullptr; const float* b_ctc = nullptr;
+    // shapes the workspace is carved for
+    int wsB = 0, wsL = 0, ws_rows = 0, ws_steps = 0;
+    struct Buf {
+        float *wav, *feats, *x, *glu, *enc_out, *act1_f, *cnn_f, *dx, *logits, *score;
+        int *utt_max, *enc_len, *tokens, *step, *has_ended, *ended_count, *pred;
+        float* rel_len;
+        __half *act1, *a_in, *h16, *f16, *qkv16, *att16, *P16, *enc16, *ckv16, *kcache, *vcache, *dh16, *dq16, *datt16, *df16;
+    } b;
+    cudaGraphExec_t step_graph = nullptr;
+    int graph_rows = -1, graph_T = -1, graph_B = -1;
+    int* host_flag = nullptr;  // pinned
+};
+
+static const float* find(const std::map<std::string, std::pair<const float*, int64_t>>& m, const std::string& k,
+                         int64_t numel, bool required = true) {
+    auto it = m.find(k);
+    if (it == m.end()) {
+        if (required) set_error("missing weight '%s'", k.c_str());
+        return nullptr;
+    }
+    if (numel >= 0 && it->second.second != numel) {
+        set_error("weight '%s' has %lld elements, expected %lld", k.c_str(), (long long)it->second.second, (long long)numel);
+        return nullptr;
+    }
+    return it->second.first;
+}
+
+struct Packer {
+    AsrModel* m;
+    const std::map<std::string, std::pair<const float*, int64_t>>* w;
+    bool ok = true;
+    std::vector<float> tmpf;
+    std::vector<__half> tmph;
+    const float* f32(const std::string& k, int64_t n) {
+        const float* src = find(*w, k, n);
+        if (!src) { ok = false; return nullptr; }
+        return f32_raw(src, n);
+    }
+    const float* f32_raw(const float* src, int64_t n) {
+        void* d = m->warena.take(n * 4);
+        if (!d) { ok = false; set_error("weight arena exhausted"); return nullptr; }
+        if (cudaMemcpy(d, src, n * 4, cudaMemcpyHostToDevice) != cudaSuccess) { ok = false; set_error("weight upload failed"); }
+        return reinterpret_cast<const float*>(d);
+    }
+    const __half* f16_raw(const float* src, int64_t n, float scale = 1.0f) {
+        tmph.resize(n);
+        for (int64_t i = 0; i < n; ++i) tmph[i] = __float2half_rn(src[i] * scale);
+        void* d = m->warena.take(n * 2);
+        if (!d) { ok = false; set_error("weight arena exhausted"); return nullptr; }
+        if (cudaMemcpy(d, tmph.data(), n * 2, cudaMemcpyHostToDevice) != cudaSuccess) { ok = false; set_error("weight upload failed"); }
+        return reinterpret_cast<const __half*>(d);
+    }
+    const __half* f16(const std::string& k, int64_t n) {
+        const float* src = find(*w, k, n);
+        if (!src) { ok = false; return nullptr; }
+        return f16_raw(src, n);
+    }
+};
+
+static size_t weight_arena_bytes(const sbk_asr_config& c) {
+    const size_t d = c.d_model, f = c.d_ffn;
+    size_t enc = (size_t)c.num_encoder_layers * (4 * d * f + 3 * d * d + d * d + d * d + 2 * d * d + d * d) * 2;
+    size_t dec = (size_t)c.num_decoder_layers * (3 * d * d + d * d + 3 * d * d + d * d + 2 * d * f) * 2;
+    size_t misc = (size_t)c.vocab * d * (4 + 2 + 2) + (size_t)c.max_len * d * (4 + 2) + (size_t)c.input_size * d * 2;
+    return enc + dec + misc + (64u << 20);
+}
+
+int asr_create(const sbk_asr_config* cfg, const sbk_tensor* weights, int n_weights, AsrModel** out) {
+    SBK_REQUIRE(cfg && weights && out, "asr_create: null argument");
+    const sbk_asr_config& c = *cfg;
+    SBK_REQUIRE(c.d_model % 8 == 0 && c.d_model % c.nhead == 0, "asr_create: bad d_model/nhead");
+    SBK_REQUIRE(c.attention_type == SBK_ATT_ROPE || c.attention_type == SBK_ATT_RELPOS,
+                "asr_create: attention_type must be RoPEMHA or RelPosMHAXL");
+    const int d = c.d_model, dh = d / c.nhead, F = c.d_ffn, K = c.kernel_size;
+    SBK_REQUIRE(dh == 64, "asr_create: head_dim=%d not built yet (64 only)", dh);
+    std::map<std::string, std::pair<const float*, int64_t>> w;
+    for (int i = 0; i < n_weights; ++i) w[weights[i].name] = {weights[i].data, weights[i].numel};
+
+    AsrModel* m = new AsrModel();
+    m->cfg = c;
+    m->warena.cap = weight_arena_bytes(c);
+    if (cudaMalloc(&m->warena.base, m->warena.cap) != cudaSuccess) {
+        set_error("asr_create: cudaMalloc(%zu) for weights failed", m->warena.cap);
+        delete m;
+        return SBK_ERR_NOMEM;
+    }
+    Packer p{m, &w};
+    int rc = SBK_OK;
+    // ---- Fbank + CMVN
+    {
+        const float* win = find(w, "fbank.window", c.n_fft);
+        const float* mel = find(w, "fbank.mel_matrix", (int64_t)(c.n_fft / 2 + 1) * c.n_mels);
+        if (!win || !mel) { rc = SBK_ERR_ARG; goto fail; }
+        rc = fbank_create(&m->fbank, c.n_fft, c.hop, c.n_mels, win, mel, 1e-10f, 80.0f);
+        if (rc) goto fail;
+        if (w.count("normalize.glob_mean")) {
+            m->glob_mean = p.f32("normalize.glob_mean", c.n_mels);
+            m->glob_std = p.f32("normalize.glob_std", c.n_mels);
+        }
+    }
+    // ---- CNN front-end
+    {
+        const int F1 = (c.n_mels - 1) / 2 + 1, F2 = (F1 - 1) / 2 + 1;
+        if (F2 * c.cnn_c2 != c.input_size) { set_error("asr_create: CNN output %d != input_size %d", F2 * c.cnn_c2, c.input_size); rc = SBK_ERR_ARG; goto fail; }
+        m->c1_w = p.f32("CNN.convblock_0.convs.conv_0.conv.weight", (int64_t)c.cnn_c1 * 9);
+        m->c1_b = p.f32("CNN.convblock_0.convs.conv_0.conv.bias", c.cnn_c1);
+        m->c1_g = p.f32("CNN.convblock_0.convs.norm_0.norm.weight", (int64_t)F1 * c.cnn_c1);
+        m->c1_be = p.f32("CNN.convblock_0.convs.norm_0.norm.bias", (int64_t)F1 * c.cnn_c1);
+        const float* w2 = find(w, "CNN.convblock_1.convs.conv_0.conv.weight", (int64_t)c.cnn_c2 * c.cnn_c1 * 9);
+        if (!w2) { rc = SBK_ERR_ARG; goto fail; }
+        std::vector<float> w2p((size_t)c.cnn_c2 * 9 * c.cnn_c1);
+        for (int o = 0; o < c.cnn_c2; ++o)
+            for (int ch = 0; ch < c.cnn_c1; ++ch)
+                for (int kf = 0; kf < 3; ++kf)
+                    for (int kt = 0; kt < 3; ++kt)
+                        w2p[((size_t)o * 9 + kf * 3 + kt) * c.cnn_c1 + ch] = w2[(((size_t)o * c.cnn_c1 + ch) * 3 + kf) * 3 + kt];
+        m->c2_w = p.f16_raw(w2p.data(), w2p.size());
+        m->c2_b = p.f32("CNN.convblock_1.convs.conv_0.conv.bias", c.cnn_c2);
+        m->c2_g = p.f32("CNN.convblock_1.convs.norm_0.norm.weight", (int64_t)F2 * c.cnn_c2);
+        m->c2_be = p.f32("CNN.convblock_1.convs.norm_0.norm.bias", (int64_t)F2 * c.cnn_c2);
+    }
+    // ---- encoder
+    m->w_in = p.f16("Transformer.custom_src_module.layers.0.w.weight", (int64_t)d * c.input_size);
+    m->b_in = p.f32("Transformer.custom_src_module.layers.0.w.bias", d);
+    m->enc.resize(c.num_encoder_layers);
+    for (int l = 0; l < c.num_encoder_layers && p.ok; ++l) {
+        const std::string q = "Transformer.encoder.layers." + std::to_string(l) + ".";
+        EncLayerW& e = m->enc[l];
+        e.ffn1_ln_g = p.f32(q + "ffn_module1.0.weight", d); e.ffn1_ln_b = p.f32(q + "ffn_module1.0.bias", d);
+        e.ffn1_w1 = p.f16(q + "ffn_module1.1.ffn.0.weight", (int64_t)F * d); e.ffn1_b1 = p.f32(q + "ffn_module1.1.ffn.0.bias", F);
+        e.ffn1_w2 = p.f16(q + "ffn_module1.1.ffn.3.weight", (int64_t)d * F); e.ffn1_b2 = p.f32(q + "ffn_module1.1.ffn.3.bias", d);
+        e.norm1_g = p.f32(q + "norm1.norm.weight", d); e.norm1_b = p.f32(q + "norm1.norm.bias", d);
+        e.wqkv = p.f16(q + "mha_layer.in_proj_weight", (int64_t)3 * d * d);
+        e.wo = p.f16(q + "mha_layer.out_proj.weight", (int64_t)d * d); e.bo = p.f32(q + "mha_layer.out_proj.bias", d);
+        e.wpos = nullptr; e.pos_u = e.pos_v = nullptr;
+        if (c.attention_type == SBK_ATT_RELPOS) {
+            e.wpos = p.f16(q + "mha_layer.linear_pos.weight", (int64_t)d * d);
+            e.pos_u = p.f32(q + "mha_layer.pos_bias_u", d); e.pos_v = p.f32(q + "mha_layer.pos_bias_v", d);
+        }
+        e.conv_ln_g = p.f32(q + "convolution_module.layer_norm.weight", d); e.conv_ln_b = p.f32(q + "convolution_module.layer_norm.bias", d);
+        {   // pointwise conv 1 (Conv1d k=1, weight (2d, d, 1)): interleave 16 value rows / 16 gate rows for the GLU epilogue
+            const float* src = find(w, q + "convolution_module.bottleneck.0.weight", (int64_t)2 * d * d);
+            const float* bs = find(w, q + "convolution_module.bottleneck.0.bias", 2 * d);
+            if (!src || !bs) { p.ok = false; break; }
+            std::vector<float> wi((size_t)2 * d * d), bi(2 * d);
+            for (int ch = 0; ch < d; ++ch) {
+                const int blk = ch / 16, j = ch % 16;
+                memcpy(&wi[((size_t)blk * 32 + j) * d], &src[(size_t)ch * d], d * 4);
+                memcpy(&wi[((size_t)blk * 32 + 16 + j) * d], &src[(size_t)(d + ch) * d], d * 4);
+                bi[blk * 32 + j] = bs[ch];
+                bi[blk * 32 + 16 + j] = bs[d + ch];
+            }
+            e.wpw1 = p.f16_raw(wi.data(), wi.size());
+            e.bpw1 = p.f32_raw(bi.data(), bi.size());
+        }
+        e.wdw = p.f32(q + "convolution_module.conv.weight", (int64_t)d * K); e.bdw = p.f32(q + "convolution_module.conv.bias", d);
+        e.aconv_ln_g = p.f32(q + "convolution_module.after_conv.0.weight", d); e.aconv_ln_b = p.f32(q + "convolution_module.after_conv.0.bias", d);
+        e.wpw2 = p.f16(q + "convolution_module.after_conv.2.weight", (int64_t)d * d); e.bpw2 = p.f32(q + "convolution_module.after_conv.2.bias", d);
+        e.ffn2_ln_g = p.f32(q + "ffn_module2.0.weight", d); e.ffn2_ln_b = p.f32(q + "ffn_module2.0.bias", d);
+        e.ffn2_w1 = p.f16(q + "ffn_module2.1.ffn.0.weight", (int64_t)F * d); e.ffn2_b1 = p.f32(q + "ffn_module2.1.ffn.0.bias", F);
+        e.ffn2_w2 = p.f16(q + "ffn_module2.1.ffn.3.weight", (int64_t)d * F); e.ffn2_b2 = p.f32(q + "ffn_module2.1.ffn.3.bias", d);
+        e.norm2_g = p.f32(q + "norm2.norm.weight", d); e.norm2_b = p.f32(q + "norm2.norm.bias", d);
+    }
+    if (!p.ok) { rc = SBK_ERR_ARG; goto fail; }
+    m->enc_norm_g = p.f32("Transformer.encoder.norm.norm.weight", d);
+    m->enc_norm_b = p.f32("Transformer.encoder.norm.norm.bias", d);
+    // positional tables
+    m->pos_len = c.max_len;
+    if (c.attention_type == SBK_ATT_ROPE) {
+        // nnet/attention.py:1012-1055: angle_{t,i} = t * exp(-2i * ln(1e4) / d_h), computed in fp32 like the reference
+        std::vector<float> cs((size_t)c.max_len * dh / 2), sn(cs.size());
+        for (int i = 0; i < dh / 2; ++i) {
+            const float ang = expf((float)(2 * i) * -(logf(10000.0f) / (float)dh));
+            for (int t = 0; t < c.max_len; ++t) {
+                const float ta = (float)t * ang;
+                cs[(size_t)t * (dh / 2) + i] = cosf(ta);
+                sn[(size_t)t * (dh / 2) + i] = sinf(ta);
+            }
+        }
+        m->rope_cos = p.f32_raw(cs.data(), cs.size());
+        m->rope_sin = p.f32_raw(sn.data(), sn.size());
+    } else {
+        // nnet/attention.py:360-408: row |r|: even cols sin(|r| f_i), odd cols cos(|r| f_i)
+        std::vector<float> pe((size_t)c.max_len * d);
+        for (int i = 0; i < d / 2; ++i) {
+            const float fr = expf((float)(2 * i) * -(logf(10000.0f) / (float)d));
+            for (int t = 0; t < c.max_len; ++t) {
+                pe[(size_t)t * d + 2 * i] = sinf((float)t * fr);
+                pe[(size_t)t * d + 2 * i + 1] = cosf((float)t * fr);
+            }
+        }
+        m->relpos_pe = p.f16_raw(pe.data(), pe.size());
+    }
+    // ---- decoder
+    if (c.num_decoder_layers > 0) {
+        m->emb = p.f32("Transformer.custom_tgt_module.layers.0.emb.Embedding.weight", (int64_t)c.vocab * d);
+        {
+            std::vector<float> pe((size_t)c.max_len * d);  // Transformer.py:252-303
+            for (int i = 0; i < d / 2; ++i) {
+                const float den = expf((float)(2 * i) * -(logf(10000.0f) / (float)d));
+                for (int t = 0; t < c.max_len; ++t) {
+                    pe[(size_t)t * d + 2 * i] = sinf((float)t * den);
+                    pe[(size_t)t * d + 2 * i + 1] = cosf((float)t * den);
+                }
+            }
+            m->dec_pe = p.f32_raw(pe.data(), pe.size());
+        }
+        const int L = c.num_decoder_layers;
+        m->dec.resize(L);
+        std::vector<float> wckv((size_t)L * 2 * d * d), bckv((size_t)L * 2 * d);
+        const float qs = 1.0f / sqrtf((float)dh);
+        for (int l = 0; l < L && p.ok; ++l) {
+            const std::string q = "Transformer.decoder.layers." + std::to_string(l) + ".";
+            DecLayerW& e = m->dec[l];
+            e.n1g = p.f32(q + "norm1.norm.weight", d); e.n1b = p.f32(q + "norm1.norm.bias", d);
+            e.n2g = p.f32(q + "norm2.norm.weight", d); e.n2b = p.f32(q + "norm2.norm.bias", d);
+            e.n3g = p.f32(q + "norm3.norm.weight", d); e.n3b = p.f32(q + "norm3.norm.bias", d);
+            const float* wi = find(w, q + "self_attn.att.in_proj_weight", (int64_t)3 * d * d);
+            const float* bi = find(w, q + "self_attn.att.in_proj_bias", 3 * d);
+            const float* wc = find(w, q + "multihead_attn.att.in_proj_weight", (int64_t)3 * d * d);
+            const float* bc = find(w, q + "multihead_attn.att.in_proj_bias", 3 * d);
+            if (!wi || !bi || !wc || !bc) { p.ok = false; break; }
+            {   // fold 1/sqrt(d_h) into the query rows
+                std::vector<float> ws(wi, wi + (size_t)3 * d * d), bs(bi, bi + 3 * d);
+                for (size_t i = 0; i < (size_t)d * d; ++i) ws[i] *= qs;
+                for (int i = 0; i < d; ++i) bs[i] *= qs;
+                e.w_self_in = p.f16_raw(ws.data(), ws.size());
+                e.b_self_in = p.f32_raw(bs.data(), bs.size());
+                std::vector<float> wq(wc, wc + (size_t)d * d), bq(bc, bc + d);
+                for (auto& v : wq) v *= qs;
+                for (auto& v : bq) v *= qs;
+                e.w_cross_q = p.f16_raw(wq.data(), wq.size());
+                e.b_cross_q = p.f32_raw(bq.data(), bq.size());
+            }
+            memcpy(&wckv[(size_t)l * 2 * d * d], wc + (size_t)d * d, (size_t)2 * d * d * 4);
+            memcpy(&bckv[(size_t)l * 2 * d], bc + d, (size_t)2 * d * 4);
+            e.w_self_out = p.f16(q + "self_attn.att.out_proj.weight", (int64_t)d * d); e.b_self_out = p.f32(q + "self_attn.att.out_proj.bias", d);
+            e.w_cross_out = p.f16(q + "multihead_attn.att.out_proj.weight", (int64_t)d * d); e.b_cross_out = p.f32(q + "multihead_attn.att.out_proj.bias", d);
+            e.w_ffn1 = p.f16(q + "pos_ffn.ffn.0.weight", (int64_t)F * d); e.b_ffn1 = p.f32(q + "pos_ffn.ffn.0.bias", F);
+            e.w_ffn2 = p.f16(q + "pos_ffn.ffn.3.weight", (int64_t)d * F); e.b_ffn2 = p.f32(q + "pos_ffn.ffn.3.bias", d);
+        }
+        if (!p.ok) { rc = SBK_ERR_ARG; goto fail; }
+        m->w_ckv = p.f16_raw(wckv.data(), wckv.size());
+        m->b_ckv = p.f32_raw(bckv.data(), bckv.size());
+        m->dec_norm_g = p.f32("Transformer.decoder.norm.norm.weight", d);
+        m->dec_norm_b = p.f32("Transformer.decoder.norm.norm.bias", d);
+        m->w_lin = p.f16("seq_lin.w.weight", (int64_t)c.vocab * d);
+        m->b_lin = p.f32("seq_lin.w.bias", c.vocab);
+    }
+    if (w.count("ctc_lin.w.weight")) {
+        m->w_ctc = p.f16("ctc_lin.w.weight", (int64_t)c.vocab * d);
+        m->b_ctc = p.f32("ctc_lin.w.bias", c.vocab);
+    }
+    if (!p.ok) { rc = SBK_ERR_ARG; goto fail; }
+    if (cudaMallocHost(&m->host_flag, 64) != cudaSuccess) { set_error("cudaMallocHost failed"); rc = SBK_ERR_NOMEM; goto fail; }
+    if (cudaDeviceSynchronize() != cudaSuccess) { set_error("asr_create: device error after upload"); rc = SBK_ERR_CUDA; goto fail; }
+    *out = m;
+    return SBK_OK;
+fail:
+    if (m->fbank) fbank_destroy(m->fbank);
+    cudaFree(m->warena.base);
+    delete m;
+    return rc;
+}
+
+void asr_destroy(AsrModel* m) {
+    if (!m) return;
+    if (m->step_graph) cudaGraphExecDestroy(m->step_graph);
+    if (m->fbank) fbank_destroy(m->fbank);
+    cudaFree(m->warena.base);
+    cudaFree(m->ws.base);
+    if (m->host_flag) cudaFreeHost(m->host_flag);
+    delete m;
+}
+
+static void frames(const sbk_asr_config& c, int L, int* T0, int* T1, int* T2) {
+    *T0 = 1 + L / c.hop;
+    *T1 = (*T0 - 1) / 2 + 1;
+    *T2 = (*T1 - 1) / 2 + 1;
+}
+
+// (Re)carve the workspace for a batch of B utterances of L samples, `rows` decoder hypotheses, `steps` max steps.
+static int ensure_workspace(AsrModel* m, int B, int L, int rows, int steps) {
+    if (m->ws.base && B <= m->wsB && L <= m->wsL && rows <= m->ws_rows && steps <= m->ws_steps) return SBK_OK;
+    B = std::max(B, m->wsB); L = std::max(L, m->wsL); rows = std::max(rows, m->ws_rows); steps = std::max(steps, m->ws_steps);
+    const sbk_asr_config& c = m->cfg;
+    int T0, T1, T2;
+    frames(c, L, &T0, &T1, &T2);
+    const int F1 = (c.n_mels - 1) / 2 + 1;
+    const size_t M = (size_t)B * T2, d = c.d_model, F = c.d_ffn, Ld = c.num_decoder_layers, S = steps + 1;
+    size_t need = 0;
+    auto sz = [&](size_t bytes) { need += (bytes + 255) & ~size_t(255); };
+    sz((size_t)B * L * 4); sz((size_t)B * T0 * c.n_mels * 4); sz(M * d * 4); sz(M * d * 4); sz(M * d * 4);
+    sz((size_t)B * T1 * F1 * c.cnn_c1 * 4); sz(M * c.input_size * 4); sz((size_t)rows * d * 4);
+    sz((size_t)rows * c.vocab * 4); sz((size_t)rows * S * 4);
+    sz(B * 4); sz(B * 4); sz((size_t)rows * (S + 1) * 4); sz(64); sz(rows * 4); sz(64); sz((size_t)rows * S * 4); sz(B * 4);
+    sz((size_t)B * T1 * F1 * c.cnn_c1 * 2); sz(M * c.input_size * 2); sz(M * d * 2); sz(M * F * 2); sz(M * 3 * d * 2);
+    sz(M * d * 2); sz((size_t)T2 * d * 2); sz(M * d * 2); sz(M * Ld * 2 * d * 2);
+    sz((size_t)Ld * rows * S * d * 2); sz((size_t)Ld * rows * S * d * 2);
+    sz((size_t)rows * d * 2); sz((size_t)rows * d * 2); sz((size_t)rows * d * 2); sz((size_t)rows * F * 2);
+    need += 1 << 20;
+    if (need > m->ws.cap) {
+        if (m->ws.base) { cudaDeviceSynchronize(); cudaFree(m->ws.base); m->ws.base = nullptr; }
+        if (cudaMalloc(&m->ws.base, need) != cudaSuccess) {
+            m->ws.cap = 0;
+            set_error("workspace cudaMalloc(%zu) failed", need);
+            return SBK_ERR_NOMEM;
+        }
+        m->ws.cap = need;
+    }
+    if (m->step_graph) { cudaGraphExecDestroy(m->step_graph); m->step_graph = nullptr; m->graph_rows = -1; }
+    m->ws.used = 0;
+    AsrModel::Buf& b = m->b;
+#define TAKE(field, type, bytes) b.field = reinterpret_cast<type*>(m->ws.take(bytes))
+    TAKE(wav, float, (size_t)B * L * 4); TAKE(feats, float, (size_t)B * T0 * c.n_mels * 4); TAKE(x, float, M * d * 4);
+    TAKE(glu, float, M * d * 4); TAKE(enc_out, float, M * d * 4); TAKE(act1_f, float, (size_t)B * T1 * F1 * c.cnn_c1 * 4);
+    TAKE(cnn_f, float, M * c.input_size * 4); TAKE(dx, float, (size_t)rows * d * 4); TAKE(logits, float, (size_t)rows * c.vocab * 4);
+    TAKE(score, float, (size_t)rows * S * 4);
+    TAKE(utt_max, int, B * 4); TAKE(enc_len, int, B * 4); TAKE(tokens, int, (size_t)rows * (S + 1) * 4); TAKE(step, int, 64);
+    TAKE(has_ended, int, rows * 4); TAKE(ended_count, int, 64); TAKE(pred, int, (size_t)rows * S * 4); TAKE(rel_len, float, B * 4);
+    TAKE(act1, __half, (size_t)B * T1 * F1 * c.cnn_c1 * 2); TAKE(a_in, __half, M * c.input_size * 2); TAKE(h16, __half, M * d * 2);
+    TAKE(f16, __half, M * F * 2); TAKE(qkv16, __half, M * 3 * d * 2); TAKE(att16, __half, M * d * 2);
+    TAKE(P16, __half, (size_t)T2 * d * 2); TAKE(enc16, __half, M * d * 2); TAKE(ckv16, __half, M * Ld * 2 * d * 2);
+    TAKE(kcache, __half, (size_t)Ld * rows * S * d * 2); TAKE(vcache, __half, (size_t)Ld * rows * S * d * 2);
+    TAKE(dh16, __half, (size_t)rows * d * 2); TAKE(dq16, __half, (size_t)rows * d * 2); TAKE(datt16, __half, (size_t)rows * d * 2);
+    TAKE(df16, __half, (size_t)rows * F * 2);
+#undef TAKE
+    if (!b.df16) { set_error("workspace carve failed"); return SBK_ERR_NOMEM; }
+    m->wsB = B; m->wsL = L; m->ws_rows = rows; m->ws_steps = steps;
+    return SBK_OK;
+}
+
+#define RC(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
+
+// feats [B, T0, n_mels] fp32 (already normalised) -> enc_out fp32 [B, T2, d] (+ enc16). enc_len device int[B].
+static int run_encoder(AsrModel* m, const float* feats, int B, int T0, const int* enc_len, float* cnn_out_f,
+                       float* enc_out, cudaStream_t st) {
+    const sbk_asr_config& c = m->cfg;
+    AsrModel::Buf& b = m->b;
+    const int T1 = (T0 - 1) / 2 + 1, T = feats ? (T1 - 1) / 2 + 1 : T0;  // feats == nullptr: b.a_in holds [B*T0, input_size]
+    const int M = B * T, d = c.d_model, F = c.d_ffn, H = c.nhead, dh = d / H;
+    SBK_REQUIRE(T <= m->pos_len, "encode: %d frames exceed max_len=%d", T, m->pos_len);
+    if (feats != nullptr)
+        RC(cnn_frontend_forward(feats, B, T0, c.n_mels, m->c1_w, m->c1_b, m->c1_g, m->c1_be, c.cnn_c1, m->c2_w, m->c2_b,
+                                m->c2_g, m->c2_be, c.cnn_c2, b.act1, nullptr, b.a_in, cnn_out_f, st));
+    GemmEpilogue e;
+    e.mode = EPI_F32; e.bias = m->b_in; e.out = b.x; e.ldo = d;
+    RC(gemm_f16(b.a_in, c.input_size, m->w_in, c.input_size, e, M, d, c.input_size, st));
+    const float att_scale = 1.0f / sqrtf((float)d);  // nnet/attention.py:521,1272: 1/sqrt(embed_dim), not head_dim
+    for (int l = 0; l < c.num_encoder_layers; ++l) {
+        const EncLayerW& w = m->enc[l];
+        // --- ffn module 1 (Conformer.py:479)
+        RC(layernorm_rows(b.x, b.h16, true, w.ffn1_ln_g, w.ffn1_ln_b, M, d, 1e-5f, false, st));
+        e = GemmEpilogue(); e.mode = EPI_F16; e.act = ACT_SILU; e.bias = w.ffn1_b1; e.out = b.f16; e.ldo = F;
+        RC(gemm_f16(b.h16, d, w.ffn1_w1, d, e, M, F, d, st));
+        e = GemmEpilogue(); e.mode = EPI_RESID; e.bias = w.ffn1_b2; e.out = b.x; e.resid = b.x; e.ldo = d; e.alpha = 0.5f;
+        RC(gemm_f16(b.f16, F, w.ffn1_w2, F, e, M, d, F, st));
+        // --- self-attention (Conformer.py:481-492)
+        RC(layernorm_rows(b.x, b.h16, true, w.norm1_g, w.norm1_b, M, d, 1e-5f, false, st));
+        e = GemmEpilogue(); e.out = b.qkv16; e.ldo = 3 * d;
+        if (c.attention_type == SBK_ATT_ROPE) {
+            e.mode = EPI_ROPE; e.alpha = att_scale; e.T = T; e.rope_cos = m->rope_cos; e.rope_sin = m->rope_sin; e.head_dim = dh;
+        } else {
+            e.mode = EPI_F16;
+        }
+        RC(gemm_f16(b.h16, d, w.wqkv, d, e, M, 3 * d, d, st));
+        if (c.attention_type == SBK_ATT_RELPOS) {
+            e = GemmEpilogue(); e.mode = EPI_F16; e.out = b.P16; e.ldo = d;
+            RC(gemm_f16(m->relpos_pe, d, w.wpos, d, e, T, d, d, st));
+        }
+        RC(encoder_attention(b.qkv16, 3 * d, B, T, H, dh, enc_len, c.attention_type == SBK_ATT_RELPOS, w.pos_u, w.pos_v,
+                             b.P16, d, att_scale, b.att16, d, st));
+        e = GemmEpilogue(); e.mode = EPI_RESID; e.bias = w.bo; e.out = b.x; e.resid = b.x; e.ldo = d; e.alpha = 1.0f;
+        RC(gemm_f16(b.att16, d, w.wo, d, e, M, d, d, st));
+        // --- convolution module (Conformer.py:314-330, 494)
+        RC(layernorm_rows(b.x, b.h16, true, w.conv_ln_g, w.conv_ln_b, M, d, 1e-5f, false, st));
+        e = GemmEpilogue(); e.mode = EPI_GLU; e.bias = w.bpw1; e.out = b.glu; e.ldo = d;
+        RC(gemm_f16(b.h16, d, w.wpw1, d, e, M, 2 * d, d, st));
+        RC(dwconv_ln_swish(b.glu, B, T, d, c.kernel_size, w.wdw, w.bdw, w.aconv_ln_g, w.aconv_ln_b, 1e-5f, b.h16, st));
+        e = GemmEpilogue(); e.mode = EPI_RESID; e.bias = w.bpw2; e.out = b.x; e.resid = b.x; e.ldo = d; e.alpha = 1.0f;
+        e.row_lens = enc_len; e.T = T;
+        RC(gemm_f16(b.h16, d, w.wpw2, d, e, M, d, d, st));
+        // --- ffn module 2 + norm2 (Conformer.py:498)
+        RC(layernorm_rows(b.x, b.h16, true, w.ffn2_ln_g, w.ffn2_ln_b, M, d, 1e-5f, false, st));
+        e = GemmEpilogue(); e.mode = EPI_F16; e.act = ACT_SILU; e.bias = w.ffn2_b1; e.out = b.f16; e.ldo = F;
+        RC(gemm_f16(b.h16, d, w.ffn2_w1, d, e, M, F, d, st));
+        e = GemmEpilogue(); e.mode = EPI_RESID; e.bias = w.ffn2_b2; e.out = b.x; e.resid = b.x; e.ldo = d; e.alpha = 0.5f;
+        RC(gemm_f16(b.f16, F, w.ffn2_w2, F, e, M, d, F, st));
+        RC(layernorm_rows(b.x, b.x, false, w.norm2_g, w.norm2_b, M, d, 1e-5f, false, st));
+    }
+    RC(layernorm_rows(b.x, enc_out, false, m->enc_norm_g, m->enc_norm_b, M, d, 1e-6f, false, st));  // Conformer.py:700
+    return SBK_OK;
+}
+
+__global__ void abs_len_kernel(const float* rel, int B, int T, int* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    // torch.round (half to even) of rel * T   (TransformerASR.py:148, seq2seq.py:206)
+    if (i < B) out[i] = min(T, max(0, __float2int_rn(rel[i] * static_cast<float>(T))));
+}
+
+__global__ void greedy_reset_kernel(int* tokens, int tok_stride, int rows, int bos, int* step, int* has_ended,
+                                    int* ended_count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < rows) { tokens[static_cast<size_t>(i) * tok_stride] = bos; has_ended[i] = 0; }
+    if (i == 0) { *step = 0; *ended_count = 0; }
+}
+
+static int enqueue_decode_step(AsrModel* m, int rows, int rows_per_utt, int T, int S_max, int eos, float* log_probs,
+                               int L_lp, cudaStream_t st) {
+    const sbk_asr_config& c = m->cfg;
+    AsrModel::Buf& b = m->b;
+    const int d = c.d_model, F = c.d_ffn, H = c.nhead, dh = d / H, Ld = c.num_decoder_layers;
+    const int ffn_epi = c.decoder_activation == SBK_ACT_GELU ? SK_F16_GELU : SK_F16_RELU;
+    RC(dec_embed(b.tokens, S_max + 1, b.step, m->emb, m->dec_pe, d, rows, b.dx, st));
+    for (int l = 0; l < Ld; ++l) {
+        const DecLayerW& w = m->dec[l];
+        __half* kc = b.kcache + (size_t)l * rows * S_max * d;
+        __half* vc = b.vcache + (size_t)l * rows * S_max * d;
+        RC(layernorm_rows(b.dx, b.dh16, true, w.n1g, w.n1b, rows, d, 1e-6f, false, st));
+        SkinnyArgs a{};
+        a.A = b.dh16; a.lda = d; a.W = w.w_self_in; a.ldw = d; a.bias = w.b_self_in; a.n_rows = rows; a.N = 3 * d; a.K = d;
+        a.epi = SK_QKV_CACHE; a.out = b.dq16; a.ldo = d; a.kcache = kc; a.vcache = vc; a.step_ptr = b.step; a.S_max = S_max;
+        a.d = d; a.q_scale = 1.0f;
+        RC(skinny_gemm(a, st));
+        DecAttnArgs t{};
+        t.q = b.dq16; t.ldq = d; t.kbase = kc; t.vbase = vc; t.row_stride = (size_t)S_max * d; t.key_stride = d;
+        t.rows_per_block = 1; t.n_keys_ptr = b.step; t.enc_len = nullptr; t.H = H; t.dh = dh; t.out = b.datt16; t.ldo = d;
+        RC(dec_attention(t, rows, S_max, st));
+        a = SkinnyArgs{}; a.A = b.datt16; a.lda = d; a.W = w.w_self_out; a.ldw = d; a.bias = w.b_self_out; a.n_rows = rows;
+        a.N = d; a.K = d; a.epi = SK_RESID; a.out = b.dx; a.ldo = d;
+        RC(skinny_gemm(a, st));
+        // cross attention
+        RC(layernorm_rows(b.dx, b.dh16, true, w.n2g, w.n2b, rows, d, 1e-6f, false, st));
+        a = SkinnyArgs{}; a.A = b.dh16; a.lda = d; a.W = w.w_cross_q; a.ldw = d; a.bias = w.b_cross_q; a.n_rows = rows;
+        a.N = d; a.K = d; a.epi = SK_F16; a.out = b.dq16; a.ldo = d;
+        RC(skinny_gemm(a, st));
+        t = DecAttnArgs{};
+        t.q = b.dq16; t.ldq = d; t.kbase = b.ckv16 + (size_t)l * 2 * d; t.vbase = t.kbase + d;
+        t.row_stride = (size_t)T * Ld * 2 * d; t.key_stride = Ld * 2 * d; t.rows_per_block = rows_per_utt;
+        t.n_keys_ptr = nullptr; t.enc_len = b.enc_len; t.H = H; t.dh = dh; t.out = b.datt16; t.ldo = d;
+        RC(dec_attention(t, rows, T, st));
+        a = SkinnyArgs{}; a.A = b.datt16; a.lda = d; a.W = w.w_cross_out; a.ldw = d; a.bias = w.b_cross_out; a.n_rows = rows;
+        a.N = d; a.K = d; a.epi = SK_RESID; a.out = b.dx; a.ldo = d;
+        RC(skinny_gemm(a, st));
+        // feed-forward
+        RC(layernorm_rows(b.dx, b.dh16, true, w.n3g, w.n3b, rows, d, 1e-6f, false, st));
+        a = SkinnyArgs{}; a.A = b.dh16; a.lda = d; a.W = w.w_ffn1; a.ldw = d; a.bias = w.b_ffn1; a.n_rows = rows;
+        a.N = F; a.K = d; a.epi = ffn_epi; a.out = b.df16; a.ldo = F;
+        RC(skinny_gemm(a, st));
+        a = SkinnyArgs{}; a.A = b.df16; a.lda = F; a.W = w.w_ffn2; a.ldw = F; a.bias = w.b_ffn2; a.n_rows = rows;
+        a.N = d; a.K = F; a.epi = SK_RESID; a.out = b.dx; a.ldo = d;
+        RC(skinny_gemm(a, st));
+    }
+    RC(layernorm_rows(b.dx, b.dh16, true, m->dec_norm_g, m->dec_norm_b, rows, d, 1e-6f, false, st));
+    SkinnyArgs a{};
+    a.A = b.dh16; a.lda = d; a.W = m->w_lin; a.ldw = d; a.bias = m->b_lin; a.n_rows = rows; a.N = c.vocab; a.K = d;
+    a.epi = SK_F32; a.out = b.logits; a.ldo = c.vocab;
+    RC(skinny_gemm(a, st));
+    RC(greedy_select(b.logits, rows, c.vocab, b.step, eos, b.tokens, S_max + 1, b.has_ended, b.ended_count, b.pred, b.score,
+                     S_max, log_probs, L_lp, st));
+    RC(advance_step(b.step, st));
+    return SBK_OK;
+}
+
+// Greedy search over encoder states already in the workspace (b.enc_out / b.enc_len).
+static int run_greedy(AsrModel* m, int B, int T, int max_steps, int bos, int eos, float* log_probs, int* steps_done,
+                      cudaStream_t st) {
+    const sbk_asr_config& c = m->cfg;
+    AsrModel::Buf& b = m->b;
+    const int d = c.d_model, Ld = c.num_decoder_layers, M = B * T, rows = B, S_max = m->ws_steps + 1;
+    SBK_REQUIRE(Ld > 0, "greedy: model has no decoder");
+    SBK_REQUIRE(max_steps <= m->ws_steps && max_steps + 1 <= c.max_len, "greedy: max_steps=%d too large", max_steps);
+    *steps_done = 0;
+    if (max_steps <= 0) return SBK_OK;
+    // cross-attention K/V for all layers: one tcgen05 GEMM  [M, d] x [L*2d, d]^T
+    RC(cast_f32_f16(b.enc_out, b.enc16, (size_t)M * d, st));
+    GemmEpilogue e;
+    e.mode = EPI_F16; e.bias = m->b_ckv; e.out = b.ckv16; e.ldo = Ld * 2 * d;
+    RC(gemm_f16(b.enc16, d, m->w_ckv, d, e, M, Ld * 2 * d, d, st));
+    greedy_reset_kernel<<<ceil_div(rows, 128), 128, 0, st>>>(b.tokens, S_max + 1, rows, bos, b.step, b.has_ended, b.ended_count);
+    SBK_LAUNCH_CHECK();
+    const bool use_graph = getenv("SBK_NO_GRAPH") == nullptr && log_probs == nullptr;
+    if (use_graph && (m->step_graph == nullptr || m->graph_rows != rows || m->graph_T != T || m->graph_B != B)) {
+        if (m->step_graph) { cudaGraphExecDestroy(m->step_graph); m->step_graph = nullptr; }
+        cudaGraph_t g;
+        SBK_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        int rc = enqueue_decode_step(m, rows, 1, T, S_max, eos, nullptr, 0, st);
+        cudaError_t ce = cudaStreamEndCapture(st, &g);
+        if (rc) return rc;
+        SBK_CUDA_CHECK(ce);
+        SBK_CUDA_CHECK(cudaGraphInstantiate(&m->step_graph, g, 0));
+        cudaGraphDestroy(g);
+        m->graph_rows = rows; m->graph_T = T; m->graph_B = B;
+    }
+    const int check_every = 8;
+    int s = 0;
+    while (s < max_steps) {
+        const int chunk = std::min(check_every, max_steps - s);
+        for (int i = 0; i < chunk; ++i) {
+            if (use_graph) SBK_CUDA_CHECK(cudaGraphLaunch(m->step_graph, st));
+            else RC(enqueue_decode_step(m, rows, 1, T, S_max, eos, log_probs, max_steps, st));
+        }
+        s += chunk;
+        if (s < max_steps) {  // seq2seq.py:256 `has_ended.all()` early exit, polled once per chunk
+            SBK_CUDA_CHECK(cudaMemcpyAsync(m->host_flag, b.ended_count, 4, cudaMemcpyDeviceToHost, st));
+            SBK_CUDA_CHECK(cudaStreamSynchronize(st));
+            if (*m->host_flag >= rows) break;
+        }
+    }
+    *steps_done = s;
+    return SBK_OK;
+}
+
+}  // namespace sbk
+
+// ============================================================================ C ABI
+using namespace sbk;
+
+extern "C" {
+
+const char* sbk_last_error(void) { return sbk::last_error(); }
+
+int sbk_version(void) { return 100; }
+
+int sbk_fbank_create(int n_fft, int hop, int n_mels, const float* window_host, const float* mel_matrix_host, float amin,
+                     float top_db, sbk_fbank** out) {
+    return fbank_create(reinterpret_cast<Fbank**>(out), n_fft, hop, n_mels, window_host, mel_matrix_host, amin, top_db);
+}
+void sbk_fbank_destroy(sbk_fbank* fb) { fbank_destroy(reinterpret_cast<Fbank*>(fb)); }
+int sbk_fbank_num_frames(const sbk_fbank* fb, int n_samples) { return fbank_num_frames(reinterpret_cast<const Fbank*>(fb), n_samples); }
+int sbk_fbank_forward(const sbk_fbank* fb, const float* wav_dev, int B, int L, float* out_dev, int* utt_max_scratch_dev,
+                      void* stream) {
+    return fbank_forward(reinterpret_cast<const Fbank*>(fb), wav_dev, B, L, out_dev, utt_max_scratch_dev, nullptr, nullptr,
+                         0.0f, static_cast<cudaStream_t>(stream));
+}
+int sbk_input_norm_global(const float* x_dev, float* out_dev, int B, int T, int F, const float* mean_dev,
+                          const float* std_dev, float eps, void* stream) {
+    return global_norm_forward(x_dev, out_dev, B, T, F, mean_dev, std_dev, eps, static_cast<cudaStream_t>(stream));
+}
+int sbk_input_norm_sentence(const float* x_dev, float* out_dev, const float* rel_len_dev, int B, int T, int F,
+                            int std_norm, int avoid_padding_norm, float eps, void* stream) {
+    return sentence_norm_forward(x_dev, out_dev, rel_len_dev, B, T, F, std_norm, avoid_padding_norm, eps,
+                                 static_cast<cudaStream_t>(stream));
+}
+
+int sbk_gemm_f16_test(const void* A_dev, const void* W_dev, const float* bias_dev, void* out_dev, int out_is_f32, int act,
+                      int M, int N, int K, void* stream) {
+    GemmEpilogue e;
+    e.mode = out_is_f32 ? EPI_F32 : EPI_F16;
+    e.act = act;
+    e.bias = bias_dev;
+    e.out = out_dev;
+    e.ldo = N;
+    return gemm_f16(A_dev, K, W_dev, K, e, M, N, K, static_cast<cudaStream_t>(stream));
+}
+
+int sbk_asr_create(const sbk_asr_config* cfg, const sbk_tensor* weights, int n_weights, sbk_asr** out) {
+    return asr_create(cfg, weights, n_weights, reinterpret_cast<AsrModel**>(out));
+}
+void sbk_asr_destroy(sbk_asr* m) { asr_destroy(reinterpret_cast<AsrModel*>(m)); }
+
+int sbk_asr_num_frames(const sbk_asr* mm, int n_samples, int* T_feat, int* T_enc) {
+    const AsrModel* m = reinterpret_cast<const AsrModel*>(mm);
+    int T0, T1, T2;
+    frames(m->cfg, n_samples, &T0, &T1, &T2);
+    if (T_feat) *T_feat = T0;
+    if (T_enc) *T_enc = T2;
+    return SBK_OK;
+}
+
+int sbk_asr_cnn_forward(sbk_asr* mm, const float* feats_dev, int B, int T0, float* out_dev, void* stream) {
+    AsrModel* m = reinterpret_cast<AsrModel*>(mm);
+    const sbk_asr_config& c = m->cfg;
+    const int L = (T0 - 1) * c.hop;
+    RC(ensure_workspace(m, B, L, std::max(B, m->ws_rows), std::max(1, m->ws_steps)));
+    return cnn_frontend_forward(feats_dev, B, T0, c.n_mels, m->c1_w, m->c1_b, m->c1_g, m->c1_be, c.cnn_c1, m->c2_w, m->c2_b,
+                                m->c2_g, m->c2_be, c.cnn_c2, m->b.act1, nullptr, m->b.a_in, out_dev,
+                                static_cast<cudaStream_t>(stream));
+}
+
+// src_dev: CNN output [B, T, input_size] fp32 -> enc_out_dev [B, T, d] fp32 (TransformerASR.encode)
+int sbk_asr_encode_feats(sbk_asr* mm, const float* feats_dev, const float* rel_len_dev, int B, int T0,
+                         float* cnn_out_dev, float* enc_out_dev, void* stream) {
+    AsrModel* m = reinterpret_cast<AsrModel*>(mm);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const sbk_asr_config& c = m->cfg;
+    const int L = (T0 - 1) * c.hop;
+    RC(ensure_workspace(m, B, L, std::max(B, m->ws_rows), std::max(1, m->ws_steps)));
+    const int T1 = (T0 - 1) / 2 + 1, T = (T1 - 1) / 2 + 1;
+    const int* enc_len = nullptr;
+    if (rel_len_dev) {
+        abs_len_kernel<<<ceil_div(B, 128), 128, 0, st>>>(rel_len_dev, B, T, m->b.enc_len);
+        SBK_LAUNCH_CHECK();
+        enc_len = m->b.enc_len;
+    }
+    return run_encoder(m, feats_dev, B, T0, enc_len, cnn_out_dev, enc_out_dev ? enc_out_dev : m->b.enc_out, st);
+}
+
+int sbk_asr_encode_from_cnn(sbk_asr* mm, const float* src_dev, const float* rel_len_dev, int B, int T,
+                            float* enc_out_dev, void* stream) {
+    AsrModel* m = reinterpret_cast<AsrModel*>(mm);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const sbk_asr_config& c = m->cfg;
+    const int L = ((T - 1) * 4) * c.hop;  // any L whose frame count maps to >= T encoder frames
+    RC(ensure_workspace(m, B, L, std::max(B, m->ws_rows), std::max(1, m->ws_steps)));
+    RC(cast_f32_f16(src_dev, m->b.a_in, (size_t)B * T * c.input_size, st));
+    const int* enc_len = nullptr;
+    if (rel_len_dev) {
+        abs_len_kernel<<<ceil_div(B, 128), 128, 0, st>>>(rel_len_dev, B, T, m->b.enc_len);
+        SBK_LAUNCH_CHECK();
+        enc_len = m->b.enc_len;
+    }
+    return run_encoder(m, nullptr, B, T, enc_len, nullptr, enc_out_dev ? enc_out_dev : m->b.enc_out, st);
+}
+
+// Full device pipeline on device-resident wav: Fbank -> global CMVN -> CNN -> encoder -> greedy.
+// Outputs (device, optional): enc_out [B,T,d] fp32; pred [B, max_steps] int32; score [B, max_steps] fp32.
+int sbk_asr_transcribe_greedy_dev(sbk_asr* mm, const float* wav_dev, const float* rel_len_dev, int B, int L,
+                                  int max_steps, int bos, int eos, float* enc_out_dev, int* pred_dev, float* score_dev,
+                                  float* log_probs_dev, int* steps_done, void* stream) {
+    AsrModel* m = reinterpret_cast<AsrModel*>(mm);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const sbk_asr_config& c = m->cfg;
+    SBK_REQUIRE(m->glob_mean != nullptr, "transcribe: model has no normalize.glob_mean/std (global CMVN) weights");
+    RC(ensure_workspace(m, B, L, std::max(B, m->ws_rows), std::max(max_steps, m->ws_steps)));
+    int T0, T1, T;
+    frames(c, L, &T0, &T1, &T);
+    AsrModel::Buf& b = m->b;
+    RC(fbank_forward(m->fbank, wav_dev, B, L, b.feats, b.utt_max, m->glob_mean, m->glob_std, 1e-10f, st));
+    const int* enc_len = nullptr;
+    if (rel_len_dev) {
+        abs_len_kernel<<<ceil_div(B, 128), 128, 0, st>>>(rel_len_dev, B, T, b.enc_len);
+        SBK_LAUNCH_CHECK();
+        enc_len = b.enc_len;
+    } else {
+        std::vector<int> full(B, T);
+        SBK_CUDA_CHECK(cudaMemcpyAsync(b.enc_len, full.data(), B * 4, cudaMemcpyHostToDevice, st));
+        SBK_CUDA_CHECK(cudaStreamSynchronize(st));
+        enc_len = b.enc_len;
+    }
+    RC(run_encoder(m, b.feats, B, T0, enc_len, nullptr, b.enc_out, st));
+    if (enc_out_dev)
+        SBK_CUDA_CHECK(cudaMemcpyAsync(enc_out_dev, b.enc_out, (size_t)B * T * c.d_model * 4, cudaMemcpyDeviceToDevice, st));
+    int done = 0;
+    if (max_steps > 0 && c.num_decoder_layers > 0) {
+        RC(run_greedy(m, B, T, max_steps, bos, eos, log_probs_dev, &done, st));
+        const int S_max = m->ws_steps + 1;
+        if (pred_dev)
+            SBK_CUDA_CHECK(cudaMemcpy2DAsync(pred_dev, (size_t)max_steps * 4, b.pred, (size_t)S_max * 4, (size_t)done * 4, B,
+                                             cudaMemcpyDeviceToDevice, st));
+        if (score_dev)
+            SBK_CUDA_CHECK(cudaMemcpy2DAsync(score_dev, (size_t)max_steps * 4, b.score, (size_t)S_max * 4, (size_t)done * 4, B,
+                                             cudaMemcpyDeviceToDevice, st));
+    }
+    if (steps_done) *steps_done = done;
+    return SBK_OK;
+}
+
+// Greedy search from caller-provided encoder states (S2STransformerGreedySearcher.forward).
+int sbk_asr_greedy_from_enc(sbk_asr* mm, const float* enc_dev, const float* rel_len_dev, int B, int T, int max_steps,
+                            int bos, int eos, int* pred_dev, float* score_dev, float* log_probs_dev, int* steps_done,
+                            void* stream) {
+    AsrModel* m = reinterpret_cast<AsrModel*>(mm);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const sbk_asr_config& c = m->cfg;
+    // workspace sized from T: pick L such that frames(L) -> T
+    const int L = std::max(m->wsL, ((T - 1) * 4) * c.hop);
+    RC(ensure_workspace(m, std::max(B, m->wsB), L, std::max(B, m->ws_rows), std::max(max_steps, m->ws_steps)));
+    AsrModel::Buf& b = m->b;
+    SBK_CUDA_CHECK(cudaMemcpyAsync(b.enc_out, enc_dev, (size_t)B * T * c.d_model * 4, cudaMemcpyDeviceToDevice, st));
+    if (rel_len_dev) {
+        abs_len_kernel<<<ceil_div(B, 128), 128, 0, st>>>(rel_len_dev, B, T, b.enc_len);
+        SBK_LAUNCH_CHECK();
+    } else {
+        std::vector<int> full(B, T);
+        SBK_CUDA_CHECK(cudaMemcpyAsync(b.enc_len, full.data(), B * 4, cudaMemcpyHostToDevice, st));
+        SBK_CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    int done = 0;
+    RC(run_greedy(m, B, T, max_steps, bos, eos, log_probs_dev, &done, st));
+    const int S_max = m->ws_steps + 1;
+    if (pred_dev && done > 0)
+        SBK_CUDA_CHECK(cudaMemcpy2DAsync(pred_dev, (size_t)max_steps * 4, b.pred, (size_t)S_max * 4, (size_t)done * 4, B,
+                                         cudaMemcpyDeviceToDevice, st));
+    if (score_dev && done > 0)
+        SBK_CUDA_CHECK(cudaMemcpy2DAsync(score_dev, (size_t)max_steps * 4, b.score, (size_t)S_max * 4, (size_t)done * 4, B,
+                                         cudaMemcpyDeviceToDevice, st));
+    if (steps_done) *steps_done = done;
+    return SBK_OK;
+}
+
+// Host-buffer entry point (the call EncoderDecoderASR.transcribe_batch makes): wav/rel_len/pred are HOST
+// (ideally pinned) buffers; H2D and D2H copies are part of the call.
+int sbk_asr_transcribe_greedy_host(sbk_asr* mm, const float* wav_host, const float* rel_len_host, int B, int L,
+                                   int max_steps, int bos, int eos, int* pred_host, float* score_host, int* steps_done,
+                                   void* stream) {
+    AsrModel* m = reinterpret_cast<AsrModel*>(mm);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    RC(ensure_workspace(m, B, L, std::max(B, m->ws_rows), std::max(max_steps, m->ws_steps)));
+    AsrModel::Buf& b = m->b;
+    SBK_CUDA_CHECK(cudaMemcpyAsync(b.wav, wav_host, (size_t)B * L * 4, cudaMemcpyHostToDevice, st));
+    const float* rel_dev = nullptr;
+    if (rel_len_host) {
+        SBK_CUDA_CHECK(cudaMemcpyAsync(b.rel_len, rel_len_host, B * 4, cudaMemcpyHostToDevice, st));
+        rel_dev = b.rel_len;
+    }
+    int done = 0;
+    RC(sbk_asr_transcribe_greedy_dev(mm, b.wav, rel_dev, B, L, max_steps, bos, eos, nullptr, nullptr, nullptr, nullptr, &done,
+                                     stream));
+    const int S_max = m->ws_steps + 1;
+    if (done > 0) {
+        if (pred_host)
+            SBK_CUDA_CHECK(cudaMemcpy2DAsync(pred_host, (size_t)max_steps * 4, b.pred, (size_t)S_max * 4, (size_t)done * 4, B,
+                                             cudaMemcpyDeviceToHost, st));
+        if (score_host)
+            SBK_CUDA_CHECK(cudaMemcpy2DAsync(score_host, (size_t)max_steps * 4, b.score, (size_t)S_max * 4, (size_t)done * 4, B,
+                                             cudaMemcpyDeviceToHost, st));
+    }
+    SBK_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (steps_done) *steps_done = done;
+    return SBK_OK;
+}
+
+}  // extern "C"

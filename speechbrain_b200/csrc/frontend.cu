@@ -1,0 +1,259 @@
+// ConvolutionFrontEnd: 2 x [reflect-pad + Conv2d(3x3, stride 2) + LayerNorm(F', C) + LeakyReLU].
+//
+// Replaces lobes/models/convolution.py:116-320 (ConvolutionFrontEnd / ConvBlock) with
+// nnet/CNN.py:654-751 (Conv2d.forward, "same" reflect padding k//2 for stride > 1) and
+// nnet/normalization.py:185-242 (LayerNorm over the last two dims), activation LeakyReLU(0.01).
+//
+// Layouts (channels-last, as the reference exposes them):
+//   feats [B, T0, F0] fp32 -> act1 [B, T1, F1, C1] fp16 (+ optional fp32) -> act2 [B, T2, F2*C2] fp16 (+ fp32)
+//   T1 = (T0-1)/2+1, F1 = (F0-1)/2+1, likewise T2/F2.
+// conv1 (C_in = 1) is HBM/latency bound: one CTA per output frame, fused LN + LeakyReLU.
+// conv2 (C1 -> C2, K = 9*C1 = 576) is an implicit GEMM on mma.sync.m16n8k16 (fp16 in, fp32 accumulate);
+// the weight matrix and a 9-frame input patch live in shared memory; LN + LeakyReLU fused.
+#include <algorithm>
+
+#include "common.cuh"
+#include "sbk_internal.h"
+
+namespace sbk {
+
+__device__ __forceinline__ int reflect_idx(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); }
+__device__ __forceinline__ float leaky(float x) { return x > 0.0f ? x : 0.01f * x; }
+
+// --------------------------------------------------------------------------- conv1
+// w1: [C1, 3(kf), 3(kt)] fp32 (reference weight (C1,1,kf,kt)), b1: [C1]; g/be: [F1, C1].
+template <int C1>
+__global__ void __launch_bounds__(256)
+conv1_ln_kernel(const float* __restrict__ feats, int T0, int F0, int T1, int F1, const float* __restrict__ w1,
+                const float* __restrict__ b1, const float* __restrict__ gamma, const float* __restrict__ beta,
+                __half* __restrict__ out_h, float* __restrict__ out_f) {
+    extern __shared__ float c1_smem[];
+    float* in = c1_smem;                  // [3][F0 + 2]
+    float* w = in + 3 * (F0 + 2);         // [C1 * 9]
+    float* bias = w + C1 * 9;             // [C1]
+    __shared__ float red[8];
+    __shared__ float stat[2];
+    const int b = blockIdx.y, t1 = blockIdx.x;
+    const int FP = F0 + 2;
+    for (int i = threadIdx.x; i < 3 * FP; i += blockDim.x) {
+        const int kt = i / FP, fp = i - kt * FP;
+        const int t = reflect_idx(2 * t1 + kt - 1, T0);
+        const int f = reflect_idx(fp - 1, F0);
+        in[i] = feats[(static_cast<size_t>(b) * T0 + t) * F0 + f];
+    }
+    for (int i = threadIdx.x; i < C1 * 9; i += blockDim.x) w[i] = w1[i];
+    for (int i = threadIdx.x; i < C1; i += blockDim.x) bias[i] = b1[i];
+    __syncthreads();
+
+    constexpr int ROWS_PER_ITER = 256 / C1;  // f' rows covered per iteration
+    const int c = threadIdx.x % C1;
+    const int fr = threadIdx.x / C1;
+    constexpr int MAX_IT = 16;
+    float v[MAX_IT];
+    float wr[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) wr[i] = w[c * 9 + i];
+    float s = 0.0f;
+    const int n_it = (F1 + ROWS_PER_ITER - 1) / ROWS_PER_ITER;
+#pragma unroll
+    for (int it = 0; it < MAX_IT; ++it) {
+        v[it] = 0.0f;
+        const int f1 = fr + it * ROWS_PER_ITER;
+        if (it < n_it && f1 < F1) {
+            float a = bias[c];
+#pragma unroll
+            for (int kf = 0; kf < 3; ++kf)
+#pragma unroll
+                for (int kt = 0; kt < 3; ++kt) a = fmaf(wr[kf * 3 + kt], in[kt * FP + 2 * f1 + kf], a);
+            v[it] = a;
+            s += a;
+        }
+    }
+    const float n = static_cast<float>(F1 * C1);
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tot = 0.0f;
+        for (int i = 0; i < 8; ++i) tot += red[i];
+        stat[0] = tot / n;
+    }
+    __syncthreads();
+    const float mean = stat[0];
+    float q = 0.0f;
+#pragma unroll
+    for (int it = 0; it < MAX_IT; ++it) {
+        const int f1 = fr + it * ROWS_PER_ITER;
+        if (it < n_it && f1 < F1) {
+            const float d = v[it] - mean;
+            q += d * d;
+        }
+    }
+    q = warp_sum(q);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = q;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tot = 0.0f;
+        for (int i = 0; i < 8; ++i) tot += red[i];
+        stat[1] = rsqrtf(tot / n + 1e-5f);
+    }
+    __syncthreads();
+    const float rstd = stat[1];
+    const size_t obase = (static_cast<size_t>(b) * T1 + t1) * F1 * C1;
+#pragma unroll
+    for (int it = 0; it < MAX_IT; ++it) {
+        const int f1 = fr + it * ROWS_PER_ITER;
+        if (it < n_it && f1 < F1) {
+            const int gi = f1 * C1 + c;
+            const float y = leaky((v[it] - mean) * rstd * __ldg(gamma + gi) + __ldg(beta + gi));
+            out_h[obase + gi] = __float2half_rn(y);
+            if (out_f) out_f[obase + gi] = y;
+        }
+    }
+}
+
+// --------------------------------------------------------------------------- conv2
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+constexpr int C2_FRAMES = 4;   // output frames per CTA
+constexpr int C2_CIN = 64;     // input channels (k16 steps per tap = 4)
+constexpr int C2_COUT = 32;
+constexpr int C2_CELL = 72;    // padded channel stride (halfs) of one (t, f) cell in smem
+constexpr int C2_WROW = 9 * C2_CIN + 8;  // padded weight row (halfs)
+
+// act1 [B, T1, F1, 64] fp16; w2p [32, 576] fp16 with k = (kf*3+kt)*64 + ch; out [B, T2, F2*32].
+// Requires F2 * C2_FRAMES <= 16 * n_warps (launch with ceil(F2*4/16) warps) and F2 * 32 <= 1024.
+__global__ void __launch_bounds__(192)
+conv2_ln_kernel(const __half* __restrict__ act1, int T1, int F1, int T2, int F2, const __half* __restrict__ w2p,
+                const float* __restrict__ b2, const float* __restrict__ gamma, const float* __restrict__ beta,
+                __half* __restrict__ out_h, float* __restrict__ out_f) {
+    extern __shared__ __align__(16) uint8_t c2_smem[];
+    const int FPAD = F1 + 2;
+    const int n_trows = 2 * C2_FRAMES + 1;
+    __half* patch = reinterpret_cast<__half*>(c2_smem);                 // [n_trows][FPAD][C2_CELL]
+    __half* wsm = patch + n_trows * FPAD * C2_CELL;                     // [32][C2_WROW]
+    float* cbuf = reinterpret_cast<float*>(wsm + C2_COUT * C2_WROW);    // [C2_FRAMES * F2][33]
+    const int b = blockIdx.y, t0 = blockIdx.x * C2_FRAMES;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // stage the input patch (reflect-padded) : 16-byte vectors of 8 channels
+    const int vec_per_cell = C2_CIN / 8;
+    for (int i = threadIdx.x; i < n_trows * FPAD * vec_per_cell; i += blockDim.x) {
+        const int cell = i / vec_per_cell, v8 = i - cell * vec_per_cell;
+        const int tr = cell / FPAD, fp = cell - tr * FPAD;
+        int t = reflect_idx(2 * t0 + tr - 1, T1);
+        t = min(max(t, 0), T1 - 1);  // tail tiles: keep loads in range (results discarded)
+        const int f = reflect_idx(fp - 1, F1);
+        const uint4 val =
+            *reinterpret_cast<const uint4*>(act1 + ((static_cast<size_t>(b) * T1 + t) * F1 + f) * C2_CIN + v8 * 8);
+        *reinterpret_cast<uint4*>(patch + cell * C2_CELL + v8 * 8) = val;
+    }
+    for (int i = threadIdx.x; i < C2_COUT * (9 * C2_CIN / 8); i += blockDim.x) {
+        const int o = i / (9 * C2_CIN / 8), v8 = i - o * (9 * C2_CIN / 8);
+        *reinterpret_cast<uint4*>(wsm + o * C2_WROW + v8 * 8) =
+            *reinterpret_cast<const uint4*>(w2p + static_cast<size_t>(o) * 9 * C2_CIN + v8 * 8);
+    }
+    __syncthreads();
+
+    const int rows = C2_FRAMES * F2;
+    const int g = lane >> 2, c = lane & 3;
+    const int r0 = warp * 16 + g, r1 = r0 + 8;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+    if (warp * 16 < rows) {
+        const int rr0 = min(r0, rows - 1), rr1 = min(r1, rows - 1);
+        const int fr0 = rr0 / F2, f20 = rr0 - fr0 * F2;
+        const int fr1 = rr1 / F2, f21 = rr1 - fr1 * F2;
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap) {
+            const int kf = tap / 3, kt = tap - kf * 3;
+            const __half* a0p = patch + ((2 * fr0 + kt) * FPAD + 2 * f20 + kf) * C2_CELL + 2 * c;
+            const __half* a1p = patch + ((2 * fr1 + kt) * FPAD + 2 * f21 + kf) * C2_CELL + 2 * c;
+#pragma unroll
+            for (int ks = 0; ks < C2_CIN / 16; ++ks) {
+                uint32_t a[4];
+                a[0] = *reinterpret_cast<const uint32_t*>(a0p + ks * 16);
+                a[1] = *reinterpret_cast<const uint32_t*>(a1p + ks * 16);
+                a[2] = *reinterpret_cast<const uint32_t*>(a0p + ks * 16 + 8);
+                a[3] = *reinterpret_cast<const uint32_t*>(a1p + ks * 16 + 8);
+                const int kk = tap * C2_CIN + ks * 16 + 2 * c;
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    uint32_t bb[2];
+                    const __half* wp = wsm + (nt * 8 + g) * C2_WROW + kk;
+                    bb[0] = *reinterpret_cast<const uint32_t*>(wp);
+                    bb[1] = *reinterpret_cast<const uint32_t*>(wp + 8);
+                    mma_16816(acc[nt], a, bb);
+                }
+            }
+        }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            const int col = nt * 8 + 2 * c;
+            const float bz0 = __ldg(b2 + col), bz1 = __ldg(b2 + col + 1);
+            if (r0 < rows) { cbuf[r0 * 33 + col] = acc[nt][0] + bz0; cbuf[r0 * 33 + col + 1] = acc[nt][1] + bz1; }
+            if (r1 < rows) { cbuf[r1 * 33 + col] = acc[nt][2] + bz0; cbuf[r1 * 33 + col + 1] = acc[nt][3] + bz1; }
+        }
+    }
+    __syncthreads();
+    // LayerNorm over (F2, 32) per frame + LeakyReLU; one warp per frame
+    if (warp < C2_FRAMES) {
+        const int t = t0 + warp;
+        if (t < T2) {
+            const int n = F2 * C2_COUT;
+            const float* src = cbuf + warp * F2 * 33;
+            float s = 0.0f;
+            for (int i = lane; i < n; i += 32) s += src[(i >> 5) * 33 + (i & 31)];
+            const float mean = warp_sum(s) / n;
+            float q = 0.0f;
+            for (int i = lane; i < n; i += 32) {
+                const float d = src[(i >> 5) * 33 + (i & 31)] - mean;
+                q += d * d;
+            }
+            const float rstd = rsqrtf(warp_sum(q) / n + 1e-5f);
+            const size_t ob = (static_cast<size_t>(b) * T2 + t) * n;
+            for (int i = lane; i < n; i += 32) {
+                const float y = leaky((src[(i >> 5) * 33 + (i & 31)] - mean) * rstd * __ldg(gamma + i) + __ldg(beta + i));
+                out_h[ob + i] = __float2half_rn(y);
+                if (out_f) out_f[ob + i] = y;
+            }
+        }
+    }
+}
+
+int cnn_frontend_forward(const float* feats, int B, int T0, int F0, const float* w1, const float* b1, const float* g1,
+                         const float* be1, int C1, const __half* w2p, const float* b2, const float* g2,
+                         const float* be2, int C2, __half* act1_h, float* act1_f, __half* out_h, float* out_f,
+                         cudaStream_t stream) {
+    SBK_REQUIRE(C1 == 64 && C2 == 32, "cnn_frontend: only out_channels=(64, 32) is built (got %d, %d)", C1, C2);
+    SBK_REQUIRE(T0 >= 2 && F0 >= 2, "cnn_frontend: input too small for reflect padding");
+    const int T1 = (T0 - 1) / 2 + 1, F1 = (F0 - 1) / 2 + 1;
+    const int T2 = (T1 - 1) / 2 + 1, F2 = (F1 - 1) / 2 + 1;
+    SBK_REQUIRE(F1 <= 64 && F2 * C2_FRAMES <= 96, "cnn_frontend: feature dim too large (F0=%d)", F0);
+    {
+        const size_t smem = (3 * (F0 + 2) + C1 * 9 + C1) * sizeof(float);
+        conv1_ln_kernel<64><<<dim3(T1, B), 256, smem, stream>>>(feats, T0, F0, T1, F1, w1, b1, g1, be1, act1_h, act1_f);
+        SBK_LAUNCH_CHECK();
+    }
+    {
+        const int n_trows = 2 * C2_FRAMES + 1;
+        const size_t smem = static_cast<size_t>(n_trows) * (F1 + 2) * C2_CELL * 2 + C2_COUT * C2_WROW * 2 +
+                            static_cast<size_t>(C2_FRAMES) * F2 * 33 * 4;
+        SBK_CUDA_CHECK(cudaFuncSetAttribute(conv2_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int warps = std::max(C2_FRAMES, ceil_div(C2_FRAMES * F2, 16));
+        conv2_ln_kernel<<<dim3(ceil_div(T2, C2_FRAMES), B), warps * 32, smem, stream>>>(act1_h, T1, F1, T2, F2, w2p, b2,
+                                                                                       g2, be2, out_h, out_f);
+        SBK_LAUNCH_CHECK();
+    }
+    return SBK_OK;
+}
+
+}  // namespace sbk

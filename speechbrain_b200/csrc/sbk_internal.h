@@ -1,0 +1,95 @@
+// Internal (C++) interfaces between the kernels' host launchers and the C-ABI layer.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sbk {
+
+enum GemmEpiMode { EPI_F16 = 0, EPI_F32 = 1, EPI_RESID = 2, EPI_GLU = 3, EPI_ROPE = 4 };
+enum GemmAct { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU = 2 };
+
+struct GemmEpilogue {
+    int mode = EPI_F16;
+    int act = ACT_NONE;
+    const float* bias = nullptr;   // [N] or null
+    void* out = nullptr;           // fp16 or fp32, row stride ldo (elements)
+    int ldo = 0;
+    const float* resid = nullptr;  // EPI_RESID: fp32 [M, ldo]
+    float alpha = 1.0f;            // EPI_RESID scale; EPI_ROPE: scale applied to q
+    const int* row_lens = nullptr; // EPI_RESID: rows (b, t >= row_lens[b]) get alpha = 0
+    int T = 1;                     // frames per utterance (row = b*T + t)
+    const float* rope_cos = nullptr;  // EPI_ROPE: [T, head_dim/2]
+    const float* rope_sin = nullptr;
+    int head_dim = 64;
+};
+
+// out = epilogue(A[M,K] fp16 x W[N,K]^T fp16), tcgen05 tensor cores. gemm_tc.cu
+int gemm_f16(const void* A, int lda, const void* W, int ldw, const GemmEpilogue& epi, int M, int N, int K,
+             cudaStream_t stream);
+
+
+const char* last_error();
+
+// ---- fbank.cu
+struct Fbank;
+int fbank_create(Fbank** out, int n_fft, int hop, int n_mels, const float* window_host, const float* mel_matrix_host,
+                 float amin, float top_db);
+void fbank_destroy(Fbank* fb);
+int fbank_num_frames(const Fbank* fb, int L);
+int fbank_forward(const Fbank* fb, const float* wav, int B, int L, float* out, int* utt_max, const float* mean,
+                  const float* stdv, float eps, cudaStream_t stream);
+int global_norm_forward(const float* x, float* out, int B, int T, int F, const float* mean, const float* stdv,
+                        float eps, cudaStream_t stream);
+int sentence_norm_forward(const float* x, float* out, const float* rel_len, int B, int T, int F, int std_norm,
+                          int avoid_padding_norm, float eps, cudaStream_t stream);
+
+// ---- frontend.cu
+int cnn_frontend_forward(const float* feats, int B, int T0, int F0, const float* w1, const float* b1, const float* g1,
+                         const float* be1, int C1, const __half* w2p, const float* b2, const float* g2,
+                         const float* be2, int C2, __half* act1_h, float* act1_f, __half* out_h, float* out_f,
+                         cudaStream_t stream);
+
+// ---- encoder_ops.cu
+int layernorm_rows(const float* x, void* out, bool out_half, const float* gamma, const float* beta, int M, int D,
+                   float eps, bool act_silu, cudaStream_t stream);
+int cast_f32_f16(const float* in, __half* out, size_t n, cudaStream_t stream);
+int dwconv_ln_swish(const float* glu, int B, int T, int D, int K, const float* wdw, const float* bdw,
+                    const float* gamma, const float* beta, float eps, __half* out, cudaStream_t stream);
+int encoder_attention(const __half* qkv, int ld, int B, int T, int H, int head_dim, const int* lens, bool relpos,
+                      const float* pos_u, const float* pos_v, const __half* P, int ldp, float scale, __half* out,
+                      int ldo, cudaStream_t stream);
+
+// ---- decoder.cu
+enum SkinnyEpi { SK_F16 = 0, SK_F16_GELU = 1, SK_F32 = 2, SK_RESID = 3, SK_QKV_CACHE = 4, SK_F16_RELU = 5 };
+struct SkinnyArgs {
+    const __half* A; int lda;
+    const __half* W; int ldw;
+    const float* bias;
+    int n_rows, N, K, epi;
+    void* out; int ldo;              // SK_F16/F32: out ; SK_RESID: fp32 x (in place) ; SK_QKV_CACHE: q buffer fp16 [n, d]
+    __half* kcache; __half* vcache;  // SK_QKV_CACHE: [n_rows, S_max, d]
+    const int* step_ptr; int S_max; int d; float q_scale;
+};
+int skinny_gemm(const SkinnyArgs& a, cudaStream_t stream);
+struct DecAttnArgs {
+    const __half* q; int ldq;
+    const __half* kbase; const __half* vbase;
+    size_t row_stride;
+    int key_stride;
+    int rows_per_block;
+    const int* n_keys_ptr;
+    const int* enc_len;
+    int n_keys_fixed;
+    int H, dh;
+    __half* out; int ldo;
+};
+int dec_attention(const DecAttnArgs& a, int n_rows, int max_keys, cudaStream_t stream);
+int dec_embed(const int* tokens, int tok_stride, const int* step_ptr, const float* emb, const float* pe, int d,
+              int n_rows, float* x, cudaStream_t stream);
+int greedy_select(const float* logits, int n_rows, int V, const int* step_ptr, int eos, int* tokens, int tok_stride,
+                  int* has_ended, int* ended_count, int* pred, float* score, int out_stride, float* log_probs, int L,
+                  cudaStream_t stream);
+int advance_step(int* step_ptr, cudaStream_t stream);
+
+}  // namespace sbk

@@ -1,0 +1,192 @@
+"""Python handle on the C-ABI model engine (sbk_asr_*): repacks a reference-keyed state_dict once and
+runs the fused device pipeline.  Used by the nn.Module mirrors and by EncoderDecoderASR."""
+import ctypes
+import math
+
+import torch
+
+from . import _lib
+from ._lib import check, lib, ptr, stream_ptr
+
+
+def stft_window(n_fft, win_length_samples):
+    """torch.hamming_window (periodic), centre-padded to n_fft like torch.stft does
+    (reference: processing/features.py:139,159-170)."""
+    w = torch.hamming_window(win_length_samples)
+    if win_length_samples < n_fft:
+        left = (n_fft - win_length_samples) // 2
+        w = torch.nn.functional.pad(w, (left, n_fft - win_length_samples - left))
+    return w.contiguous()
+
+
+def mel_filter_matrix(n_mels, n_fft, sample_rate=16000, f_min=0, f_max=None):
+    """The (n_fft//2+1, n_mels) triangular matrix of processing/features.py:487-507,620-650, built with the
+    same torch ops so the filter values are bit-identical to the reference's."""
+    if f_max is None:
+        f_max = sample_rate // 2
+    n_stft = n_fft // 2 + 1
+    to_mel = lambda hz: 2595 * math.log10(1 + hz / 700)
+    mel = torch.linspace(to_mel(f_min), to_mel(f_max), n_mels + 2)
+    hz = 700 * (10 ** (mel / 2595) - 1)
+    band = (hz[1:] - hz[:-1])[:-1]
+    f_central = hz[1:-1]
+    all_freqs = torch.linspace(0, sample_rate // 2, n_stft)
+    all_freqs_mat = all_freqs.repeat(f_central.shape[0], 1)
+    f_central_mat = f_central.repeat(all_freqs_mat.shape[1], 1).transpose(0, 1)
+    band_mat = band.repeat(all_freqs_mat.shape[1], 1).transpose(0, 1)
+    slope = (all_freqs_mat - f_central_mat) / band_mat
+    m = torch.max(torch.zeros(1), torch.min(slope + 1.0, -slope + 1.0)).transpose(0, 1)
+    return m.contiguous()
+
+
+class FbankHandle:
+    """sbk_fbank_* handle."""
+
+    def __init__(self, n_fft, hop, n_mels, window, mel_matrix, amin=1e-10, top_db=80.0):
+        self.n_fft, self.hop, self.n_mels = n_fft, hop, n_mels
+        self._h = ctypes.c_void_p()
+        w = window.float().contiguous().cpu()
+        mm = mel_matrix.float().contiguous().cpu()
+        check(lib().sbk_fbank_create(n_fft, hop, n_mels, ptr(w), ptr(mm), ctypes.c_float(amin), ctypes.c_float(top_db),
+                                     ctypes.byref(self._h)), "sbk_fbank_create")
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().sbk_fbank_destroy(self._h)
+            self._h = None
+
+    def forward(self, wav):
+        _lib.require_cuda(wav, "Fbank")
+        wav = wav.float().contiguous()
+        B, L = wav.shape
+        T = 1 + L // self.hop
+        out = torch.empty(B, T, self.n_mels, device=wav.device, dtype=torch.float32)
+        scratch = torch.empty(B, device=wav.device, dtype=torch.int32)
+        with torch.cuda.device(wav.device):
+            check(lib().sbk_fbank_forward(self._h, ptr(wav), B, L, ptr(out), ptr(scratch), stream_ptr(wav.device)),
+                  "sbk_fbank_forward")
+        return out
+
+
+class AsrEngine:
+    """One repacked model on one GPU.  ``cfg`` keys: n_fft, hop, win (samples), n_mels, cnn_channels, input_size,
+    d_model, nhead, num_encoder_layers, num_decoder_layers, d_ffn, vocab, kernel_size, attention_type
+    ("RoPEMHA"|"RelPosMHAXL"), decoder_activation ("gelu"|"relu"), max_length.
+    ``state``: {reference key with recipe prefix: CPU fp32 tensor}."""
+
+    def __init__(self, cfg, state, device="cuda"):
+        self.cfg = dict(cfg)
+        self.device = torch.device(device)
+        c = _lib.sbk_asr_config()
+        c.n_fft, c.hop, c.n_mels = cfg["n_fft"], cfg["hop"], cfg["n_mels"]
+        c.cnn_c1, c.cnn_c2 = cfg["cnn_channels"]
+        c.input_size, c.d_model, c.nhead = cfg["input_size"], cfg["d_model"], cfg["nhead"]
+        c.num_encoder_layers, c.num_decoder_layers = cfg["num_encoder_layers"], cfg["num_decoder_layers"]
+        c.d_ffn, c.vocab, c.kernel_size = cfg["d_ffn"], cfg["vocab"], cfg.get("kernel_size", 31)
+        att = cfg["attention_type"]
+        if att not in ("RoPEMHA", "RelPosMHAXL"):
+            raise NotImplementedError(f"attention_type={att!r}: only RoPEMHA and RelPosMHAXL are built")
+        c.attention_type = _lib.SBK_ATT_ROPE if att == "RoPEMHA" else _lib.SBK_ATT_RELPOS
+        c.decoder_activation = _lib.SBK_ACT_GELU if cfg.get("decoder_activation", "gelu") == "gelu" else _lib.SBK_ACT_RELU
+        c.max_len = cfg.get("max_length", 2500)
+        st = {k: v.detach().float().contiguous().cpu() for k, v in state.items() if torch.is_tensor(v) and v.is_floating_point()}
+        st["fbank.window"] = stft_window(cfg["n_fft"], cfg["win"])
+        st["fbank.mel_matrix"] = mel_filter_matrix(cfg["n_mels"], cfg["n_fft"], cfg.get("sample_rate", 16000))
+        names = [k.encode() for k in st]
+        arr = (_lib.sbk_tensor * len(st))()
+        for i, (k, v) in enumerate(st.items()):
+            arr[i].name, arr[i].data, arr[i].numel = names[i], v.data_ptr(), v.numel()
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib().sbk_asr_create(ctypes.byref(c), arr, len(st), ctypes.byref(self._h)), "sbk_asr_create")
+        self._keep = (st, names, arr)
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().sbk_asr_destroy(self._h)
+            self._h = None
+
+    def _sp(self):
+        return stream_ptr(self.device)
+
+    def num_frames(self, n_samples):
+        a, b = ctypes.c_int(), ctypes.c_int()
+        check(lib().sbk_asr_num_frames(self._h, n_samples, ctypes.byref(a), ctypes.byref(b)), "sbk_asr_num_frames")
+        return a.value, b.value
+
+    def cnn(self, feats):
+        feats = feats.float().contiguous()
+        B, T0, _ = feats.shape
+        T1 = (T0 - 1) // 2 + 1
+        T2 = (T1 - 1) // 2 + 1
+        out = torch.empty(B, T2, self.cfg["input_size"], device=feats.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            check(lib().sbk_asr_cnn_forward(self._h, ptr(feats), B, T0, ptr(out), self._sp()), "sbk_asr_cnn_forward")
+        return out
+
+    def encode_from_cnn(self, src, wav_lens=None):
+        src = src.float().contiguous()
+        B, T, _ = src.shape
+        out = torch.empty(B, T, self.cfg["d_model"], device=src.device, dtype=torch.float32)
+        wl = wav_lens.float().contiguous().to(src.device) if wav_lens is not None else None
+        with torch.cuda.device(self.device):
+            check(lib().sbk_asr_encode_from_cnn(self._h, ptr(src), ptr(wl), B, T, ptr(out), self._sp()),
+                  "sbk_asr_encode_from_cnn")
+        return out
+
+    def encode_feats(self, feats, wav_lens=None, want_cnn=False):
+        feats = feats.float().contiguous()
+        B, T0, _ = feats.shape
+        T1 = (T0 - 1) // 2 + 1
+        T2 = (T1 - 1) // 2 + 1
+        out = torch.empty(B, T2, self.cfg["d_model"], device=feats.device, dtype=torch.float32)
+        cnn = torch.empty(B, T2, self.cfg["input_size"], device=feats.device, dtype=torch.float32) if want_cnn else None
+        wl = wav_lens.float().contiguous().to(feats.device) if wav_lens is not None else None
+        with torch.cuda.device(self.device):
+            check(lib().sbk_asr_encode_feats(self._h, ptr(feats), ptr(wl), B, T0, ptr(cnn), ptr(out), self._sp()),
+                  "sbk_asr_encode_feats")
+        return (out, cnn) if want_cnn else out
+
+    def greedy_from_enc(self, enc, wav_lens, max_steps, bos, eos, want_log_probs=False):
+        enc = enc.float().contiguous()
+        B, T, _ = enc.shape
+        pred = torch.full((B, max(max_steps, 1)), eos, device=enc.device, dtype=torch.int32)
+        score = torch.zeros(B, max(max_steps, 1), device=enc.device, dtype=torch.float32)
+        lp = torch.empty(B, max_steps, self.cfg["vocab"], device=enc.device, dtype=torch.float32) if want_log_probs else None
+        wl = wav_lens.float().contiguous().to(enc.device) if wav_lens is not None else None
+        done = ctypes.c_int()
+        with torch.cuda.device(self.device):
+            check(lib().sbk_asr_greedy_from_enc(self._h, ptr(enc), ptr(wl), B, T, max_steps, bos, eos, ptr(pred), ptr(score),
+                                                ptr(lp), ctypes.byref(done), self._sp()), "sbk_asr_greedy_from_enc")
+        return pred, score, lp, done.value
+
+    def transcribe_greedy_dev(self, wav, wav_lens, max_steps, bos, eos, want_enc=False):
+        wav = wav.float().contiguous()
+        B, L = wav.shape
+        _, T = self.num_frames(L)
+        pred = torch.full((B, max(max_steps, 1)), eos, device=wav.device, dtype=torch.int32)
+        score = torch.zeros(B, max(max_steps, 1), device=wav.device, dtype=torch.float32)
+        enc = torch.empty(B, T, self.cfg["d_model"], device=wav.device, dtype=torch.float32) if want_enc else None
+        wl = wav_lens.float().contiguous().to(wav.device) if wav_lens is not None else None
+        done = ctypes.c_int()
+        with torch.cuda.device(self.device):
+            check(lib().sbk_asr_transcribe_greedy_dev(self._h, ptr(wav), ptr(wl), B, L, max_steps, bos, eos, ptr(enc),
+                                                      ptr(pred), ptr(score), None, ctypes.byref(done), self._sp()),
+                  "sbk_asr_transcribe_greedy_dev")
+        return pred, score, enc, done.value
+
+    def transcribe_greedy_host(self, wav_host, lens_host, max_steps, bos, eos, pred_host=None):
+        """wav_host/lens_host/pred_host: CPU (ideally pinned) tensors; copies happen inside the call."""
+        assert not wav_host.is_cuda
+        wav_host = wav_host.float().contiguous()
+        B, L = wav_host.shape
+        if pred_host is None:
+            pred_host = torch.empty(B, max(max_steps, 1), dtype=torch.int32).pin_memory()
+        pred_host.fill_(eos)
+        lh = lens_host.float().contiguous() if lens_host is not None else None
+        done = ctypes.c_int()
+        with torch.cuda.device(self.device):
+            check(lib().sbk_asr_transcribe_greedy_host(self._h, ptr(wav_host), ptr(lh), B, L, max_steps, bos, eos,
+                                                       ptr(pred_host), None, ctypes.byref(done), self._sp()),
+                  "sbk_asr_transcribe_greedy_host")
+        return pred_host, done.value

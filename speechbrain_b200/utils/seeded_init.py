@@ -60,3 +60,24 @@ def seeded_state_dict(module_or_state_dict, seed: int = 0):
             continue
         out[k] = seeded_tensor(seed, k, v.shape).to(v.dtype)
     return out
+
+
+def seeded_asr_state(cfg, seed: int = 0):
+    """Full flat state for the recipe's modules (CNN., Transformer., seq_lin., ctc_lin.) plus fixed global-CMVN
+    statistics (normalize.glob_mean / glob_std), exactly as oracle/make_goldens.py gave the reference."""
+    from .shapes import asr_model_shapes
+
+    sd = {k: seeded_tensor(seed, k, shp) for k, shp in asr_model_shapes(cfg).items()}
+    sd["normalize.glob_mean"] = seeded_tensor(seed, "normalize.glob_mean", (cfg["n_mels"],)) * 3.0 - 20.0
+    sd["normalize.glob_std"] = seeded_tensor(seed, "normalize.glob_std", (cfg["n_mels"],)) * 8.0
+    return sd
+
+
+CONFORMER_LARGE = dict(name="conformer_large", sample_rate=16000, n_fft=512, win=512, hop=160, n_mels=80,
+                       cnn_channels=(64, 32), input_size=640, d_model=512, nhead=8, num_encoder_layers=12,
+                       num_decoder_layers=6, d_ffn=2048, vocab=5000, kernel_size=31, attention_type="RoPEMHA",
+                       decoder_activation="gelu", max_length=2500)
+CONFORMER_SMALL = dict(name="conformer_small", sample_rate=16000, n_fft=400, win=400, hop=160, n_mels=80,
+                       cnn_channels=(64, 32), input_size=640, d_model=144, nhead=4, num_encoder_layers=12,
+                       num_decoder_layers=4, d_ffn=1024, vocab=5000, kernel_size=31, attention_type="RelPosMHAXL",
+                       decoder_activation="gelu", max_length=2500)

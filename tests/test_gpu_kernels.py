@@ -1,0 +1,164 @@
+"""-m gpu parity tests: every CUDA path is called through the C ABI (libsbk.so) and compared with the
+CPU oracle / the committed reference goldens on the same seeded inputs."""
+import os
+
+import pytest
+import torch
+
+from tests.conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+# ----------------------------------------------------------------------------------------- tcgen05 GEMM
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 128, 512), (200, 256, 512), (251, 5000, 512),
+                                   (1000, 1536, 640), (8032, 2048, 512), (8032, 512, 2048), (300, 144, 144)])
+@pytest.mark.parametrize("out_f32,act", [(1, 0), (0, 1)])
+def test_gemm_tc(dev, M, N, K, out_f32, act):
+    import ctypes
+
+    from speechbrain_b200._lib import check, lib, ptr, stream_ptr
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    A = torch.randn(M, K, generator=g).half()
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).half()
+    bias = torch.randn(N, generator=g)
+    ref = A.float() @ W.float().T + bias
+    if act == 1:
+        ref = torch.nn.functional.silu(ref)
+    Ad, Wd, bd = A.to(dev), W.to(dev), bias.to(dev)
+    out = torch.zeros(M, N, device=dev, dtype=torch.float32 if out_f32 else torch.float16)
+    check(lib().sbk_gemm_f16_test(ptr(Ad), ptr(Wd), ptr(bd), ptr(out), out_f32, act, M, N, K, stream_ptr(dev)), "gemm")
+    torch.cuda.synchronize()
+    got = out.float().cpu()
+    err = (got - ref).abs().max().item()
+    tol = 2e-3 if out_f32 else 2e-2
+    print(f"gemm M={M} N={N} K={K} f32={out_f32} act={act}: max abs err {err:.3e}")
+    assert err < tol, f"max abs err {err}"
+
+
+# ----------------------------------------------------------------------------------------- Fbank
+def test_fbank_golden(dev):
+    """Fbank vs the reference's outputs (BASELINE config 1 + ragged / n_fft=512 / n_mels=40 cases).
+    Tolerance from north_star: 1e-4 relative fp32, |a-b| / max(|b|, 1e-3)."""
+    from speechbrain_b200.lobes.features import Fbank
+    gold = torch.load(os.path.join(GOLDEN, "fbank.pt"))
+    for name, case in gold.items():
+        fb = Fbank(**case["kwargs"]).to(dev)
+        out = fb(case["wav"].to(dev)).cpu()
+        ref = case["out"]
+        assert out.shape == ref.shape, name
+        rel = ((out - ref).abs() / ref.abs().clamp_min(1e-3)).max().item()
+        print(f"fbank[{name}] shape {tuple(ref.shape)} max rel err {rel:.3e}")
+        assert rel < 1e-4, f"{name}: {rel}"
+
+
+def test_fbank_large_matches_oracle(dev):
+    from oracle import asr_oracle as O
+    from speechbrain_b200.lobes.features import Fbank
+    g = torch.Generator().manual_seed(5)
+    wav = torch.randn(4, 160000, generator=g)
+    wav[1, 100000:] = 0
+    ref = O.fbank(wav, n_fft=512, n_mels=80, win_length_ms=32)
+    out = Fbank(n_fft=512, n_mels=80, win_length=32).to(dev)(wav.to(dev)).cpu()
+    rel = ((out - ref).abs() / ref.abs().clamp_min(1e-3)).max().item()
+    print("fbank 4x10s max rel err", rel)
+    assert rel < 1e-4
+    # L % 4 != 0 exercises the non-TMA staging path
+    wav2 = wav[:, :159999].contiguous()
+    out2 = Fbank(n_fft=512, n_mels=80, win_length=32).to(dev)(wav2.to(dev)).cpu()
+    ref2 = O.fbank(wav2, n_fft=512, n_mels=80, win_length_ms=32)
+    assert ((out2 - ref2).abs() / ref2.abs().clamp_min(1e-3)).max().item() < 1e-4
+
+
+def test_input_norm_golden(dev):
+    from speechbrain_b200.processing.features import InputNormalization
+    gold = torch.load(os.path.join(GOLDEN, "input_norm.pt"))
+    x, lens = gold["x"].to(dev), gold["lens"].to(dev)
+    n = InputNormalization(norm_type="global")
+    n.glob_mean, n.glob_std, n.count = gold["glob_mean"], gold["glob_std"], 1
+    n.eval()
+    assert (n(x, lens).cpu() - gold["global"]).abs().max() < 1e-5
+    n = InputNormalization(norm_type="sentence").eval()
+    assert (n(x, lens).cpu() - gold["sentence"]).abs().max() < 1e-4
+    n = InputNormalization(norm_type="sentence", avoid_padding_norm=True).eval()
+    assert (n(x, lens).cpu() - gold["sentence_avoid_pad"]).abs().max() < 1e-4
+    kat = InputNormalization(norm_type="sentence").eval()(torch.tensor([[[1.0], [3.0], [0.0], [0.0], [0.0]]], device=dev),
+                                                          torch.tensor([0.4], device=dev))
+    assert torch.allclose(kat.cpu(), gold["kat"], atol=1e-5)  # tests/unittests/test_features.py:112-118
+
+
+# ----------------------------------------------------------------------------------------- model stages
+def _engine(cfg, dev):
+    from speechbrain_b200.engine import AsrEngine
+    from speechbrain_b200.utils.seeded_init import seeded_asr_state
+    sd = seeded_asr_state(cfg, 0)
+    return AsrEngine(cfg, sd, device=dev), sd
+
+
+def _cfg_from_gold(g):
+    from speechbrain_b200.utils.seeded_init import CONFORMER_LARGE, CONFORMER_SMALL
+    base = CONFORMER_LARGE if g["cfg"]["name"] == "conformer_large" else CONFORMER_SMALL
+    return dict(base, attention_type=g["cfg"]["attention_type"])
+
+
+@pytest.mark.parametrize("tag", ["conformer_large_rope", "conformer_large_relpos"])
+def test_model_stages_golden(dev, tag):
+    """CNN front-end, Conformer encoder and KV-cached greedy search vs the REFERENCE outputs in tests/golden
+    (B=2 x 2 s, ragged lengths).  Tolerances: CNN 2e-3 abs (fp16 conv2 operands), encoder <= 1e-3 rel-L2
+    (north_star 'within 1e-3 rel'), greedy tokens identical unless the reference top-2 margin is below 5e-3."""
+    from oracle import asr_oracle as O
+    g = torch.load(os.path.join(GOLDEN, tag + ".pt"))
+    cfg = _cfg_from_gold(g)
+    eng, sd = _engine(cfg, dev)
+    chk = float(sum(v.double().abs().sum() for k, v in sd.items() if k != "fbank.window"))
+    assert abs(chk - g["weight_checksum"]) / g["weight_checksum"] < 1e-9, "seeded weights differ from golden run"
+    feats = O.input_norm(g["fbank"], g["wav_lens"], "global", sd["normalize.glob_mean"], sd["normalize.glob_std"])
+    cnn = eng.cnn(feats.to(dev)).cpu()
+    ref_cnn = g["cnn_out"].reshape(cnn.shape)
+    e = (cnn - ref_cnn).abs().max().item()
+    print(f"[{tag}] cnn max abs err {e:.3e} (ref absmax {ref_cnn.abs().max():.2f})")
+    assert e < 5e-3
+    enc = eng.encode_from_cnn(g["cnn_out"].reshape(cnn.shape).to(dev), g["wav_lens"].to(dev)).cpu()
+    r = _rel(enc, g["enc_out"])
+    print(f"[{tag}] encoder rel-L2 err {r:.3e} max abs {(enc - g['enc_out']).abs().max():.3e}")
+    assert r < 1e-3
+    n_steps = g["greedy_logits"].shape[1]
+    pred, score, lp, done = eng.greedy_from_enc(g["enc_out"].to(dev), g["wav_lens"].to(dev), n_steps, 1, 2, want_log_probs=True)
+    pred = pred.cpu()
+    ref_lp = torch.log_softmax(g["greedy_logits"], -1)
+    top2 = g["greedy_logits"].topk(2, -1).values
+    margin = top2[..., 0] - top2[..., 1]
+    ref_tok = g["greedy_logits"].argmax(-1)
+    for b in range(pred.shape[0]):
+        for s in range(n_steps):
+            if pred[b, s] != ref_tok[b, s]:
+                assert margin[b, s] < 5e-3, f"token mismatch at b={b} s={s} with margin {margin[b, s]}"
+                break
+            d = (lp[b, s].cpu() - ref_lp[b, s]).abs().max().item()
+            assert d < 2e-2, f"log-prob err {d} at b={b} s={s}"
+    print(f"[{tag}] greedy tokens {pred.tolist()} ref {g['hyps']}")
+
+
+def test_transcribe_end_to_end(dev):
+    """wav -> tokens through the fused device pipeline and through the host-buffer entry point."""
+    g = torch.load(os.path.join(GOLDEN, "conformer_large_rope.pt"))
+    cfg = _cfg_from_gold(g)
+    eng, sd = _engine(cfg, dev)
+    n_steps = g["greedy_logits"].shape[1]
+    pred, score, enc, done = eng.transcribe_greedy_dev(g["wav"].to(dev), g["wav_lens"].to(dev), n_steps, 1, 2, want_enc=True)
+    r = _rel(enc.cpu(), g["enc_out"])
+    print("e2e encoder rel-L2", r, "tokens", pred.cpu().tolist(), "ref", g["hyps"])
+    assert r < 1.5e-3
+    pred_h, done_h = eng.transcribe_greedy_host(g["wav"].pin_memory(), g["wav_lens"], n_steps, 1, 2)
+    assert torch.equal(pred_h, pred.cpu())
