@@ -20,7 +20,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 from oracle import asr_oracle as O  # noqa: E402
-from speechbrain_b200.utils.seeded_init import seeded_state_dict  # noqa: E402
+from speechbrain_b200.utils.seeded_init import seeded_asr_state, seeded_state_dict  # noqa: E402
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
@@ -30,6 +30,12 @@ CFG_L = dict(name="conformer_large", d_model=512, nhead=8, num_encoder_layers=12
 CFG_S = dict(name="conformer_small", d_model=144, nhead=4, num_encoder_layers=12, num_decoder_layers=4,
              d_ffn=1024, vocab=5000, n_fft=400, win_length=25, n_mels=80, kernel_size=31,
              cnn_channels=(64, 32), input_size=640)
+
+
+def _product_cfg(cfg, attention_type):
+    from speechbrain_b200.utils.seeded_init import CONFORMER_LARGE, CONFORMER_SMALL
+    base = CONFORMER_LARGE if cfg["name"] == "conformer_large" else CONFORMER_SMALL
+    return dict(base, attention_type=attention_type)
 
 
 def rel(a, b):
@@ -159,7 +165,7 @@ def model_case(cfg, attention_type, B, L, lens, n_steps, tag):
     gold = dict(cfg=ocfg, wav=wav, wav_lens=wav_lens, fbank=f, cnn_out=c, enc_out=enc,
                 enc_layer0=olayers[0], enc_layer5=olayers[5], hyps=hyps, greedy_logits=logits,
                 ctc_logits_head=ctc_logits[:, :, :64].clone(),
-                weight_checksum=float(sum(v.double().abs().sum() for v in sd.values() if v.is_floating_point())))
+                weight_checksum=float(sum(v.double().abs().sum() for k, v in sorted(seeded_asr_state(_product_cfg(cfg, attention_type), 0).items()))))
     torch.save(gold, os.path.join(OUT, f"{tag}.pt"))
 
 

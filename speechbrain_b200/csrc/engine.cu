@@ -92,6 +92,7 @@ struct AsrModel {
     cudaGraphExec_t step_graph = nullptr;
     int graph_rows = -1, graph_T = -1, graph_B = -1;
     int* host_flag = nullptr;  // pinned
+    cudaStream_t cap_stream = nullptr;  // private stream for graph capture (the legacy default stream cannot capture)
 };
 
 static const float* find(const std::map<std::string, std::pair<const float*, int64_t>>& m, const std::string& k,
@@ -353,6 +354,7 @@ void asr_destroy(AsrModel* m) {
     cudaFree(m->warena.base);
     cudaFree(m->ws.base);
     if (m->host_flag) cudaFreeHost(m->host_flag);
+    if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
     delete m;
 }
 
@@ -566,9 +568,10 @@ static int run_greedy(AsrModel* m, int B, int T, int max_steps, int bos, int eos
     if (use_graph && (m->step_graph == nullptr || m->graph_rows != rows || m->graph_T != T || m->graph_B != B)) {
         if (m->step_graph) { cudaGraphExecDestroy(m->step_graph); m->step_graph = nullptr; }
         cudaGraph_t g;
-        SBK_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-        int rc = enqueue_decode_step(m, rows, 1, T, S_max, eos, nullptr, 0, st);
-        cudaError_t ce = cudaStreamEndCapture(st, &g);
+        if (!m->cap_stream) SBK_CUDA_CHECK(cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
+        SBK_CUDA_CHECK(cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal));
+        int rc = enqueue_decode_step(m, rows, 1, T, S_max, eos, nullptr, 0, m->cap_stream);
+        cudaError_t ce = cudaStreamEndCapture(m->cap_stream, &g);
         if (rc) return rc;
         SBK_CUDA_CHECK(ce);
         SBK_CUDA_CHECK(cudaGraphInstantiate(&m->step_graph, g, 0));
