@@ -40,6 +40,10 @@ typedef struct {
 
 const char* sbk_last_error(void); /* thread-local message of the last failing call */
 int sbk_version(void);
+long long sbk_launch_count(void); /* kernels launched by this library so far (graph replays included) */
+/* live per-launch timing of the tcgen05 GEMM (CUDA events on the launching stream); read after a sync */
+void sbk_gemm_profile_enable(int on);
+int sbk_gemm_profile_read(int* n_launches, double* total_ms, double* total_flops);
 
 /* ---- Fbank.forward (lobes/features.py:147-169 = STFT processing/features.py:141-188 + spectral_magnitude
  *      :341-378 + Filterbank.forward :512-586 + _amplitude_to_DB :736-759).  window_host[n_fft] is the (centre-

@@ -29,7 +29,7 @@ SBK_ACT_RELU, SBK_ACT_GELU = 0, 1
 
 # every symbol include/sbk.h declares (tests check the library exports all of them)
 EXPORTS = [
-    "sbk_last_error", "sbk_version", "sbk_fbank_create", "sbk_fbank_destroy", "sbk_fbank_num_frames",
+    "sbk_last_error", "sbk_version", "sbk_launch_count", "sbk_gemm_profile_enable", "sbk_gemm_profile_read", "sbk_fbank_create", "sbk_fbank_destroy", "sbk_fbank_num_frames",
     "sbk_fbank_forward", "sbk_input_norm_global", "sbk_input_norm_sentence", "sbk_gemm_f16_test",
     "sbk_asr_create", "sbk_asr_destroy", "sbk_asr_num_frames", "sbk_asr_cnn_forward", "sbk_asr_encode_from_cnn",
     "sbk_asr_encode_feats", "sbk_asr_greedy_from_enc", "sbk_asr_transcribe_greedy_dev",
@@ -50,8 +50,11 @@ def lib():
         for name in EXPORTS:
             getattr(L, name)  # AttributeError if the ABI is incomplete
         for name in EXPORTS:
-            if name not in ("sbk_last_error", "sbk_fbank_destroy", "sbk_asr_destroy"):
+            if name not in ("sbk_last_error", "sbk_fbank_destroy", "sbk_asr_destroy", "sbk_launch_count",
+                            "sbk_gemm_profile_enable"):
                 getattr(L, name).restype = ctypes.c_int
+        L.sbk_launch_count.restype = ctypes.c_longlong
+        L.sbk_gemm_profile_enable.restype = None
         _lib = L
     return _lib
 

@@ -25,7 +25,13 @@ void set_error(const char* fmt, ...);
         }                                                                                 \
     } while (0)
 
-#define SBK_LAUNCH_CHECK() SBK_CUDA_CHECK(cudaGetLastError())
+// every kernel launch goes through this: counts launches (bench.py "gpu_launches") and checks the launch
+void count_launch();
+#define SBK_LAUNCH_CHECK()                   \
+    do {                                     \
+        sbk::count_launch();                 \
+        SBK_CUDA_CHECK(cudaGetLastError());  \
+    } while (0)
 
 #define SBK_REQUIRE(cond, ...)            \
     do {                                  \

@@ -37,80 +37,92 @@ __global__ void dec_embed_kernel(const int* __restrict__ tokens, int tok_stride,
 
 // --------------------------------------------------------------------------- skinny GEMM (weight streaming)
 // y[n_rows, N] = epi( A[n_rows, K] (fp16) x W[N, K]^T (fp16) + bias ).  n_rows is the number of live
-// hypotheses (32..320): the cost is streaming W once, so one CTA owns 8 output columns for up to 128 rows,
-// its 4 warps split K (deterministic in-CTA reduction through shared memory).
-constexpr int SK_ROWS = 128;
+// hypotheses (32..320): the cost is streaming W once and the chain of dependent L2 round trips, so one CTA
+// owns 8 output columns x 32 rows, its 8 warps split K, and every warp issues all the loads of a chunk of
+// SK_UNR k-steps before the first mma (memory-level parallelism instead of a load->mma->load chain).
+// Deterministic in-CTA reduction through shared memory.
+constexpr int SK_ROWS = 32;
+constexpr int SK_WARPS = 8;
 
-__global__ void __launch_bounds__(128) skinny_gemm_kernel(const SkinnyArgs a) {
-    __shared__ float red[4][SK_ROWS][9];
+template <int UNR>
+__global__ void __launch_bounds__(SK_WARPS * 32) skinny_gemm_kernel(const SkinnyArgs a) {
+    __shared__ float red[SK_WARPS][SK_ROWS][9];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
     const int n0 = blockIdx.x * 8;
     const int row0 = blockIdx.y * SK_ROWS;
     const int rows = min(SK_ROWS, a.n_rows - row0);
-    const int m_tiles = (rows + 15) >> 4;
-    const int k_per_warp = ((a.K / 16 + 3) / 4) * 16;
+    const int k_per_warp = ((a.K / 16 + SK_WARPS - 1) / SK_WARPS) * 16;
     const int k_begin = warp * k_per_warp, k_end = min(a.K, k_begin + k_per_warp);
 
-    float acc[SK_ROWS / 16][4];
+    float acc[2][4];
 #pragma unroll
-    for (int i = 0; i < SK_ROWS / 16; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0f;
+    for (int i = 0; i < 2; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0f;
     const int wn = min(n0 + g, a.N - 1);  // clamp for the N tail (results discarded)
     const __half* wrow = a.W + static_cast<size_t>(wn) * a.ldw + 2 * c;
-    for (int k0 = k_begin; k0 < k_end; k0 += 16) {
-        const uint32_t b0 = __ldg(reinterpret_cast<const uint32_t*>(wrow + k0));
-        const uint32_t b1 = __ldg(reinterpret_cast<const uint32_t*>(wrow + k0 + 8));
+    const __half* arow[4];
 #pragma unroll
-        for (int mt = 0; mt < SK_ROWS / 16; ++mt) {
-            if (mt < m_tiles) {
-                const int r0 = min(row0 + mt * 16 + g, a.n_rows - 1), r1 = min(row0 + mt * 16 + g + 8, a.n_rows - 1);
-                const __half* a0 = a.A + static_cast<size_t>(r0) * a.lda + k0 + 2 * c;
-                const __half* a1 = a.A + static_cast<size_t>(r1) * a.lda + k0 + 2 * c;
-                uint32_t af[4];
-                af[0] = *reinterpret_cast<const uint32_t*>(a0);
-                af[1] = *reinterpret_cast<const uint32_t*>(a1);
-                af[2] = *reinterpret_cast<const uint32_t*>(a0 + 8);
-                af[3] = *reinterpret_cast<const uint32_t*>(a1 + 8);
-                mma16816_d(acc[mt], af, b0, b1);
+    for (int i = 0; i < 4; ++i)
+        arow[i] = a.A + static_cast<size_t>(min(row0 + i * 8 + g, a.n_rows - 1)) * a.lda + 2 * c;
+    for (int k0 = k_begin; k0 < k_end; k0 += 16 * UNR) {
+        uint32_t bf[UNR][2], af[UNR][2][4];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int k = k0 + 16 * u;
+            const bool ok = k < k_end;
+            bf[u][0] = ok ? __ldg(reinterpret_cast<const uint32_t*>(wrow + k)) : 0u;
+            bf[u][1] = ok ? __ldg(reinterpret_cast<const uint32_t*>(wrow + k + 8)) : 0u;
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                af[u][mt][0] = ok ? *reinterpret_cast<const uint32_t*>(arow[2 * mt] + k) : 0u;
+                af[u][mt][1] = ok ? *reinterpret_cast<const uint32_t*>(arow[2 * mt + 1] + k) : 0u;
+                af[u][mt][2] = ok ? *reinterpret_cast<const uint32_t*>(arow[2 * mt] + k + 8) : 0u;
+                af[u][mt][3] = ok ? *reinterpret_cast<const uint32_t*>(arow[2 * mt + 1] + k + 8) : 0u;
             }
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            mma16816_d(acc[0], af[u][0], bf[u][0], bf[u][1]);
+            mma16816_d(acc[1], af[u][1], bf[u][0], bf[u][1]);
         }
     }
 #pragma unroll
-    for (int mt = 0; mt < SK_ROWS / 16; ++mt) {
-        if (mt < m_tiles) {
-            red[warp][mt * 16 + g][2 * c] = acc[mt][0];
-            red[warp][mt * 16 + g][2 * c + 1] = acc[mt][1];
-            red[warp][mt * 16 + g + 8][2 * c] = acc[mt][2];
-            red[warp][mt * 16 + g + 8][2 * c + 1] = acc[mt][3];
-        }
+    for (int mt = 0; mt < 2; ++mt) {
+        red[warp][mt * 16 + g][2 * c] = acc[mt][0];
+        red[warp][mt * 16 + g][2 * c + 1] = acc[mt][1];
+        red[warp][mt * 16 + g + 8][2 * c] = acc[mt][2];
+        red[warp][mt * 16 + g + 8][2 * c + 1] = acc[mt][3];
     }
     __syncthreads();
     const int step = a.step_ptr ? *a.step_ptr : 0;
-    for (int i = threadIdx.x; i < rows * 8; i += blockDim.x) {
-        const int r = i >> 3, j = i & 7;
+    {
+        const int r = threadIdx.x >> 3, j = threadIdx.x & 7;  // 32 rows x 8 columns = 256 threads
         const int col = n0 + j;
-        if (col >= a.N) continue;
-        float v = red[0][r][j] + red[1][r][j] + red[2][r][j] + red[3][r][j];
-        if (a.bias) v += __ldg(a.bias + col);
         const int row = row0 + r;
-        switch (a.epi) {
-            case SK_F16: reinterpret_cast<__half*>(a.out)[static_cast<size_t>(row) * a.ldo + col] = __float2half_rn(v); break;
-            case SK_F16_RELU:
-                reinterpret_cast<__half*>(a.out)[static_cast<size_t>(row) * a.ldo + col] = __float2half_rn(fmaxf(v, 0.0f));
-                break;
-            case SK_F16_GELU:
-                reinterpret_cast<__half*>(a.out)[static_cast<size_t>(row) * a.ldo + col] = __float2half_rn(gelu_erf_f(v));
-                break;
-            case SK_F32: reinterpret_cast<float*>(a.out)[static_cast<size_t>(row) * a.ldo + col] = v; break;
-            case SK_RESID: reinterpret_cast<float*>(a.out)[static_cast<size_t>(row) * a.ldo + col] += v; break;
-            case SK_QKV_CACHE: {
-                if (col < a.d) {
-                    reinterpret_cast<__half*>(a.out)[static_cast<size_t>(row) * a.ldo + col] = __float2half_rn(v * a.q_scale);
-                } else if (col < 2 * a.d) {
-                    a.kcache[(static_cast<size_t>(row) * a.S_max + step) * a.d + (col - a.d)] = __float2half_rn(v);
-                } else {
-                    a.vcache[(static_cast<size_t>(row) * a.S_max + step) * a.d + (col - 2 * a.d)] = __float2half_rn(v);
+        if (r < rows && col < a.N) {
+            float v = 0.0f;
+#pragma unroll
+            for (int w = 0; w < SK_WARPS; ++w) v += red[w][r][j];
+            if (a.bias) v += __ldg(a.bias + col);
+            switch (a.epi) {
+                case SK_F16: reinterpret_cast<__half*>(a.out)[static_cast<size_t>(row) * a.ldo + col] = __float2half_rn(v); break;
+                case SK_F16_RELU:
+                    reinterpret_cast<__half*>(a.out)[static_cast<size_t>(row) * a.ldo + col] = __float2half_rn(fmaxf(v, 0.0f));
+                    break;
+                case SK_F16_GELU:
+                    reinterpret_cast<__half*>(a.out)[static_cast<size_t>(row) * a.ldo + col] = __float2half_rn(gelu_erf_f(v));
+                    break;
+                case SK_F32: reinterpret_cast<float*>(a.out)[static_cast<size_t>(row) * a.ldo + col] = v; break;
+                case SK_RESID: reinterpret_cast<float*>(a.out)[static_cast<size_t>(row) * a.ldo + col] += v; break;
+                case SK_QKV_CACHE: {
+                    if (col < a.d) {
+                        reinterpret_cast<__half*>(a.out)[static_cast<size_t>(row) * a.ldo + col] = __float2half_rn(v * a.q_scale);
+                    } else if (col < 2 * a.d) {
+                        a.kcache[(static_cast<size_t>(row) * a.S_max + step) * a.d + (col - a.d)] = __float2half_rn(v);
+                    } else {
+                        a.vcache[(static_cast<size_t>(row) * a.S_max + step) * a.d + (col - 2 * a.d)] = __float2half_rn(v);
+                    }
+                    break;
                 }
-                break;
             }
         }
     }
@@ -120,88 +132,147 @@ int skinny_gemm(const SkinnyArgs& a, cudaStream_t stream) {
     SBK_REQUIRE(a.K % 16 == 0 && a.lda % 2 == 0 && a.ldw % 2 == 0, "skinny_gemm: K %% 16 required (K=%d)", a.K);
     if (a.n_rows == 0) return SBK_OK;
     dim3 grid(ceil_div(a.N, 8), ceil_div(a.n_rows, SK_ROWS));
-    skinny_gemm_kernel<<<grid, 128, 0, stream>>>(a);
+    if (a.K <= 1024) skinny_gemm_kernel<4><<<grid, SK_WARPS * 32, 0, stream>>>(a);
+    else skinny_gemm_kernel<8><<<grid, SK_WARPS * 32, 0, stream>>>(a);
     SBK_LAUNCH_CHECK();
     return SBK_OK;
 }
 
 // --------------------------------------------------------------------------- decode-time attention (1 query / row)
-// One warp per (row, head): lanes parallel over keys for q.k, warp softmax, lanes parallel over dims for p.V.
+// One CTA per (row, head), 4 warps split the keys (flash-decoding style): each warp scores its key slice with
+// lanes parallel over keys, then accumulates p.V with 4 lane-groups over keys x 8 lanes over 16-byte dim chunks;
+// the 4 partial (max, sum, out) triples are merged through shared memory.
 // Self-attention: keys = cache positions [0, step]; cross-attention: keys = encoder frames [0, enc_len[utt]).
-// (nn.MultiheadAttention semantics, scale 1/sqrt(d_h) already folded into q.)
-__global__ void __launch_bounds__(256) dec_attention_kernel(const DecAttnArgs a) {
-    extern __shared__ float da_smem[];  // [warps][max_keys]
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
-    const int r = blockIdx.x;
+// (nn.MultiheadAttention semantics, scale 1/sqrt(d_h) already folded into q.)  head_dim == 64.
+constexpr int DA_WARPS = 4;
+
+__global__ void __launch_bounds__(DA_WARPS * 32) dec_attention_kernel(const DecAttnArgs a) {
+    extern __shared__ float da_smem[];            // [max_keys] scores
+    __shared__ float part_o[DA_WARPS][64];
+    __shared__ float part_m[DA_WARPS], part_l[DA_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x, h = blockIdx.y;
     const int blk = r / a.rows_per_block;
     int n_keys;
-    if (a.n_keys_ptr) {
-        n_keys = *a.n_keys_ptr + 1;
-    } else {
-        n_keys = a.enc_len ? min(a.enc_len[blk], a.n_keys_fixed) : a.n_keys_fixed;
-    }
-    float* sc = da_smem + static_cast<size_t>(warp) * a.n_keys_fixed;
-    for (int h = warp; h < a.H; h += n_warps) {
-        const __half* q = a.q + static_cast<size_t>(r) * a.ldq + h * a.dh;
-        const __half* kb = a.kbase + static_cast<size_t>(blk) * a.row_stride + h * a.dh;
-        const __half* vb = a.vbase + static_cast<size_t>(blk) * a.row_stride + h * a.dh;
-        // q in registers (dh <= 128): every lane holds the full query vector as half2 pairs
-        float mx = -INFINITY;
-        for (int j = lane; j < n_keys; j += 32) {
-            const __half* kr = kb + static_cast<size_t>(j) * a.key_stride;
-            float dot = 0.0f;
-            for (int e = 0; e < a.dh; e += 8) {
-                const uint4 kv = *reinterpret_cast<const uint4*>(kr + e);
-                const uint4 qv = *reinterpret_cast<const uint4*>(q + e);
-                const __half2* k2 = reinterpret_cast<const __half2*>(&kv);
-                const __half2* q2 = reinterpret_cast<const __half2*>(&qv);
+    if (a.n_keys_ptr) n_keys = *a.n_keys_ptr + 1;
+    else n_keys = a.enc_len ? min(a.enc_len[blk], a.n_keys_fixed) : a.n_keys_fixed;
+    const int per = (n_keys + DA_WARPS - 1) / DA_WARPS;
+    const int kb = warp * per, ke = min(n_keys, kb + per);
+    const __half* q = a.q + static_cast<size_t>(r) * a.ldq + h * 64;
+    const __half* kbase = a.kbase + static_cast<size_t>(blk) * a.row_stride + h * 64;
+    const __half* vbase = a.vbase + static_cast<size_t>(blk) * a.row_stride + h * 64;
+    // full query vector in registers (every lane)
+    float qf[64];
 #pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const float2 kf = __half22float2(k2[t]), qf = __half22float2(q2[t]);
-                    dot = fmaf(kf.x, qf.x, dot);
-                    dot = fmaf(kf.y, qf.y, dot);
-                }
+    for (int e = 0; e < 64; e += 8) {
+        const uint4 qv = *reinterpret_cast<const uint4*>(q + e);
+        const __half2* q2 = reinterpret_cast<const __half2*>(&qv);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const float2 f = __half22float2(q2[t]);
+            qf[e + 2 * t] = f.x;
+            qf[e + 2 * t + 1] = f.y;
+        }
+    }
+    float mx = -INFINITY;
+    for (int j = kb + lane; j < ke; j += 32) {
+        const __half* kr = kbase + static_cast<size_t>(j) * a.key_stride;
+        uint4 kv[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) kv[e] = *reinterpret_cast<const uint4*>(kr + e * 8);
+        float dot = 0.0f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const __half2* k2 = reinterpret_cast<const __half2*>(&kv[e]);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const float2 kf = __half22float2(k2[t]);
+                dot = fmaf(kf.x, qf[e * 8 + 2 * t], dot);
+                dot = fmaf(kf.y, qf[e * 8 + 2 * t + 1], dot);
             }
-            sc[j] = dot;
-            mx = fmaxf(mx, dot);
         }
-        mx = warp_max(mx);
-        float sum = 0.0f;
-        for (int j = lane; j < n_keys; j += 32) {
-            const float p = __expf(sc[j] - mx);
-            sc[j] = p;
-            sum += p;
+        da_smem[j] = dot;
+        mx = fmaxf(mx, dot);
+    }
+    mx = warp_max(mx);
+    float sum = 0.0f;
+    for (int j = kb + lane; j < ke; j += 32) {
+        const float p = __expf(da_smem[j] - mx);
+        da_smem[j] = p;
+        sum += p;
+    }
+    sum = warp_sum(sum);
+    __syncwarp();
+    // p.V : lane group gq handles keys kb+gq, kb+gq+4, ...; lane%8 owns dims [8*(lane%8), +8)
+    const int gq = lane >> 3, dl = (lane & 7) * 8;
+    float o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = 0.0f;
+    int j = kb + gq;
+    for (; j + 12 < ke; j += 16) {  // 4 keys in flight per lane
+        uint4 vv[4];
+        float p[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            vv[u] = *reinterpret_cast<const uint4*>(vbase + static_cast<size_t>(j + 4 * u) * a.key_stride + dl);
+            p[u] = da_smem[j + 4 * u];
         }
-        sum = warp_sum(sum);
-        __syncwarp();
-        const float inv = 1.0f / sum;
-        // p.V : lane owns dims [2*lane, 2*lane+1] (+64 per extra pass)
-        for (int d0 = 2 * lane; d0 < a.dh; d0 += 64) {
-            float o0 = 0.0f, o1 = 0.0f;
-            for (int j = 0; j < n_keys; ++j) {
-                const float p = sc[j];
-                const float2 vf = __half22float2(*reinterpret_cast<const __half2*>(vb + static_cast<size_t>(j) * a.key_stride + d0));
-                o0 = fmaf(p, vf.x, o0);
-                o1 = fmaf(p, vf.y, o1);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const __half2* v2 = reinterpret_cast<const __half2*>(&vv[u]);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const float2 vf = __half22float2(v2[t]);
+                o[2 * t] = fmaf(p[u], vf.x, o[2 * t]);
+                o[2 * t + 1] = fmaf(p[u], vf.y, o[2 * t + 1]);
             }
-            *reinterpret_cast<__half2*>(a.out + static_cast<size_t>(r) * a.ldo + h * a.dh + d0) =
-                __floats2half2_rn(o0 * inv, o1 * inv);
         }
-        __syncwarp();
+    }
+    for (; j < ke; j += 4) {
+        const uint4 vv = *reinterpret_cast<const uint4*>(vbase + static_cast<size_t>(j) * a.key_stride + dl);
+        const float p = da_smem[j];
+        const __half2* v2 = reinterpret_cast<const __half2*>(&vv);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const float2 vf = __half22float2(v2[t]);
+            o[2 * t] = fmaf(p, vf.x, o[2 * t]);
+            o[2 * t + 1] = fmaf(p, vf.y, o[2 * t + 1]);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        o[e] += __shfl_xor_sync(0xffffffffu, o[e], 8);
+        o[e] += __shfl_xor_sync(0xffffffffu, o[e], 16);
+    }
+    if (lane < 8) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) part_o[warp][dl + e] = o[e];
+    }
+    if (lane == 0) { part_m[warp] = mx; part_l[warp] = sum; }
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        float M = part_m[0];
+#pragma unroll
+        for (int w = 1; w < DA_WARPS; ++w) M = fmaxf(M, part_m[w]);
+        float num = 0.0f, den = 0.0f;
+#pragma unroll
+        for (int w = 0; w < DA_WARPS; ++w) {
+            const float sc = part_m[w] == -INFINITY ? 0.0f : __expf(part_m[w] - M);
+            num += part_o[w][threadIdx.x] * sc;
+            den += part_l[w] * sc;
+        }
+        a.out[static_cast<size_t>(r) * a.ldo + h * 64 + threadIdx.x] = __float2half_rn(num / den);
     }
 }
 
 int dec_attention(const DecAttnArgs& a, int n_rows, int max_keys, cudaStream_t stream) {
-    SBK_REQUIRE(a.dh % 8 == 0 && a.dh <= 128, "dec_attention: head_dim=%d unsupported", a.dh);
+    SBK_REQUIRE(a.dh == 64, "dec_attention: head_dim=%d not built (64 only)", a.dh);
     if (n_rows == 0) return SBK_OK;
-    const int warps = std::min(8, a.H);
-    const size_t smem = static_cast<size_t>(warps) * max_keys * sizeof(float);
-    SBK_REQUIRE(smem <= 160 * 1024, "dec_attention: too many keys (%d)", max_keys);
-    if (smem > 48 * 1024)
-        SBK_CUDA_CHECK(cudaFuncSetAttribute(dec_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = static_cast<size_t>(max_keys) * sizeof(float);
+    SBK_REQUIRE(smem <= 40 * 1024, "dec_attention: too many keys (%d)", max_keys);
     DecAttnArgs b = a;
     b.n_keys_fixed = max_keys;
-    dec_attention_kernel<<<n_rows, warps * 32, smem, stream>>>(b);
+    dec_attention_kernel<<<dim3(n_rows, a.H), DA_WARPS * 32, smem, stream>>>(b);
     SBK_LAUNCH_CHECK();
     return SBK_OK;
 }

@@ -91,6 +91,7 @@ struct AsrModel {
     } b;
     cudaGraphExec_t step_graph = nullptr;
     int graph_rows = -1, graph_T = -1, graph_B = -1;
+    long long graph_nodes = 0;
     int* host_flag = nullptr;  // pinned
     cudaStream_t cap_stream = nullptr;  // private stream for graph capture (the legacy default stream cannot capture)
 };
@@ -496,6 +497,7 @@ static int enqueue_decode_step(AsrModel* m, int rows, int rows_per_utt, int T, i
     AsrModel::Buf& b = m->b;
     const int d = c.d_model, F = c.d_ffn, H = c.nhead, dh = d / H, Ld = c.num_decoder_layers;
     const int ffn_epi = c.decoder_activation == SBK_ACT_GELU ? SK_F16_GELU : SK_F16_RELU;
+    const int n_utt = rows / rows_per_utt;
     RC(dec_embed(b.tokens, S_max + 1, b.step, m->emb, m->dec_pe, d, rows, b.dx, st));
     for (int l = 0; l < Ld; ++l) {
         const DecLayerW& w = m->dec[l];
@@ -520,8 +522,8 @@ static int enqueue_decode_step(AsrModel* m, int rows, int rows_per_utt, int T, i
         a.N = d; a.K = d; a.epi = SK_F16; a.out = b.dq16; a.ldo = d;
         RC(skinny_gemm(a, st));
         t = DecAttnArgs{};
-        t.q = b.dq16; t.ldq = d; t.kbase = b.ckv16 + (size_t)l * 2 * d; t.vbase = t.kbase + d;
-        t.row_stride = (size_t)T * Ld * 2 * d; t.key_stride = Ld * 2 * d; t.rows_per_block = rows_per_utt;
+        t.q = b.dq16; t.ldq = d; t.kbase = b.ckv16 + (size_t)l * n_utt * T * 2 * d; t.vbase = t.kbase + d;
+        t.row_stride = (size_t)T * 2 * d; t.key_stride = 2 * d; t.rows_per_block = rows_per_utt;
         t.n_keys_ptr = nullptr; t.enc_len = b.enc_len; t.H = H; t.dh = dh; t.out = b.datt16; t.ldo = d;
         RC(dec_attention(t, rows, T, st));
         a = SkinnyArgs{}; a.A = b.datt16; a.lda = d; a.W = w.w_cross_out; a.ldw = d; a.bias = w.b_cross_out; a.n_rows = rows;
@@ -559,9 +561,12 @@ static int run_greedy(AsrModel* m, int B, int T, int max_steps, int bos, int eos
     if (max_steps <= 0) return SBK_OK;
     // cross-attention K/V for all layers: one tcgen05 GEMM  [M, d] x [L*2d, d]^T
     RC(cast_f32_f16(b.enc_out, b.enc16, (size_t)M * d, st));
-    GemmEpilogue e;
-    e.mode = EPI_F16; e.bias = m->b_ckv; e.out = b.ckv16; e.ldo = Ld * 2 * d;
-    RC(gemm_f16(b.enc16, d, m->w_ckv, d, e, M, Ld * 2 * d, d, st));
+    // layout ckv16[layer][B*T][K(d) | V(d)]: one GEMM per layer so each layer's K/V rows are contiguous
+    for (int l = 0; l < Ld; ++l) {
+        GemmEpilogue e;
+        e.mode = EPI_F16; e.bias = m->b_ckv + (size_t)l * 2 * d; e.out = b.ckv16 + (size_t)l * M * 2 * d; e.ldo = 2 * d;
+        RC(gemm_f16(b.enc16, d, m->w_ckv + (size_t)l * 2 * d * d, d, e, M, 2 * d, d, st));
+    }
     greedy_reset_kernel<<<ceil_div(rows, 128), 128, 0, st>>>(b.tokens, S_max + 1, rows, bos, b.step, b.has_ended, b.ended_count);
     SBK_LAUNCH_CHECK();
     const bool use_graph = getenv("SBK_NO_GRAPH") == nullptr && log_probs == nullptr;
@@ -570,7 +575,9 @@ static int run_greedy(AsrModel* m, int B, int T, int max_steps, int bos, int eos
         cudaGraph_t g;
         if (!m->cap_stream) SBK_CUDA_CHECK(cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
         SBK_CUDA_CHECK(cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal));
+        launch_count_begin_capture();
         int rc = enqueue_decode_step(m, rows, 1, T, S_max, eos, nullptr, 0, m->cap_stream);
+        m->graph_nodes = launch_count_end_capture();
         cudaError_t ce = cudaStreamEndCapture(m->cap_stream, &g);
         if (rc) return rc;
         SBK_CUDA_CHECK(ce);
@@ -583,7 +590,7 @@ static int run_greedy(AsrModel* m, int B, int T, int max_steps, int bos, int eos
     while (s < max_steps) {
         const int chunk = std::min(check_every, max_steps - s);
         for (int i = 0; i < chunk; ++i) {
-            if (use_graph) SBK_CUDA_CHECK(cudaGraphLaunch(m->step_graph, st));
+            if (use_graph) { SBK_CUDA_CHECK(cudaGraphLaunch(m->step_graph, st)); launch_count_add(m->graph_nodes); }
             else RC(enqueue_decode_step(m, rows, 1, T, S_max, eos, log_probs, max_steps, st));
         }
         s += chunk;
@@ -607,6 +614,34 @@ extern "C" {
 const char* sbk_last_error(void) { return sbk::last_error(); }
 
 int sbk_version(void) { return 100; }
+
+long long sbk_launch_count(void) { return sbk::launch_count(); }
+
+void sbk_gemm_profile_enable(int on) {
+    GemmProfile* p = gemm_profile();
+    for (cudaEvent_t e : p->ev) cudaEventDestroy(e);
+    p->ev.clear();
+    p->flops.clear();
+    p->enabled = on != 0;
+}
+// After a device sync: number of timed GEMM launches, their total milliseconds and total FLOPs.
+int sbk_gemm_profile_read(int* n_launches, double* total_ms, double* total_flops) {
+    GemmProfile* p = gemm_profile();
+    double ms = 0.0, fl = 0.0;
+    for (size_t i = 0; i < p->flops.size(); ++i) {
+        float t = 0.0f;
+        if (cudaEventElapsedTime(&t, p->ev[2 * i], p->ev[2 * i + 1]) != cudaSuccess) {
+            set_error("sbk_gemm_profile_read: events not complete (synchronize first)");
+            return SBK_ERR_CUDA;
+        }
+        ms += t;
+        fl += p->flops[i];
+    }
+    if (n_launches) *n_launches = (int)p->flops.size();
+    if (total_ms) *total_ms = ms;
+    if (total_flops) *total_flops = fl;
+    return SBK_OK;
+}
 
 int sbk_fbank_create(int n_fft, int hop, int n_mels, const float* window_host, const float* mel_matrix_host, float amin,
                      float top_db, sbk_fbank** out) {

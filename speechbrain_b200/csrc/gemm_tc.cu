@@ -245,13 +245,22 @@ static int launch_gemm(const void* A, int lda, const void* W, int ldw, const Gem
     rc = make_tmap_2d_f16(&tb, W, N, K, ldw, BN, GEMM_BK);
     if (rc) return rc;
     auto kern = gemm_tc_kernel<BN, STAGES>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        SBK_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-        attr_set = true;
-    }
+    SBK_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     dim3 grid(ceil_div(N, BN), ceil_div(M, GEMM_BM));
+    GemmProfile* prof = gemm_profile();
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (prof->enabled) {
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0, stream);
+    }
     kern<<<grid, GEMM_THREADS, S::TOTAL, stream>>>(ta, tb, epi, M, N, K);
+    if (prof->enabled) {
+        cudaEventRecord(e1, stream);
+        prof->ev.push_back(e0);
+        prof->ev.push_back(e1);
+        prof->flops.push_back(2.0 * M * N * K);
+    }
     SBK_LAUNCH_CHECK();
     return SBK_OK;
 }

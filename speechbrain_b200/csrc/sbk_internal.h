@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 namespace sbk {
 
 enum GemmEpiMode { EPI_F16 = 0, EPI_F32 = 1, EPI_RESID = 2, EPI_GLU = 3, EPI_ROPE = 4 };
@@ -30,6 +32,18 @@ int gemm_f16(const void* A, int lda, const void* W, int ldw, const GemmEpilogue&
 
 
 const char* last_error();
+void launch_count_begin_capture();
+long long launch_count_end_capture();
+void launch_count_add(long long n);
+long long launch_count();
+
+// Optional live timing of every tcgen05 GEMM launch (CUDA events on the launching stream).
+struct GemmProfile {
+    bool enabled = false;
+    std::vector<cudaEvent_t> ev;   // start/stop pairs
+    std::vector<double> flops;     // 2*M*N*K per launch
+};
+GemmProfile* gemm_profile();
 
 // ---- fbank.cu
 struct Fbank;

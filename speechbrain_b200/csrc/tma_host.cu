@@ -5,6 +5,7 @@
 #include <stdio.h>
 
 #include "common.cuh"
+#include "sbk_internal.h"
 
 namespace sbk {
 
@@ -17,6 +18,22 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 const char* last_error() { return g_err; }
+
+// ---- launch accounting + optional per-GEMM timing (bench.py roofline leg)
+static long long g_launches = 0;
+static bool g_capturing = false;
+static long long g_capture_count = 0;
+void count_launch() {
+    if (g_capturing) ++g_capture_count;
+    else ++g_launches;
+}
+void launch_count_begin_capture() { g_capturing = true; g_capture_count = 0; }
+long long launch_count_end_capture() { g_capturing = false; return g_capture_count; }
+void launch_count_add(long long n) { g_launches += n; }
+long long launch_count() { return g_launches; }
+
+static GemmProfile g_prof;
+GemmProfile* gemm_profile() { return &g_prof; }
 
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
