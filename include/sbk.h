@@ -19,6 +19,7 @@ typedef struct sbk_asr sbk_asr;     /* opaque */
 
 enum { SBK_ATT_ROPE = 0, SBK_ATT_RELPOS = 1 };
 enum { SBK_ACT_RELU = 0, SBK_ACT_GELU = 1 };
+enum { SBK_PART_FBANK = 1, SBK_PART_CNN = 2, SBK_PART_ENCODER = 4, SBK_PART_DECODER = 8, SBK_PART_ALL = 15 };
 
 typedef struct {
     const char* name;  /* reference state_dict key with recipe prefix, e.g. "Transformer.encoder.layers.0.norm1.norm.weight" */
@@ -36,6 +37,7 @@ typedef struct {
     int attention_type;     /* SBK_ATT_ROPE (RoPEMHA) | SBK_ATT_RELPOS (RelPosMHAXL) */
     int decoder_activation; /* SBK_ACT_RELU | SBK_ACT_GELU (the `activation` ctor kwarg) */
     int max_len;            /* positional tables (ctor kwarg max_length, default 2500) */
+    int parts;              /* bitmask of SBK_PART_*: which sub-models the weight table carries */
 } sbk_asr_config;
 
 const char* sbk_last_error(void); /* thread-local message of the last failing call */

@@ -21,11 +21,13 @@ class sbk_tensor(ctypes.Structure):
 class sbk_asr_config(ctypes.Structure):
     _fields_ = [(k, ctypes.c_int) for k in (
         "n_fft", "hop", "n_mels", "cnn_c1", "cnn_c2", "input_size", "d_model", "nhead", "num_encoder_layers",
-        "num_decoder_layers", "d_ffn", "vocab", "kernel_size", "attention_type", "decoder_activation", "max_len")]
+        "num_decoder_layers", "d_ffn", "vocab", "kernel_size", "attention_type", "decoder_activation", "max_len",
+        "parts")]
 
 
 SBK_ATT_ROPE, SBK_ATT_RELPOS = 0, 1
 SBK_ACT_RELU, SBK_ACT_GELU = 0, 1
+SBK_PARTS = {"fbank": 1, "cnn": 2, "encoder": 4, "decoder": 8}
 
 # every symbol include/sbk.h declares (tests check the library exports all of them)
 EXPORTS = [

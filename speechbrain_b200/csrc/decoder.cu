@@ -23,54 +23,127 @@ __device__ __forceinline__ void mma16816_d(float (&d)[4], const uint32_t (&a)[4]
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// --------------------------------------------------------------------------- embedding + positional encoding
-// x[r] = emb[tok[r]] * sqrt(d) + pe[step]   (Transformer.py:966-995 NormalizedEmbedding, :252-303 PositionalEncoding)
-__global__ void dec_embed_kernel(const int* __restrict__ tokens, int tok_stride, const int* __restrict__ step_ptr,
-                                 const float* __restrict__ emb, const float* __restrict__ pe, int d, float sqrt_d,
-                                 float* __restrict__ x) {
-    const int r = blockIdx.x, step = *step_ptr;
-    const int tok = tokens[static_cast<size_t>(r) * tok_stride + step];
-    const float* e = emb + static_cast<size_t>(tok) * d;
-    const float* p = pe + static_cast<size_t>(step) * d;
-    for (int i = threadIdx.x; i < d; i += blockDim.x) x[static_cast<size_t>(r) * d + i] = e[i] * sqrt_d + p[i];
+// Programmatic dependent launch: every decode-step kernel lets its successor start launching immediately and
+// waits for its predecessor's memory only right before it touches activations, so launch latency and the
+// weight prefetch of kernel N+1 overlap the tail of kernel N.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+static bool g_use_pdl = true;
+void set_pdl(bool on) { g_use_pdl = on; }
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_use_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
 }
 
 // --------------------------------------------------------------------------- skinny GEMM (weight streaming)
-// y[n_rows, N] = epi( A[n_rows, K] (fp16) x W[N, K]^T (fp16) + bias ).  n_rows is the number of live
-// hypotheses (32..320): the cost is streaming W once and the chain of dependent L2 round trips, so one CTA
-// owns 8 output columns x 32 rows, its 8 warps split K, and every warp issues all the loads of a chunk of
-// SK_UNR k-steps before the first mma (memory-level parallelism instead of a load->mma->load chain).
-// Deterministic in-CTA reduction through shared memory.
+// y[n_rows, N] = epi( A[n_rows, K] x W[N, K]^T (fp16) + bias ).  n_rows is the number of live hypotheses
+// (32..320): the cost is streaming W once plus a chain of dependent L2 round trips, so one CTA owns 8 output
+// columns x 32 rows, its 8 warps split K, and every warp issues all the loads of a chunk of UNR k-steps
+// before the first mma.  A is either fp16 in global memory, or (LN variant) LayerNorm(x fp32) computed by the
+// CTA itself into shared memory -- this fuses the decoder's pre-norms (Transformer.py:788-827) into the
+// projection that consumes them.  Deterministic in-CTA split-K reduction through shared memory.
 constexpr int SK_ROWS = 32;
 constexpr int SK_WARPS = 8;
 
-template <int UNR>
+template <int UNR, bool LN>
 __global__ void __launch_bounds__(SK_WARPS * 32) skinny_gemm_kernel(const SkinnyArgs a) {
     __shared__ float red[SK_WARPS][SK_ROWS][9];
+    extern __shared__ __align__(16) __half a_sm[];  // LN: [32][K + 8]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
     const int n0 = blockIdx.x * 8;
     const int row0 = blockIdx.y * SK_ROWS;
     const int rows = min(SK_ROWS, a.n_rows - row0);
     const int k_per_warp = ((a.K / 16 + SK_WARPS - 1) / SK_WARPS) * 16;
     const int k_begin = warp * k_per_warp, k_end = min(a.K, k_begin + k_per_warp);
+    pdl_trigger();
 
     float acc[2][4];
 #pragma unroll
     for (int i = 0; i < 2; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0f;
     const int wn = min(n0 + g, a.N - 1);  // clamp for the N tail (results discarded)
     const __half* wrow = a.W + static_cast<size_t>(wn) * a.ldw + 2 * c;
+    // weights do not depend on the previous kernel: fetch the first chunk before waiting on it
+    uint32_t bf[UNR][2];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+        const int k = k_begin + 16 * u;
+        const bool ok = k < k_end;
+        bf[u][0] = ok ? __ldg(reinterpret_cast<const uint32_t*>(wrow + k)) : 0u;
+        bf[u][1] = ok ? __ldg(reinterpret_cast<const uint32_t*>(wrow + k + 8)) : 0u;
+    }
+    pdl_wait();
+
+    const int astr = LN ? a.K + 8 : a.lda;
+    const __half* abase = LN ? a_sm : a.A;
+    if constexpr (LN) {
+        // LayerNorm of this CTA's 32 rows (each warp 4 rows), fp32 statistics (two-pass), fp16 result in smem
+        constexpr int MAXV = 8;  // K <= 32 * 4 * MAXV = 1024
+        const int nv = a.K >> 2;
+        for (int rr = warp; rr < SK_ROWS; rr += SK_WARPS) {
+            const int row = min(row0 + rr, a.n_rows - 1);
+            const float* xr = a.X + static_cast<size_t>(row) * a.K;
+            float4 v[MAXV];
+            float s = 0.0f;
+#pragma unroll
+            for (int i = 0; i < MAXV; ++i) {
+                const int vi = lane + 32 * i;
+                v[i] = vi < nv ? *reinterpret_cast<const float4*>(xr + 4 * vi) : make_float4(0.f, 0.f, 0.f, 0.f);
+                s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+            }
+            const float mean = warp_sum(s) / a.K;
+            float q = 0.0f;
+#pragma unroll
+            for (int i = 0; i < MAXV; ++i)
+                if (lane + 32 * i < nv) {
+                    const float d0 = v[i].x - mean, d1 = v[i].y - mean, d2 = v[i].z - mean, d3 = v[i].w - mean;
+                    q += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+                }
+            const float rstd = rsqrtf(warp_sum(q) / a.K + a.ln_eps);
+#pragma unroll
+            for (int i = 0; i < MAXV; ++i) {
+                const int vi = lane + 32 * i;
+                if (vi < nv) {
+                    const float4 gm = __ldg(reinterpret_cast<const float4*>(a.ln_g + 4 * vi));
+                    const float4 bt = __ldg(reinterpret_cast<const float4*>(a.ln_b + 4 * vi));
+                    __half2 h0 = __floats2half2_rn((v[i].x - mean) * rstd * gm.x + bt.x, (v[i].y - mean) * rstd * gm.y + bt.y);
+                    __half2 h1 = __floats2half2_rn((v[i].z - mean) * rstd * gm.z + bt.z, (v[i].w - mean) * rstd * gm.w + bt.w);
+                    uint2 u;
+                    u.x = *reinterpret_cast<uint32_t*>(&h0);
+                    u.y = *reinterpret_cast<uint32_t*>(&h1);
+                    *reinterpret_cast<uint2*>(a_sm + rr * astr + 4 * vi) = u;
+                }
+            }
+        }
+        __syncthreads();
+    }
     const __half* arow[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-        arow[i] = a.A + static_cast<size_t>(min(row0 + i * 8 + g, a.n_rows - 1)) * a.lda + 2 * c;
+    for (int i = 0; i < 4; ++i) {
+        const int rr = LN ? (i * 8 + g) : min(row0 + i * 8 + g, a.n_rows - 1);
+        arow[i] = abase + static_cast<size_t>(rr) * astr + 2 * c;
+    }
     for (int k0 = k_begin; k0 < k_end; k0 += 16 * UNR) {
-        uint32_t bf[UNR][2], af[UNR][2][4];
+        uint32_t af[UNR][2][4];
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
             const int k = k0 + 16 * u;
             const bool ok = k < k_end;
-            bf[u][0] = ok ? __ldg(reinterpret_cast<const uint32_t*>(wrow + k)) : 0u;
-            bf[u][1] = ok ? __ldg(reinterpret_cast<const uint32_t*>(wrow + k + 8)) : 0u;
+            if (k0 != k_begin) {
+                bf[u][0] = ok ? __ldg(reinterpret_cast<const uint32_t*>(wrow + k)) : 0u;
+                bf[u][1] = ok ? __ldg(reinterpret_cast<const uint32_t*>(wrow + k + 8)) : 0u;
+            }
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) {
                 af[u][mt][0] = ok ? *reinterpret_cast<const uint32_t*>(arow[2 * mt] + k) : 0u;
@@ -132,8 +205,17 @@ int skinny_gemm(const SkinnyArgs& a, cudaStream_t stream) {
     SBK_REQUIRE(a.K % 16 == 0 && a.lda % 2 == 0 && a.ldw % 2 == 0, "skinny_gemm: K %% 16 required (K=%d)", a.K);
     if (a.n_rows == 0) return SBK_OK;
     dim3 grid(ceil_div(a.N, 8), ceil_div(a.n_rows, SK_ROWS));
-    if (a.K <= 1024) skinny_gemm_kernel<4><<<grid, SK_WARPS * 32, 0, stream>>>(a);
-    else skinny_gemm_kernel<8><<<grid, SK_WARPS * 32, 0, stream>>>(a);
+    cudaError_t e;
+    if (a.X != nullptr) {
+        SBK_REQUIRE(a.K <= 1024 && a.K % 4 == 0, "skinny_gemm(LN): K=%d unsupported", a.K);
+        const size_t smem = static_cast<size_t>(SK_ROWS) * (a.K + 8) * 2;
+        e = launch_k(skinny_gemm_kernel<4, true>, grid, dim3(SK_WARPS * 32), smem, stream, a);
+    } else if (a.K <= 1024) {
+        e = launch_k(skinny_gemm_kernel<4, false>, grid, dim3(SK_WARPS * 32), 0, stream, a);
+    } else {
+        e = launch_k(skinny_gemm_kernel<8, false>, grid, dim3(SK_WARPS * 32), 0, stream, a);
+    }
+    SBK_CUDA_CHECK(e);
     SBK_LAUNCH_CHECK();
     return SBK_OK;
 }
@@ -153,6 +235,8 @@ __global__ void __launch_bounds__(DA_WARPS * 32) dec_attention_kernel(const DecA
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = blockIdx.x, h = blockIdx.y;
     const int blk = r / a.rows_per_block;
+    pdl_trigger();
+    pdl_wait();
     int n_keys;
     if (a.n_keys_ptr) n_keys = *a.n_keys_ptr + 1;
     else n_keys = a.enc_len ? min(a.enc_len[blk], a.n_keys_fixed) : a.n_keys_fixed;
@@ -272,23 +356,29 @@ int dec_attention(const DecAttnArgs& a, int n_rows, int max_keys, cudaStream_t s
     SBK_REQUIRE(smem <= 40 * 1024, "dec_attention: too many keys (%d)", max_keys);
     DecAttnArgs b = a;
     b.n_keys_fixed = max_keys;
-    dec_attention_kernel<<<dim3(n_rows, a.H), DA_WARPS * 32, smem, stream>>>(b);
+    SBK_CUDA_CHECK(launch_k(dec_attention_kernel, dim3(n_rows, a.H), dim3(DA_WARPS * 32), smem, stream, b));
     SBK_LAUNCH_CHECK();
     return SBK_OK;
 }
 
+
 // --------------------------------------------------------------------------- greedy step bookkeeping
 // decoders/seq2seq.py:226-257: argmax, fp32 log_softmax, has_ended |= (tok == eos); ended rows get
 // log_probs = -inf (=> prediction eos, score 0 after :259-263) and keep feeding eos.
-// One CTA per row. Writes tokens[r][step+1], pred[r][step], score[r][step], optional log-prob row.
+// One CTA per row. Writes tokens[r][step+1], pred[r][step], score[r][step], optional log-prob row, then the
+// NEXT step's decoder input x[r] = emb[tok] * sqrt(d) + pe[step+1] (Transformer.py:966-995, :252-303) and
+// advances this row's step counter (every kernel of the next step reads step[0] after this kernel is done).
 __global__ void __launch_bounds__(256)
-greedy_select_kernel(const float* __restrict__ logits, int V, const int* __restrict__ step_ptr, int eos, int* tokens,
+greedy_select_kernel(const float* __restrict__ logits, int V, int* __restrict__ step_arr, int eos, int* tokens,
                      int tok_stride, int* has_ended, int* ended_count, int* pred, float* score, int out_stride,
-                     float* log_probs /* [n, L, V] or null */, int L) {
+                     float* log_probs /* [n, L, V] or null */, int L, const float* __restrict__ emb,
+                     const float* __restrict__ pe, int d, float sqrt_d, float* __restrict__ x_next) {
     __shared__ float s_val[8];
     __shared__ int s_idx[8];
     __shared__ float s_sum[8];
-    const int r = blockIdx.x, step = *step_ptr;
+    pdl_trigger();
+    pdl_wait();
+    const int r = blockIdx.x, step = step_arr[r];
     const float* lg = logits + static_cast<size_t>(r) * V;
     float best = -INFINITY;
     int bi = 0x7fffffff;
@@ -321,8 +411,9 @@ greedy_select_kernel(const float* __restrict__ logits, int V, const int* __restr
         float* lp = log_probs + (static_cast<size_t>(r) * L + step) * V;
         for (int i = threadIdx.x; i < V; i += blockDim.x) lp[i] = ended ? -INFINITY : lg[i] - lse;
     }
+    const int tok = ended ? eos : bi;
+    __syncthreads();  // everyone has read has_ended[r] / step_arr[r] before thread 0 updates them
     if (threadIdx.x == 0) {
-        const int tok = ended ? eos : bi;
         tokens[static_cast<size_t>(r) * tok_stride + step + 1] = tok;
         pred[static_cast<size_t>(r) * out_stride + step] = tok;
         score[static_cast<size_t>(r) * out_stride + step] = ended ? 0.0f : best - lse;
@@ -330,31 +421,44 @@ greedy_select_kernel(const float* __restrict__ logits, int V, const int* __restr
             has_ended[r] = 1;
             atomicAdd(ended_count, 1);
         }
+        step_arr[r] = step + 1;
     }
+    const float* e = emb + static_cast<size_t>(tok) * d;
+    const float* p = pe + static_cast<size_t>(step + 1) * d;
+    for (int i = threadIdx.x; i < d; i += blockDim.x) x_next[static_cast<size_t>(r) * d + i] = e[i] * sqrt_d + p[i];
 }
 
-__global__ void advance_step_kernel(int* step_ptr) { *step_ptr += 1; }
+// tokens[r][0] = bos, step[r] = 0, x[r] = emb[bos] * sqrt(d) + pe[0]
+__global__ void greedy_reset_kernel(int* tokens, int tok_stride, int bos, int* step_arr, int* has_ended,
+                                    int* ended_count, const float* __restrict__ emb, const float* __restrict__ pe, int d,
+                                    float sqrt_d, float* __restrict__ x) {
+    const int r = blockIdx.x;
+    if (threadIdx.x == 0) {
+        tokens[static_cast<size_t>(r) * tok_stride] = bos;
+        has_ended[r] = 0;
+        step_arr[r] = 0;
+        if (r == 0) *ended_count = 0;
+    }
+    const float* e = emb + static_cast<size_t>(bos) * d;
+    for (int i = threadIdx.x; i < d; i += blockDim.x) x[static_cast<size_t>(r) * d + i] = e[i] * sqrt_d + pe[i];
+}
 
-int dec_embed(const int* tokens, int tok_stride, const int* step_ptr, const float* emb, const float* pe, int d,
-              int n_rows, float* x, cudaStream_t stream) {
+int greedy_reset(int* tokens, int tok_stride, int n_rows, int bos, int* step_arr, int* has_ended, int* ended_count,
+                 const float* emb, const float* pe, int d, float* x, cudaStream_t stream) {
     if (n_rows == 0) return SBK_OK;
-    dec_embed_kernel<<<n_rows, 128, 0, stream>>>(tokens, tok_stride, step_ptr, emb, pe, d, sqrtf(static_cast<float>(d)), x);
+    greedy_reset_kernel<<<n_rows, 128, 0, stream>>>(tokens, tok_stride, bos, step_arr, has_ended, ended_count, emb, pe, d,
+                                                   sqrtf(static_cast<float>(d)), x);
     SBK_LAUNCH_CHECK();
     return SBK_OK;
 }
 
-int greedy_select(const float* logits, int n_rows, int V, const int* step_ptr, int eos, int* tokens, int tok_stride,
+int greedy_select(const float* logits, int n_rows, int V, int* step_arr, int eos, int* tokens, int tok_stride,
                   int* has_ended, int* ended_count, int* pred, float* score, int out_stride, float* log_probs, int L,
-                  cudaStream_t stream) {
+                  const float* emb, const float* pe, int d, float* x_next, cudaStream_t stream) {
     if (n_rows == 0) return SBK_OK;
-    greedy_select_kernel<<<n_rows, 256, 0, stream>>>(logits, V, step_ptr, eos, tokens, tok_stride, has_ended, ended_count,
-                                                     pred, score, out_stride, log_probs, L);
-    SBK_LAUNCH_CHECK();
-    return SBK_OK;
-}
-
-int advance_step(int* step_ptr, cudaStream_t stream) {
-    advance_step_kernel<<<1, 1, 0, stream>>>(step_ptr);
+    SBK_CUDA_CHECK(launch_k(greedy_select_kernel, dim3(n_rows), dim3(256), 0, stream, logits, V, step_arr, eos, tokens,
+                            tok_stride, has_ended, ended_count, pred, score, out_stride, log_probs, L, emb, pe, d,
+                            sqrtf(static_cast<float>(d)), x_next));
     SBK_LAUNCH_CHECK();
     return SBK_OK;
 }

@@ -93,6 +93,7 @@ struct AsrModel {
     int graph_rows = -1, graph_T = -1, graph_B = -1;
     long long graph_nodes = 0;
     int* host_flag = nullptr;  // pinned
+    bool has_fbank = false, has_cnn = false, has_enc = false, has_dec = false;
     cudaStream_t cap_stream = nullptr;  // private stream for graph capture (the legacy default stream cannot capture)
 };
 
@@ -171,8 +172,12 @@ int asr_create(const sbk_asr_config* cfg, const sbk_tensor* weights, int n_weigh
     }
     Packer p{m, &w};
     int rc = SBK_OK;
+    const bool has_fbank = c.parts & SBK_PART_FBANK, has_cnn = c.parts & SBK_PART_CNN;
+    const bool has_enc = (c.parts & SBK_PART_ENCODER) && c.num_encoder_layers >= 0;
+    const bool has_dec = (c.parts & SBK_PART_DECODER) && c.num_decoder_layers > 0;
+    m->has_fbank = has_fbank; m->has_cnn = has_cnn; m->has_enc = has_enc; m->has_dec = has_dec;
     // ---- Fbank + CMVN
-    {
+    if (has_fbank) {
         const float* win = find(w, "fbank.window", c.n_fft);
         const float* mel = find(w, "fbank.mel_matrix", (int64_t)(c.n_fft / 2 + 1) * c.n_mels);
         if (!win || !mel) { rc = SBK_ERR_ARG; goto fail; }
@@ -184,7 +189,7 @@ int asr_create(const sbk_asr_config* cfg, const sbk_tensor* weights, int n_weigh
         }
     }
     // ---- CNN front-end
-    {
+    if (has_cnn) {
         const int F1 = (c.n_mels - 1) / 2 + 1, F2 = (F1 - 1) / 2 + 1;
         if (F2 * c.cnn_c2 != c.input_size) { set_error("asr_create: CNN output %d != input_size %d", F2 * c.cnn_c2, c.input_size); rc = SBK_ERR_ARG; goto fail; }
         m->c1_w = p.f32("CNN.convblock_0.convs.conv_0.conv.weight", (int64_t)c.cnn_c1 * 9);
@@ -205,6 +210,7 @@ int asr_create(const sbk_asr_config* cfg, const sbk_tensor* weights, int n_weigh
         m->c2_be = p.f32("CNN.convblock_1.convs.norm_0.norm.bias", (int64_t)F2 * c.cnn_c2);
     }
     // ---- encoder
+    if (has_enc) {
     m->w_in = p.f16("Transformer.custom_src_module.layers.0.w.weight", (int64_t)d * c.input_size);
     m->b_in = p.f32("Transformer.custom_src_module.layers.0.w.bias", d);
     m->enc.resize(c.num_encoder_layers);
@@ -276,8 +282,9 @@ int asr_create(const sbk_asr_config* cfg, const sbk_tensor* weights, int n_weigh
         }
         m->relpos_pe = p.f16_raw(pe.data(), pe.size());
     }
+    }  // has_enc
     // ---- decoder
-    if (c.num_decoder_layers > 0) {
+    if (has_dec) {
         m->emb = p.f32("Transformer.custom_tgt_module.layers.0.emb.Embedding.weight", (int64_t)c.vocab * d);
         {
             std::vector<float> pe((size_t)c.max_len * d);  // Transformer.py:252-303
@@ -379,7 +386,7 @@ static int ensure_workspace(AsrModel* m, int B, int L, int rows, int steps) {
     sz((size_t)B * L * 4); sz((size_t)B * T0 * c.n_mels * 4); sz(M * d * 4); sz(M * d * 4); sz(M * d * 4);
     sz((size_t)B * T1 * F1 * c.cnn_c1 * 4); sz(M * c.input_size * 4); sz((size_t)rows * d * 4);
     sz((size_t)rows * c.vocab * 4); sz((size_t)rows * S * 4);
-    sz(B * 4); sz(B * 4); sz((size_t)rows * (S + 1) * 4); sz(64); sz(rows * 4); sz(64); sz((size_t)rows * S * 4); sz(B * 4);
+    sz(B * 4); sz(B * 4); sz((size_t)rows * (S + 1) * 4); sz(rows * 4 + 64); sz(rows * 4); sz(64); sz((size_t)rows * S * 4); sz(B * 4);
     sz((size_t)B * T1 * F1 * c.cnn_c1 * 2); sz(M * c.input_size * 2); sz(M * d * 2); sz(M * F * 2); sz(M * 3 * d * 2);
     sz(M * d * 2); sz((size_t)T2 * d * 2); sz(M * d * 2); sz(M * Ld * 2 * d * 2);
     sz((size_t)Ld * rows * S * d * 2); sz((size_t)Ld * rows * S * d * 2);
@@ -402,7 +409,7 @@ static int ensure_workspace(AsrModel* m, int B, int L, int rows, int steps) {
     TAKE(glu, float, M * d * 4); TAKE(enc_out, float, M * d * 4); TAKE(act1_f, float, (size_t)B * T1 * F1 * c.cnn_c1 * 4);
     TAKE(cnn_f, float, M * c.input_size * 4); TAKE(dx, float, (size_t)rows * d * 4); TAKE(logits, float, (size_t)rows * c.vocab * 4);
     TAKE(score, float, (size_t)rows * S * 4);
-    TAKE(utt_max, int, B * 4); TAKE(enc_len, int, B * 4); TAKE(tokens, int, (size_t)rows * (S + 1) * 4); TAKE(step, int, 64);
+    TAKE(utt_max, int, B * 4); TAKE(enc_len, int, B * 4); TAKE(tokens, int, (size_t)rows * (S + 1) * 4); TAKE(step, int, rows * 4 + 64);
     TAKE(has_ended, int, rows * 4); TAKE(ended_count, int, 64); TAKE(pred, int, (size_t)rows * S * 4); TAKE(rel_len, float, B * 4);
     TAKE(act1, __half, (size_t)B * T1 * F1 * c.cnn_c1 * 2); TAKE(a_in, __half, M * c.input_size * 2); TAKE(h16, __half, M * d * 2);
     TAKE(f16, __half, M * F * 2); TAKE(qkv16, __half, M * 3 * d * 2); TAKE(att16, __half, M * d * 2);
@@ -425,6 +432,8 @@ static int run_encoder(AsrModel* m, const float* feats, int B, int T0, const int
     AsrModel::Buf& b = m->b;
     const int T1 = (T0 - 1) / 2 + 1, T = feats ? (T1 - 1) / 2 + 1 : T0;  // feats == nullptr: b.a_in holds [B*T0, input_size]
     const int M = B * T, d = c.d_model, F = c.d_ffn, H = c.nhead, dh = d / H;
+    SBK_REQUIRE(m->has_enc, "encode: this handle was created without encoder weights");
+    SBK_REQUIRE(feats == nullptr || m->has_cnn, "encode: this handle was created without CNN weights");
     SBK_REQUIRE(T <= m->pos_len, "encode: %d frames exceed max_len=%d", T, m->pos_len);
     if (feats != nullptr)
         RC(cnn_frontend_forward(feats, B, T0, c.n_mels, m->c1_w, m->c1_b, m->c1_g, m->c1_be, c.cnn_c1, m->c2_w, m->c2_b,
@@ -484,13 +493,6 @@ __global__ void abs_len_kernel(const float* rel, int B, int T, int* out) {
     if (i < B) out[i] = min(T, max(0, __float2int_rn(rel[i] * static_cast<float>(T))));
 }
 
-__global__ void greedy_reset_kernel(int* tokens, int tok_stride, int rows, int bos, int* step, int* has_ended,
-                                    int* ended_count) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < rows) { tokens[static_cast<size_t>(i) * tok_stride] = bos; has_ended[i] = 0; }
-    if (i == 0) { *step = 0; *ended_count = 0; }
-}
-
 static int enqueue_decode_step(AsrModel* m, int rows, int rows_per_utt, int T, int S_max, int eos, float* log_probs,
                                int L_lp, cudaStream_t st) {
     const sbk_asr_config& c = m->cfg;
@@ -498,14 +500,14 @@ static int enqueue_decode_step(AsrModel* m, int rows, int rows_per_utt, int T, i
     const int d = c.d_model, F = c.d_ffn, H = c.nhead, dh = d / H, Ld = c.num_decoder_layers;
     const int ffn_epi = c.decoder_activation == SBK_ACT_GELU ? SK_F16_GELU : SK_F16_RELU;
     const int n_utt = rows / rows_per_utt;
-    RC(dec_embed(b.tokens, S_max + 1, b.step, m->emb, m->dec_pe, d, rows, b.dx, st));
+    // b.dx already holds emb[token] * sqrt(d) + pe[step] (written by greedy_reset / the previous greedy_select)
     for (int l = 0; l < Ld; ++l) {
         const DecLayerW& w = m->dec[l];
         __half* kc = b.kcache + (size_t)l * rows * S_max * d;
         __half* vc = b.vcache + (size_t)l * rows * S_max * d;
-        RC(layernorm_rows(b.dx, b.dh16, true, w.n1g, w.n1b, rows, d, 1e-6f, false, st));
-        SkinnyArgs a{};
-        a.A = b.dh16; a.lda = d; a.W = w.w_self_in; a.ldw = d; a.bias = w.b_self_in; a.n_rows = rows; a.N = 3 * d; a.K = d;
+        SkinnyArgs a{};  // LN1 + self-attention in_proj; k/v appended to the cache at position step
+        a.X = b.dx; a.ln_g = w.n1g; a.ln_b = w.n1b; a.ln_eps = 1e-6f;
+        a.W = w.w_self_in; a.ldw = d; a.bias = w.b_self_in; a.n_rows = rows; a.N = 3 * d; a.K = d;
         a.epi = SK_QKV_CACHE; a.out = b.dq16; a.ldo = d; a.kcache = kc; a.vcache = vc; a.step_ptr = b.step; a.S_max = S_max;
         a.d = d; a.q_scale = 1.0f;
         RC(skinny_gemm(a, st));
@@ -516,9 +518,9 @@ static int enqueue_decode_step(AsrModel* m, int rows, int rows_per_utt, int T, i
         a = SkinnyArgs{}; a.A = b.datt16; a.lda = d; a.W = w.w_self_out; a.ldw = d; a.bias = w.b_self_out; a.n_rows = rows;
         a.N = d; a.K = d; a.epi = SK_RESID; a.out = b.dx; a.ldo = d;
         RC(skinny_gemm(a, st));
-        // cross attention
-        RC(layernorm_rows(b.dx, b.dh16, true, w.n2g, w.n2b, rows, d, 1e-6f, false, st));
-        a = SkinnyArgs{}; a.A = b.dh16; a.lda = d; a.W = w.w_cross_q; a.ldw = d; a.bias = w.b_cross_q; a.n_rows = rows;
+        // cross attention: LN2 + (pre-scaled) query projection
+        a = SkinnyArgs{}; a.X = b.dx; a.ln_g = w.n2g; a.ln_b = w.n2b; a.ln_eps = 1e-6f;
+        a.W = w.w_cross_q; a.ldw = d; a.bias = w.b_cross_q; a.n_rows = rows;
         a.N = d; a.K = d; a.epi = SK_F16; a.out = b.dq16; a.ldo = d;
         RC(skinny_gemm(a, st));
         t = DecAttnArgs{};
@@ -529,23 +531,22 @@ static int enqueue_decode_step(AsrModel* m, int rows, int rows_per_utt, int T, i
         a = SkinnyArgs{}; a.A = b.datt16; a.lda = d; a.W = w.w_cross_out; a.ldw = d; a.bias = w.b_cross_out; a.n_rows = rows;
         a.N = d; a.K = d; a.epi = SK_RESID; a.out = b.dx; a.ldo = d;
         RC(skinny_gemm(a, st));
-        // feed-forward
-        RC(layernorm_rows(b.dx, b.dh16, true, w.n3g, w.n3b, rows, d, 1e-6f, false, st));
-        a = SkinnyArgs{}; a.A = b.dh16; a.lda = d; a.W = w.w_ffn1; a.ldw = d; a.bias = w.b_ffn1; a.n_rows = rows;
+        // feed-forward: LN3 + ffn1 + activation, then ffn2 + residual
+        a = SkinnyArgs{}; a.X = b.dx; a.ln_g = w.n3g; a.ln_b = w.n3b; a.ln_eps = 1e-6f;
+        a.W = w.w_ffn1; a.ldw = d; a.bias = w.b_ffn1; a.n_rows = rows;
         a.N = F; a.K = d; a.epi = ffn_epi; a.out = b.df16; a.ldo = F;
         RC(skinny_gemm(a, st));
         a = SkinnyArgs{}; a.A = b.df16; a.lda = F; a.W = w.w_ffn2; a.ldw = F; a.bias = w.b_ffn2; a.n_rows = rows;
         a.N = d; a.K = F; a.epi = SK_RESID; a.out = b.dx; a.ldo = d;
         RC(skinny_gemm(a, st));
     }
-    RC(layernorm_rows(b.dx, b.dh16, true, m->dec_norm_g, m->dec_norm_b, rows, d, 1e-6f, false, st));
-    SkinnyArgs a{};
-    a.A = b.dh16; a.lda = d; a.W = m->w_lin; a.ldw = d; a.bias = m->b_lin; a.n_rows = rows; a.N = c.vocab; a.K = d;
+    SkinnyArgs a{};  // final LayerNorm + seq_lin
+    a.X = b.dx; a.ln_g = m->dec_norm_g; a.ln_b = m->dec_norm_b; a.ln_eps = 1e-6f;
+    a.W = m->w_lin; a.ldw = d; a.bias = m->b_lin; a.n_rows = rows; a.N = c.vocab; a.K = d;
     a.epi = SK_F32; a.out = b.logits; a.ldo = c.vocab;
     RC(skinny_gemm(a, st));
     RC(greedy_select(b.logits, rows, c.vocab, b.step, eos, b.tokens, S_max + 1, b.has_ended, b.ended_count, b.pred, b.score,
-                     S_max, log_probs, L_lp, st));
-    RC(advance_step(b.step, st));
+                     S_max, log_probs, L_lp, m->emb, m->dec_pe, d, b.dx, st));
     return SBK_OK;
 }
 
@@ -555,7 +556,7 @@ static int run_greedy(AsrModel* m, int B, int T, int max_steps, int bos, int eos
     const sbk_asr_config& c = m->cfg;
     AsrModel::Buf& b = m->b;
     const int d = c.d_model, Ld = c.num_decoder_layers, M = B * T, rows = B, S_max = m->ws_steps + 1;
-    SBK_REQUIRE(Ld > 0, "greedy: model has no decoder");
+    SBK_REQUIRE(m->has_dec, "greedy: this handle was created without decoder weights");
     SBK_REQUIRE(max_steps <= m->ws_steps && max_steps + 1 <= c.max_len, "greedy: max_steps=%d too large", max_steps);
     *steps_done = 0;
     if (max_steps <= 0) return SBK_OK;
@@ -567,8 +568,8 @@ static int run_greedy(AsrModel* m, int B, int T, int max_steps, int bos, int eos
         e.mode = EPI_F16; e.bias = m->b_ckv + (size_t)l * 2 * d; e.out = b.ckv16 + (size_t)l * M * 2 * d; e.ldo = 2 * d;
         RC(gemm_f16(b.enc16, d, m->w_ckv + (size_t)l * 2 * d * d, d, e, M, 2 * d, d, st));
     }
-    greedy_reset_kernel<<<ceil_div(rows, 128), 128, 0, st>>>(b.tokens, S_max + 1, rows, bos, b.step, b.has_ended, b.ended_count);
-    SBK_LAUNCH_CHECK();
+    RC(greedy_reset(b.tokens, S_max + 1, rows, bos, b.step, b.has_ended, b.ended_count, m->emb, m->dec_pe, d, b.dx, st));
+    set_pdl(getenv("SBK_NO_PDL") == nullptr);
     const bool use_graph = getenv("SBK_NO_GRAPH") == nullptr && log_probs == nullptr;
     if (use_graph && (m->step_graph == nullptr || m->graph_rows != rows || m->graph_T != T || m->graph_B != B)) {
         if (m->step_graph) { cudaGraphExecDestroy(m->step_graph); m->step_graph = nullptr; }
@@ -692,6 +693,7 @@ int sbk_asr_num_frames(const sbk_asr* mm, int n_samples, int* T_feat, int* T_enc
 int sbk_asr_cnn_forward(sbk_asr* mm, const float* feats_dev, int B, int T0, float* out_dev, void* stream) {
     AsrModel* m = reinterpret_cast<AsrModel*>(mm);
     const sbk_asr_config& c = m->cfg;
+    SBK_REQUIRE(m->has_cnn, "cnn_forward: this handle was created without CNN weights");
     const int L = (T0 - 1) * c.hop;
     RC(ensure_workspace(m, B, L, std::max(B, m->ws_rows), std::max(1, m->ws_steps)));
     return cnn_frontend_forward(feats_dev, B, T0, c.n_mels, m->c1_w, m->c1_b, m->c1_g, m->c1_be, c.cnn_c1, m->c2_w, m->c2_b,
@@ -742,6 +744,7 @@ int sbk_asr_transcribe_greedy_dev(sbk_asr* mm, const float* wav_dev, const float
     AsrModel* m = reinterpret_cast<AsrModel*>(mm);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const sbk_asr_config& c = m->cfg;
+    SBK_REQUIRE(m->has_fbank && m->has_cnn && m->has_enc, "transcribe: handle lacks fbank/CNN/encoder weights");
     SBK_REQUIRE(m->glob_mean != nullptr, "transcribe: model has no normalize.glob_mean/std (global CMVN) weights");
     RC(ensure_workspace(m, B, L, std::max(B, m->ws_rows), std::max(max_steps, m->ws_steps)));
     int T0, T1, T;
@@ -763,7 +766,7 @@ int sbk_asr_transcribe_greedy_dev(sbk_asr* mm, const float* wav_dev, const float
     if (enc_out_dev)
         SBK_CUDA_CHECK(cudaMemcpyAsync(enc_out_dev, b.enc_out, (size_t)B * T * c.d_model * 4, cudaMemcpyDeviceToDevice, st));
     int done = 0;
-    if (max_steps > 0 && c.num_decoder_layers > 0) {
+    if (max_steps > 0 && m->has_dec) {
         RC(run_greedy(m, B, T, max_steps, bos, eos, log_probs_dev, &done, st));
         const int S_max = m->ws_steps + 1;
         if (pred_dev)

@@ -84,7 +84,10 @@ struct SkinnyArgs {
     void* out; int ldo;              // SK_F16/F32: out ; SK_RESID: fp32 x (in place) ; SK_QKV_CACHE: q buffer fp16 [n, d]
     __half* kcache; __half* vcache;  // SK_QKV_CACHE: [n_rows, S_max, d]
     const int* step_ptr; int S_max; int d; float q_scale;
+    // LayerNorm-fused variant: A = LayerNorm(X fp32 [n_rows, K]) computed in-kernel (X != nullptr)
+    const float* X; const float* ln_g; const float* ln_b; float ln_eps;
 };
+void set_pdl(bool on);
 int skinny_gemm(const SkinnyArgs& a, cudaStream_t stream);
 struct DecAttnArgs {
     const __half* q; int ldq;
@@ -99,11 +102,10 @@ struct DecAttnArgs {
     __half* out; int ldo;
 };
 int dec_attention(const DecAttnArgs& a, int n_rows, int max_keys, cudaStream_t stream);
-int dec_embed(const int* tokens, int tok_stride, const int* step_ptr, const float* emb, const float* pe, int d,
-              int n_rows, float* x, cudaStream_t stream);
-int greedy_select(const float* logits, int n_rows, int V, const int* step_ptr, int eos, int* tokens, int tok_stride,
+int greedy_reset(int* tokens, int tok_stride, int n_rows, int bos, int* step_arr, int* has_ended, int* ended_count,
+                 const float* emb, const float* pe, int d, float* x, cudaStream_t stream);
+int greedy_select(const float* logits, int n_rows, int V, int* step_arr, int eos, int* tokens, int tok_stride,
                   int* has_ended, int* ended_count, int* pred, float* score, int out_stride, float* log_probs, int L,
-                  cudaStream_t stream);
-int advance_step(int* step_ptr, cudaStream_t stream);
+                  const float* emb, const float* pe, int d, float* x_next, cudaStream_t stream);
 
 }  // namespace sbk

@@ -74,8 +74,9 @@ class AsrEngine:
     ("RoPEMHA"|"RelPosMHAXL"), decoder_activation ("gelu"|"relu"), max_length.
     ``state``: {reference key with recipe prefix: CPU fp32 tensor}."""
 
-    def __init__(self, cfg, state, device="cuda"):
+    def __init__(self, cfg, state, device="cuda", parts=("fbank", "cnn", "encoder", "decoder")):
         self.cfg = dict(cfg)
+        self.parts = tuple(parts)
         self.device = torch.device(device)
         c = _lib.sbk_asr_config()
         c.n_fft, c.hop, c.n_mels = cfg["n_fft"], cfg["hop"], cfg["n_mels"]
@@ -89,9 +90,13 @@ class AsrEngine:
         c.attention_type = _lib.SBK_ATT_ROPE if att == "RoPEMHA" else _lib.SBK_ATT_RELPOS
         c.decoder_activation = _lib.SBK_ACT_GELU if cfg.get("decoder_activation", "gelu") == "gelu" else _lib.SBK_ACT_RELU
         c.max_len = cfg.get("max_length", 2500)
+        c.parts = sum(_lib.SBK_PARTS[p] for p in self.parts)
+        if cfg["num_decoder_layers"] == 0:
+            c.parts &= ~_lib.SBK_PARTS["decoder"]
         st = {k: v.detach().float().contiguous().cpu() for k, v in state.items() if torch.is_tensor(v) and v.is_floating_point()}
-        st["fbank.window"] = stft_window(cfg["n_fft"], cfg["win"])
-        st["fbank.mel_matrix"] = mel_filter_matrix(cfg["n_mels"], cfg["n_fft"], cfg.get("sample_rate", 16000))
+        if "fbank" in self.parts:
+            st["fbank.window"] = stft_window(cfg["n_fft"], cfg["win"])
+            st["fbank.mel_matrix"] = mel_filter_matrix(cfg["n_mels"], cfg["n_fft"], cfg.get("sample_rate", 16000))
         names = [k.encode() for k in st]
         arr = (_lib.sbk_tensor * len(st))()
         for i, (k, v) in enumerate(st.items()):
