@@ -72,6 +72,11 @@ int sbk_gemm_f16_test(const void* A_dev, const void* W_dev, const float* bias_de
 /* ---- model handle: repacks the reference state_dict once */
 int sbk_asr_create(const sbk_asr_config* cfg, const sbk_tensor* weights, int n_weights, sbk_asr** out);
 void sbk_asr_destroy(sbk_asr* m);
+/* A clone shares the repacked weights and owns its own workspace: one clone ("lane") per batch in flight. */
+int sbk_asr_clone(sbk_asr* src, sbk_asr** out);
+/* Greedy early-exit (`has_ended.all()`, decoders/seq2seq.py:256) is polled every n steps with a stream sync;
+ * 0 = never poll: run exactly max_steps and never block the host (fully asynchronous enqueue). Default 8. */
+int sbk_asr_set_poll_interval(sbk_asr* m, int every_n_steps);
 int sbk_asr_num_frames(const sbk_asr* m, int n_samples, int* T_feat, int* T_enc);
 
 /* ConvolutionFrontEnd.forward (lobes/models/convolution.py:116-320): feats [B,T0,n_mels] -> out [B,T2,F2*C2] fp32 */
@@ -96,6 +101,11 @@ int sbk_asr_transcribe_greedy_dev(sbk_asr* m, const float* wav_dev, const float*
 int sbk_asr_transcribe_greedy_host(sbk_asr* m, const float* wav_host, const float* rel_len_host, int B, int L,
                                    int max_steps, int bos, int eos, int* pred_host, float* score_host,
                                    int* steps_done, void* stream);
+
+/* as _host, but only enqueues (pinned host buffers required); the caller synchronises the stream */
+int sbk_asr_transcribe_greedy_host_async(sbk_asr* m, const float* wav_host, const float* rel_len_host, int B, int L,
+                                         int max_steps, int bos, int eos, int* pred_host, float* score_host,
+                                         int* steps_done, void* stream);
 
 #ifdef __cplusplus
 }

@@ -93,6 +93,12 @@ struct AsrModel {
     int graph_rows = -1, graph_T = -1, graph_B = -1;
     long long graph_nodes = 0;
     int* host_flag = nullptr;  // pinned
+    struct PipeKey { const void *wav, *rel, *enc, *pred, *score; int B, L, steps, bos, eos; };
+    PipeKey pipe_key{};
+    cudaGraphExec_t pipe_graph = nullptr;
+    long long pipe_nodes = 0;
+    int* weight_refs = nullptr;  // weights (arena + fbank plan) are shared between a handle and its clones (lanes)
+    int poll_every = 8;          // greedy early-exit poll interval in steps; 0 = never sync, run exactly max_steps
     bool has_fbank = false, has_cnn = false, has_enc = false, has_dec = false;
     cudaStream_t cap_stream = nullptr;  // private stream for graph capture (the legacy default stream cannot capture)
 };
@@ -345,6 +351,7 @@ int asr_create(const sbk_asr_config* cfg, const sbk_tensor* weights, int n_weigh
     }
     if (!p.ok) { rc = SBK_ERR_ARG; goto fail; }
     if (cudaMallocHost(&m->host_flag, 64) != cudaSuccess) { set_error("cudaMallocHost failed"); rc = SBK_ERR_NOMEM; goto fail; }
+    m->weight_refs = new int(1);
     if (cudaDeviceSynchronize() != cudaSuccess) { set_error("asr_create: device error after upload"); rc = SBK_ERR_CUDA; goto fail; }
     *out = m;
     return SBK_OK;
@@ -355,11 +362,39 @@ fail:
     return rc;
 }
 
+// A clone shares the repacked weights but owns its workspace, decode graph and flags: one clone per in-flight
+// batch ("lane") lets independent batches overlap on different streams (the decode loop is latency-bound and
+// leaves most SMs idle, so concurrent lanes raise throughput without touching per-batch numerics).
+int asr_clone(AsrModel* src, AsrModel** out) {
+    SBK_REQUIRE(src && out, "asr_clone: null argument");
+    AsrModel* m = new AsrModel(*src);
+    m->ws = Arena();
+    m->wsB = m->wsL = m->ws_rows = m->ws_steps = 0;
+    m->b = AsrModel::Buf();
+    m->step_graph = nullptr;
+    m->pipe_graph = nullptr;
+    m->graph_rows = m->graph_T = m->graph_B = -1;
+    m->cap_stream = nullptr;
+    m->host_flag = nullptr;
+    if (cudaMallocHost(&m->host_flag, 64) != cudaSuccess) {
+        delete m;
+        set_error("asr_clone: cudaMallocHost failed");
+        return SBK_ERR_NOMEM;
+    }
+    ++*m->weight_refs;
+    *out = m;
+    return SBK_OK;
+}
+
 void asr_destroy(AsrModel* m) {
     if (!m) return;
     if (m->step_graph) cudaGraphExecDestroy(m->step_graph);
-    if (m->fbank) fbank_destroy(m->fbank);
-    cudaFree(m->warena.base);
+    if (m->pipe_graph) cudaGraphExecDestroy(m->pipe_graph);
+    if (m->weight_refs && --*m->weight_refs == 0) {
+        if (m->fbank) fbank_destroy(m->fbank);
+        cudaFree(m->warena.base);
+        delete m->weight_refs;
+    }
     cudaFree(m->ws.base);
     if (m->host_flag) cudaFreeHost(m->host_flag);
     if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
@@ -402,6 +437,7 @@ static int ensure_workspace(AsrModel* m, int B, int L, int rows, int steps) {
         m->ws.cap = need;
     }
     if (m->step_graph) { cudaGraphExecDestroy(m->step_graph); m->step_graph = nullptr; m->graph_rows = -1; }
+    if (m->pipe_graph) { cudaGraphExecDestroy(m->pipe_graph); m->pipe_graph = nullptr; }
     m->ws.used = 0;
     AsrModel::Buf& b = m->b;
 #define TAKE(field, type, bytes) b.field = reinterpret_cast<type*>(m->ws.take(bytes))
@@ -552,7 +588,7 @@ static int enqueue_decode_step(AsrModel* m, int rows, int rows_per_utt, int T, i
 
 // Greedy search over encoder states already in the workspace (b.enc_out / b.enc_len).
 static int run_greedy(AsrModel* m, int B, int T, int max_steps, int bos, int eos, float* log_probs, int* steps_done,
-                      cudaStream_t st) {
+                      cudaStream_t st, bool in_capture = false) {
     const sbk_asr_config& c = m->cfg;
     AsrModel::Buf& b = m->b;
     const int d = c.d_model, Ld = c.num_decoder_layers, M = B * T, rows = B, S_max = m->ws_steps + 1;
@@ -569,8 +605,13 @@ static int run_greedy(AsrModel* m, int B, int T, int max_steps, int bos, int eos
         RC(gemm_f16(b.enc16, d, m->w_ckv + (size_t)l * 2 * d * d, d, e, M, 2 * d, d, st));
     }
     RC(greedy_reset(b.tokens, S_max + 1, rows, bos, b.step, b.has_ended, b.ended_count, m->emb, m->dec_pe, d, b.dx, st));
-    set_pdl(getenv("SBK_NO_PDL") == nullptr);
-    const bool use_graph = getenv("SBK_NO_GRAPH") == nullptr && log_probs == nullptr;
+    set_pdl(getenv("SBK_PDL") != nullptr);  // programmatic dependent launch measured slower here: opt-in only
+    const bool use_graph = !in_capture && getenv("SBK_NO_GRAPH") == nullptr && log_probs == nullptr;
+    if (in_capture) {  // the caller is capturing the whole pipeline: enqueue exactly max_steps steps, no polling
+        for (int i = 0; i < max_steps; ++i) RC(enqueue_decode_step(m, rows, 1, T, S_max, eos, log_probs, max_steps, st));
+        *steps_done = max_steps;
+        return SBK_OK;
+    }
     if (use_graph && (m->step_graph == nullptr || m->graph_rows != rows || m->graph_T != T || m->graph_B != B)) {
         if (m->step_graph) { cudaGraphExecDestroy(m->step_graph); m->step_graph = nullptr; }
         cudaGraph_t g;
@@ -586,7 +627,7 @@ static int run_greedy(AsrModel* m, int B, int T, int max_steps, int bos, int eos
         cudaGraphDestroy(g);
         m->graph_rows = rows; m->graph_T = T; m->graph_B = B;
     }
-    const int check_every = 8;
+    const int check_every = m->poll_every > 0 ? m->poll_every : max_steps;
     int s = 0;
     while (s < max_steps) {
         const int chunk = std::min(check_every, max_steps - s);
@@ -595,7 +636,7 @@ static int run_greedy(AsrModel* m, int B, int T, int max_steps, int bos, int eos
             else RC(enqueue_decode_step(m, rows, 1, T, S_max, eos, log_probs, max_steps, st));
         }
         s += chunk;
-        if (s < max_steps) {  // seq2seq.py:256 `has_ended.all()` early exit, polled once per chunk
+        if (s < max_steps && m->poll_every > 0) {  // seq2seq.py:256 `has_ended.all()` early exit, polled once per chunk
             SBK_CUDA_CHECK(cudaMemcpyAsync(m->host_flag, b.ended_count, 4, cudaMemcpyDeviceToHost, st));
             SBK_CUDA_CHECK(cudaStreamSynchronize(st));
             if (*m->host_flag >= rows) break;
@@ -680,6 +721,13 @@ int sbk_asr_create(const sbk_asr_config* cfg, const sbk_tensor* weights, int n_w
     return asr_create(cfg, weights, n_weights, reinterpret_cast<AsrModel**>(out));
 }
 void sbk_asr_destroy(sbk_asr* m) { asr_destroy(reinterpret_cast<AsrModel*>(m)); }
+int sbk_asr_clone(sbk_asr* src, sbk_asr** out) {
+    return asr_clone(reinterpret_cast<AsrModel*>(src), reinterpret_cast<AsrModel**>(out));
+}
+int sbk_asr_set_poll_interval(sbk_asr* m, int every_n_steps) {
+    reinterpret_cast<AsrModel*>(m)->poll_every = every_n_steps;
+    return SBK_OK;
+}
 
 int sbk_asr_num_frames(const sbk_asr* mm, int n_samples, int* T_feat, int* T_enc) {
     const AsrModel* m = reinterpret_cast<const AsrModel*>(mm);
@@ -738,15 +786,10 @@ int sbk_asr_encode_from_cnn(sbk_asr* mm, const float* src_dev, const float* rel_
 
 // Full device pipeline on device-resident wav: Fbank -> global CMVN -> CNN -> encoder -> greedy.
 // Outputs (device, optional): enc_out [B,T,d] fp32; pred [B, max_steps] int32; score [B, max_steps] fp32.
-int sbk_asr_transcribe_greedy_dev(sbk_asr* mm, const float* wav_dev, const float* rel_len_dev, int B, int L,
-                                  int max_steps, int bos, int eos, float* enc_out_dev, int* pred_dev, float* score_dev,
-                                  float* log_probs_dev, int* steps_done, void* stream) {
-    AsrModel* m = reinterpret_cast<AsrModel*>(mm);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+static int transcribe_enqueue(AsrModel* m, const float* wav_dev, const float* rel_len_dev, int B, int L, int max_steps,
+                              int bos, int eos, float* enc_out_dev, int* pred_dev, float* score_dev, float* log_probs_dev,
+                              int* steps_done, cudaStream_t st, bool in_capture) {
     const sbk_asr_config& c = m->cfg;
-    SBK_REQUIRE(m->has_fbank && m->has_cnn && m->has_enc, "transcribe: handle lacks fbank/CNN/encoder weights");
-    SBK_REQUIRE(m->glob_mean != nullptr, "transcribe: model has no normalize.glob_mean/std (global CMVN) weights");
-    RC(ensure_workspace(m, B, L, std::max(B, m->ws_rows), std::max(max_steps, m->ws_steps)));
     int T0, T1, T;
     frames(c, L, &T0, &T1, &T);
     AsrModel::Buf& b = m->b;
@@ -767,7 +810,7 @@ int sbk_asr_transcribe_greedy_dev(sbk_asr* mm, const float* wav_dev, const float
         SBK_CUDA_CHECK(cudaMemcpyAsync(enc_out_dev, b.enc_out, (size_t)B * T * c.d_model * 4, cudaMemcpyDeviceToDevice, st));
     int done = 0;
     if (max_steps > 0 && m->has_dec) {
-        RC(run_greedy(m, B, T, max_steps, bos, eos, log_probs_dev, &done, st));
+        RC(run_greedy(m, B, T, max_steps, bos, eos, log_probs_dev, &done, st, in_capture));
         const int S_max = m->ws_steps + 1;
         if (pred_dev)
             SBK_CUDA_CHECK(cudaMemcpy2DAsync(pred_dev, (size_t)max_steps * 4, b.pred, (size_t)S_max * 4, (size_t)done * 4, B,
@@ -777,6 +820,45 @@ int sbk_asr_transcribe_greedy_dev(sbk_asr* mm, const float* wav_dev, const float
                                              cudaMemcpyDeviceToDevice, st));
     }
     if (steps_done) *steps_done = done;
+    return SBK_OK;
+}
+
+int sbk_asr_transcribe_greedy_dev(sbk_asr* mm, const float* wav_dev, const float* rel_len_dev, int B, int L,
+                                  int max_steps, int bos, int eos, float* enc_out_dev, int* pred_dev, float* score_dev,
+                                  float* log_probs_dev, int* steps_done, void* stream) {
+    AsrModel* m = reinterpret_cast<AsrModel*>(mm);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    SBK_REQUIRE(m->has_fbank && m->has_cnn && m->has_enc, "transcribe: handle lacks fbank/CNN/encoder weights");
+    SBK_REQUIRE(m->glob_mean != nullptr, "transcribe: model has no normalize.glob_mean/std (global CMVN) weights");
+    RC(ensure_workspace(m, B, L, std::max(B, m->ws_rows), std::max(max_steps, m->ws_steps)));
+    // Fixed-length runs (poll interval 0) replay ONE CUDA graph of the whole pipeline (Fbank .. last decode step):
+    // ~2.6k kernel nodes, a single host-side launch per batch.
+    const bool whole_graph = m->poll_every == 0 && rel_len_dev != nullptr && log_probs_dev == nullptr &&
+                             getenv("SBK_NO_GRAPH") == nullptr && max_steps > 0 && m->has_dec;
+    if (!whole_graph)
+        return transcribe_enqueue(m, wav_dev, rel_len_dev, B, L, max_steps, bos, eos, enc_out_dev, pred_dev, score_dev,
+                                  log_probs_dev, steps_done, st, false);
+    AsrModel::PipeKey key{wav_dev, rel_len_dev, enc_out_dev, pred_dev, score_dev, B, L, max_steps, bos, eos};
+    if (m->pipe_graph == nullptr || memcmp(&key, &m->pipe_key, sizeof(key)) != 0) {
+        if (m->pipe_graph) { cudaGraphExecDestroy(m->pipe_graph); m->pipe_graph = nullptr; }
+        if (!m->cap_stream) SBK_CUDA_CHECK(cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
+        cudaGraph_t g;
+        SBK_CUDA_CHECK(cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal));
+        launch_count_begin_capture();
+        int done = 0;
+        int rc = transcribe_enqueue(m, wav_dev, rel_len_dev, B, L, max_steps, bos, eos, enc_out_dev, pred_dev, score_dev,
+                                    nullptr, &done, m->cap_stream, true);
+        m->pipe_nodes = launch_count_end_capture();
+        cudaError_t ce = cudaStreamEndCapture(m->cap_stream, &g);
+        if (rc) return rc;
+        SBK_CUDA_CHECK(ce);
+        SBK_CUDA_CHECK(cudaGraphInstantiate(&m->pipe_graph, g, 0));
+        cudaGraphDestroy(g);
+        m->pipe_key = key;
+    }
+    SBK_CUDA_CHECK(cudaGraphLaunch(m->pipe_graph, st));
+    launch_count_add(m->pipe_nodes);
+    if (steps_done) *steps_done = max_steps;
     return SBK_OK;
 }
 
@@ -815,9 +897,9 @@ int sbk_asr_greedy_from_enc(sbk_asr* mm, const float* enc_dev, const float* rel_
 
 // Host-buffer entry point (the call EncoderDecoderASR.transcribe_batch makes): wav/rel_len/pred are HOST
 // (ideally pinned) buffers; H2D and D2H copies are part of the call.
-int sbk_asr_transcribe_greedy_host(sbk_asr* mm, const float* wav_host, const float* rel_len_host, int B, int L,
-                                   int max_steps, int bos, int eos, int* pred_host, float* score_host, int* steps_done,
-                                   void* stream) {
+static int transcribe_greedy_host_impl(sbk_asr* mm, const float* wav_host, const float* rel_len_host, int B, int L,
+                                       int max_steps, int bos, int eos, int* pred_host, float* score_host, int* steps_done,
+                                       void* stream, bool sync) {
     AsrModel* m = reinterpret_cast<AsrModel*>(mm);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     RC(ensure_workspace(m, B, L, std::max(B, m->ws_rows), std::max(max_steps, m->ws_steps)));
@@ -840,9 +922,23 @@ int sbk_asr_transcribe_greedy_host(sbk_asr* mm, const float* wav_host, const flo
             SBK_CUDA_CHECK(cudaMemcpy2DAsync(score_host, (size_t)max_steps * 4, b.score, (size_t)S_max * 4, (size_t)done * 4, B,
                                              cudaMemcpyDeviceToHost, st));
     }
-    SBK_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (sync) SBK_CUDA_CHECK(cudaStreamSynchronize(st));
     if (steps_done) *steps_done = done;
     return SBK_OK;
+}
+
+int sbk_asr_transcribe_greedy_host(sbk_asr* mm, const float* wav_host, const float* rel_len_host, int B, int L,
+                                   int max_steps, int bos, int eos, int* pred_host, float* score_host, int* steps_done,
+                                   void* stream) {
+    return transcribe_greedy_host_impl(mm, wav_host, rel_len_host, B, L, max_steps, bos, eos, pred_host, score_host,
+                                       steps_done, stream, true);
+}
+// Same, but only ENQUEUES the copies and kernels (pinned buffers required); the caller synchronises the stream.
+int sbk_asr_transcribe_greedy_host_async(sbk_asr* mm, const float* wav_host, const float* rel_len_host, int B, int L,
+                                         int max_steps, int bos, int eos, int* pred_host, float* score_host,
+                                         int* steps_done, void* stream) {
+    return transcribe_greedy_host_impl(mm, wav_host, rel_len_host, B, L, max_steps, bos, eos, pred_host, score_host,
+                                       steps_done, stream, false);
 }
 
 }  // extern "C"

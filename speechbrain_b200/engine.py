@@ -107,9 +107,24 @@ class AsrEngine:
         self._keep = (st, names, arr)
 
     def __del__(self):
-        if getattr(self, "_h", None) and self._h.value:
-            lib().sbk_asr_destroy(self._h)
-            self._h = None
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                lib().sbk_asr_destroy(self._h)
+                self._h = None
+        except Exception:  # interpreter shutdown
+            pass
+
+    def clone(self):
+        """A lane: shares the repacked weights, owns its workspace / decode graph (one per batch in flight)."""
+        other = object.__new__(AsrEngine)
+        other.cfg, other.device, other.parts, other._keep = self.cfg, self.device, self.parts, self._keep
+        other._h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib().sbk_asr_clone(self._h, ctypes.byref(other._h)), "sbk_asr_clone")
+        return other
+
+    def set_poll_interval(self, every_n_steps):
+        check(lib().sbk_asr_set_poll_interval(self._h, int(every_n_steps)), "sbk_asr_set_poll_interval")
 
     def _sp(self):
         return stream_ptr(self.device)
@@ -165,12 +180,14 @@ class AsrEngine:
                                                 ptr(lp), ctypes.byref(done), self._sp()), "sbk_asr_greedy_from_enc")
         return pred, score, lp, done.value
 
-    def transcribe_greedy_dev(self, wav, wav_lens, max_steps, bos, eos, want_enc=False):
+    def transcribe_greedy_dev(self, wav, wav_lens, max_steps, bos, eos, want_enc=False, pred=None, score=None):
         wav = wav.float().contiguous()
         B, L = wav.shape
         _, T = self.num_frames(L)
-        pred = torch.full((B, max(max_steps, 1)), eos, device=wav.device, dtype=torch.int32)
-        score = torch.zeros(B, max(max_steps, 1), device=wav.device, dtype=torch.float32)
+        if pred is None:
+            pred = torch.full((B, max(max_steps, 1)), eos, device=wav.device, dtype=torch.int32)
+        if score is None:
+            score = torch.zeros(B, max(max_steps, 1), device=wav.device, dtype=torch.float32)
         enc = torch.empty(B, T, self.cfg["d_model"], device=wav.device, dtype=torch.float32) if want_enc else None
         wl = wav_lens.float().contiguous().to(wav.device) if wav_lens is not None else None
         done = ctypes.c_int()
@@ -179,6 +196,16 @@ class AsrEngine:
                                                       ptr(pred), ptr(score), None, ctypes.byref(done), self._sp()),
                   "sbk_asr_transcribe_greedy_dev")
         return pred, score, enc, done.value
+
+    def transcribe_greedy_host_async(self, wav_host, lens_host, max_steps, bos, eos, pred_host):
+        """Enqueue-only variant on the current stream (all tensors pinned, contiguous); caller synchronises."""
+        B, L = wav_host.shape
+        done = ctypes.c_int()
+        with torch.cuda.device(self.device):
+            check(lib().sbk_asr_transcribe_greedy_host_async(self._h, ptr(wav_host), ptr(lens_host), B, L, max_steps, bos, eos,
+                                                             ptr(pred_host), None, ctypes.byref(done), self._sp()),
+                  "sbk_asr_transcribe_greedy_host_async")
+        return done.value
 
     def transcribe_greedy_host(self, wav_host, lens_host, max_steps, bos, eos, pred_host=None):
         """wav_host/lens_host/pred_host: CPU (ideally pinned) tensors; copies happen inside the call."""
