@@ -6,6 +6,7 @@ recipe on the hot path uses (conformer_{small,large}.yaml).  Anything else raise
 """
 import torch
 
+from .._lib import require_cuda
 from ..engine import FbankHandle, mel_filter_matrix, stft_window
 
 
@@ -55,6 +56,7 @@ class Fbank(torch.nn.Module):
         """wav [B, L] (any float dtype; computed in fp32 like the reference's fwd_default_precision decorator)."""
         if wav.dim() != 2:
             raise NotImplementedError("speechbrain_b200.Fbank: only mono [batch, time] input is built")
+        require_cuda(wav, "Fbank")
         return self._get_handle().forward(wav)
 
     def get_filter_properties(self):

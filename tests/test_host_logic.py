@@ -1,0 +1,91 @@
+"""CPU tests of the host side: the C ABI loads and exports every declared symbol, argument validation mirrors the
+reference's error behaviour, and the product never falls back to the CPU."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from speechbrain_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "sbk.h")).read()
+    declared = set(re.findall(r"\b(sbk_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/sbk.h but not exported by libsbk.so"
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    assert _lib.lib().sbk_version() >= 100
+
+
+def test_no_cpu_fallback():
+    from speechbrain_b200.lobes.features import Fbank
+    from speechbrain_b200.processing.features import InputNormalization
+    with pytest.raises(RuntimeError, match="CUDA"):
+        Fbank(n_fft=400, n_mels=80)(torch.zeros(1, 1600))
+    n = InputNormalization(norm_type="sentence").eval()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        n(torch.zeros(1, 4, 8))
+
+
+def test_product_does_not_import_oracle():
+    for dp, _, files in os.walk(os.path.join(ROOT, "speechbrain_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f"{f} references oracle/"
+
+
+def test_constructor_validation_mirrors_reference():
+    from speechbrain_b200.lobes.features import Fbank
+    from speechbrain_b200.lobes.models.transformer.TransformerASR import TransformerASR
+    from speechbrain_b200.processing.features import InputNormalization
+    with pytest.raises(ValueError):
+        InputNormalization(mean_norm=False)  # processing/features.py:1374-1375
+    with pytest.raises(ValueError):
+        InputNormalization(norm_type="speaker")
+    with pytest.raises(ValueError):
+        InputNormalization(avg_factor=0.1)
+    with pytest.raises(AssertionError):
+        TransformerASR(tgt_vocab=10, input_size=640, attention_type="nope")  # Transformer.py:141-147
+    with pytest.raises(AssertionError):
+        TransformerASR(tgt_vocab=10, input_size=640, encoder_module="conformer", attention_type="RoPEMHA",
+                       normalize_before=False, causal=False)
+    with pytest.raises(NotImplementedError):
+        Fbank(deltas=True)
+    f = Fbank(n_fft=512, n_mels=80, win_length=32)
+    assert (f.win_length, f.hop_length) == (512, 160)  # ms -> samples (processing/features.py:132-137)
+    assert list(f.state_dict().keys()) == ["compute_deltas.kernel"]
+
+
+def test_input_norm_checkpoint_roundtrip(tmp_path):
+    from speechbrain_b200.processing.features import InputNormalization
+    n = InputNormalization(norm_type="global")
+    n.glob_mean, n.glob_std, n.count = torch.arange(4.0), torch.ones(4) * 2, 7
+    p = str(tmp_path / "normalizer.ckpt")
+    n._save(p)
+    stats = torch.load(p)
+    assert set(stats) == {"count", "glob_mean", "glob_std"}  # processing/features.py:1488-1495
+    m = InputNormalization(norm_type="global")
+    m._load(p)
+    assert m.count == 7 and torch.equal(m.glob_mean, n.glob_mean)
+
+
+def test_greedy_outputs_match_reference_postprocessing():
+    from speechbrain_b200.decoders.seq2seq import greedy_outputs
+    pred = torch.tensor([[5, 6, 2, 2], [7, 8, 9, 10]], dtype=torch.int32)
+    hyps, lens, scores, lp = greedy_outputs(pred, torch.zeros(2, 4), None, eos_index=2)
+    assert hyps == [[5, 6], [7, 8, 9, 10]]  # decoders/seq2seq.py:306-310 + undo_padding
+    assert torch.allclose(lens.flatten(), torch.tensor([0.5, 1.0]))
+    assert scores.shape == (2, 1, 4)
+
+
+def test_seeded_weights_are_order_independent():
+    from speechbrain_b200.utils.seeded_init import seeded_tensor
+    a = seeded_tensor(0, "Transformer.encoder.layers.3.norm1.norm.weight", (512,))
+    b = seeded_tensor(0, "Transformer.encoder.layers.3.norm1.norm.weight", (512,))
+    assert torch.equal(a, b) and abs(float(a.mean()) - 1.0) < 0.05
