@@ -57,73 +57,100 @@ static cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_
 constexpr int SK_ROWS = 32;
 constexpr int SK_WARPS = 8;
 
-template <int UNR, bool LN>
-__global__ void __launch_bounds__(SK_WARPS * 32) skinny_gemm_kernel(const SkinnyArgs a) {
-    __shared__ float red[SK_WARPS][SK_ROWS][9];
+// UNR: k-steps whose loads are issued back to back; NT: 8-column tiles per CTA; VPL: LayerNorm-fused variant
+// when > 0, with K == 128 * VPL (each lane holds VPL float4 of each of its 4 rows).
+template <int UNR, int NT, int VPL>
+__global__ void __launch_bounds__(SK_WARPS * 32, (VPL <= 4 ? 2 : 1)) skinny_gemm_kernel(const SkinnyArgs a) {
+    constexpr bool LN = VPL > 0;
+    __shared__ float red[SK_WARPS][SK_ROWS][8 * NT + 1];
     extern __shared__ __align__(16) __half a_sm[];  // LN: [32][K + 8]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
-    const int n0 = blockIdx.x * 8;
+    const int n0 = blockIdx.x * 8 * NT;
     const int row0 = blockIdx.y * SK_ROWS;
     const int rows = min(SK_ROWS, a.n_rows - row0);
     const int k_per_warp = ((a.K / 16 + SK_WARPS - 1) / SK_WARPS) * 16;
     const int k_begin = warp * k_per_warp, k_end = min(a.K, k_begin + k_per_warp);
     pdl_trigger();
 
-    float acc[2][4];
+    float acc[2][NT][4];
 #pragma unroll
-    for (int i = 0; i < 2; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0f;
-    const int wn = min(n0 + g, a.N - 1);  // clamp for the N tail (results discarded)
-    const __half* wrow = a.W + static_cast<size_t>(wn) * a.ldw + 2 * c;
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.0f;
+    const __half* wrow[NT];
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+        wrow[j] = a.W + static_cast<size_t>(min(n0 + 8 * j + g, a.N - 1)) * a.ldw + 2 * c;  // clamp: N tail discarded
     // weights do not depend on the previous kernel: fetch the first chunk before waiting on it
-    uint32_t bf[UNR][2];
+    uint32_t bf[UNR][NT][2];
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
         const int k = k_begin + 16 * u;
         const bool ok = k < k_end;
-        bf[u][0] = ok ? __ldg(reinterpret_cast<const uint32_t*>(wrow + k)) : 0u;
-        bf[u][1] = ok ? __ldg(reinterpret_cast<const uint32_t*>(wrow + k + 8)) : 0u;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            bf[u][j][0] = ok ? __ldg(reinterpret_cast<const uint32_t*>(wrow[j] + k)) : 0u;
+            bf[u][j][1] = ok ? __ldg(reinterpret_cast<const uint32_t*>(wrow[j] + k + 8)) : 0u;
+        }
     }
     pdl_wait();
 
     const int astr = LN ? a.K + 8 : a.lda;
     const __half* abase = LN ? a_sm : a.A;
     if constexpr (LN) {
-        // LayerNorm of this CTA's 32 rows (each warp 4 rows), fp32 statistics (two-pass), fp16 result in smem
-        constexpr int MAXV = 8;  // K <= 32 * 4 * MAXV = 1024
-        const int nv = a.K >> 2;
-        for (int rr = warp; rr < SK_ROWS; rr += SK_WARPS) {
-            const int row = min(row0 + rr, a.n_rows - 1);
-            const float* xr = a.X + static_cast<size_t>(row) * a.K;
-            float4 v[MAXV];
-            float s = 0.0f;
+        // LayerNorm of this CTA's 32 rows: warp w owns rows w, w+8, w+16, w+24; all 4*VPL loads are issued before
+        // the first reduction (fp32 statistics, two-pass), result fp16 in shared memory.
+        float4 v[4][VPL];
 #pragma unroll
-            for (int i = 0; i < MAXV; ++i) {
-                const int vi = lane + 32 * i;
-                v[i] = vi < nv ? *reinterpret_cast<const float4*>(xr + 4 * vi) : make_float4(0.f, 0.f, 0.f, 0.f);
-                s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        for (int r = 0; r < 4; ++r) {
+            const float* xr = a.X + static_cast<size_t>(min(row0 + warp + 8 * r, a.n_rows - 1)) * a.K;
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) v[r][i] = *reinterpret_cast<const float4*>(xr + 4 * (lane + 32 * i));
+        }
+        float4 gm[VPL], bt[VPL];
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            gm[i] = __ldg(reinterpret_cast<const float4*>(a.ln_g + 4 * (lane + 32 * i)));
+            bt[i] = __ldg(reinterpret_cast<const float4*>(a.ln_b + 4 * (lane + 32 * i)));
+        }
+        float s[4], q[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            s[r] = 0.0f;
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) s[r] += (v[r][i].x + v[r][i].y) + (v[r][i].z + v[r][i].w);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) s[r] += __shfl_xor_sync(0xffffffffu, s[r], o);
+        const float inv_k = 1.0f / static_cast<float>(a.K);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            s[r] *= inv_k;  // mean
+            q[r] = 0.0f;
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) {
+                v[r][i].x -= s[r]; v[r][i].y -= s[r]; v[r][i].z -= s[r]; v[r][i].w -= s[r];
+                q[r] += (v[r][i].x * v[r][i].x + v[r][i].y * v[r][i].y) + (v[r][i].z * v[r][i].z + v[r][i].w * v[r][i].w);
             }
-            const float mean = warp_sum(s) / a.K;
-            float q = 0.0f;
+        }
 #pragma unroll
-            for (int i = 0; i < MAXV; ++i)
-                if (lane + 32 * i < nv) {
-                    const float d0 = v[i].x - mean, d1 = v[i].y - mean, d2 = v[i].z - mean, d3 = v[i].w - mean;
-                    q += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
-                }
-            const float rstd = rsqrtf(warp_sum(q) / a.K + a.ln_eps);
+        for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-            for (int i = 0; i < MAXV; ++i) {
-                const int vi = lane + 32 * i;
-                if (vi < nv) {
-                    const float4 gm = __ldg(reinterpret_cast<const float4*>(a.ln_g + 4 * vi));
-                    const float4 bt = __ldg(reinterpret_cast<const float4*>(a.ln_b + 4 * vi));
-                    __half2 h0 = __floats2half2_rn((v[i].x - mean) * rstd * gm.x + bt.x, (v[i].y - mean) * rstd * gm.y + bt.y);
-                    __half2 h1 = __floats2half2_rn((v[i].z - mean) * rstd * gm.z + bt.z, (v[i].w - mean) * rstd * gm.w + bt.w);
-                    uint2 u;
-                    u.x = *reinterpret_cast<uint32_t*>(&h0);
-                    u.y = *reinterpret_cast<uint32_t*>(&h1);
-                    *reinterpret_cast<uint2*>(a_sm + rr * astr + 4 * vi) = u;
-                }
+            for (int r = 0; r < 4; ++r) q[r] += __shfl_xor_sync(0xffffffffu, q[r], o);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const float rstd = rsqrtf(q[r] * inv_k + a.ln_eps);
+            __half* dst = a_sm + (warp + 8 * r) * astr;
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) {
+                __half2 h0 = __floats2half2_rn(v[r][i].x * rstd * gm[i].x + bt[i].x, v[r][i].y * rstd * gm[i].y + bt[i].y);
+                __half2 h1 = __floats2half2_rn(v[r][i].z * rstd * gm[i].z + bt[i].z, v[r][i].w * rstd * gm[i].w + bt[i].w);
+                uint2 u;
+                u.x = *reinterpret_cast<uint32_t*>(&h0);
+                u.y = *reinterpret_cast<uint32_t*>(&h1);
+                *reinterpret_cast<uint2*>(dst + 4 * (lane + 32 * i)) = u;
             }
         }
         __syncthreads();
@@ -141,8 +168,11 @@ __global__ void __launch_bounds__(SK_WARPS * 32) skinny_gemm_kernel(const Skinny
             const int k = k0 + 16 * u;
             const bool ok = k < k_end;
             if (k0 != k_begin) {
-                bf[u][0] = ok ? __ldg(reinterpret_cast<const uint32_t*>(wrow + k)) : 0u;
-                bf[u][1] = ok ? __ldg(reinterpret_cast<const uint32_t*>(wrow + k + 8)) : 0u;
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+                    bf[u][j][0] = ok ? __ldg(reinterpret_cast<const uint32_t*>(wrow[j] + k)) : 0u;
+                    bf[u][j][1] = ok ? __ldg(reinterpret_cast<const uint32_t*>(wrow[j] + k + 8)) : 0u;
+                }
             }
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) {
@@ -153,22 +183,28 @@ __global__ void __launch_bounds__(SK_WARPS * 32) skinny_gemm_kernel(const Skinny
             }
         }
 #pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-            mma16816_d(acc[0], af[u][0], bf[u][0], bf[u][1]);
-            mma16816_d(acc[1], af[u][1], bf[u][0], bf[u][1]);
-        }
+        for (int u = 0; u < UNR; ++u)
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                mma16816_d(acc[0][j], af[u][0], bf[u][j][0], bf[u][j][1]);
+                mma16816_d(acc[1][j], af[u][1], bf[u][j][0], bf[u][j][1]);
+            }
     }
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
-        red[warp][mt * 16 + g][2 * c] = acc[mt][0];
-        red[warp][mt * 16 + g][2 * c + 1] = acc[mt][1];
-        red[warp][mt * 16 + g + 8][2 * c] = acc[mt][2];
-        red[warp][mt * 16 + g + 8][2 * c + 1] = acc[mt][3];
-    }
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            red[warp][mt * 16 + g][8 * j + 2 * c] = acc[mt][j][0];
+            red[warp][mt * 16 + g][8 * j + 2 * c + 1] = acc[mt][j][1];
+            red[warp][mt * 16 + g + 8][8 * j + 2 * c] = acc[mt][j][2];
+            red[warp][mt * 16 + g + 8][8 * j + 2 * c + 1] = acc[mt][j][3];
+        }
     __syncthreads();
     const int step = a.step_ptr ? *a.step_ptr : 0;
-    {
-        const int r = threadIdx.x >> 3, j = threadIdx.x & 7;  // 32 rows x 8 columns = 256 threads
+#pragma unroll
+    for (int it = 0; it < NT; ++it) {
+        const int idx = threadIdx.x + it * SK_WARPS * 32;  // 32 rows x (8*NT) columns
+        const int r = idx / (8 * NT), j = idx - r * (8 * NT);
         const int col = n0 + j;
         const int row = row0 + r;
         if (r < rows && col < a.N) {
@@ -204,16 +240,31 @@ __global__ void __launch_bounds__(SK_WARPS * 32) skinny_gemm_kernel(const Skinny
 int skinny_gemm(const SkinnyArgs& a, cudaStream_t stream) {
     SBK_REQUIRE(a.K % 16 == 0 && a.lda % 2 == 0 && a.ldw % 2 == 0, "skinny_gemm: K %% 16 required (K=%d)", a.K);
     if (a.n_rows == 0) return SBK_OK;
-    dim3 grid(ceil_div(a.N, 8), ceil_div(a.n_rows, SK_ROWS));
     cudaError_t e;
+    const int ry = ceil_div(a.n_rows, SK_ROWS);
     if (a.X != nullptr) {
-        SBK_REQUIRE(a.K <= 1024 && a.K % 4 == 0, "skinny_gemm(LN): K=%d unsupported", a.K);
         const size_t smem = static_cast<size_t>(SK_ROWS) * (a.K + 8) * 2;
-        e = launch_k(skinny_gemm_kernel<4, true>, grid, dim3(SK_WARPS * 32), smem, stream, a);
+        dim3 grid(ceil_div(a.N, 16), ry);
+        static bool attr_done = false;  // static + dynamic shared memory exceeds the 48 KB default
+        if (!attr_done) {
+            cudaFuncSetAttribute(skinny_gemm_kernel<4, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+            cudaFuncSetAttribute(skinny_gemm_kernel<2, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+            cudaFuncSetAttribute(skinny_gemm_kernel<4, 2, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+            cudaFuncSetAttribute(skinny_gemm_kernel<8, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+            attr_done = true;
+        }
+        if (a.K == 512) e = launch_k(skinny_gemm_kernel<4, 2, 4>, grid, dim3(SK_WARPS * 32), smem, stream, a);
+        else if (a.K == 256) e = launch_k(skinny_gemm_kernel<2, 2, 2>, grid, dim3(SK_WARPS * 32), smem, stream, a);
+        else if (a.K == 768) e = launch_k(skinny_gemm_kernel<4, 2, 6>, grid, dim3(SK_WARPS * 32), smem, stream, a);
+        else if (a.K == 1024) e = launch_k(skinny_gemm_kernel<8, 2, 8>, grid, dim3(SK_WARPS * 32), smem, stream, a);
+        else {
+            set_error("skinny_gemm(LN): d_model=%d not built (256/512/768/1024)", a.K);
+            return SBK_ERR_UNSUPPORTED;
+        }
     } else if (a.K <= 1024) {
-        e = launch_k(skinny_gemm_kernel<4, false>, grid, dim3(SK_WARPS * 32), 0, stream, a);
+        e = launch_k(skinny_gemm_kernel<4, 1, 0>, dim3(ceil_div(a.N, 8), ry), dim3(SK_WARPS * 32), 0, stream, a);
     } else {
-        e = launch_k(skinny_gemm_kernel<8, false>, grid, dim3(SK_WARPS * 32), 0, stream, a);
+        e = launch_k(skinny_gemm_kernel<8, 1, 0>, dim3(ceil_div(a.N, 8), ry), dim3(SK_WARPS * 32), 0, stream, a);
     }
     SBK_CUDA_CHECK(e);
     SBK_LAUNCH_CHECK();

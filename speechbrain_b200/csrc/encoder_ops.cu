@@ -113,63 +113,87 @@ int cast_f32_f16(const float* in, __half* out, size_t n, cudaStream_t stream) {
 constexpr int DW_TT = 16;
 
 template <int KT>  // KT > 0: compile-time kernel size (taps held in registers); KT == 0: runtime K
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 dwconv_ln_swish_kernel(const float* __restrict__ glu, int T, int D, int K, const float* __restrict__ wdw /*[D,K]*/,
                        const float* __restrict__ bdw, const float* __restrict__ gamma, const float* __restrict__ beta,
                        float eps, __half* __restrict__ out) {
-    extern __shared__ float dw_smem[];
+    extern __shared__ __align__(128) float dw_smem[];
+    __shared__ uint64_t bar;
     const int halo = (K - 1) / 2;
     const int rows_in = DW_TT + K - 1;
-    float* slab = dw_smem;                 // [rows_in][D]
-    float* conv = slab + rows_in * D;      // [DW_TT][D]
+    float* slab = dw_smem;   // [rows_in][D]; rows [0, DW_TT) are re-used for the conv outputs after the tap loop
     const int b = blockIdx.y, t0 = blockIdx.x * DW_TT;
     const float* src = glu + static_cast<size_t>(b) * T * D;
-    const int nv = D >> 2;
-    for (int i = threadIdx.x; i < rows_in * nv; i += blockDim.x) {
-        const int r = i / nv, vi = i - r * nv;
-        const int t = t0 - halo + r;
-        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (t >= 0 && t < T) val = *reinterpret_cast<const float4*>(src + static_cast<size_t>(t) * D + vi * 4);
-        *reinterpret_cast<float4*>(slab + r * D + vi * 4) = val;
+    // valid input rows [r_lo, r_hi) of the slab are contiguous in global memory: stage them with bulk TMA copies
+    const int r_lo = max(0, halo - t0), r_hi = min(rows_in, T + halo - t0);
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
     }
     __syncthreads();
-    for (int ch = threadIdx.x; ch < D; ch += blockDim.x) {
-        float acc[DW_TT];
-        const float bz = __ldg(bdw + ch);
+    if (threadIdx.x == 0) {
+        const uint32_t row_bytes = static_cast<uint32_t>(D) * 4;
+        mbar_arrive_expect_tx(&bar, row_bytes * static_cast<uint32_t>(r_hi - r_lo));
+        for (int r = r_lo; r < r_hi; ++r)
+            bulk_load_1d(slab + r * D, src + static_cast<size_t>(t0 - halo + r) * D, row_bytes, &bar);
+    }
+    // zero rows outside the utterance (Conv1d zero padding)
+    for (int i = threadIdx.x; i < (r_lo + rows_in - r_hi) * D; i += blockDim.x) {
+        int r = i / D;
+        const int ch = i - r * D;
+        if (r >= r_lo) r += r_hi - r_lo;
+        slab[r * D + ch] = 0.0f;
+    }
+    mbar_wait(&bar, 0);
+    __syncthreads();
+    constexpr int MAXC = 4;  // channels per thread: D <= 256 * MAXC
+    float acc[MAXC][DW_TT];
 #pragma unroll
-        for (int i = 0; i < DW_TT; ++i) acc[i] = bz;
-        const float* w = wdw + static_cast<size_t>(ch) * K;
-        // sliding window: each input row contributes to up to DW_TT outputs
-        if constexpr (KT > 0) {
-            float wr[KT];
+    for (int cc = 0; cc < MAXC; ++cc) {
+        const int ch = threadIdx.x + cc * 256;
+        if (ch < D) {
+            const float bz = __ldg(bdw + ch);
 #pragma unroll
-            for (int k = 0; k < KT; ++k) wr[k] = __ldg(w + k);
+            for (int i = 0; i < DW_TT; ++i) acc[cc][i] = bz;
+            const float* w = wdw + static_cast<size_t>(ch) * K;
+            if constexpr (KT > 0) {
+                float wr[KT];
 #pragma unroll
-            for (int r = 0; r < DW_TT + KT - 1; ++r) {
-                const float xv = slab[r * D + ch];
+                for (int k = 0; k < KT; ++k) wr[k] = __ldg(w + k);
 #pragma unroll
-                for (int i = 0; i < DW_TT; ++i)
-                    if (r - i >= 0 && r - i < KT) acc[i] = fmaf(xv, wr[r - i], acc[i]);
-            }
-        } else {
-            for (int r = 0; r < rows_in; ++r) {
-                const float xv = slab[r * D + ch];
+                for (int r = 0; r < DW_TT + KT - 1; ++r) {
+                    const float xv = slab[r * D + ch];
 #pragma unroll
-                for (int i = 0; i < DW_TT; ++i) {
-                    const int k = r - i;  // tap index for output i
-                    if (k >= 0 && k < K) acc[i] = fmaf(xv, __ldg(w + k), acc[i]);
+                    for (int i = 0; i < DW_TT; ++i)
+                        if (r - i >= 0 && r - i < KT) acc[cc][i] = fmaf(xv, wr[r - i], acc[cc][i]);
+                }
+            } else {
+                for (int r = 0; r < rows_in; ++r) {
+                    const float xv = slab[r * D + ch];
+#pragma unroll
+                    for (int i = 0; i < DW_TT; ++i) {
+                        const int k = r - i;
+                        if (k >= 0 && k < K) acc[cc][i] = fmaf(xv, __ldg(w + k), acc[cc][i]);
+                    }
                 }
             }
         }
+    }
+    __syncthreads();  // every thread is done reading the slab: rows [0, DW_TT) now hold the conv outputs
 #pragma unroll
-        for (int i = 0; i < DW_TT; ++i) conv[i * D + ch] = acc[i];
+    for (int cc = 0; cc < MAXC; ++cc) {
+        const int ch = threadIdx.x + cc * 256;
+        if (ch < D) {
+#pragma unroll
+            for (int i = 0; i < DW_TT; ++i) slab[i * D + ch] = acc[cc][i];
+        }
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = warp; i < DW_TT; i += (blockDim.x >> 5)) {
         const int t = t0 + i;
         if (t >= T) continue;
-        const float* c = conv + i * D;
+        const float* c = slab + i * D;
         float s = 0.0f;
         for (int j = lane; j < D; j += 32) s += c[j];
         const float mean = warp_sum(s) / D;
@@ -180,15 +204,19 @@ dwconv_ln_swish_kernel(const float* __restrict__ glu, int T, int D, int K, const
         }
         const float rstd = rsqrtf(warp_sum(q) / D + eps);
         __half* o = out + (static_cast<size_t>(b) * T + t) * D;
-        for (int j = lane; j < D; j += 32)
-            o[j] = __float2half_rn(silu_f((c[j] - mean) * rstd * __ldg(gamma + j) + __ldg(beta + j)));
+        for (int j = 2 * lane; j < D; j += 64) {
+            const float y0 = silu_f((c[j] - mean) * rstd * __ldg(gamma + j) + __ldg(beta + j));
+            const float y1 = silu_f((c[j + 1] - mean) * rstd * __ldg(gamma + j + 1) + __ldg(beta + j + 1));
+            *reinterpret_cast<__half2*>(o + j) = __floats2half2_rn(y0, y1);
+        }
     }
 }
 
 int dwconv_ln_swish(const float* glu, int B, int T, int D, int K, const float* wdw, const float* bdw,
                     const float* gamma, const float* beta, float eps, __half* out, cudaStream_t stream) {
-    SBK_REQUIRE(D % 4 == 0 && (K & 1) == 1, "dwconv_ln_swish: D %% 4 and odd K required (D=%d K=%d)", D, K);
-    const size_t smem = static_cast<size_t>(DW_TT + K - 1 + DW_TT) * D * sizeof(float);
+    SBK_REQUIRE(D % 4 == 0 && D <= 1024 && (K & 1) == 1, "dwconv_ln_swish: D %% 4, D <= 1024 and odd K required (D=%d K=%d)", D, K);
+    SBK_REQUIRE((reinterpret_cast<uintptr_t>(glu) & 15) == 0, "dwconv_ln_swish: input must be 16-byte aligned");
+    const size_t smem = static_cast<size_t>(DW_TT + K - 1) * D * sizeof(float);
     SBK_REQUIRE(smem <= 200 * 1024, "dwconv_ln_swish: tile too large for shared memory (D=%d K=%d)", D, K);
     auto kern = (K == 31) ? dwconv_ln_swish_kernel<31> : dwconv_ln_swish_kernel<0>;
     SBK_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -196,8 +224,6 @@ int dwconv_ln_swish(const float* glu, int B, int T, int D, int K, const float* w
     SBK_LAUNCH_CHECK();
     return SBK_OK;
 }
-
-
 
 // =========================================================================== self-attention
 // Flash-style attention for the Conformer encoder on mma.sync.m16n8k16 (fp16 operands, fp32
