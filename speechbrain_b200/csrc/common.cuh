@@ -172,8 +172,15 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int ab_forma
 }
 
 // ---------------------------------------------------------------- misc math
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// MUFU.EX2 + MUFU.RCP (approximate reciprocal, ~1 ulp) instead of an IEEE division: the GEMM epilogues are
+// instruction-bound, and a full-precision divide costs ~8 extra instructions per element.
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return rcp_approx(1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu_f(float x) { return x * sigmoid_f(x); }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
 // ordered-int encoding so that atomicMax on int orders floats correctly

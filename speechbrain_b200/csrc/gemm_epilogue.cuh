@@ -1,0 +1,256 @@
+// Fused GEMM epilogues shared by the 1-CTA and the 2-CTA tcgen05 kernels: applied to 32 consecutive fp32
+// accumulator columns of one output row straight out of TMEM (tcgen05.ld 32x32b.x32).
+#pragma once
+#include "common.cuh"
+#include "sbk_internal.h"
+
+namespace sbk {
+
+// Apply the epilogue to 32 consecutive accumulator columns of one row.
+__device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const uint32_t (&acc)[32], int row, int col0,
+                                               int M, int N) {
+    if (row >= M || col0 >= N) return;
+    const bool full = (col0 + 32 <= N);
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+    if (e.bias != nullptr) {
+        if (full) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col0 + j));
+                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (col0 + j < N) v[j] += __ldg(e.bias + col0 + j);
+        }
+    }
+    switch (e.mode) {
+        case EPI_F16: {
+            if (e.act == ACT_SILU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+            } else if (e.act == ACT_GELU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = gelu_erf_f(v[j]);
+            }
+            __half* o = reinterpret_cast<__half*>(e.out) + static_cast<size_t>(row) * e.ldo + col0;
+            if (full) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    __half2 h0 = __floats2half2_rn(v[j], v[j + 1]), h1 = __floats2half2_rn(v[j + 2], v[j + 3]);
+                    __half2 h2 = __floats2half2_rn(v[j + 4], v[j + 5]), h3 = __floats2half2_rn(v[j + 6], v[j + 7]);
+                    uint4 u;
+                    u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+                    u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+                    *reinterpret_cast<uint4*>(o + j) = u;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (col0 + j < N) o[j] = __float2half_rn(v[j]);
+            }
+            break;
+        }
+        case EPI_F32: {
+            float* o = reinterpret_cast<float*>(e.out) + static_cast<size_t>(row) * e.ldo + col0;
+            if (full) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (col0 + j < N) o[j] = v[j];
+            }
+            break;
+        }
+        case EPI_RESID: {  // out = resid + alpha * (acc + bias); masked rows contribute 0
+            float alpha = e.alpha;
+            if (e.row_lens != nullptr) {
+                const int b = row / e.T, t = row - b * e.T;
+                if (t >= e.row_lens[b]) alpha = 0.0f;
+            }
+            const float* r = e.resid + static_cast<size_t>(row) * e.ldo + col0;
+            float* o = reinterpret_cast<float*>(e.out) + static_cast<size_t>(row) * e.ldo + col0;
+            if (full) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 x = *reinterpret_cast<const float4*>(r + j);
+                    *reinterpret_cast<float4*>(o + j) = make_float4(fmaf(alpha, v[j], x.x), fmaf(alpha, v[j + 1], x.y),
+                                                                    fmaf(alpha, v[j + 2], x.z), fmaf(alpha, v[j + 3], x.w));
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (col0 + j < N) o[j] = fmaf(alpha, v[j], r[j]);
+            }
+            break;
+        }
+        case EPI_GLU: {  // weight rows pre-interleaved [16 values | 16 gates] per 32 columns
+            float* o = reinterpret_cast<float*>(e.out) + static_cast<size_t>(row) * e.ldo + (col0 >> 1);
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+                *reinterpret_cast<float4*>(o + j) =
+                    make_float4(v[j] * sigmoid_f(v[j + 16]), v[j + 1] * sigmoid_f(v[j + 17]),
+                                v[j + 2] * sigmoid_f(v[j + 18]), v[j + 3] * sigmoid_f(v[j + 19]));
+            break;
+        }
+        case EPI_ROPE: {  // columns = per-head [q(dh) | k(dh) | v(dh)], dh % 32 == 0
+            const int dh = e.head_dim;
+            const int within = col0 % (3 * dh);
+            const int sect = within / dh;  // 0 q, 1 k, 2 v
+            if (sect < 2) {
+                const int t = row % e.T;
+                const int p0 = (within - sect * dh) >> 1;
+                const float* cs = e.rope_cos + static_cast<size_t>(t) * (dh >> 1) + p0;
+                const float* sn = e.rope_sin + static_cast<size_t>(t) * (dh >> 1) + p0;
+                const float sc = sect == 0 ? e.alpha : 1.0f;
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    const float c = __ldg(cs + (j >> 1)), s = __ldg(sn + (j >> 1));
+                    const float x0 = v[j], x1 = v[j + 1];
+                    v[j] = (x0 * c - x1 * s) * sc;
+                    v[j + 1] = (x1 * c + x0 * s) * sc;
+                }
+            }
+            __half* o = reinterpret_cast<__half*>(e.out) + static_cast<size_t>(row) * e.ldo + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+                __half2 h0 = __floats2half2_rn(v[j], v[j + 1]), h1 = __floats2half2_rn(v[j + 2], v[j + 3]);
+                __half2 h2 = __floats2half2_rn(v[j + 4], v[j + 5]), h3 = __floats2half2_rn(v[j + 6], v[j + 7]);
+                uint4 u;
+                u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+                u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+                *reinterpret_cast<uint4*>(o + j) = u;
+            }
+            break;
+        }
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// Warp-cooperative, COALESCED variant (used by the 2-CTA kernel; needs N % 32 == 0 columns per chunk).
+// After tcgen05.ld each lane owns one row x 32 columns; storing that directly makes every warp-wide store touch
+// 32 different 128-byte lines (measured: the epilogue, not the MMA, bounded the GEMM).  Here the chunk is staged
+// through a per-warp shared-memory tile (row pitch 144 B, conflict-free for 16-byte accesses) and written back
+// with each instruction covering whole row segments (4 rows x 128 B or 8 rows x 64 B).
+constexpr int EPI_STG_PITCH = 144;                 // bytes per staged row (32 fp32 + 16 B pad)
+constexpr int EPI_STG_BYTES = 32 * EPI_STG_PITCH;  // per warp
+
+template <int MODE, int ACT>
+__device__ __forceinline__ void epilogue_chunk_coalesced(const GemmEpilogue& e, const uint32_t (&acc)[32], uint8_t* stg,
+                                                         int row_base, int col0, int M, int lane) {
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+    if (e.bias != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col0 + j));
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+        }
+    }
+    const int my_row = row_base + lane;
+    uint8_t* my = stg + lane * EPI_STG_PITCH;
+    constexpr int out_bytes_per_row = (MODE == EPI_F32 || MODE == EPI_RESID) ? 128 : 64;  // 32 fp32 | 32 fp16 / 16 fp32
+    {
+        if constexpr (MODE == EPI_F32 || MODE == EPI_RESID) {
+            if constexpr (MODE == EPI_RESID) {
+                float alpha = e.alpha;
+                if (e.row_lens != nullptr && my_row < M) {
+                    const int b = my_row / e.T, t = my_row - b * e.T;
+                    if (t >= e.row_lens[b]) alpha = 0.0f;
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] *= alpha;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(my + j * 4) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else if constexpr (MODE == EPI_GLU) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+                *reinterpret_cast<float4*>(my + j * 4) =
+                    make_float4(v[j] * sigmoid_f(v[j + 16]), v[j + 1] * sigmoid_f(v[j + 17]),
+                                v[j + 2] * sigmoid_f(v[j + 18]), v[j + 3] * sigmoid_f(v[j + 19]));
+        } else {  // EPI_F16, EPI_ROPE -> 32 halfs
+            if constexpr (MODE == EPI_ROPE) {
+                const int dh = e.head_dim;
+                const int within = col0 % (3 * dh);
+                const int sect = within / dh;  // 0 q, 1 k, 2 v
+                if (sect < 2) {
+                    const int t = my_row % e.T;
+                    const int p0 = (within - sect * dh) >> 1;
+                    const float* cs = e.rope_cos + static_cast<size_t>(t) * (dh >> 1) + p0;
+                    const float* sn = e.rope_sin + static_cast<size_t>(t) * (dh >> 1) + p0;
+                    const float sc = sect == 0 ? e.alpha : 1.0f;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float2 c2 = __ldg(reinterpret_cast<const float2*>(cs + (j >> 1)));
+                        const float2 s2 = __ldg(reinterpret_cast<const float2*>(sn + (j >> 1)));
+                        const float x0 = v[j], x1 = v[j + 1], x2 = v[j + 2], x3 = v[j + 3];
+                        v[j] = (x0 * c2.x - x1 * s2.x) * sc;
+                        v[j + 1] = (x1 * c2.x + x0 * s2.x) * sc;
+                        v[j + 2] = (x2 * c2.y - x3 * s2.y) * sc;
+                        v[j + 3] = (x3 * c2.y + x2 * s2.y) * sc;
+                    }
+                }
+            } else if constexpr (ACT == ACT_SILU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+            } else if constexpr (ACT == ACT_GELU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = gelu_erf_f(v[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+                __half2 h0 = __floats2half2_rn(v[j], v[j + 1]), h1 = __floats2half2_rn(v[j + 2], v[j + 3]);
+                __half2 h2 = __floats2half2_rn(v[j + 4], v[j + 5]), h3 = __floats2half2_rn(v[j + 6], v[j + 7]);
+                uint4 u;
+                u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+                u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+                *reinterpret_cast<uint4*>(my + j * 2) = u;
+            }
+        }
+    }
+    __syncwarp();
+    if constexpr (out_bytes_per_row == 128) {
+        const int seg = lane & 7, rsub = lane >> 3;  // 8 lanes x 16 B per row, 4 rows per instruction
+        float* outp = reinterpret_cast<float*>(e.out);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = i * 4 + rsub;
+            const int row = row_base + r;
+            if (row < M) {
+                float4 val = *reinterpret_cast<const float4*>(stg + r * EPI_STG_PITCH + seg * 16);
+                const size_t off = static_cast<size_t>(row) * e.ldo + col0 + seg * 4;
+                if constexpr (MODE == EPI_RESID) {
+                    const float4 x = *reinterpret_cast<const float4*>(e.resid + off);
+                    val.x += x.x; val.y += x.y; val.z += x.z; val.w += x.w;
+                }
+                *reinterpret_cast<float4*>(outp + off) = val;
+            }
+        }
+    } else {
+        const int seg = lane & 3, rsub = lane >> 2;  // 4 lanes x 16 B per row, 8 rows per instruction
+        uint8_t* outp = reinterpret_cast<uint8_t*>(e.out);
+        // byte offset of this chunk inside a row: fp16 -> col0 * 2 ; GLU fp32 (16 columns) -> (col0 / 2) * 4
+        const size_t row_pitch = MODE == EPI_GLU ? static_cast<size_t>(e.ldo) * 4 : static_cast<size_t>(e.ldo) * 2;
+        const size_t col_off = static_cast<size_t>(col0) * 2;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = i * 8 + rsub;
+            const int row = row_base + r;
+            if (row < M)
+                *reinterpret_cast<uint4*>(outp + static_cast<size_t>(row) * row_pitch + col_off + seg * 16) =
+                    *reinterpret_cast<const uint4*>(stg + r * EPI_STG_PITCH + seg * 16);
+        }
+    }
+    __syncwarp();  // staging tile is reused by the next chunk
+}
+
+}  // namespace sbk

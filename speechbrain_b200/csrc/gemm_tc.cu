@@ -12,7 +12,10 @@
 // smem ring of STAGES (A 16 KB + B BN*128 B) guarded by full/empty mbarriers; the MMA
 // completion is published with tcgen05.commit.  Two CTAs fit per SM (3 x 32 KB stages,
 // 128 TMEM columns each) so one CTA's epilogue overlaps the other's main loop.
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "gemm_epilogue.cuh"
 #include "sbk_internal.h"
 
 namespace sbk {
@@ -29,131 +32,6 @@ struct GemmSmem {
     static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
     static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // + barriers + alignment slack
 };
-
-// Apply the epilogue to 32 consecutive accumulator columns of one row.
-__device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const uint32_t (&acc)[32], int row, int col0,
-                                               int M, int N) {
-    if (row >= M || col0 >= N) return;
-    const bool full = (col0 + 32 <= N);
-    float v[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-    if (e.bias != nullptr) {
-        if (full) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col0 + j));
-                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-                if (col0 + j < N) v[j] += __ldg(e.bias + col0 + j);
-        }
-    }
-    switch (e.mode) {
-        case EPI_F16: {
-            if (e.act == ACT_SILU) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
-            } else if (e.act == ACT_GELU) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = gelu_erf_f(v[j]);
-            }
-            __half* o = reinterpret_cast<__half*>(e.out) + static_cast<size_t>(row) * e.ldo + col0;
-            if (full) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                    __half2 h0 = __floats2half2_rn(v[j], v[j + 1]), h1 = __floats2half2_rn(v[j + 2], v[j + 3]);
-                    __half2 h2 = __floats2half2_rn(v[j + 4], v[j + 5]), h3 = __floats2half2_rn(v[j + 6], v[j + 7]);
-                    uint4 u;
-                    u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
-                    u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
-                    *reinterpret_cast<uint4*>(o + j) = u;
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (col0 + j < N) o[j] = __float2half_rn(v[j]);
-            }
-            break;
-        }
-        case EPI_F32: {
-            float* o = reinterpret_cast<float*>(e.out) + static_cast<size_t>(row) * e.ldo + col0;
-            if (full) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (col0 + j < N) o[j] = v[j];
-            }
-            break;
-        }
-        case EPI_RESID: {  // out = resid + alpha * (acc + bias); masked rows contribute 0
-            float alpha = e.alpha;
-            if (e.row_lens != nullptr) {
-                const int b = row / e.T, t = row - b * e.T;
-                if (t >= e.row_lens[b]) alpha = 0.0f;
-            }
-            const float* r = e.resid + static_cast<size_t>(row) * e.ldo + col0;
-            float* o = reinterpret_cast<float*>(e.out) + static_cast<size_t>(row) * e.ldo + col0;
-            if (full) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 x = *reinterpret_cast<const float4*>(r + j);
-                    *reinterpret_cast<float4*>(o + j) = make_float4(fmaf(alpha, v[j], x.x), fmaf(alpha, v[j + 1], x.y),
-                                                                    fmaf(alpha, v[j + 2], x.z), fmaf(alpha, v[j + 3], x.w));
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (col0 + j < N) o[j] = fmaf(alpha, v[j], r[j]);
-            }
-            break;
-        }
-        case EPI_GLU: {  // weight rows pre-interleaved [16 values | 16 gates] per 32 columns
-            float* o = reinterpret_cast<float*>(e.out) + static_cast<size_t>(row) * e.ldo + (col0 >> 1);
-#pragma unroll
-            for (int j = 0; j < 16; j += 4)
-                *reinterpret_cast<float4*>(o + j) =
-                    make_float4(v[j] * sigmoid_f(v[j + 16]), v[j + 1] * sigmoid_f(v[j + 17]),
-                                v[j + 2] * sigmoid_f(v[j + 18]), v[j + 3] * sigmoid_f(v[j + 19]));
-            break;
-        }
-        case EPI_ROPE: {  // columns = per-head [q(dh) | k(dh) | v(dh)], dh % 32 == 0
-            const int dh = e.head_dim;
-            const int within = col0 % (3 * dh);
-            const int sect = within / dh;  // 0 q, 1 k, 2 v
-            if (sect < 2) {
-                const int t = row % e.T;
-                const int p0 = (within - sect * dh) >> 1;
-                const float* cs = e.rope_cos + static_cast<size_t>(t) * (dh >> 1) + p0;
-                const float* sn = e.rope_sin + static_cast<size_t>(t) * (dh >> 1) + p0;
-                const float sc = sect == 0 ? e.alpha : 1.0f;
-#pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    const float c = __ldg(cs + (j >> 1)), s = __ldg(sn + (j >> 1));
-                    const float x0 = v[j], x1 = v[j + 1];
-                    v[j] = (x0 * c - x1 * s) * sc;
-                    v[j + 1] = (x1 * c + x0 * s) * sc;
-                }
-            }
-            __half* o = reinterpret_cast<__half*>(e.out) + static_cast<size_t>(row) * e.ldo + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-                __half2 h0 = __floats2half2_rn(v[j], v[j + 1]), h1 = __floats2half2_rn(v[j + 2], v[j + 3]);
-                __half2 h2 = __floats2half2_rn(v[j + 4], v[j + 5]), h3 = __floats2half2_rn(v[j + 6], v[j + 7]);
-                uint4 u;
-                u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
-                u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
-                *reinterpret_cast<uint4*>(o + j) = u;
-            }
-            break;
-        }
-    }
-}
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS, (BN <= 128 ? 2 : 1))
@@ -274,6 +152,7 @@ int gemm_f16(const void* A, int lda, const void* W, int ldw, const GemmEpilogue&
     if (epi.mode == EPI_GLU || epi.mode == EPI_ROPE)
         SBK_REQUIRE(N % 32 == 0, "gemm_f16: GLU/RoPE epilogues need N %% 32 == 0");
     if (epi.mode == EPI_ROPE) SBK_REQUIRE(epi.head_dim % 32 == 0, "gemm_f16: RoPE epilogue needs head_dim %% 32 == 0");
+    if (N % 256 == 0 && getenv("SBK_GEMM_V1") == nullptr) return gemm_f16_2cta(A, lda, W, ldw, epi, M, N, K, stream);
     return launch_gemm<128, 3>(A, lda, W, ldw, epi, M, N, K, stream);
 }
 

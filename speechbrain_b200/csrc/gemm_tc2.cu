@@ -1,0 +1,266 @@
+// 2-CTA (cta_group::2) persistent tcgen05 GEMM: out = epilogue(A[M,K] x W[N,K]^T), fp16 in / fp32 accumulate.
+//
+// A CTA pair (cluster 2x1x1, two SMs of one TPC) owns a 256 x 256 output tile: CTA r holds rows
+// [m0 + 128 r, +128) of A and rows [n0 + 128 r, +128) of W in its shared memory, the leader issues
+// tcgen05.mma.cta_group::2 (UMMA 256 x 256 x 16) which reads both halves, and each CTA's TMEM receives its
+// own 128 accumulator rows.  Versus the 1-CTA 128x128 kernel this halves the L2->SM operand traffic per FLOP
+// (32 KB per 2 MMACs per CTA instead of 32 KB per 1 MMAC), which is what bounds these K = 512..2048 GEMMs.
+//
+// Persistent: 74 pairs loop over the tiles (n fastest, so pairs working on the same rows of A run together).
+// Warp roles per CTA: warp 0 TMA producer (6-stage ring, loads signal the LEADER's full barrier through the
+// cta_group::2 TMA form), warp 1 MMA issuer (leader only; commits multicast to both CTAs' barriers),
+// warps 2..5 epilogue.  TMEM holds two 256-column accumulator buffers, so the epilogue of tile i overlaps
+// the main loop of tile i+1.
+#include <stdio.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "gemm_epilogue.cuh"
+#include "sbk_internal.h"
+
+namespace sbk {
+
+constexpr int G2_BM = 128;        // rows per CTA (256 per pair)
+constexpr int G2_BN = 256;        // columns per pair tile
+constexpr int G2_BK = 64;
+constexpr int G2_STAGES = 5;
+constexpr int G2_EPI_WARPS = 8;      // two warps per TMEM lane quarter, each drains half of the columns
+constexpr int G2_THREADS = 64 + 32 * G2_EPI_WARPS;
+constexpr int G2_A_BYTES = G2_BM * G2_BK * 2;            // 16 KB
+constexpr int G2_B_BYTES = (G2_BN / 2) * G2_BK * 2;      // 16 KB (this CTA's half of W's tile rows)
+constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
+constexpr int G2_BAR_OFFSET = G2_STAGES * G2_STAGE_BYTES;
+constexpr int G2_STG_OFFSET = G2_BAR_OFFSET + 256;   // 4 epilogue warps x EPI_STG_BYTES staging tiles
+constexpr int G2_SMEM = G2_STG_OFFSET + G2_EPI_WARPS * EPI_STG_BYTES + 1024;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// bounded wait: a protocol bug must trap (and fail the test), never hang the GPU
+__device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity, int tag) {
+    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
+        if (spins > (1u << 26)) {
+            printf("gemm2: barrier timeout tag=%d block=%d thread=%d\n", tag, blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+    uint32_t raddr;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(cta));
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+// 2-SM TMA load: data lands in THIS CTA's shared memory, the transaction bytes are counted on the LEADER's barrier
+// (peer bit of the barrier address cleared, cute::Sm100MmaPeerBitMask).
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+    const uint32_t bar_leader = smem_u32(bar) & 0xFEFFFFFFu;
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_leader), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive (once) on the barrier at this offset in BOTH CTAs when all prior MMAs of this thread complete
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_result, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+                 "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+template <int MODE, int ACT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                const GemmEpilogue epi, int M, int N, int K) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + G2_BAR_OFFSET);   // [STAGES]  (used on the leader)
+    uint64_t* empty_bar = full_bar + G2_STAGES;                               // [STAGES]  (each CTA its own)
+    uint64_t* tmem_full_bar = empty_bar + G2_STAGES;                          // [2]       (each CTA its own)
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;                             // [2]       (used on the leader)
+    uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+    const int n_tiles = (N + G2_BN - 1) / G2_BN, m_tiles = (M + 2 * G2_BM - 1) / (2 * G2_BM);
+    const int total_tiles = n_tiles * m_tiles;
+    const int num_kb = (K + G2_BK - 1) / G2_BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+        for (int s = 0; s < G2_STAGES; ++s) {
+            mbar_init(&full_bar[s], 2);   // leader's expect_tx arrive + the peer's remote arrive
+            mbar_init(&empty_bar[s], 1);  // multicast tcgen05.commit
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full_bar[i], 1);   // multicast tcgen05.commit
+            mbar_init(&tmem_empty_bar[i], 2);  // one elected epilogue thread per CTA
+        }
+        mbar_fence_init();
+    }
+    cluster_sync_all();  // both CTAs' barriers exist before any remote arrive / multicast
+    if (warp == 1) tmem_alloc_2sm(tmem_base_ptr, 512);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;  // running k-block counter across tiles (ring position)
+            for (int tile = pair; tile < total_tiles; tile += num_pairs) {
+                const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
+                const int m_row = mt * 2 * G2_BM + static_cast<int>(rank) * G2_BM;
+                const int n_row = nt * G2_BN + static_cast<int>(rank) * (G2_BN / 2);
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % G2_STAGES;
+                    const uint32_t ph = (it / G2_STAGES) & 1;
+                    mbar_wait_b(&empty_bar[s], ph ^ 1, 1);
+                    uint8_t* a_dst = smem + s * G2_STAGE_BYTES;
+                    tma_load_2d_2sm(a_dst, &tmap_a, &full_bar[s], kb * G2_BK, m_row);
+                    tma_load_2d_2sm(a_dst + G2_A_BYTES, &tmap_b, &full_bar[s], kb * G2_BK, n_row);
+                    if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * G2_STAGE_BYTES);
+                    else mbar_arrive_remote(&full_bar[s], 0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (leader && lane == 0) {
+            const uint32_t idesc = make_idesc_f16(2 * G2_BM, G2_BN, 0);
+            int it = 0, local_tile = 0;
+            for (int tile = pair; tile < total_tiles; tile += num_pairs, ++local_tile) {
+                const int buf = local_tile & 1;
+                const uint32_t acc_ph = (local_tile >> 1) & 1;
+                mbar_wait_b(&tmem_empty_bar[buf], acc_ph ^ 1, 2);  // epilogues of both CTAs drained this buffer
+                tc_fence_after();
+                const uint32_t d_addr = tmem_base + buf * G2_BN;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % G2_STAGES;
+                    const uint32_t ph = (it / G2_STAGES) & 1;
+                    mbar_wait_b(&full_bar[s], ph, 3);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + s * G2_STAGE_BYTES);
+                    const uint64_t da = make_kmajor_sw128_desc(a_addr);
+                    const uint64_t db = make_kmajor_sw128_desc(a_addr + G2_A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < G2_BK / 16; ++k)
+                        umma_f16_2sm(d_addr, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    umma_commit_2sm(&empty_bar[s]);  // frees this stage in both CTAs
+                }
+                umma_commit_2sm(&tmem_full_bar[buf]);  // accumulators ready in both CTAs
+            }
+        }
+    } else {
+        const int q = warp & 3;             // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;   // which half of the tile's columns this warp drains
+        constexpr int CHUNKS = G2_BN / 32 / 2;
+        uint8_t* stg = smem + G2_STG_OFFSET + (warp - 2) * EPI_STG_BYTES;
+        int local_tile = 0;
+        for (int tile = pair; tile < total_tiles; tile += num_pairs, ++local_tile) {
+            const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
+            const int buf = local_tile & 1;
+            const uint32_t acc_ph = (local_tile >> 1) & 1;
+            mbar_wait_b(&tmem_full_bar[buf], acc_ph, 4);
+            tc_fence_after();
+            const int row_base = mt * 2 * G2_BM + static_cast<int>(rank) * G2_BM + q * 32;
+            const int n0 = nt * G2_BN + half * (G2_BN / 2);
+            const uint32_t t0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * G2_BN + half * (G2_BN / 2);
+            uint32_t acc[2][32];
+            tmem_ld_32x32(t0, acc[0]);
+#pragma unroll 1
+            for (int c = 0; c < CHUNKS; c += 2) {  // two chunks per iteration keep the double buffer statically indexed
+                tmem_ld_wait();
+                tmem_ld_32x32(t0 + (c + 1) * 32, acc[1]);  // next chunk in flight
+                epilogue_chunk_coalesced<MODE, ACT>(epi, acc[0], stg, row_base, n0 + c * 32, M, lane);
+                tmem_ld_wait();
+                if (c + 2 < CHUNKS) tmem_ld_32x32(t0 + (c + 2) * 32, acc[0]);
+                epilogue_chunk_coalesced<MODE, ACT>(epi, acc[1], stg, row_base, n0 + (c + 1) * 32, M, lane);
+            }
+            tc_fence_before();
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * G2_EPI_WARPS) : "memory");  // all epilogue warps are done with `buf`
+            if (warp == 2 && lane == 0) {
+                if (leader) mbar_arrive(&tmem_empty_bar[buf]);
+                else mbar_arrive_remote(&tmem_empty_bar[buf], 0);
+            }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) tmem_dealloc_2sm(tmem_base, 512);
+}
+
+int gemm_f16_2cta(const void* A, int lda, const void* W, int ldw, const GemmEpilogue& epi, int M, int N, int K,
+                  cudaStream_t stream) {
+    CUtensorMap ta, tb;
+    int rc = make_tmap_2d_f16(&ta, A, M, K, lda, G2_BM, G2_BK);
+    if (rc) return rc;
+    rc = make_tmap_2d_f16(&tb, W, N, K, ldw, G2_BN / 2, G2_BK);
+    if (rc) return rc;
+    void (*kern)(const CUtensorMap, const CUtensorMap, const GemmEpilogue, int, int, int) = nullptr;
+    switch (epi.mode) {
+        case EPI_F16:
+            kern = epi.act == ACT_SILU ? gemm_tc2_kernel<EPI_F16, ACT_SILU>
+                 : epi.act == ACT_GELU ? gemm_tc2_kernel<EPI_F16, ACT_GELU> : gemm_tc2_kernel<EPI_F16, ACT_NONE>;
+            break;
+        case EPI_F32: kern = gemm_tc2_kernel<EPI_F32, ACT_NONE>; break;
+        case EPI_RESID: kern = gemm_tc2_kernel<EPI_RESID, ACT_NONE>; break;
+        case EPI_GLU: kern = gemm_tc2_kernel<EPI_GLU, ACT_NONE>; break;
+        case EPI_ROPE: kern = gemm_tc2_kernel<EPI_ROPE, ACT_NONE>; break;
+        default: set_error("gemm_f16_2cta: bad epilogue mode %d", epi.mode); return SBK_ERR_ARG;
+    }
+    SBK_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM));
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int n_tiles = ceil_div(N, G2_BN), m_tiles = ceil_div(M, 2 * G2_BM);
+    int pairs = std::min(num_sms / 2, n_tiles * m_tiles);
+    GemmProfile* prof = gemm_profile();
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (prof->enabled) {
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0, stream);
+    }
+    kern<<<2 * pairs, G2_THREADS, G2_SMEM, stream>>>(ta, tb, epi, M, N, K);
+    if (prof->enabled) {
+        cudaEventRecord(e1, stream);
+        prof->ev.push_back(e0);
+        prof->ev.push_back(e1);
+        prof->flops.push_back(2.0 * M * N * K);
+    }
+    SBK_LAUNCH_CHECK();
+    return SBK_OK;
+}
+
+}  // namespace sbk

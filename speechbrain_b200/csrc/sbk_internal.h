@@ -29,6 +29,9 @@ struct GemmEpilogue {
 // out = epilogue(A[M,K] fp16 x W[N,K]^T fp16), tcgen05 tensor cores. gemm_tc.cu
 int gemm_f16(const void* A, int lda, const void* W, int ldw, const GemmEpilogue& epi, int M, int N, int K,
              cudaStream_t stream);
+// 2-CTA (cta_group::2) persistent variant, N % 256 == 0. gemm_tc2.cu
+int gemm_f16_2cta(const void* A, int lda, const void* W, int ldw, const GemmEpilogue& epi, int M, int N, int K,
+                  cudaStream_t stream);
 
 
 const char* last_error();

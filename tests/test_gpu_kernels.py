@@ -23,7 +23,8 @@ def dev():
 
 # ----------------------------------------------------------------------------------------- tcgen05 GEMM
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 128, 512), (200, 256, 512), (251, 5000, 512),
-                                   (1000, 1536, 640), (8032, 2048, 512), (8032, 512, 2048), (300, 144, 144)])
+                                   (1000, 1536, 640), (8032, 2048, 512), (8032, 512, 2048), (300, 144, 144),
+                                   (8032, 1536, 512), (8032, 1024, 512), (37, 512, 640), (20000, 256, 64)])
 @pytest.mark.parametrize("out_f32,act", [(1, 0), (0, 1)])
 def test_gemm_tc(dev, M, N, K, out_f32, act):
     import ctypes
