@@ -40,6 +40,16 @@ typedef struct {
     int parts;              /* bitmask of SBK_PART_*: which sub-models the weight table carries */
 } sbk_asr_config;
 
+typedef struct {
+    /* S2SBeamSearcher kwargs (decoders/seq2seq.py:752-804); steps are absolute: int(T * ratio) */
+    int beam_size, max_steps, min_steps, bos, eos;
+    float temperature;
+    int using_eos_threshold;
+    float eos_threshold;
+    int length_normalization;
+    float minus_inf;
+} sbk_beam_params;
+
 const char* sbk_last_error(void); /* thread-local message of the last failing call */
 int sbk_version(void);
 long long sbk_launch_count(void); /* kernels launched by this library so far (graph replays included) */
@@ -93,6 +103,13 @@ int sbk_asr_encode_feats(sbk_asr* m, const float* feats_dev, const float* rel_le
 int sbk_asr_greedy_from_enc(sbk_asr* m, const float* enc_dev, const float* rel_len_dev, int B, int T, int max_steps,
                             int bos, int eos, int* pred_dev, float* score_dev, float* log_probs_dev, int* steps_done,
                             void* stream);
+/* S2STransformerBeamSearcher.forward, scorer=None (decoders/seq2seq.py:1632-1723,1853-1934), KV-cached with a
+ * cache-row lineage table instead of index_select copies.  Writes the per-step search history
+ * hist_*[max_steps, B * beam_size]: token, predecessor row, length-normalised score, raw log-prob; the host replays
+ * the finished-hypothesis bookkeeping (:1371-1476) from it. */
+int sbk_asr_beam_from_enc(sbk_asr* m, const float* enc_dev, const float* rel_len_dev, int B, int T,
+                          const sbk_beam_params* params, int* hist_tok_dev, int* hist_pred_dev, float* hist_score_dev,
+                          float* hist_lp_dev, int* steps_done, void* stream);
 /* EncoderDecoderASR.transcribe_batch minus the tokenizer (inference/ASR.py:131-169): wav -> token ids.
  * _dev: wav already on the device; _host: HOST buffers, H2D/D2H inside the call (synchronises the stream). */
 int sbk_asr_transcribe_greedy_dev(sbk_asr* m, const float* wav_dev, const float* rel_len_dev, int B, int L,

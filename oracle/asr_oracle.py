@@ -411,3 +411,102 @@ def full_pipeline_features(wav, wav_lens, sd, cfg):
     f = fbank(wav, n_fft=cfg["n_fft"], n_mels=cfg["n_mels"], win_length_ms=cfg["win_length"])
     f = input_norm(f, wav_lens, "global", sd["normalize.glob_mean"], sd["normalize.glob_std"])
     return cnn_frontend(f, sd, "CNN.")
+
+
+# --------------------------------------------------------------------------
+# Beam search (no scorers): decoders/seq2seq.py:752-1749 S2SBeamSearcher + :1853-1934
+# --------------------------------------------------------------------------
+
+
+def beam_search(enc_states, wav_len, sd, cfg, seq_lin_w, seq_lin_b, bos_index=1, eos_index=2, beam_size=4,
+                min_decode_ratio=0.0, max_decode_ratio=1.0, temperature=1.0, using_eos_threshold=True,
+                eos_threshold=1.5, length_normalization=True, minus_inf=-1e20, topk=1, prefix="", return_history=False):
+    """S2STransformerBeamSearcher.forward with scorer=None, using_max_attn_shift=False.
+
+    Follows init_beam_search_data (:1267-1369), search_step (:1478-1598), _compute_scores_and_next_inp_tokens
+    (:1204-1265), _update_sequences_and_log_probs (:1152-1202), _update_hyps_and_scores_if_eos_token (:1371-1416),
+    _fill_alived_hyps_with_eos_token (:1600-1630), _get_topk_prediction (:1418-1476) -- whole-prefix decode, no cache.
+    Returns (hyps, best_lens, best_scores, best_log_probs) like return_topk=False."""
+    B, T, _ = enc_states.shape
+    V = seq_lin_w.shape[0]
+    n_bh = B * beam_size
+    enc_lens = torch.round(T * wav_len).int()
+    enc = enc_states.repeat_interleave(beam_size, dim=0)
+    enc_l = enc_lens.repeat_interleave(beam_size, dim=0)
+    inp = torch.full((n_bh,), bos_index, dtype=torch.long)
+    beam_offset = torch.arange(B) * beam_size
+    seq_scores = torch.full((n_bh,), float("-inf"))
+    seq_scores[beam_offset] = 0.0
+    alived_seq = torch.empty(n_bh, 0, dtype=torch.long)
+    alived_lp = torch.empty(n_bh, 0)
+    finished = [[] for _ in range(B)]
+    min_steps, max_steps = int(T * min_decode_ratio), int(T * max_decode_ratio)
+    memory = None
+    scores = None
+    history = []
+
+    def add_eos_hyps(tokens, scores_):
+        is_eos = tokens.eq(eos_index)
+        for index in torch.nonzero(is_eos, as_tuple=True)[0].tolist():
+            b = index // beam_size
+            if len(finished[b]) == beam_size:
+                continue
+            finished[b].append((alived_seq[index, :], alived_lp[index, :], scores_[index].clone()))
+        return is_eos
+
+    for step in range(max_steps):
+        if [len(f) for f in finished] == [beam_size] * B:
+            break
+        memory = inp.unsqueeze(1) if memory is None else torch.cat([memory, inp.unsqueeze(1)], dim=-1)
+        pred, _ = decode(memory, enc, enc_l, sd, cfg, prefix)
+        log_probs = F.log_softmax(F.linear(pred, seq_lin_w, seq_lin_b) / temperature, dim=-1)[:, -1, :]
+        lp_clone = log_probs.clone().reshape(B, -1)
+        if step < min_steps:
+            log_probs[:, eos_index] = minus_inf
+        if using_eos_threshold:
+            max_probs, _ = torch.max(log_probs, dim=-1)
+            cond = log_probs[:, eos_index] > (eos_threshold * max_probs)
+            log_probs[:, eos_index] = torch.where(cond, log_probs[:, eos_index], torch.tensor(minus_inf))
+        sc = seq_scores.unsqueeze(1) + log_probs
+        if length_normalization:
+            sc = sc / (step + 1)
+        scores, cand = sc.view(B, -1).topk(beam_size, dim=-1)
+        inp = (cand % V).view(n_bh)
+        scores = scores.view(n_bh)
+        seq_scores = scores * (step + 1) if length_normalization else scores.clone()
+        predecessors = (torch.div(cand, V, rounding_mode="floor") + beam_offset.unsqueeze(1)).view(n_bh)
+        memory = torch.index_select(memory, 0, predecessors)
+        beam_lp = lp_clone[torch.arange(B).unsqueeze(1), cand].reshape(n_bh)
+        alived_seq = torch.cat([torch.index_select(alived_seq, 0, predecessors), inp.unsqueeze(1)], dim=-1)
+        alived_lp = torch.cat([torch.index_select(alived_lp, 0, predecessors), beam_lp.unsqueeze(1)], dim=-1)
+        history.append((inp.clone(), predecessors.clone(), scores.clone(), beam_lp.clone()))
+        is_eos = add_eos_hyps(inp, scores)
+        seq_scores = seq_scores.masked_fill(is_eos, float("-inf"))
+    if [len(f) for f in finished] != [beam_size] * B:
+        add_eos_hyps(torch.full((n_bh,), eos_index, dtype=torch.long), scores)
+    out = finalize_beams(finished, beam_size, topk)
+    return out + (history,) if return_history else out
+
+
+def finalize_beams(finished, beam_size, topk=1):
+    """_get_topk_prediction (:1418-1476) + the return_topk=False tail of forward (:1709-1723)."""
+    B = len(finished)
+    top_hyps, top_lp, top_scores, top_len = [], [], [], []
+    for i in range(B):
+        hyps, lps, scs = zip(*finished[i])
+        top_hyps += hyps
+        top_scores += scs
+        top_lp += lps
+        top_len += [len(h) for h in hyps]
+    top_hyps = torch.nn.utils.rnn.pad_sequence(top_hyps, batch_first=True, padding_value=0)
+    top_lp = torch.nn.utils.rnn.pad_sequence(top_lp, batch_first=True, padding_value=0)
+    top_len = (torch.tensor(top_len, dtype=torch.float) - 1) / top_hyps.size(1)
+    top_scores = torch.stack(top_scores, dim=0).view(B, -1)
+    tk_scores, idx = top_scores.topk(topk, dim=-1)
+    idx = (idx + (torch.arange(B) * beam_size).unsqueeze(1)).view(B * topk)
+    tk_hyps = torch.index_select(top_hyps, 0, idx).view(B, topk, -1)
+    tk_len = torch.index_select(top_len, 0, idx).view(B, topk)
+    tk_lp = torch.index_select(top_lp, 0, idx).view(B, topk, -1)
+    best_hyps, best_lens = tk_hyps[:, 0, :], tk_len[:, 0]
+    hyps = [best_hyps[b, : int(torch.round(best_lens[b] * best_hyps.shape[1]))].tolist() for b in range(B)]
+    return hyps, best_lens, tk_scores[:, 0], tk_lp[:, 0, :]

@@ -169,10 +169,42 @@ def model_case(cfg, attention_type, B, L, lens, n_steps, tag):
     torch.save(gold, os.path.join(OUT, f"{tag}.pt"))
 
 
+def beam_case(tag="beam_conformer_large_rope"):
+    """S2STransformerBeamSearcher (no scorer) on the conformer_large_rope golden's encoder states.  seq_lin's EOS
+    bias is raised so that EOS hypotheses actually finish (random weights never emit EOS otherwise)."""
+    from speechbrain.decoders.seq2seq import S2STransformerBeamSearcher
+    fb, norm, mods, sd = build_reference(CFG_L, "RoPEMHA")
+    g = torch.load(os.path.join(OUT, "conformer_large_rope.pt"))
+    enc, wav_lens = g["enc_out"], g["wav_lens"]
+    T = enc.shape[1]
+    out = {}
+    for name, kw, eos_bias in [("thr_on", dict(beam_size=4, using_eos_threshold=True, temperature=1.0), 4.0),
+                               ("recipe", dict(beam_size=5, using_eos_threshold=False, temperature=1.15, min_decode_ratio=2.5 / T), 5.5),
+                               ("no_eos", dict(beam_size=3, using_eos_threshold=False, length_normalization=False), 0.0)]:
+        with torch.no_grad():
+            bias = sd["seq_lin.w.bias"].clone()
+            bias[2] += eos_bias
+            mods["seq_lin"].w.bias.copy_(bias)
+            kwargs = dict(kw)
+            kwargs.setdefault("min_decode_ratio", 0.0)
+            bs = S2STransformerBeamSearcher(modules=[mods["Transformer"], mods["seq_lin"]], bos_index=1, eos_index=2,
+                                            max_decode_ratio=8.5 / T, **kwargs)
+            hyps, lens, scores, lp = bs(enc, wav_lens)
+            ocfg = dict(CFG_L, attention_type="RoPEMHA")
+            okw = dict(kwargs)
+            ohyps, olens, oscores, olp = O.beam_search(enc, wav_lens, sd, ocfg, sd["seq_lin.w.weight"], bias, 1, 2,
+                                                       max_decode_ratio=8.5 / T, prefix="Transformer.", **okw)
+        print(f"[beam {name}] ref hyps {hyps} scores {scores.tolist()} | oracle equal: {ohyps == hyps} "
+              f"score err {(oscores - scores).abs().max():.2e} lp err {(olp - lp).abs().max():.2e}")
+        assert ohyps == hyps and (oscores - scores).abs().max() < 1e-4
+        out[name] = dict(kwargs=kwargs, eos_bias=eos_bias, max_decode_ratio=8.5 / T, hyps=hyps, lens=lens, scores=scores, log_probs=lp)
+    torch.save(out, os.path.join(OUT, f"{tag}.pt"))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
-    which = sys.argv[1:] or ["fbank", "norm", "L_rope", "L_relpos", "S_relpos"]
+    which = sys.argv[1:] or ["fbank", "norm", "L_rope", "L_relpos", "S_relpos", "beam"]
     if "fbank" in which:
         fbank_cases()
     if "norm" in which:
@@ -183,5 +215,7 @@ if __name__ == "__main__":
         model_case(CFG_L, "RelPosMHAXL", 2, 32000, [1.0, 0.7], 6, "conformer_large_relpos")
     if "S_relpos" in which:
         model_case(CFG_S, "RelPosMHAXL", 2, 24000, [0.8, 1.0], 6, "conformer_small_relpos")
+    if "beam" in which:
+        beam_case()
     for fn in sorted(os.listdir(OUT)):
         print(fn, os.path.getsize(os.path.join(OUT, fn)))

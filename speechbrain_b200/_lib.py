@@ -25,6 +25,13 @@ class sbk_asr_config(ctypes.Structure):
         "parts")]
 
 
+class sbk_beam_params(ctypes.Structure):
+    _fields_ = [("beam_size", ctypes.c_int), ("max_steps", ctypes.c_int), ("min_steps", ctypes.c_int),
+                ("bos", ctypes.c_int), ("eos", ctypes.c_int), ("temperature", ctypes.c_float),
+                ("using_eos_threshold", ctypes.c_int), ("eos_threshold", ctypes.c_float),
+                ("length_normalization", ctypes.c_int), ("minus_inf", ctypes.c_float)]
+
+
 SBK_ATT_ROPE, SBK_ATT_RELPOS = 0, 1
 SBK_ACT_RELU, SBK_ACT_GELU = 0, 1
 SBK_PARTS = {"fbank": 1, "cnn": 2, "encoder": 4, "decoder": 8}
@@ -36,7 +43,7 @@ EXPORTS = [
     "sbk_asr_create", "sbk_asr_destroy", "sbk_asr_num_frames", "sbk_asr_cnn_forward", "sbk_asr_encode_from_cnn",
     "sbk_asr_encode_feats", "sbk_asr_greedy_from_enc", "sbk_asr_transcribe_greedy_dev",
     "sbk_asr_transcribe_greedy_host", "sbk_asr_transcribe_greedy_host_async", "sbk_asr_clone",
-    "sbk_asr_set_poll_interval",
+    "sbk_asr_set_poll_interval", "sbk_asr_beam_from_enc",
 ]
 
 

@@ -296,6 +296,9 @@ __global__ void __launch_bounds__(DA_WARPS * 32) dec_attention_kernel(const DecA
     const __half* q = a.q + static_cast<size_t>(r) * a.ldq + h * 64;
     const __half* kbase = a.kbase + static_cast<size_t>(blk) * a.row_stride + h * 64;
     const __half* vbase = a.vbase + static_cast<size_t>(blk) * a.row_stride + h * 64;
+    // beam search: position j of hypothesis r lives in the cache row of the ancestor that wrote it
+    const int* lin = nullptr;
+    if (a.lineage) lin = a.lineage + static_cast<size_t>((n_keys - 1) & 1) * gridDim.x * a.lin_stride + static_cast<size_t>(r) * a.lin_stride;
     // full query vector in registers (every lane)
     float qf[64];
 #pragma unroll
@@ -312,6 +315,7 @@ __global__ void __launch_bounds__(DA_WARPS * 32) dec_attention_kernel(const DecA
     float mx = -INFINITY;
     for (int j = kb + lane; j < ke; j += 32) {
         const __half* kr = kbase + static_cast<size_t>(j) * a.key_stride;
+        if (lin) kr += (static_cast<ptrdiff_t>(lin[j]) - r) * static_cast<ptrdiff_t>(a.row_stride);
         uint4 kv[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) kv[e] = *reinterpret_cast<const uint4*>(kr + e * 8);
@@ -349,7 +353,9 @@ __global__ void __launch_bounds__(DA_WARPS * 32) dec_attention_kernel(const DecA
         float p[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            vv[u] = *reinterpret_cast<const uint4*>(vbase + static_cast<size_t>(j + 4 * u) * a.key_stride + dl);
+            const __half* vr = vbase + static_cast<size_t>(j + 4 * u) * a.key_stride + dl;
+            if (lin) vr += (static_cast<ptrdiff_t>(lin[j + 4 * u]) - r) * static_cast<ptrdiff_t>(a.row_stride);
+            vv[u] = *reinterpret_cast<const uint4*>(vr);
             p[u] = da_smem[j + 4 * u];
         }
 #pragma unroll
@@ -364,7 +370,9 @@ __global__ void __launch_bounds__(DA_WARPS * 32) dec_attention_kernel(const DecA
         }
     }
     for (; j < ke; j += 4) {
-        const uint4 vv = *reinterpret_cast<const uint4*>(vbase + static_cast<size_t>(j) * a.key_stride + dl);
+        const __half* vr = vbase + static_cast<size_t>(j) * a.key_stride + dl;
+        if (lin) vr += (static_cast<ptrdiff_t>(lin[j]) - r) * static_cast<ptrdiff_t>(a.row_stride);
+        const uint4 vv = *reinterpret_cast<const uint4*>(vr);
         const float p = da_smem[j];
         const __half2* v2 = reinterpret_cast<const __half2*>(&vv);
 #pragma unroll
@@ -510,6 +518,222 @@ int greedy_select(const float* logits, int n_rows, int V, int* step_arr, int eos
     SBK_CUDA_CHECK(launch_k(greedy_select_kernel, dim3(n_rows), dim3(256), 0, stream, logits, V, step_arr, eos, tokens,
                             tok_stride, has_ended, ended_count, pred, score, out_stride, log_probs, L, emb, pe, d,
                             sqrtf(static_cast<float>(d)), x_next));
+    SBK_LAUNCH_CHECK();
+    return SBK_OK;
+}
+
+
+// --------------------------------------------------------------------------- beam search step
+// decoders/seq2seq.py search_step (:1478-1598) for one utterance per CTA, scorer-less path:
+//   log_probs = log_softmax(logits / temperature)                                   (:1929-1934)
+//   eos -> minus_inf while step < min_decode_steps (:978-996); eos threshold (:998-1017, :851-867)
+//   scores = (sequence_scores + log_probs) / (step + 1) if length_normalization      (:1229-1234)
+//   top-`beam` over beam * V candidates, tokens = cand % V, predecessors = cand // V (:1237-1257)
+//   sequence_scores of beams that emitted eos -> -inf                                (:1586)
+// plus: the per-step history the host needs to replay hypothesis bookkeeping, the KV-cache lineage of the new
+// beams, their next decoder input (embedding + positional encoding) and the per-utterance finished counters.
+constexpr int BS_MAXB = 16;
+constexpr int BS_THREADS = 256;
+
+struct BeamArgs {
+    const float* logits; int V; int beam; int n_bh; int S_max;
+    float* seq_scores;            // [2][n_bh] ping-pong by step parity
+    int* lineage;                 // [2][n_bh][S_max] ping-pong by step parity
+    int* step_arr;                // [n_bh]
+    int* finished;                // [B] eos hypotheses seen so far (capped at beam)
+    int* n_full;                  // number of utterances whose beam is full
+    int* hist_tok; int* hist_pred; float* hist_score; float* hist_lp;  // [max_steps][n_bh]
+    float inv_temp, eos_threshold, minus_inf;
+    int min_steps, eos, use_eos_threshold, length_norm;
+    const float* emb; const float* pe; int d; float sqrt_d; float* x_next;
+};
+
+__global__ void __launch_bounds__(BS_THREADS) beam_step_kernel(const BeamArgs a) {
+    __shared__ float s_red[BS_THREADS / 32];
+    __shared__ int s_redi[BS_THREADS / 32];
+    __shared__ float s_lse[BS_MAXB], s_eos[BS_MAXB];
+    __shared__ float s_val[BS_THREADS][BS_MAXB + 1];
+    __shared__ int s_idx[BS_THREADS][BS_MAXB + 1];
+    __shared__ int s_wtok[BS_MAXB], s_wpred[BS_MAXB];
+    __shared__ int s_redx[BS_THREADS / 32];
+    pdl_trigger();
+    pdl_wait();
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int beam = a.beam, V = a.V;
+    const int row0 = b * beam;
+    const int step = a.step_arr[row0];
+    const float* seq_in = a.seq_scores + static_cast<size_t>(step & 1) * a.n_bh;
+    float* seq_out = a.seq_scores + static_cast<size_t>((step + 1) & 1) * a.n_bh;
+    // ---- phase 1: per beam row log-sum-exp of logits / T and the (masked) eos log-prob
+    for (int k = 0; k < beam; ++k) {
+        const float* lg = a.logits + static_cast<size_t>(row0 + k) * V;
+        float mx = -INFINITY;
+        for (int j = tid; j < V; j += BS_THREADS) mx = fmaxf(mx, lg[j] * a.inv_temp);
+        mx = warp_max(mx);
+        if (lane == 0) s_red[warp] = mx;
+        __syncthreads();
+        mx = s_red[0];
+        for (int w = 1; w < BS_THREADS / 32; ++w) mx = fmaxf(mx, s_red[w]);
+        __syncthreads();
+        float sm = 0.0f, mx_noeos = -INFINITY;
+        for (int j = tid; j < V; j += BS_THREADS) {
+            const float v = lg[j] * a.inv_temp;
+            sm += expf(v - mx);
+            if (j != a.eos) mx_noeos = fmaxf(mx_noeos, v);
+        }
+        sm = warp_sum(sm);
+        mx_noeos = warp_max(mx_noeos);
+        if (lane == 0) { s_red[warp] = sm; s_redi[warp] = __float_as_int(mx_noeos); }
+        __syncthreads();
+        if (tid == 0) {
+            float tot = 0.0f, mne = -INFINITY;
+            for (int w = 0; w < BS_THREADS / 32; ++w) { tot += s_red[w]; mne = fmaxf(mne, __int_as_float(s_redi[w])); }
+            const float lse = mx + logf(tot);
+            float eos_lp = lg[a.eos] * a.inv_temp - lse;
+            if (step < a.min_steps) eos_lp = a.minus_inf;
+            if (a.use_eos_threshold) {
+                const float max_lp = fmaxf(mne - lse, eos_lp);
+                if (!(eos_lp > a.eos_threshold * max_lp)) eos_lp = a.minus_inf;
+            }
+            s_lse[k] = lse;
+            s_eos[k] = eos_lp;
+        }
+        __syncthreads();
+    }
+    // ---- phase 2: every thread keeps its own sorted top-`beam` of the candidates it scans
+    float bv[BS_MAXB];
+    int bi[BS_MAXB];
+#pragma unroll
+    for (int i = 0; i < BS_MAXB; ++i) { bv[i] = -INFINITY; bi[i] = 0x7fffffff; }
+    const float inv_len = a.length_norm ? 1.0f / static_cast<float>(step + 1) : 1.0f;
+    const int n_cand = beam * V;
+    for (int cidx = tid; cidx < n_cand; cidx += BS_THREADS) {
+        const int k = cidx / V, j = cidx - k * V;
+        const float lp = (j == a.eos) ? s_eos[k] : a.logits[static_cast<size_t>(row0 + k) * V + j] * a.inv_temp - s_lse[k];
+        const float sc = (seq_in[row0 + k] + lp) * inv_len;
+        if (sc > bv[BS_MAXB - 1] && sc > -INFINITY) {  // insert (list sorted descending; only the first `beam` matter)
+            float v = sc;
+            int ix = cidx;
+#pragma unroll
+            for (int i = 0; i < BS_MAXB; ++i) {
+                if (v > bv[i] || (v == bv[i] && ix < bi[i])) {
+                    const float tv = bv[i]; const int ti = bi[i];
+                    bv[i] = v; bi[i] = ix;
+                    v = tv; ix = ti;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < BS_MAXB; ++i) { s_val[tid][i] = bv[i]; s_idx[tid][i] = bi[i]; }
+    s_val[tid][BS_MAXB] = -INFINITY;
+    s_idx[tid][BS_MAXB] = 0x7fffffff;
+    __syncthreads();
+    // ---- phase 3: merge -- `beam` rounds of a block-wide arg-max over the heads of the per-thread lists
+    int head = 0;
+    for (int k = 0; k < beam; ++k) {
+        float v = s_val[tid][head];
+        int ix = s_idx[tid][head];
+        int who = tid;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, ix, o);
+            const int ow = __shfl_xor_sync(0xffffffffu, who, o);
+            if (ov > v || (ov == v && oi < ix)) { v = ov; ix = oi; who = ow; }
+        }
+        if (lane == 0) { s_red[warp] = v; s_redi[warp] = who; s_redx[warp] = ix; }
+        __syncthreads();
+        if (tid == 0) {
+            float best = s_red[0];
+            int bw = s_redi[0], bx = s_redx[0];
+            for (int w = 1; w < BS_THREADS / 32; ++w)
+                if (s_red[w] > best || (s_red[w] == best && s_redx[w] < bx)) { best = s_red[w]; bw = s_redi[w]; bx = s_redx[w]; }
+            s_redi[0] = bw;
+        }
+        __syncthreads();
+        const int winner = s_redi[0];
+        if (tid == winner) {
+            const int cand = s_idx[tid][head];
+            const float sc = s_val[tid][head];
+            int kk = 0, tok = 0;
+            if (cand != 0x7fffffff) { kk = cand / V; tok = cand - kk * V; }
+            const int row = row0 + k, prow = row0 + kk;
+            const float raw_lp = a.logits[static_cast<size_t>(prow) * V + tok] * a.inv_temp - s_lse[kk];
+            const size_t h = static_cast<size_t>(step) * a.n_bh + row;
+            a.hist_tok[h] = tok; a.hist_pred[h] = prow; a.hist_score[h] = sc; a.hist_lp[h] = raw_lp;
+            float ns = a.length_norm ? sc * static_cast<float>(step + 1) : sc;
+            if (tok == a.eos) ns = -INFINITY;
+            seq_out[row] = ns;
+            s_wtok[k] = tok; s_wpred[k] = prow;
+            ++head;
+        }
+        __syncthreads();
+    }
+    // ---- phase 4: finished counters, lineage of the new beams, next decoder inputs, step counters
+    if (tid == 0) {
+        int n_eos = 0;
+        for (int k = 0; k < beam; ++k) n_eos += (s_wtok[k] == a.eos) ? 1 : 0;
+        const int before = a.finished[b];
+        const int after = min(beam, before + n_eos);
+        a.finished[b] = after;
+        if (before < beam && after >= beam) atomicAdd(a.n_full, 1);
+    }
+    const int* lin_in = a.lineage + static_cast<size_t>(step & 1) * a.n_bh * a.S_max;
+    int* lin_out = a.lineage + static_cast<size_t>((step + 1) & 1) * a.n_bh * a.S_max;
+    for (int i = tid; i < beam * (step + 2); i += BS_THREADS) {
+        const int k = i / (step + 2), p = i - k * (step + 2);
+        const int row = row0 + k, prow = s_wpred[k];
+        int src;
+        if (p < step) src = lin_in[static_cast<size_t>(prow) * a.S_max + p];
+        else if (p == step) src = prow;   // this step's K/V were written at the predecessor's physical row
+        else src = row;                   // next step writes at the new row itself
+        lin_out[static_cast<size_t>(row) * a.S_max + p] = src;
+    }
+    for (int i = tid; i < beam * a.d; i += BS_THREADS) {
+        const int k = i / a.d, c = i - k * a.d;
+        a.x_next[static_cast<size_t>(row0 + k) * a.d + c] =
+            a.emb[static_cast<size_t>(s_wtok[k]) * a.d + c] * a.sqrt_d + a.pe[static_cast<size_t>(step + 1) * a.d + c];
+    }
+    __syncthreads();
+    if (tid < beam) a.step_arr[row0 + tid] = step + 1;
+}
+
+// step = 0 state: x = emb[bos] * sqrt(d) + pe[0]; beam 0 alive (score 0), others -inf; identity lineage.
+__global__ void beam_reset_kernel(int n_bh, int beam, int S_max, int bos, int* step_arr, float* seq_scores, int* lineage,
+                                  int* finished, int* n_full, const float* __restrict__ emb, const float* __restrict__ pe,
+                                  int d, float sqrt_d, float* __restrict__ x) {
+    const int r = blockIdx.x;
+    if (threadIdx.x == 0) {
+        step_arr[r] = 0;
+        seq_scores[r] = (r % beam == 0) ? 0.0f : -INFINITY;
+        seq_scores[n_bh + r] = -INFINITY;
+        lineage[static_cast<size_t>(r) * S_max] = r;
+        if (r % beam == 0) finished[r / beam] = 0;
+        if (r == 0) *n_full = 0;
+    }
+    const float* e = emb + static_cast<size_t>(bos) * d;
+    for (int i = threadIdx.x; i < d; i += blockDim.x) x[static_cast<size_t>(r) * d + i] = e[i] * sqrt_d + pe[i];
+}
+
+int beam_reset(int n_bh, int beam, int S_max, int bos, int* step_arr, float* seq_scores, int* lineage, int* finished,
+               int* n_full, const float* emb, const float* pe, int d, float* x, cudaStream_t stream) {
+    beam_reset_kernel<<<n_bh, 128, 0, stream>>>(n_bh, beam, S_max, bos, step_arr, seq_scores, lineage, finished, n_full, emb,
+                                                pe, d, sqrtf(static_cast<float>(d)), x);
+    SBK_LAUNCH_CHECK();
+    return SBK_OK;
+}
+
+int beam_step(const BeamStepArgs& p, int B, cudaStream_t stream) {
+    SBK_REQUIRE(p.beam >= 1 && p.beam <= BS_MAXB, "beam_step: beam_size=%d not in [1, %d]", p.beam, BS_MAXB);
+    BeamArgs a;
+    a.logits = p.logits; a.V = p.V; a.beam = p.beam; a.n_bh = B * p.beam; a.S_max = p.S_max;
+    a.seq_scores = p.seq_scores; a.lineage = p.lineage; a.step_arr = p.step_arr; a.finished = p.finished; a.n_full = p.n_full;
+    a.hist_tok = p.hist_tok; a.hist_pred = p.hist_pred; a.hist_score = p.hist_score; a.hist_lp = p.hist_lp;
+    a.inv_temp = 1.0f / p.temperature; a.eos_threshold = p.eos_threshold; a.minus_inf = p.minus_inf;
+    a.min_steps = p.min_steps; a.eos = p.eos; a.use_eos_threshold = p.use_eos_threshold; a.length_norm = p.length_norm;
+    a.emb = p.emb; a.pe = p.pe; a.d = p.d; a.sqrt_d = sqrtf(static_cast<float>(p.d)); a.x_next = p.x_next;
+    SBK_CUDA_CHECK(launch_k(beam_step_kernel, dim3(B), dim3(BS_THREADS), 0, stream, a));
     SBK_LAUNCH_CHECK();
     return SBK_OK;
 }

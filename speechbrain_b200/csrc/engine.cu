@@ -84,8 +84,8 @@ struct AsrModel {
     // shapes the workspace is carved for
     int wsB = 0, wsL = 0, ws_rows = 0, ws_steps = 0;
     struct Buf {
-        float *wav, *feats, *x, *glu, *enc_out, *act1_f, *cnn_f, *dx, *logits, *score;
-        int *utt_max, *enc_len, *tokens, *step, *has_ended, *ended_count, *pred;
+        float *wav, *feats, *x, *glu, *enc_out, *act1_f, *cnn_f, *dx, *logits, *score, *seq_scores;
+        int *utt_max, *enc_len, *tokens, *step, *has_ended, *ended_count, *pred, *lineage, *finished;
         float* rel_len;
         __half *act1, *a_in, *h16, *f16, *qkv16, *att16, *P16, *enc16, *ckv16, *kcache, *vcache, *dh16, *dq16, *datt16, *df16;
     } b;
@@ -426,6 +426,7 @@ static int ensure_workspace(AsrModel* m, int B, int L, int rows, int steps) {
     sz(M * d * 2); sz((size_t)T2 * d * 2); sz(M * d * 2); sz(M * Ld * 2 * d * 2);
     sz((size_t)Ld * rows * S * d * 2); sz((size_t)Ld * rows * S * d * 2);
     sz((size_t)rows * d * 2); sz((size_t)rows * d * 2); sz((size_t)rows * d * 2); sz((size_t)rows * F * 2);
+    sz((size_t)2 * rows * S * 4); sz(B * 4 + 64); sz((size_t)2 * rows * 4);
     need += 1 << 20;
     if (need > m->ws.cap) {
         if (m->ws.base) { cudaDeviceSynchronize(); cudaFree(m->ws.base); m->ws.base = nullptr; }
@@ -453,8 +454,9 @@ static int ensure_workspace(AsrModel* m, int B, int L, int rows, int steps) {
     TAKE(kcache, __half, (size_t)Ld * rows * S * d * 2); TAKE(vcache, __half, (size_t)Ld * rows * S * d * 2);
     TAKE(dh16, __half, (size_t)rows * d * 2); TAKE(dq16, __half, (size_t)rows * d * 2); TAKE(datt16, __half, (size_t)rows * d * 2);
     TAKE(df16, __half, (size_t)rows * F * 2);
+    TAKE(lineage, int, (size_t)2 * rows * S * 4); TAKE(finished, int, B * 4 + 64); TAKE(seq_scores, float, (size_t)2 * rows * 4);
 #undef TAKE
-    if (!b.df16) { set_error("workspace carve failed"); return SBK_ERR_NOMEM; }
+    if (!b.df16 || !b.seq_scores) { set_error("workspace carve failed"); return SBK_ERR_NOMEM; }
     m->wsB = B; m->wsL = L; m->ws_rows = rows; m->ws_steps = steps;
     return SBK_OK;
 }
@@ -529,8 +531,8 @@ __global__ void abs_len_kernel(const float* rel, int B, int T, int* out) {
     if (i < B) out[i] = min(T, max(0, __float2int_rn(rel[i] * static_cast<float>(T))));
 }
 
-static int enqueue_decode_step(AsrModel* m, int rows, int rows_per_utt, int T, int S_max, int eos, float* log_probs,
-                               int L_lp, cudaStream_t st) {
+static int enqueue_decode_layers(AsrModel* m, int rows, int rows_per_utt, int T, int S_max, const int* lineage,
+                                 cudaStream_t st) {
     const sbk_asr_config& c = m->cfg;
     AsrModel::Buf& b = m->b;
     const int d = c.d_model, F = c.d_ffn, H = c.nhead, dh = d / H, Ld = c.num_decoder_layers;
@@ -550,6 +552,7 @@ static int enqueue_decode_step(AsrModel* m, int rows, int rows_per_utt, int T, i
         DecAttnArgs t{};
         t.q = b.dq16; t.ldq = d; t.kbase = kc; t.vbase = vc; t.row_stride = (size_t)S_max * d; t.key_stride = d;
         t.rows_per_block = 1; t.n_keys_ptr = b.step; t.enc_len = nullptr; t.H = H; t.dh = dh; t.out = b.datt16; t.ldo = d;
+        t.lineage = lineage; t.lin_stride = S_max;
         RC(dec_attention(t, rows, S_max, st));
         a = SkinnyArgs{}; a.A = b.datt16; a.lda = d; a.W = w.w_self_out; a.ldw = d; a.bias = w.b_self_out; a.n_rows = rows;
         a.N = d; a.K = d; a.epi = SK_RESID; a.out = b.dx; a.ldo = d;
@@ -581,8 +584,62 @@ static int enqueue_decode_step(AsrModel* m, int rows, int rows_per_utt, int T, i
     a.W = m->w_lin; a.ldw = d; a.bias = m->b_lin; a.n_rows = rows; a.N = c.vocab; a.K = d;
     a.epi = SK_F32; a.out = b.logits; a.ldo = c.vocab;
     RC(skinny_gemm(a, st));
-    RC(greedy_select(b.logits, rows, c.vocab, b.step, eos, b.tokens, S_max + 1, b.has_ended, b.ended_count, b.pred, b.score,
-                     S_max, log_probs, L_lp, m->emb, m->dec_pe, d, b.dx, st));
+    return SBK_OK;
+}
+
+static int enqueue_decode_step(AsrModel* m, int rows, int rows_per_utt, int T, int S_max, int eos, float* log_probs,
+                               int L_lp, cudaStream_t st) {
+    AsrModel::Buf& b = m->b;
+    RC(enqueue_decode_layers(m, rows, rows_per_utt, T, S_max, nullptr, st));
+    RC(greedy_select(b.logits, rows, m->cfg.vocab, b.step, eos, b.tokens, S_max + 1, b.has_ended, b.ended_count, b.pred,
+                     b.score, S_max, log_probs, L_lp, m->emb, m->dec_pe, m->cfg.d_model, b.dx, st));
+    return SBK_OK;
+}
+
+// Beam search (decoders/seq2seq.py:1632-1723 with scorer=None): the device runs decoder step + beam_step_kernel and
+// records the per-step (token, predecessor, normalised score, log-prob) history; hypothesis bookkeeping is replayed
+// on the host from that history (speechbrain_b200/decoders/seq2seq.py).
+static int run_beam(AsrModel* m, int B, int T, const sbk_beam_params& p, int* hist_tok, int* hist_pred, float* hist_score,
+                    float* hist_lp, int* steps_done, cudaStream_t st) {
+    const sbk_asr_config& c = m->cfg;
+    AsrModel::Buf& b = m->b;
+    const int d = c.d_model, Ld = c.num_decoder_layers, M = B * T, beam = p.beam_size, rows = B * beam, S_max = m->ws_steps + 1;
+    SBK_REQUIRE(m->has_dec, "beam: this handle was created without decoder weights");
+    SBK_REQUIRE(p.max_steps <= m->ws_steps && p.max_steps + 1 <= c.max_len, "beam: max_steps=%d too large", p.max_steps);
+    *steps_done = 0;
+    if (p.max_steps <= 0) return SBK_OK;
+    RC(cast_f32_f16(b.enc_out, b.enc16, (size_t)M * d, st));
+    for (int l = 0; l < Ld; ++l) {
+        GemmEpilogue e;
+        e.mode = EPI_F16; e.bias = m->b_ckv + (size_t)l * 2 * d; e.out = b.ckv16 + (size_t)l * M * 2 * d; e.ldo = 2 * d;
+        RC(gemm_f16(b.enc16, d, m->w_ckv + (size_t)l * 2 * d * d, d, e, M, 2 * d, d, st));
+    }
+    set_pdl(getenv("SBK_PDL") != nullptr);
+    RC(beam_reset(rows, beam, S_max, p.bos, b.step, b.seq_scores, b.lineage, b.finished, b.ended_count, m->emb, m->dec_pe, d,
+                  b.dx, st));
+    BeamStepArgs a{};
+    a.logits = b.logits; a.V = c.vocab; a.beam = beam; a.S_max = S_max; a.seq_scores = b.seq_scores; a.lineage = b.lineage;
+    a.step_arr = b.step; a.finished = b.finished; a.n_full = b.ended_count;
+    a.hist_tok = hist_tok; a.hist_pred = hist_pred; a.hist_score = hist_score; a.hist_lp = hist_lp;
+    a.temperature = p.temperature; a.eos_threshold = p.eos_threshold; a.minus_inf = p.minus_inf; a.min_steps = p.min_steps;
+    a.eos = p.eos; a.use_eos_threshold = p.using_eos_threshold; a.length_norm = p.length_normalization;
+    a.emb = m->emb; a.pe = m->dec_pe; a.d = d; a.x_next = b.dx;
+    const int check_every = m->poll_every > 0 ? m->poll_every : p.max_steps;
+    int s = 0;
+    while (s < p.max_steps) {
+        const int chunk = std::min(check_every, p.max_steps - s);
+        for (int i = 0; i < chunk; ++i) {
+            RC(enqueue_decode_layers(m, rows, beam, T, S_max, b.lineage, st));
+            RC(beam_step(a, B, st));
+        }
+        s += chunk;
+        if (s < p.max_steps && m->poll_every > 0) {  // `_check_full_beams` (:806-822), polled once per chunk
+            SBK_CUDA_CHECK(cudaMemcpyAsync(m->host_flag, b.ended_count, 4, cudaMemcpyDeviceToHost, st));
+            SBK_CUDA_CHECK(cudaStreamSynchronize(st));
+            if (*m->host_flag >= B) break;
+        }
+    }
+    *steps_done = s;
     return SBK_OK;
 }
 
@@ -664,6 +721,7 @@ void sbk_gemm_profile_enable(int on) {
     for (cudaEvent_t e : p->ev) cudaEventDestroy(e);
     p->ev.clear();
     p->flops.clear();
+    p->shape.clear();
     p->enabled = on != 0;
 }
 // After a device sync: number of timed GEMM launches, their total milliseconds and total FLOPs.
@@ -678,6 +736,9 @@ int sbk_gemm_profile_read(int* n_launches, double* total_ms, double* total_flops
         }
         ms += t;
         fl += p->flops[i];
+        if (getenv("SBK_GEMM_TRACE"))
+            fprintf(stderr, "gemm M=%d N=%d K=%d epi=%d : %.1f us  %.0f TFLOP/s\n", p->shape[4 * i], p->shape[4 * i + 1],
+                    p->shape[4 * i + 2], p->shape[4 * i + 3], t * 1e3, p->flops[i] / (t * 1e-3) / 1e12);
     }
     if (n_launches) *n_launches = (int)p->flops.size();
     if (total_ms) *total_ms = ms;
@@ -891,6 +952,33 @@ int sbk_asr_greedy_from_enc(sbk_asr* mm, const float* enc_dev, const float* rel_
     if (score_dev && done > 0)
         SBK_CUDA_CHECK(cudaMemcpy2DAsync(score_dev, (size_t)max_steps * 4, b.score, (size_t)S_max * 4, (size_t)done * 4, B,
                                          cudaMemcpyDeviceToDevice, st));
+    if (steps_done) *steps_done = done;
+    return SBK_OK;
+}
+
+// S2STransformerBeamSearcher.forward device part: history arrays are [max_steps, B * beam_size] (device).
+int sbk_asr_beam_from_enc(sbk_asr* mm, const float* enc_dev, const float* rel_len_dev, int B, int T,
+                          const sbk_beam_params* params, int* hist_tok_dev, int* hist_pred_dev, float* hist_score_dev,
+                          float* hist_lp_dev, int* steps_done, void* stream) {
+    AsrModel* m = reinterpret_cast<AsrModel*>(mm);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const sbk_asr_config& c = m->cfg;
+    SBK_REQUIRE(params && params->beam_size >= 1, "beam: bad params");
+    const int rows = B * params->beam_size;
+    const int L = std::max(m->wsL, ((T - 1) * 4) * c.hop);
+    RC(ensure_workspace(m, std::max(B, m->wsB), L, std::max(rows, m->ws_rows), std::max(params->max_steps, m->ws_steps)));
+    AsrModel::Buf& b = m->b;
+    SBK_CUDA_CHECK(cudaMemcpyAsync(b.enc_out, enc_dev, (size_t)B * T * c.d_model * 4, cudaMemcpyDeviceToDevice, st));
+    if (rel_len_dev) {
+        abs_len_kernel<<<ceil_div(B, 128), 128, 0, st>>>(rel_len_dev, B, T, b.enc_len);
+        SBK_LAUNCH_CHECK();
+    } else {
+        std::vector<int> full(B, T);
+        SBK_CUDA_CHECK(cudaMemcpyAsync(b.enc_len, full.data(), B * 4, cudaMemcpyHostToDevice, st));
+        SBK_CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    int done = 0;
+    RC(run_beam(m, B, T, *params, hist_tok_dev, hist_pred_dev, hist_score_dev, hist_lp_dev, &done, st));
     if (steps_done) *steps_done = done;
     return SBK_OK;
 }

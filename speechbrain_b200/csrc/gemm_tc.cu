@@ -138,6 +138,7 @@ static int launch_gemm(const void* A, int lda, const void* W, int ldw, const Gem
         prof->ev.push_back(e0);
         prof->ev.push_back(e1);
         prof->flops.push_back(2.0 * M * N * K);
+        prof->shape.insert(prof->shape.end(), {M, N, K, epi.mode});
     }
     SBK_LAUNCH_CHECK();
     return SBK_OK;

@@ -258,6 +258,7 @@ int gemm_f16_2cta(const void* A, int lda, const void* W, int ldw, const GemmEpil
         prof->ev.push_back(e0);
         prof->ev.push_back(e1);
         prof->flops.push_back(2.0 * M * N * K);
+        prof->shape.insert(prof->shape.end(), {M, N, K, epi.mode});
     }
     SBK_LAUNCH_CHECK();
     return SBK_OK;

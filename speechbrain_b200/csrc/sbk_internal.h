@@ -45,6 +45,7 @@ struct GemmProfile {
     bool enabled = false;
     std::vector<cudaEvent_t> ev;   // start/stop pairs
     std::vector<double> flops;     // 2*M*N*K per launch
+    std::vector<int> shape;        // M, N, K, epilogue mode per launch
 };
 GemmProfile* gemm_profile();
 
@@ -103,8 +104,20 @@ struct DecAttnArgs {
     int n_keys_fixed;
     int H, dh;
     __half* out; int ldo;
+    const int* lineage; int lin_stride;  // beam search: [2][n_rows][lin_stride] cache-row table (null for greedy)
 };
 int dec_attention(const DecAttnArgs& a, int n_rows, int max_keys, cudaStream_t stream);
+struct BeamStepArgs {
+    const float* logits; int V; int beam; int S_max;
+    float* seq_scores; int* lineage; int* step_arr; int* finished; int* n_full;
+    int* hist_tok; int* hist_pred; float* hist_score; float* hist_lp;
+    float temperature, eos_threshold, minus_inf;
+    int min_steps, eos, use_eos_threshold, length_norm;
+    const float* emb; const float* pe; int d; float* x_next;
+};
+int beam_reset(int n_bh, int beam, int S_max, int bos, int* step_arr, float* seq_scores, int* lineage, int* finished,
+               int* n_full, const float* emb, const float* pe, int d, float* x, cudaStream_t stream);
+int beam_step(const BeamStepArgs& p, int B, cudaStream_t stream);
 int greedy_reset(int* tokens, int tok_stride, int n_rows, int bos, int* step_arr, int* has_ended, int* ended_count,
                  const float* emb, const float* pe, int d, float* x, cudaStream_t stream);
 int greedy_select(const float* logits, int n_rows, int V, int* step_arr, int eos, int* tokens, int tok_stride,

@@ -45,6 +45,110 @@ class S2STransformerGreedySearcher(torch.nn.Module):
         return greedy_outputs(pred[:, :done], score[:, :done], lp[:, :done] if lp is not None else None, self.eos_index)
 
 
+class S2STransformerBeamSearcher(torch.nn.Module):
+    """Drop-in for speechbrain.decoders.seq2seq.S2STransformerBeamSearcher (decoders/seq2seq.py:752-804,1853-1934)
+    without scorers: same constructor kwargs, same return values as ``forward(enc_states, wav_len)``.
+
+    The decoder steps, log-softmax, EOS masking/threshold, length-normalised top-k, predecessor bookkeeping of the
+    KV cache and the sequence scores run on the device (one kernel per step, ``beam_step_kernel``); the device
+    records the per-step (token, predecessor, score, log-prob) history, and the finished-hypothesis bookkeeping of
+    ``_update_hyps_and_scores_if_eos_token`` / ``_fill_alived_hyps_with_eos_token`` / ``_get_topk_prediction``
+    (:1371-1476,1600-1630) is replayed from that history on the host (it is a few hundred integers)."""
+
+    def __init__(self, modules, temperature=1.0, bos_index=None, eos_index=None, min_decode_ratio=0.0, max_decode_ratio=1.0,
+                 beam_size=None, scorer=None, return_topk=False, topk=1, using_eos_threshold=True, eos_threshold=1.5,
+                 length_normalization=True, using_max_attn_shift=False, max_attn_shift=60, minus_inf=-1e20):
+        super().__init__()
+        if bos_index is None or eos_index is None or beam_size is None:
+            raise TypeError("bos_index, eos_index and beam_size are required")
+        if scorer is not None:
+            raise NotImplementedError("speechbrain_b200 beam searcher: scorers (CTC / TransformerLM / ...) are not built yet")
+        if using_max_attn_shift:
+            raise NotImplementedError("speechbrain_b200 beam searcher: using_max_attn_shift is not built")
+        if topk > beam_size:
+            raise ValueError("topk must be <= beam_size")
+        self.model, self.fc = modules[0], modules[1]
+        self.temperature, self.bos_index, self.eos_index = temperature, bos_index, eos_index
+        self.min_decode_ratio, self.max_decode_ratio = min_decode_ratio, max_decode_ratio
+        self.beam_size, self.return_topk, self.topk = beam_size, return_topk, topk
+        self.using_eos_threshold, self.eos_threshold = using_eos_threshold, eos_threshold
+        self.length_normalization, self.minus_inf = length_normalization, minus_inf
+        self._engine = None
+
+    def set_n_out(self):
+        return self.fc.w.out_features
+
+    def _get_engine(self, device):
+        if self._engine is None or self._engine.device != torch.device(device):
+            from ..engine import AsrEngine
+            sd = self.model.prefixed_state("Transformer.")
+            sd.update({"seq_lin." + k: v for k, v in self.fc.state_dict().items()})
+            self._engine = AsrEngine(self.model.engine_cfg(), sd, device=device, parts=("decoder",))
+        return self._engine
+
+    @torch.no_grad()
+    def forward(self, enc_states, wav_len):
+        require_cuda(enc_states, "S2STransformerBeamSearcher")
+        B, T, _ = enc_states.shape
+        min_steps, max_steps = int(T * self.min_decode_ratio), int(T * self.max_decode_ratio)
+        if max_steps <= 0:
+            raise ValueError("max_decode_ratio gives zero decoding steps")  # the reference fails on `scores` too
+        hist = self._get_engine(enc_states.device).beam_from_enc(
+            enc_states, wav_len, self.beam_size, max_steps, min_steps, self.bos_index, self.eos_index, self.temperature,
+            self.using_eos_threshold, self.eos_threshold, self.length_normalization, self.minus_inf)
+        out = replay_beam_history(hist, B, self.beam_size, self.eos_index, self.topk)
+        topk_hyps, topk_lengths, topk_scores, topk_log_probs = (t.to(enc_states.device) for t in out)
+        if self.return_topk:
+            return topk_hyps, topk_lengths, topk_scores, topk_log_probs
+        best_hyps, best_lens = topk_hyps[:, 0, :], topk_lengths[:, 0]
+        L = best_hyps.shape[1]
+        hyps = [best_hyps[b, : int(torch.round(best_lens[b] * L))].tolist() for b in range(B)]  # undo_padding
+        return hyps, best_lens, topk_scores[:, 0], topk_log_probs[:, 0, :]
+
+
+def replay_beam_history(hist, B, beam_size, eos_index, topk=1):
+    """Host replay of the hypothesis bookkeeping (decoders/seq2seq.py:1152-1202 sequences/log-probs, :1371-1416 EOS
+    hypotheses, :1600-1630 final fill, :1418-1476 top-k) from the device's per-step history."""
+    tok, pred, score, lp = hist
+    n_bh = B * beam_size
+    alived_seq = torch.empty(n_bh, 0, dtype=torch.long)
+    alived_lp = torch.empty(n_bh, 0)
+    finished = [[] for _ in range(B)]
+
+    def add_eos_hyps(tokens, scores_):
+        for index in torch.nonzero(tokens.eq(eos_index), as_tuple=True)[0].tolist():
+            b = index // beam_size
+            if len(finished[b]) == beam_size:
+                continue
+            finished[b].append((alived_seq[index, :], alived_lp[index, :], scores_[index].clone()))
+
+    last_scores = None
+    for s in range(tok.shape[0]):
+        if all(len(f) == beam_size for f in finished):  # `_check_full_beams` at the top of the loop (:1668)
+            break
+        alived_seq = torch.cat([alived_seq.index_select(0, pred[s]), tok[s].unsqueeze(1)], dim=-1)
+        alived_lp = torch.cat([alived_lp.index_select(0, pred[s]), lp[s].unsqueeze(1)], dim=-1)
+        last_scores = score[s]
+        add_eos_hyps(tok[s], last_scores)
+    if not all(len(f) == beam_size for f in finished):
+        add_eos_hyps(torch.full((n_bh,), eos_index, dtype=torch.long), last_scores)
+    top_hyps, top_lp, top_scores, top_len = [], [], [], []
+    for i in range(B):
+        hyps, lps, scs = zip(*finished[i])
+        top_hyps += hyps
+        top_scores += scs
+        top_lp += lps
+        top_len += [len(h) for h in hyps]
+    top_hyps = torch.nn.utils.rnn.pad_sequence(top_hyps, batch_first=True, padding_value=0)
+    top_lp = torch.nn.utils.rnn.pad_sequence(top_lp, batch_first=True, padding_value=0)
+    top_len = (torch.tensor(top_len, dtype=torch.float) - 1) / top_hyps.size(1)
+    top_scores = torch.stack(top_scores, dim=0).view(B, -1)
+    tk_scores, idx = top_scores.topk(topk, dim=-1)
+    idx = (idx + (torch.arange(B) * beam_size).unsqueeze(1)).view(B * topk)
+    return (top_hyps.index_select(0, idx).view(B, topk, -1), top_len.index_select(0, idx).view(B, topk), tk_scores,
+            top_lp.index_select(0, idx).view(B, topk, -1))
+
+
 def greedy_outputs(pred, score, log_probs, eos_index):
     """decoders/seq2seq.py:259-276,280-327: lengths = first EOS position (else L) / L; hyps exclude EOS."""
     B, L = pred.shape

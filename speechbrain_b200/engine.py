@@ -180,6 +180,27 @@ class AsrEngine:
                                                 ptr(lp), ctypes.byref(done), self._sp()), "sbk_asr_greedy_from_enc")
         return pred, score, lp, done.value
 
+    def beam_from_enc(self, enc, wav_lens, beam_size, max_steps, min_steps, bos, eos, temperature=1.0,
+                      using_eos_threshold=True, eos_threshold=1.5, length_normalization=True, minus_inf=-1e20):
+        """Device part of the beam search: returns the per-step history (tok, pred, score, lp) [steps, B*beam] on CPU."""
+        enc = enc.float().contiguous()
+        B, T, _ = enc.shape
+        n_bh = B * beam_size
+        S = max(max_steps, 1)
+        tok = torch.zeros(S, n_bh, device=enc.device, dtype=torch.int32)
+        pred = torch.zeros(S, n_bh, device=enc.device, dtype=torch.int32)
+        score = torch.zeros(S, n_bh, device=enc.device, dtype=torch.float32)
+        lp = torch.zeros(S, n_bh, device=enc.device, dtype=torch.float32)
+        wl = wav_lens.float().contiguous().to(enc.device) if wav_lens is not None else None
+        prm = _lib.sbk_beam_params(beam_size, max_steps, min_steps, bos, eos, temperature, int(bool(using_eos_threshold)),
+                                   eos_threshold, int(bool(length_normalization)), minus_inf)
+        done = ctypes.c_int()
+        with torch.cuda.device(self.device):
+            check(lib().sbk_asr_beam_from_enc(self._h, ptr(enc), ptr(wl), B, T, ctypes.byref(prm), ptr(tok), ptr(pred),
+                                              ptr(score), ptr(lp), ctypes.byref(done), self._sp()), "sbk_asr_beam_from_enc")
+        n = done.value
+        return tok[:n].cpu().long(), pred[:n].cpu().long(), score[:n].cpu(), lp[:n].cpu()
+
     def transcribe_greedy_dev(self, wav, wav_lens, max_steps, bos, eos, want_enc=False, pred=None, score=None):
         wav = wav.float().contiguous()
         B, L = wav.shape

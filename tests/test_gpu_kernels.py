@@ -172,3 +172,34 @@ def test_transcribe_end_to_end(dev):
     assert r < 1.5e-3
     pred_h, done_h = eng.transcribe_greedy_host(g["wav"].pin_memory(), g["wav_lens"], n_steps, 1, 2)
     assert torch.equal(pred_h, pred.cpu())
+
+
+@pytest.mark.parametrize("case", ["thr_on", "recipe", "no_eos"])
+def test_beam_search_golden(dev, case):
+    """S2STransformerBeamSearcher (no scorer) vs the REFERENCE's hypotheses / scores / log-probs on the golden encoder
+    states: EOS threshold on, the recipe's settings (temperature 1.15, min steps, no threshold), and the path where no
+    hypothesis ever ends (final fill).  Scores within 2e-2 (fp16 decoder), hypotheses identical."""
+    from speechbrain_b200.decoders.seq2seq import S2STransformerBeamSearcher
+    from speechbrain_b200.lobes.models.transformer.TransformerASR import TransformerASR
+    from speechbrain_b200.nnet.linear import Linear
+    from speechbrain_b200.utils.seeded_init import CONFORMER_LARGE, seeded_asr_state
+    g = torch.load(os.path.join(GOLDEN, "conformer_large_rope.pt"))
+    gb = torch.load(os.path.join(GOLDEN, "beam_conformer_large_rope.pt"))[case]
+    cfg = dict(CONFORMER_LARGE)
+    sd = seeded_asr_state(cfg, 0)
+    tr = TransformerASR(input_size=640, tgt_vocab=5000, d_model=512, nhead=8, num_encoder_layers=12, num_decoder_layers=6,
+                        d_ffn=2048, activation=torch.nn.GELU, encoder_module="conformer", attention_type="RoPEMHA",
+                        normalize_before=True, causal=False)
+    tr.load_state_dict({k[len("Transformer."):]: v for k, v in sd.items() if k.startswith("Transformer.")}, strict=False)
+    lin = Linear(input_size=512, n_neurons=5000)
+    bias = sd["seq_lin.w.bias"].clone()
+    bias[2] += gb["eos_bias"]
+    lin.load_state_dict({"w.weight": sd["seq_lin.w.weight"], "w.bias": bias})
+    bs = S2STransformerBeamSearcher(modules=[tr, lin], bos_index=1, eos_index=2, max_decode_ratio=gb["max_decode_ratio"],
+                                    **gb["kwargs"])
+    hyps, lens, scores, lp = bs(g["enc_out"].to(dev), g["wav_lens"].to(dev))
+    print(f"beam[{case}] hyps {hyps} ref {gb['hyps']} scores {scores.tolist()} ref {gb['scores'].tolist()}")
+    assert hyps == gb["hyps"]
+    assert (scores.cpu() - gb["scores"]).abs().max() < 2e-2
+    assert torch.allclose(lens.cpu(), gb["lens"])
+    assert (lp.cpu() - gb["log_probs"]).abs().max() < 3e-2
