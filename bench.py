@@ -163,7 +163,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--attention", default="RoPEMHA", choices=["RoPEMHA", "RelPosMHAXL"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--lanes", type=int, default=4, help="batches in flight per GPU (engine clones on their own streams)")
+    ap.add_argument("--lanes", type=int, default=8, help="batches in flight per GPU (engine clones on their own streams)")
+    ap.add_argument("--fuse-dec-ln", type=int, default=0, help="1: decoder LayerNorm fused into projections (latency mode)")
     args = ap.parse_args()
     args.steps_ref = max(1, min(args.steps, 2))
     args.warmup_ref = 1 if args.warmup > 0 else 0
@@ -205,6 +206,7 @@ def main():
     NL = max(1, args.lanes)
     lanes = [eng] + [eng.clone() for _ in range(NL - 1)]
     for e in lanes:
+        e.set_decoder_ln_fusion(args.fuse_dec_ln)
         e.set_poll_interval(0)  # exactly DECODE_STEPS steps, never block the host (random weights never emit EOS)
     streams = [torch.cuda.Stream(device=dev) for _ in range(NL)]
     preds = [torch.empty(BATCH, DECODE_STEPS, dtype=torch.int32, device=dev) for _ in range(NL)]
@@ -330,7 +332,7 @@ def main():
                                        f"+ greedy {DECODE_STEPS} steps (6L decoder, KV-cached), 32 x 10 s per GPU",
                            "global_batch": world * BATCH, "utt_seconds": UTT_SECONDS, "enc_frames": T,
                            "parallelism": f"dp{world} (utterance shards, one NCCL all-gather of token ids)",
-                           "lanes": NL, "single_lane_ms_per_step": ms_single, "host_enqueue_ms_per_step": host_enqueue_ms,
+                           "lanes": NL, "decoder_ln_fused": bool(args.fuse_dec_ln), "single_lane_ms_per_step": ms_single, "host_enqueue_ms_per_step": host_enqueue_ms,
                            "l2": "no flush inside the K-step bracket: per-step working set (0.25 GB weights + 0.3 GB "
                                  "activations/KV per lane) exceeds the 126 MB L2; single_lane_ms_per_step is flushed (256 MiB) per step",
                            "timing": f"one CUDA-event pair around K steps, {NL} batches in flight on {NL} streams; max over ranks"},

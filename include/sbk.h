@@ -87,6 +87,9 @@ int sbk_asr_clone(sbk_asr* src, sbk_asr** out);
 /* Greedy early-exit (`has_ended.all()`, decoders/seq2seq.py:256) is polled every n steps with a stream sync;
  * 0 = never poll: run exactly max_steps and never block the host (fully asynchronous enqueue). Default 8. */
 int sbk_asr_set_poll_interval(sbk_asr* m, int every_n_steps);
+/* Decoder pre-norms: 1 (default) = fused into the consuming projection kernel (best single-batch latency);
+ * 0 = separate LayerNorm kernel (less total GPU time when several batches are in flight). Same numerics. */
+int sbk_asr_set_decoder_ln_fusion(sbk_asr* m, int on);
 int sbk_asr_num_frames(const sbk_asr* m, int n_samples, int* T_feat, int* T_enc);
 
 /* ConvolutionFrontEnd.forward (lobes/models/convolution.py:116-320): feats [B,T0,n_mels] -> out [B,T2,F2*C2] fp32 */

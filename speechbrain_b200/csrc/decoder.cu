@@ -261,6 +261,8 @@ int skinny_gemm(const SkinnyArgs& a, cudaStream_t stream) {
             set_error("skinny_gemm(LN): d_model=%d not built (256/512/768/1024)", a.K);
             return SBK_ERR_UNSUPPORTED;
         }
+    } else if (a.K <= 1024 && a.N >= 1024) {
+        e = launch_k(skinny_gemm_kernel<4, 2, 0>, dim3(ceil_div(a.N, 16), ry), dim3(SK_WARPS * 32), 0, stream, a);
     } else if (a.K <= 1024) {
         e = launch_k(skinny_gemm_kernel<4, 1, 0>, dim3(ceil_div(a.N, 8), ry), dim3(SK_WARPS * 32), 0, stream, a);
     } else {
@@ -278,9 +280,11 @@ int skinny_gemm(const SkinnyArgs& a, cudaStream_t stream) {
 // Self-attention: keys = cache positions [0, step]; cross-attention: keys = encoder frames [0, enc_len[utt]).
 // (nn.MultiheadAttention semantics, scale 1/sqrt(d_h) already folded into q.)  head_dim == 64.
 constexpr int DA_WARPS = 4;
+constexpr int DA_CHUNK = 32;  // keys a warp scores per round: 1 per lane for q.k, 8 per lane-group for p.V
+constexpr int DA_KPL = DA_CHUNK / 32, DA_VPL = DA_CHUNK / 4;
 
-__global__ void __launch_bounds__(DA_WARPS * 32) dec_attention_kernel(const DecAttnArgs a) {
-    extern __shared__ float da_smem[];            // [max_keys] scores
+__global__ void __launch_bounds__(DA_WARPS * 32, 4) dec_attention_kernel(const DecAttnArgs a) {
+    __shared__ float s_p[DA_WARPS][DA_CHUNK];
     __shared__ float part_o[DA_WARPS][64];
     __shared__ float part_m[DA_WARPS], part_l[DA_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -299,88 +303,92 @@ __global__ void __launch_bounds__(DA_WARPS * 32) dec_attention_kernel(const DecA
     // beam search: position j of hypothesis r lives in the cache row of the ancestor that wrote it
     const int* lin = nullptr;
     if (a.lineage) lin = a.lineage + static_cast<size_t>((n_keys - 1) & 1) * gridDim.x * a.lin_stride + static_cast<size_t>(r) * a.lin_stride;
-    // full query vector in registers (every lane)
-    float qf[64];
+    // query vector (every lane holds all 64 dims as half2 pairs)
+    uint4 qv[8];
 #pragma unroll
-    for (int e = 0; e < 64; e += 8) {
-        const uint4 qv = *reinterpret_cast<const uint4*>(q + e);
-        const __half2* q2 = reinterpret_cast<const __half2*>(&qv);
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const float2 f = __half22float2(q2[t]);
-            qf[e + 2 * t] = f.x;
-            qf[e + 2 * t + 1] = f.y;
-        }
-    }
-    float mx = -INFINITY;
-    for (int j = kb + lane; j < ke; j += 32) {
-        const __half* kr = kbase + static_cast<size_t>(j) * a.key_stride;
-        if (lin) kr += (static_cast<ptrdiff_t>(lin[j]) - r) * static_cast<ptrdiff_t>(a.row_stride);
-        uint4 kv[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) kv[e] = *reinterpret_cast<const uint4*>(kr + e * 8);
-        float dot = 0.0f;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const __half2* k2 = reinterpret_cast<const __half2*>(&kv[e]);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const float2 kf = __half22float2(k2[t]);
-                dot = fmaf(kf.x, qf[e * 8 + 2 * t], dot);
-                dot = fmaf(kf.y, qf[e * 8 + 2 * t + 1], dot);
-            }
-        }
-        da_smem[j] = dot;
-        mx = fmaxf(mx, dot);
-    }
-    mx = warp_max(mx);
-    float sum = 0.0f;
-    for (int j = kb + lane; j < ke; j += 32) {
-        const float p = __expf(da_smem[j] - mx);
-        da_smem[j] = p;
-        sum += p;
-    }
-    sum = warp_sum(sum);
-    __syncwarp();
-    // p.V : lane group gq handles keys kb+gq, kb+gq+4, ...; lane%8 owns dims [8*(lane%8), +8)
+    for (int e = 0; e < 8; ++e) qv[e] = *reinterpret_cast<const uint4*>(q + e * 8);
     const int gq = lane >> 3, dl = (lane & 7) * 8;
+    float m_run = -INFINITY, l_run = 0.0f;
     float o[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) o[e] = 0.0f;
-    int j = kb + gq;
-    for (; j + 12 < ke; j += 16) {  // 4 keys in flight per lane
-        uint4 vv[4];
-        float p[4];
+    for (int c0 = kb; c0 < ke; c0 += DA_CHUNK) {
+        // ---- issue every load of this chunk up front: 2 keys x 128 B (K) and 16 keys x 16 B (V) per lane
+        uint4 kv[DA_KPL][8];
+        uint4 vv[DA_VPL];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const __half* vr = vbase + static_cast<size_t>(j + 4 * u) * a.key_stride + dl;
-            if (lin) vr += (static_cast<ptrdiff_t>(lin[j + 4 * u]) - r) * static_cast<ptrdiff_t>(a.row_stride);
-            vv[u] = *reinterpret_cast<const uint4*>(vr);
-            p[u] = da_smem[j + 4 * u];
-        }
+        for (int t = 0; t < DA_KPL; ++t) {
+            const int j = c0 + lane + 32 * t;
+            if (j < ke) {
+                const __half* kr = kbase + static_cast<size_t>(j) * a.key_stride;
+                if (lin) kr += (static_cast<ptrdiff_t>(lin[j]) - r) * static_cast<ptrdiff_t>(a.row_stride);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const __half2* v2 = reinterpret_cast<const __half2*>(&vv[u]);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const float2 vf = __half22float2(v2[t]);
-                o[2 * t] = fmaf(p[u], vf.x, o[2 * t]);
-                o[2 * t + 1] = fmaf(p[u], vf.y, o[2 * t + 1]);
+                for (int e = 0; e < 8; ++e) kv[t][e] = *reinterpret_cast<const uint4*>(kr + e * 8);
             }
         }
-    }
-    for (; j < ke; j += 4) {
-        const __half* vr = vbase + static_cast<size_t>(j) * a.key_stride + dl;
-        if (lin) vr += (static_cast<ptrdiff_t>(lin[j]) - r) * static_cast<ptrdiff_t>(a.row_stride);
-        const uint4 vv = *reinterpret_cast<const uint4*>(vr);
-        const float p = da_smem[j];
-        const __half2* v2 = reinterpret_cast<const __half2*>(&vv);
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const float2 vf = __half22float2(v2[t]);
-            o[2 * t] = fmaf(p, vf.x, o[2 * t]);
-            o[2 * t + 1] = fmaf(p, vf.y, o[2 * t + 1]);
+        for (int i = 0; i < DA_VPL; ++i) {
+            const int j = c0 + gq + 4 * i;
+            if (j < ke) {
+                const __half* vr = vbase + static_cast<size_t>(j) * a.key_stride + dl;
+                if (lin) vr += (static_cast<ptrdiff_t>(lin[j]) - r) * static_cast<ptrdiff_t>(a.row_stride);
+                vv[i] = *reinterpret_cast<const uint4*>(vr);
+            } else {
+                vv[i] = make_uint4(0u, 0u, 0u, 0u);
+            }
         }
+        // ---- scores
+        float sc[DA_KPL];
+#pragma unroll
+        for (int t = 0; t < DA_KPL; ++t) {
+            const int j = c0 + lane + 32 * t;
+            float dot = -INFINITY;
+            if (j < ke) {
+                dot = 0.0f;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const __half2* k2 = reinterpret_cast<const __half2*>(&kv[t][e]);
+                    const __half2* q2 = reinterpret_cast<const __half2*>(&qv[e]);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float2 kf = __half22float2(k2[u]), qf = __half22float2(q2[u]);
+                        dot = fmaf(kf.x, qf.x, dot);
+                        dot = fmaf(kf.y, qf.y, dot);
+                    }
+                }
+            }
+            sc[t] = dot;
+        }
+        float cm = sc[0];
+#pragma unroll
+        for (int t = 1; t < DA_KPL; ++t) cm = fmaxf(cm, sc[t]);
+        const float m_new = fmaxf(m_run, warp_max(cm));
+        const float alpha = (m_run == -INFINITY) ? 0.0f : __expf(m_run - m_new);
+        float psum = 0.0f;
+#pragma unroll
+        for (int t = 0; t < DA_KPL; ++t) {
+            const float p = (sc[t] == -INFINITY) ? 0.0f : __expf(sc[t] - m_new);
+            s_p[warp][lane + 32 * t] = p;
+            psum += p;
+        }
+        l_run = l_run * alpha + warp_sum(psum);
+        m_run = m_new;
+        __syncwarp();
+        // ---- p.V : lane group gq owns keys c0 + gq + 4 i; lane % 8 owns dims [dl, dl + 8)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] *= alpha;
+#pragma unroll
+        for (int i = 0; i < DA_VPL; ++i) {
+            const float p = s_p[warp][gq + 4 * i];
+            const __half2* v2 = reinterpret_cast<const __half2*>(&vv[i]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float2 vf = __half22float2(v2[u]);
+                o[2 * u] = fmaf(p, vf.x, o[2 * u]);
+                o[2 * u + 1] = fmaf(p, vf.y, o[2 * u + 1]);
+            }
+        }
+        __syncwarp();
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -391,7 +399,7 @@ __global__ void __launch_bounds__(DA_WARPS * 32) dec_attention_kernel(const DecA
 #pragma unroll
         for (int e = 0; e < 8; ++e) part_o[warp][dl + e] = o[e];
     }
-    if (lane == 0) { part_m[warp] = mx; part_l[warp] = sum; }
+    if (lane == 0) { part_m[warp] = m_run; part_l[warp] = l_run; }
     __syncthreads();
     if (threadIdx.x < 64) {
         float M = part_m[0];
@@ -411,8 +419,7 @@ __global__ void __launch_bounds__(DA_WARPS * 32) dec_attention_kernel(const DecA
 int dec_attention(const DecAttnArgs& a, int n_rows, int max_keys, cudaStream_t stream) {
     SBK_REQUIRE(a.dh == 64, "dec_attention: head_dim=%d not built (64 only)", a.dh);
     if (n_rows == 0) return SBK_OK;
-    const size_t smem = static_cast<size_t>(max_keys) * sizeof(float);
-    SBK_REQUIRE(smem <= 40 * 1024, "dec_attention: too many keys (%d)", max_keys);
+    const size_t smem = 0;
     DecAttnArgs b = a;
     b.n_keys_fixed = max_keys;
     SBK_CUDA_CHECK(launch_k(dec_attention_kernel, dim3(n_rows, a.H), dim3(DA_WARPS * 32), smem, stream, b));

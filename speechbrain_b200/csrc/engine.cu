@@ -98,6 +98,7 @@ struct AsrModel {
     cudaGraphExec_t pipe_graph = nullptr;
     long long pipe_nodes = 0;
     int* weight_refs = nullptr;  // weights (arena + fbank plan) are shared between a handle and its clones (lanes)
+    int fuse_dec_ln = 1;         // 1: LayerNorm inside the projection kernel (latency); 0: separate LN kernel (throughput)
     int poll_every = 8;          // greedy early-exit poll interval in steps; 0 = never sync, run exactly max_steps
     bool has_fbank = false, has_cnn = false, has_enc = false, has_dec = false;
     cudaStream_t cap_stream = nullptr;  // private stream for graph capture (the legacy default stream cannot capture)
@@ -531,6 +532,20 @@ __global__ void abs_len_kernel(const float* rel, int B, int T, int* out) {
     if (i < B) out[i] = min(T, max(0, __float2int_rn(rel[i] * static_cast<float>(T))));
 }
 
+// Decoder pre-norm feeding a projection: either fused into the projection kernel (a.X) or a separate tiny kernel
+// writing fp16 (a.A).  Fusion saves a launch per projection (single-batch latency); the separate kernel avoids
+// recomputing the same 32-row LayerNorm in ~100-300 CTAs (GPU time when several batches are in flight).
+static int dec_ln(AsrModel* m, SkinnyArgs& a, const float* g, const float* bta, int rows, cudaStream_t st) {
+    AsrModel::Buf& b = m->b;
+    const int d = m->cfg.d_model;
+    if (m->fuse_dec_ln) {
+        a.X = b.dx; a.ln_g = g; a.ln_b = bta; a.ln_eps = 1e-6f;
+        return SBK_OK;
+    }
+    a.A = b.dh16; a.lda = d;
+    return layernorm_rows(b.dx, b.dh16, true, g, bta, rows, d, 1e-6f, false, st);
+}
+
 static int enqueue_decode_layers(AsrModel* m, int rows, int rows_per_utt, int T, int S_max, const int* lineage,
                                  cudaStream_t st) {
     const sbk_asr_config& c = m->cfg;
@@ -544,7 +559,7 @@ static int enqueue_decode_layers(AsrModel* m, int rows, int rows_per_utt, int T,
         __half* kc = b.kcache + (size_t)l * rows * S_max * d;
         __half* vc = b.vcache + (size_t)l * rows * S_max * d;
         SkinnyArgs a{};  // LN1 + self-attention in_proj; k/v appended to the cache at position step
-        a.X = b.dx; a.ln_g = w.n1g; a.ln_b = w.n1b; a.ln_eps = 1e-6f;
+        RC(dec_ln(m, a, w.n1g, w.n1b, rows, st));
         a.W = w.w_self_in; a.ldw = d; a.bias = w.b_self_in; a.n_rows = rows; a.N = 3 * d; a.K = d;
         a.epi = SK_QKV_CACHE; a.out = b.dq16; a.ldo = d; a.kcache = kc; a.vcache = vc; a.step_ptr = b.step; a.S_max = S_max;
         a.d = d; a.q_scale = 1.0f;
@@ -558,7 +573,8 @@ static int enqueue_decode_layers(AsrModel* m, int rows, int rows_per_utt, int T,
         a.N = d; a.K = d; a.epi = SK_RESID; a.out = b.dx; a.ldo = d;
         RC(skinny_gemm(a, st));
         // cross attention: LN2 + (pre-scaled) query projection
-        a = SkinnyArgs{}; a.X = b.dx; a.ln_g = w.n2g; a.ln_b = w.n2b; a.ln_eps = 1e-6f;
+        a = SkinnyArgs{};
+        RC(dec_ln(m, a, w.n2g, w.n2b, rows, st));
         a.W = w.w_cross_q; a.ldw = d; a.bias = w.b_cross_q; a.n_rows = rows;
         a.N = d; a.K = d; a.epi = SK_F16; a.out = b.dq16; a.ldo = d;
         RC(skinny_gemm(a, st));
@@ -571,7 +587,8 @@ static int enqueue_decode_layers(AsrModel* m, int rows, int rows_per_utt, int T,
         a.N = d; a.K = d; a.epi = SK_RESID; a.out = b.dx; a.ldo = d;
         RC(skinny_gemm(a, st));
         // feed-forward: LN3 + ffn1 + activation, then ffn2 + residual
-        a = SkinnyArgs{}; a.X = b.dx; a.ln_g = w.n3g; a.ln_b = w.n3b; a.ln_eps = 1e-6f;
+        a = SkinnyArgs{};
+        RC(dec_ln(m, a, w.n3g, w.n3b, rows, st));
         a.W = w.w_ffn1; a.ldw = d; a.bias = w.b_ffn1; a.n_rows = rows;
         a.N = F; a.K = d; a.epi = ffn_epi; a.out = b.df16; a.ldo = F;
         RC(skinny_gemm(a, st));
@@ -580,7 +597,7 @@ static int enqueue_decode_layers(AsrModel* m, int rows, int rows_per_utt, int T,
         RC(skinny_gemm(a, st));
     }
     SkinnyArgs a{};  // final LayerNorm + seq_lin
-    a.X = b.dx; a.ln_g = m->dec_norm_g; a.ln_b = m->dec_norm_b; a.ln_eps = 1e-6f;
+    RC(dec_ln(m, a, m->dec_norm_g, m->dec_norm_b, rows, st));
     a.W = m->w_lin; a.ldw = d; a.bias = m->b_lin; a.n_rows = rows; a.N = c.vocab; a.K = d;
     a.epi = SK_F32; a.out = b.logits; a.ldo = c.vocab;
     RC(skinny_gemm(a, st));
@@ -784,6 +801,15 @@ int sbk_asr_create(const sbk_asr_config* cfg, const sbk_tensor* weights, int n_w
 void sbk_asr_destroy(sbk_asr* m) { asr_destroy(reinterpret_cast<AsrModel*>(m)); }
 int sbk_asr_clone(sbk_asr* src, sbk_asr** out) {
     return asr_clone(reinterpret_cast<AsrModel*>(src), reinterpret_cast<AsrModel**>(out));
+}
+int sbk_asr_set_decoder_ln_fusion(sbk_asr* m, int on) {
+    AsrModel* mm = reinterpret_cast<AsrModel*>(m);
+    if (mm->fuse_dec_ln != (on != 0)) {  // cached graphs were captured with the other kernel sequence
+        if (mm->step_graph) { cudaGraphExecDestroy(mm->step_graph); mm->step_graph = nullptr; mm->graph_rows = -1; }
+        if (mm->pipe_graph) { cudaGraphExecDestroy(mm->pipe_graph); mm->pipe_graph = nullptr; }
+    }
+    mm->fuse_dec_ln = on != 0;
+    return SBK_OK;
 }
 int sbk_asr_set_poll_interval(sbk_asr* m, int every_n_steps) {
     reinterpret_cast<AsrModel*>(m)->poll_every = every_n_steps;

@@ -144,6 +144,19 @@ constexpr int EPI_STG_BYTES = 32 * EPI_STG_PITCH;  // per warp
 template <int MODE, int ACT>
 __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmEpilogue& e, const uint32_t (&acc)[32], uint8_t* stg,
                                                          int row_base, int col0, int M, int lane) {
+    float4 res[8];
+    if constexpr (MODE == EPI_RESID) {
+        // out aliases resid (x += ...): issue all 8 residual loads up front -- before the epilogue math and before the
+        // first store (otherwise the compiler must order load i after store i-1 and every iteration eats a full
+        // L2/HBM round trip; measured as the dominant long-scoreboard stall of the N=512 GEMMs)
+        const int seg = lane & 7, rsub = lane >> 3;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int row = row_base + i * 4 + rsub;
+            res[i] = row < M ? __ldcg(reinterpret_cast<const float4*>(e.resid + static_cast<size_t>(row) * e.ldo + col0 + seg * 4))
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
@@ -227,12 +240,10 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmEpilogue& e, 
             const int row = row_base + r;
             if (row < M) {
                 float4 val = *reinterpret_cast<const float4*>(stg + r * EPI_STG_PITCH + seg * 16);
-                const size_t off = static_cast<size_t>(row) * e.ldo + col0 + seg * 4;
                 if constexpr (MODE == EPI_RESID) {
-                    const float4 x = *reinterpret_cast<const float4*>(e.resid + off);
-                    val.x += x.x; val.y += x.y; val.z += x.z; val.w += x.w;
+                    val.x += res[i].x; val.y += res[i].y; val.z += res[i].z; val.w += res[i].w;
                 }
-                *reinterpret_cast<float4*>(outp + off) = val;
+                *reinterpret_cast<float4*>(outp + static_cast<size_t>(row) * e.ldo + col0 + seg * 4) = val;
             }
         }
     } else {

@@ -126,6 +126,9 @@ class AsrEngine:
     def set_poll_interval(self, every_n_steps):
         check(lib().sbk_asr_set_poll_interval(self._h, int(every_n_steps)), "sbk_asr_set_poll_interval")
 
+    def set_decoder_ln_fusion(self, on):
+        check(lib().sbk_asr_set_decoder_ln_fusion(self._h, int(bool(on))), "sbk_asr_set_decoder_ln_fusion")
+
     def _sp(self):
         return stream_ptr(self.device)
 
