@@ -255,14 +255,15 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <int DH, bool RELPOS>
+template <int DH, int DHP, bool RELPOS>  // DHP = DH rounded up to a multiple of 16 (zero-padded in shared memory)
 __global__ void __launch_bounds__(128)
 encoder_attention_kernel(const __half* __restrict__ qkv, int ld, int T, const int* __restrict__ lens,
                          const float* __restrict__ pos_u, const float* __restrict__ pos_v,
                          const __half* __restrict__ P, int ldp, float scale, __half* __restrict__ out, int ldo) {
-    constexpr int STR = DH + 8;  // padded row stride (halfs): conflict-free fragment loads
-    constexpr int KS = DH / 16;
-    constexpr int GW = 80;       // relpos band width (16 + 64 - 1 rounded to 8)
+    constexpr int STR = DHP + 8;  // padded row stride (halfs): conflict-free fragment loads
+    constexpr int KS = DHP / 16;
+    constexpr int GW = 80;        // relpos band width (16 + 64 - 1 rounded to 8)
+    constexpr int VPR = DH / 4;   // 8-byte vectors per row (DH % 4 == 0)
     extern __shared__ __align__(16) uint8_t att_smem[];
     __half* Qs = reinterpret_cast<__half*>(att_smem);  // [64][STR]   (RELPOS: Qu)
     __half* Ks = Qs + ATT_BQ * STR;                    // [64][STR]
@@ -275,33 +276,40 @@ encoder_attention_kernel(const __half* __restrict__ qkv, int ld, int T, const in
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
     const int len = lens ? min(lens[b], T) : T;
     const __half* base = qkv + static_cast<size_t>(b) * T * ld + h * 3 * DH;
-    constexpr int VPR = DH / 8;  // 16-byte vectors per row
 
+    if constexpr (DHP != DH) {  // zero the padding columns once (they take part in the k-loop / PV n-tiles)
+        constexpr int PADC = DHP - DH;
+        const int n_rows_pad = 4 * ATT_BQ + (RELPOS ? T : 0);
+        for (int i = threadIdx.x; i < n_rows_pad * PADC; i += blockDim.x) {
+            const int r = i / PADC, cc = i - r * PADC;
+            Qs[r * STR + DH + cc] = __float2half(0.0f);  // Qs, Ks, Vs, Qv, Ps are contiguous with the same stride
+        }
+    }
     // ---- stage Q (and RELPOS: Qu/Qv, P_h)
     for (int i = threadIdx.x; i < ATT_BQ * VPR; i += blockDim.x) {
-        const int r = i / VPR, v8 = i - r * VPR;
-        uint4 val = make_uint4(0, 0, 0, 0);
-        if (i0 + r < T) val = *reinterpret_cast<const uint4*>(base + static_cast<size_t>(i0 + r) * ld + v8 * 8);
+        const int r = i / VPR, v4 = i - r * VPR;
+        uint2 val = make_uint2(0, 0);
+        if (i0 + r < T) val = *reinterpret_cast<const uint2*>(base + static_cast<size_t>(i0 + r) * ld + v4 * 4);
         if constexpr (RELPOS) {
             const __half* hv = reinterpret_cast<const __half*>(&val);
-            __half qu[8], qv[8];
+            __half qu[4], qv[4];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
+            for (int e = 0; e < 4; ++e) {
                 const float q = __half2float(hv[e]);
-                qu[e] = __float2half_rn((q + __ldg(pos_u + h * DH + v8 * 8 + e)) * scale);
-                qv[e] = __float2half_rn((q + __ldg(pos_v + h * DH + v8 * 8 + e)) * scale);
+                qu[e] = __float2half_rn((q + __ldg(pos_u + h * DH + v4 * 4 + e)) * scale);
+                qv[e] = __float2half_rn((q + __ldg(pos_v + h * DH + v4 * 4 + e)) * scale);
             }
-            *reinterpret_cast<uint4*>(Qs + r * STR + v8 * 8) = *reinterpret_cast<uint4*>(qu);
-            *reinterpret_cast<uint4*>(Qv + r * STR + v8 * 8) = *reinterpret_cast<uint4*>(qv);
+            *reinterpret_cast<uint2*>(Qs + r * STR + v4 * 4) = *reinterpret_cast<uint2*>(qu);
+            *reinterpret_cast<uint2*>(Qv + r * STR + v4 * 4) = *reinterpret_cast<uint2*>(qv);
         } else {
-            *reinterpret_cast<uint4*>(Qs + r * STR + v8 * 8) = val;
+            *reinterpret_cast<uint2*>(Qs + r * STR + v4 * 4) = val;
         }
     }
     if constexpr (RELPOS) {
         for (int i = threadIdx.x; i < T * VPR; i += blockDim.x) {
-            const int r = i / VPR, v8 = i - r * VPR;
-            *reinterpret_cast<uint4*>(Ps + r * STR + v8 * 8) =
-                *reinterpret_cast<const uint4*>(P + static_cast<size_t>(r) * ldp + h * DH + v8 * 8);
+            const int r = i / VPR, v4 = i - r * VPR;
+            *reinterpret_cast<uint2*>(Ps + r * STR + v4 * 4) =
+                *reinterpret_cast<const uint2*>(P + static_cast<size_t>(r) * ldp + h * DH + v4 * 4);
         }
     }
     __syncthreads();
@@ -329,9 +337,9 @@ encoder_attention_kernel(const __half* __restrict__ qkv, int ld, int T, const in
         }
     }
 
-    float o[DH / 8][4];
+    float o[DHP / 8][4];
 #pragma unroll
-    for (int i = 0; i < DH / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.0f;
+    for (int i = 0; i < DHP / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.0f;
     float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.0f, 0.0f};
     const float LOG2E = 1.4426950408889634f;
     const int n_blk = (len + ATT_BK - 1) / ATT_BK;
@@ -340,15 +348,15 @@ encoder_attention_kernel(const __half* __restrict__ qkv, int ld, int T, const in
         const int j0 = jb * ATT_BK;
         __syncthreads();  // previous block's K/V fully consumed
         for (int i = threadIdx.x; i < ATT_BK * VPR; i += blockDim.x) {
-            const int r = i / VPR, v8 = i - r * VPR;
-            uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+            const int r = i / VPR, v4 = i - r * VPR;
+            uint2 kv = make_uint2(0, 0), vv = make_uint2(0, 0);
             if (j0 + r < T) {
-                const __half* rowp = base + static_cast<size_t>(j0 + r) * ld + v8 * 8;
-                kv = *reinterpret_cast<const uint4*>(rowp + DH);
-                vv = *reinterpret_cast<const uint4*>(rowp + 2 * DH);
+                const __half* rowp = base + static_cast<size_t>(j0 + r) * ld + v4 * 4;
+                kv = *reinterpret_cast<const uint2*>(rowp + DH);
+                vv = *reinterpret_cast<const uint2*>(rowp + 2 * DH);
             }
-            *reinterpret_cast<uint4*>(Ks + r * STR + v8 * 8) = kv;
-            *reinterpret_cast<uint4*>(Vs + r * STR + v8 * 8) = vv;
+            *reinterpret_cast<uint2*>(Ks + r * STR + v4 * 4) = kv;
+            *reinterpret_cast<uint2*>(Vs + r * STR + v4 * 4) = vv;
         }
         __syncthreads();
 
@@ -431,7 +439,7 @@ encoder_attention_kernel(const __half* __restrict__ qkv, int ld, int T, const in
             l_run[r] = l_run[r] * alpha[r] + rs[r];
         }
 #pragma unroll
-        for (int nt = 0; nt < DH / 8; ++nt) {
+        for (int nt = 0; nt < DHP / 8; ++nt) {
             o[nt][0] *= alpha[0]; o[nt][1] *= alpha[0];
             o[nt][2] *= alpha[1]; o[nt][3] *= alpha[1];
         }
@@ -439,7 +447,7 @@ encoder_attention_kernel(const __half* __restrict__ qkv, int ld, int T, const in
 #pragma unroll
         for (int kk = 0; kk < ATT_BK / 16; ++kk) {
 #pragma unroll
-            for (int nt = 0; nt < DH / 8; ++nt) {
+            for (int nt = 0; nt < DHP / 8; ++nt) {
                 uint32_t b0, b1;
                 ldmatrix_x2_trans(b0, b1, Vs + (kk * 16 + (lane & 15)) * STR + nt * 8);
                 mma16816(o[nt], pa[kk], b0, b1);
@@ -451,35 +459,50 @@ encoder_attention_kernel(const __half* __restrict__ qkv, int ld, int T, const in
     const float inv0 = 1.0f / l_run[0], inv1 = 1.0f / l_run[1];
     __half* ob = out + static_cast<size_t>(b) * T * ldo + h * DH;
 #pragma unroll
-    for (int nt = 0; nt < DH / 8; ++nt) {
+    for (int nt = 0; nt < DHP / 8; ++nt) {
         const int col = nt * 8 + 2 * c;
+        if (col >= DH) continue;  // zero-padding columns
         if (r0 < T) *reinterpret_cast<uint32_t*>(ob + static_cast<size_t>(r0) * ldo + col) = pack_half2(o[nt][0] * inv0, o[nt][1] * inv0);
         if (r1 < T) *reinterpret_cast<uint32_t*>(ob + static_cast<size_t>(r1) * ldo + col) = pack_half2(o[nt][2] * inv1, o[nt][3] * inv1);
     }
+}
+
+template <int DH, int DHP>
+static int launch_encoder_attention(const __half* qkv, int ld, int B, int T, int H, const int* lens, bool relpos,
+                                    const float* pos_u, const float* pos_v, const __half* P, int ldp, float scale,
+                                    __half* out, int ldo, cudaStream_t stream) {
+    constexpr int STR = DHP + 8;
+    dim3 grid(ceil_div(T, ATT_BQ), H, B);
+    if (!relpos) {
+        const size_t smem = 4ull * ATT_BQ * STR * 2;
+        auto kern = encoder_attention_kernel<DH, DHP, false>;
+        SBK_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, 128, smem, stream>>>(qkv, ld, T, lens, nullptr, nullptr, nullptr, 0, scale, out, ldo);
+    } else {
+        SBK_REQUIRE(ldp % 4 == 0, "encoder_attention: bad ldp");
+        const size_t smem = 4ull * ATT_BQ * STR * 2 + static_cast<size_t>(T) * STR * 2 + 4ull * 16 * 81 * 4;
+        SBK_REQUIRE(smem <= 220 * 1024, "encoder_attention(RelPos): T=%d too long for the shared-memory table", T);
+        auto kern = encoder_attention_kernel<DH, DHP, true>;
+        SBK_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, 128, smem, stream>>>(qkv, ld, T, lens, pos_u, pos_v, P, ldp, scale, out, ldo);
+    }
+    SBK_LAUNCH_CHECK();
+    return SBK_OK;
 }
 
 // qkv [B*T, ld] fp16 with per-head [q | k | v] blocks of head_dim; out [B*T, ldo] fp16.
 int encoder_attention(const __half* qkv, int ld, int B, int T, int H, int head_dim, const int* lens, bool relpos,
                       const float* pos_u, const float* pos_v, const __half* P, int ldp, float scale, __half* out,
                       int ldo, cudaStream_t stream) {
-    SBK_REQUIRE(head_dim == 64, "encoder_attention: head_dim=%d not built (64 only)", head_dim);
-    SBK_REQUIRE(ld % 8 == 0 && ldo % 2 == 0, "encoder_attention: bad leading dims");
-    constexpr int DH = 64, STR = DH + 8;
-    dim3 grid(ceil_div(T, ATT_BQ), H, B);
-    if (!relpos) {
-        const size_t smem = 3ull * ATT_BQ * STR * 2;
-        encoder_attention_kernel<DH, false><<<grid, 128, smem, stream>>>(qkv, ld, T, lens, nullptr, nullptr, nullptr, 0,
-                                                                         scale, out, ldo);
-    } else {
-        SBK_REQUIRE(ldp % 8 == 0, "encoder_attention: bad ldp");
-        const size_t smem = 4ull * ATT_BQ * STR * 2 + static_cast<size_t>(T) * STR * 2 + 4ull * 16 * 81 * 4;
-        SBK_REQUIRE(smem <= 220 * 1024, "encoder_attention(RelPos): T=%d too long for the shared-memory table", T);
-        auto kern = encoder_attention_kernel<DH, true>;
-        SBK_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, 128, smem, stream>>>(qkv, ld, T, lens, pos_u, pos_v, P, ldp, scale, out, ldo);
-    }
-    SBK_LAUNCH_CHECK();
-    return SBK_OK;
+    SBK_REQUIRE(ld % 4 == 0 && ldo % 2 == 0, "encoder_attention: bad leading dims");
+    if (head_dim == 64)
+        return launch_encoder_attention<64, 64>(qkv, ld, B, T, H, lens, relpos, pos_u, pos_v, P, ldp, scale, out, ldo, stream);
+    if (head_dim == 36)  // conformer_small: 144 / 4 heads, zero-padded to 48 for the k16 steps
+        return launch_encoder_attention<36, 48>(qkv, ld, B, T, H, lens, relpos, pos_u, pos_v, P, ldp, scale, out, ldo, stream);
+    if (head_dim == 32)
+        return launch_encoder_attention<32, 32>(qkv, ld, B, T, H, lens, relpos, pos_u, pos_v, P, ldp, scale, out, ldo, stream);
+    set_error("encoder_attention: head_dim=%d not built (64, 36, 32)", head_dim);
+    return SBK_ERR_UNSUPPORTED;
 }
 
 }  // namespace sbk

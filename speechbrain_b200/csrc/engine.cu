@@ -165,7 +165,10 @@ int asr_create(const sbk_asr_config* cfg, const sbk_tensor* weights, int n_weigh
     SBK_REQUIRE(c.attention_type == SBK_ATT_ROPE || c.attention_type == SBK_ATT_RELPOS,
                 "asr_create: attention_type must be RoPEMHA or RelPosMHAXL");
     const int d = c.d_model, dh = d / c.nhead, F = c.d_ffn, K = c.kernel_size;
-    SBK_REQUIRE(dh == 64, "asr_create: head_dim=%d not built yet (64 only)", dh);
+    SBK_REQUIRE(dh == 64 || dh == 36 || dh == 32, "asr_create: encoder head_dim=%d not built (64, 36, 32)", dh);
+    SBK_REQUIRE(!((c.parts & SBK_PART_DECODER) && c.num_decoder_layers > 0) || dh == 64,
+                "asr_create: the decoder kernels are built for head_dim 64 only (got %d)", dh);
+    SBK_REQUIRE(c.attention_type != SBK_ATT_ROPE || dh % 32 == 0, "asr_create: RoPEMHA needs head_dim %% 32 == 0");
     std::map<std::string, std::pair<const float*, int64_t>> w;
     for (int i = 0; i < n_weights; ++i) w[weights[i].name] = {weights[i].data, weights[i].numel};
 

@@ -55,8 +55,8 @@ class TransformerASR(torch.nn.Module):
             unsupported.append("output_hidden_states=True")
         if conformer_activation is not None and getattr(conformer_activation, "__name__", "") not in ("Swish", "SiLU"):
             unsupported.append("conformer_activation other than Swish")
-        if d_model % nhead or d_model // nhead != 64:
-            unsupported.append(f"head_dim={d_model // max(nhead, 1)} (64 only in this round)")
+        if d_model % nhead or d_model // nhead not in (64, 36, 32):
+            unsupported.append(f"head_dim={d_model // max(nhead, 1)} (64, 36 or 32)")
         if unsupported:
             raise NotImplementedError("speechbrain_b200.TransformerASR: not built: " + ", ".join(unsupported))
         act_name = getattr(activation, "__name__", str(activation))

@@ -109,17 +109,30 @@ def test_input_norm_golden(dev):
 
 
 # ----------------------------------------------------------------------------------------- model stages
-def _engine(cfg, dev):
+def _engine(cfg, dev, parts=("fbank", "cnn", "encoder", "decoder")):
     from speechbrain_b200.engine import AsrEngine
     from speechbrain_b200.utils.seeded_init import seeded_asr_state
     sd = seeded_asr_state(cfg, 0)
-    return AsrEngine(cfg, sd, device=dev), sd
+    return AsrEngine(cfg, sd, device=dev, parts=parts), sd
 
 
 def _cfg_from_gold(g):
     from speechbrain_b200.utils.seeded_init import CONFORMER_LARGE, CONFORMER_SMALL
     base = CONFORMER_LARGE if g["cfg"]["name"] == "conformer_large" else CONFORMER_SMALL
     return dict(base, attention_type=g["cfg"]["attention_type"])
+
+
+def test_conformer_small_encoder_golden(dev):
+    """BASELINE config 2 family: Conformer-small (12L / 144d / 4 heads of 36 / RelPosMHAXL / n_fft 400) CNN + encoder
+    vs the reference goldens (head_dim 36 is zero-padded to 48 in the attention kernel; K = 144 GEMMs)."""
+    g = torch.load(os.path.join(GOLDEN, "conformer_small_relpos.pt"))
+    cfg = _cfg_from_gold(g)
+    eng, sd = _engine(cfg, dev, parts=("cnn", "encoder"))
+    cnn_shape = (g["cnn_out"].shape[0], g["cnn_out"].shape[1], -1)
+    enc = eng.encode_from_cnn(g["cnn_out"].reshape(cnn_shape).to(dev), g["wav_lens"].to(dev)).cpu()
+    r = _rel(enc, g["enc_out"])
+    print(f"[conformer_small_relpos] encoder rel-L2 err {r:.3e} max abs {(enc - g['enc_out']).abs().max():.3e}")
+    assert r < 1e-3
 
 
 @pytest.mark.parametrize("tag", ["conformer_large_rope", "conformer_large_relpos"])
