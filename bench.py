@@ -164,10 +164,14 @@ def main():
     ap.add_argument("--attention", default="RoPEMHA", choices=["RoPEMHA", "RelPosMHAXL"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lanes", type=int, default=8, help="batches in flight per GPU (engine clones on their own streams)")
+    ap.add_argument("--group", type=int, default=8, help="batches whose decode is coalesced into one greedy loop (engine-level)")
+    ap.add_argument("--decode-steps", type=int, default=48, help="diagnostic: override the pinned 48 greedy steps")
     ap.add_argument("--fuse-dec-ln", type=int, default=0, help="1: decoder LayerNorm fused into projections (latency mode)")
     args = ap.parse_args()
     args.steps_ref = max(1, min(args.steps, 2))
     args.warmup_ref = 1 if args.warmup > 0 else 0
+    global DECODE_STEPS
+    DECODE_STEPS = args.decode_steps
     if args.impl == "reference":
         return run_reference(args)
 
@@ -202,32 +206,42 @@ def main():
     gathered = [torch.empty(BATCH, DECODE_STEPS, dtype=torch.int32, device=dev) for _ in range(world)] if world > 1 else None
     lib = _lib.lib()
 
-    # ---- lanes: independent batches in flight on their own streams; weights shared, workspaces private
-    NL = max(1, args.lanes)
+    # ---- lanes: independent GROUPS of batches in flight on their own streams; weights shared, workspaces private.
+    # A group = G batches of 32 x 10 s: each batch is encoded on its own, the G*32 hypotheses are decoded together.
+    G = max(1, min(args.group, K))
+    sizes = [G] * (K // G) + ([K % G] if K % G else [])  # exactly K batches are timed; the last group may be smaller
+    n_calls = len(sizes)
+    NL = max(1, min(args.lanes, n_calls))
     lanes = [eng] + [eng.clone() for _ in range(NL - 1)]
     for e in lanes:
         e.set_decoder_ln_fusion(args.fuse_dec_ln)
         e.set_poll_interval(0)  # exactly DECODE_STEPS steps, never block the host (random weights never emit EOS)
     streams = [torch.cuda.Stream(device=dev) for _ in range(NL)]
-    preds = [torch.empty(BATCH, DECODE_STEPS, dtype=torch.int32, device=dev) for _ in range(NL)]
+    wavs = [[wav_dev.clone() for _ in range(G)] for _ in range(NL)]
+    lens = [[lens_dev.clone() for _ in range(G)] for _ in range(NL)]
+    preds = [[torch.empty(BATCH, DECODE_STEPS, dtype=torch.int32, device=dev) for _ in range(G)] for _ in range(NL)]
     scores = [torch.empty(BATCH, DECODE_STEPS, dtype=torch.float32, device=dev) for _ in range(NL)]
-    preds_host = [torch.empty(BATCH, DECODE_STEPS, dtype=torch.int32).pin_memory() for _ in range(NL)]
+    preds_host = [[torch.empty(BATCH, DECODE_STEPS, dtype=torch.int32).pin_memory() for _ in range(G)] for _ in range(NL)]
 
     def step_dev(i):
-        ln = i % NL
+        ln, g = i % NL, sizes[i % n_calls]
         with torch.cuda.stream(streams[ln]):
-            eng_l = lanes[ln]
-            pred, _, _, done = eng_l.transcribe_greedy_dev(wav_dev, lens_dev, DECODE_STEPS, BOS, EOS, pred=preds[ln], score=scores[ln])
+            lanes[ln].transcribe_greedy_group_dev(wavs[ln][:g], lens[ln][:g], DECODE_STEPS, BOS, EOS, preds[ln][:g])
             if world > 1:
-                dist.all_gather(gathered, pred)  # the path's only collective: final hypothesis gather
-        return pred
+                for g_ in range(g):
+                    dist.all_gather(gathered, preds[ln][g_])  # the path's only collective: final hypothesis gather
 
     def step_host(i):
-        ln = i % NL
+        ln, g = i % NL, sizes[i % n_calls]
         with torch.cuda.stream(streams[ln]):
-            lanes[ln].transcribe_greedy_host_async(wav_host, lens_host, DECODE_STEPS, BOS, EOS, preds_host[ln])
-            if world > 1:
-                dist.all_gather(gathered, preds[ln])
+            for g_ in range(g):  # H2D of every batch's wav / lengths from pinned host memory, inside the timed region
+                wavs[ln][g_].copy_(wav_host, non_blocking=True)
+                lens[ln][g_].copy_(lens_host, non_blocking=True)
+            lanes[ln].transcribe_greedy_group_dev(wavs[ln][:g], lens[ln][:g], DECODE_STEPS, BOS, EOS, preds[ln][:g])
+            for g_ in range(g):  # D2H of every batch's token ids
+                preds_host[ln][g_].copy_(preds[ln][g_], non_blocking=True)
+                if world > 1:
+                    dist.all_gather(gathered, preds[ln][g_])
 
     def timed(fn, n):
         """n steps between ONE pair of CUDA events; every lane stream starts after the start event and the stop
@@ -252,21 +266,22 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(max(W, NL)):
-        step_dev(i)
+    for rep in range(max(1, -(-W // K))):  # warm-up = the timed schedule itself (captures every (lane, group size) graph)
+        for i in range(n_calls):
+            step_dev(i)
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     launches0 = lib.sbk_launch_count()
-    ms_dev = timed(step_dev, K)
-    host_enqueue_ms = timed.host_ms
+    ms_dev = timed(step_dev, n_calls)
+    host_enqueue_ms = timed.host_ms * n_calls / K
     launches = (lib.sbk_launch_count() - launches0) // max(K, 1)
     barrier()
-    for i in range(NL):
+    for i in range(n_calls):
         step_host(i)
     barrier()
-    ms_host = timed(step_host, K)
+    ms_host = timed(step_host, n_calls)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     # single batch in flight (latency view): per-step events, 256 MiB L2 flush between steps
@@ -275,7 +290,7 @@ def main():
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        eng.transcribe_greedy_dev(wav_dev, lens_dev, DECODE_STEPS, BOS, EOS, pred=preds[0], score=scores[0])
+        eng.transcribe_greedy_dev(wav_dev, lens_dev, DECODE_STEPS, BOS, EOS, pred=preds[0][0], score=scores[0])
         e1.record()
         e1.synchronize()
         ms_single += e0.elapsed_time(e1) / min(K, 5)
@@ -290,7 +305,7 @@ def main():
 
     def step_dev1():
         eng.set_poll_interval(8)  # per-kernel launches (no whole-pipeline graph) so the GEMM launches can be event-timed
-        eng.transcribe_greedy_dev(wav_dev, lens_dev, DECODE_STEPS, BOS, EOS, pred=preds[0], score=scores[0])
+        eng.transcribe_greedy_dev(wav_dev, lens_dev, DECODE_STEPS, BOS, EOS, pred=preds[0][0], score=scores[0])
         eng.set_poll_interval(0)
 
     # ---- roofline leg: dominant kernel = gemm_tc_kernel (tcgen05 GEMM), timed live per launch with CUDA events
@@ -332,10 +347,11 @@ def main():
                                        f"+ greedy {DECODE_STEPS} steps (6L decoder, KV-cached), 32 x 10 s per GPU",
                            "global_batch": world * BATCH, "utt_seconds": UTT_SECONDS, "enc_frames": T,
                            "parallelism": f"dp{world} (utterance shards, one NCCL all-gather of token ids)",
-                           "lanes": NL, "decoder_ln_fused": bool(args.fuse_dec_ln), "single_lane_ms_per_step": ms_single, "host_enqueue_ms_per_step": host_enqueue_ms,
+                           "lanes": NL, "decode_group": G, "decoder_ln_fused": bool(args.fuse_dec_ln), "single_lane_ms_per_step": ms_single, "host_enqueue_ms_per_step": host_enqueue_ms,
                            "l2": "no flush inside the K-step bracket: per-step working set (0.25 GB weights + 0.3 GB "
                                  "activations/KV per lane) exceeds the 126 MB L2; single_lane_ms_per_step is flushed (256 MiB) per step",
-                           "timing": f"one CUDA-event pair around K steps, {NL} batches in flight on {NL} streams; max over ranks"},
+                           "timing": f"one CUDA-event pair around K steps (= {n_calls} group calls of {G} batches), {NL} groups in flight "
+                                     f"on {NL} streams; max over ranks"},
                 "e2e": {"value": e2e, "unit": "audio-sec/sec", "ms_per_step": ms_host / K,
                         "h2d_bytes_per_step": BATCH * L * 4 + BATCH * 4, "d2h_bytes_per_step": BATCH * DECODE_STEPS * 4},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base}

@@ -118,6 +118,11 @@ int sbk_asr_beam_from_enc(sbk_asr* m, const float* enc_dev, const float* rel_len
 int sbk_asr_transcribe_greedy_dev(sbk_asr* m, const float* wav_dev, const float* rel_len_dev, int B, int L,
                                   int max_steps, int bos, int eos, float* enc_out_dev, int* pred_dev,
                                   float* score_dev, float* log_probs_dev, int* steps_done, void* stream);
+/* Decode coalescing: G batches (B utterances each, separate device buffers) are encoded batch by batch and decoded
+ * by ONE greedy loop over G*B hypotheses; pred_dev[g] receives batch g's [B, max_steps] token ids. */
+int sbk_asr_transcribe_greedy_group_dev(sbk_asr* m, int G, const float* const* wav_dev, const float* const* rel_len_dev,
+                                        int B, int L, int max_steps, int bos, int eos, int* const* pred_dev,
+                                        int* steps_done, void* stream);
 int sbk_asr_transcribe_greedy_host(sbk_asr* m, const float* wav_host, const float* rel_len_host, int B, int L,
                                    int max_steps, int bos, int eos, int* pred_host, float* score_host,
                                    int* steps_done, void* stream);

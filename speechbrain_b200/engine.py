@@ -221,6 +221,21 @@ class AsrEngine:
                   "sbk_asr_transcribe_greedy_dev")
         return pred, score, enc, done.value
 
+    def transcribe_greedy_group_dev(self, wavs, lens, max_steps, bos, eos, preds):
+        """Decode coalescing: ``wavs`` / ``lens`` / ``preds`` are lists of G per-batch device tensors ([B, L] fp32,
+        [B] fp32, [B, max_steps] int32).  Each batch is encoded on its own, all G*B hypotheses are decoded together."""
+        G = len(wavs)
+        B, L = wavs[0].shape
+        VP = ctypes.c_void_p * G
+        w = VP(*[t.data_ptr() for t in wavs])
+        r = VP(*[t.data_ptr() for t in lens])
+        p = VP(*[t.data_ptr() for t in preds])
+        done = ctypes.c_int()
+        with torch.cuda.device(self.device):
+            check(lib().sbk_asr_transcribe_greedy_group_dev(self._h, G, w, r, B, L, max_steps, bos, eos, p, ctypes.byref(done),
+                                                            self._sp()), "sbk_asr_transcribe_greedy_group_dev")
+        return done.value
+
     def transcribe_greedy_host_async(self, wav_host, lens_host, max_steps, bos, eos, pred_host):
         """Enqueue-only variant on the current stream (all tensors pinned, contiguous); caller synchronises."""
         B, L = wav_host.shape
