@@ -9,6 +9,8 @@
 //
 // All step kernels read the current step index from device memory so that a single captured CUDA graph
 // can be replayed for every step.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -54,14 +56,17 @@ static cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_
 // before the first mma.  A is either fp16 in global memory, or (LN variant) LayerNorm(x fp32) computed by the
 // CTA itself into shared memory -- this fuses the decoder's pre-norms (Transformer.py:788-827) into the
 // projection that consumes them.  Deterministic in-CTA split-K reduction through shared memory.
-constexpr int SK_ROWS = 32;
 constexpr int SK_WARPS = 8;
 
 // UNR: k-steps whose loads are issued back to back; NT: 8-column tiles per CTA; VPL: LayerNorm-fused variant
 // when > 0, with K == 128 * VPL (each lane holds VPL float4 of each of its 4 rows).
-template <int UNR, int NT, int VPL>
-__global__ void __launch_bounds__(SK_WARPS * 32, (VPL <= 4 ? 2 : 1)) skinny_gemm_kernel(const SkinnyArgs a) {
+// MT: 16-row tiles per CTA (2 -> 32 rows, the single-batch case; 8 -> 128 rows when several batches are decoded
+// together, so W is streamed once per 128 rows instead of once per 32).
+template <int UNR, int NT, int VPL, int MT = 2>
+__global__ void __launch_bounds__(SK_WARPS * 32, ((VPL <= 4 && MT == 2) ? 2 : 1)) skinny_gemm_kernel(const SkinnyArgs a) {
     constexpr bool LN = VPL > 0;
+    constexpr int SK_ROWS = 16 * MT;
+    static_assert(!LN || MT == 2, "the LayerNorm-fused variant owns 32 rows per CTA");
     __shared__ float red[SK_WARPS][SK_ROWS][8 * NT + 1];
     extern __shared__ __align__(16) __half a_sm[];  // LN: [32][K + 8]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
@@ -72,9 +77,9 @@ __global__ void __launch_bounds__(SK_WARPS * 32, (VPL <= 4 ? 2 : 1)) skinny_gemm
     const int k_begin = warp * k_per_warp, k_end = min(a.K, k_begin + k_per_warp);
     pdl_trigger();
 
-    float acc[2][NT][4];
+    float acc[MT][NT][4];
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < MT; ++i)
 #pragma unroll
         for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.0f;
     const __half* wrow[NT];
@@ -155,14 +160,14 @@ __global__ void __launch_bounds__(SK_WARPS * 32, (VPL <= 4 ? 2 : 1)) skinny_gemm
         }
         __syncthreads();
     }
-    const __half* arow[4];
+    const __half* arow[2 * MT];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 2 * MT; ++i) {
         const int rr = LN ? (i * 8 + g) : min(row0 + i * 8 + g, a.n_rows - 1);
         arow[i] = abase + static_cast<size_t>(rr) * astr + 2 * c;
     }
     for (int k0 = k_begin; k0 < k_end; k0 += 16 * UNR) {
-        uint32_t af[UNR][2][4];
+        uint32_t af[UNR][MT][4];
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
             const int k = k0 + 16 * u;
@@ -175,7 +180,7 @@ __global__ void __launch_bounds__(SK_WARPS * 32, (VPL <= 4 ? 2 : 1)) skinny_gemm
                 }
             }
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt) {
+            for (int mt = 0; mt < MT; ++mt) {
                 af[u][mt][0] = ok ? *reinterpret_cast<const uint32_t*>(arow[2 * mt] + k) : 0u;
                 af[u][mt][1] = ok ? *reinterpret_cast<const uint32_t*>(arow[2 * mt + 1] + k) : 0u;
                 af[u][mt][2] = ok ? *reinterpret_cast<const uint32_t*>(arow[2 * mt] + k + 8) : 0u;
@@ -185,13 +190,12 @@ __global__ void __launch_bounds__(SK_WARPS * 32, (VPL <= 4 ? 2 : 1)) skinny_gemm
 #pragma unroll
         for (int u = 0; u < UNR; ++u)
 #pragma unroll
-            for (int j = 0; j < NT; ++j) {
-                mma16816_d(acc[0][j], af[u][0], bf[u][j][0], bf[u][j][1]);
-                mma16816_d(acc[1][j], af[u][1], bf[u][j][0], bf[u][j][1]);
-            }
+            for (int j = 0; j < NT; ++j)
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) mma16816_d(acc[mt][j], af[u][mt], bf[u][j][0], bf[u][j][1]);
     }
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
             red[warp][mt * 16 + g][8 * j + 2 * c] = acc[mt][j][0];
@@ -202,8 +206,8 @@ __global__ void __launch_bounds__(SK_WARPS * 32, (VPL <= 4 ? 2 : 1)) skinny_gemm
     __syncthreads();
     const int step = a.step_ptr ? *a.step_ptr : 0;
 #pragma unroll
-    for (int it = 0; it < NT; ++it) {
-        const int idx = threadIdx.x + it * SK_WARPS * 32;  // 32 rows x (8*NT) columns
+    for (int it = 0; it < NT * MT / 2; ++it) {
+        const int idx = threadIdx.x + it * SK_WARPS * 32;  // (16*MT) rows x (8*NT) columns
         const int r = idx / (8 * NT), j = idx - r * (8 * NT);
         const int col = n0 + j;
         const int row = row0 + r;
@@ -241,9 +245,17 @@ int skinny_gemm(const SkinnyArgs& a, cudaStream_t stream) {
     SBK_REQUIRE(a.K % 16 == 0 && a.lda % 2 == 0 && a.ldw % 2 == 0, "skinny_gemm: K %% 16 required (K=%d)", a.K);
     if (a.n_rows == 0) return SBK_OK;
     cudaError_t e;
-    const int ry = ceil_div(a.n_rows, SK_ROWS);
+    const int ry = ceil_div(a.n_rows, 32);
+    if (a.X == nullptr && a.n_rows >= 96 && getenv("SBK_SKINNY_MT8") != nullptr) {  // 128-row tiles: measured slower (64 fat CTAs), opt-in only
+        const dim3 grid(ceil_div(a.N, 8), ceil_div(a.n_rows, 128));
+        if (a.K <= 1024) e = launch_k(skinny_gemm_kernel<2, 1, 0, 8>, grid, dim3(SK_WARPS * 32), 0, stream, a);
+        else e = launch_k(skinny_gemm_kernel<4, 1, 0, 8>, grid, dim3(SK_WARPS * 32), 0, stream, a);
+        SBK_CUDA_CHECK(e);
+        SBK_LAUNCH_CHECK();
+        return SBK_OK;
+    }
     if (a.X != nullptr) {
-        const size_t smem = static_cast<size_t>(SK_ROWS) * (a.K + 8) * 2;
+        const size_t smem = static_cast<size_t>(32) * (a.K + 8) * 2;
         dim3 grid(ceil_div(a.N, 16), ry);
         static bool attr_done = false;  // static + dynamic shared memory exceeds the 48 KB default
         if (!attr_done) {
