@@ -158,17 +158,17 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=32)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--attention", default="RoPEMHA", choices=["RoPEMHA", "RelPosMHAXL"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--lanes", type=int, default=8, help="batches in flight per GPU (engine clones on their own streams)")
+    ap.add_argument("--lanes", type=int, default=4, help="batches in flight per GPU (engine clones on their own streams)")
     ap.add_argument("--group", type=int, default=8, help="batches whose decode is coalesced into one greedy loop (engine-level)")
     ap.add_argument("--decode-steps", type=int, default=48, help="diagnostic: override the pinned 48 greedy steps")
-    ap.add_argument("--fuse-dec-ln", type=int, default=0, help="1: decoder LayerNorm fused into projections (latency mode)")
+    ap.add_argument("--fuse-dec-ln", type=int, default=1, help="1: decoder LayerNorm fused into projections (latency mode)")
     args = ap.parse_args()
-    args.steps_ref = max(1, min(args.steps, 2))
+    args.steps_ref = max(1, min(args.steps, 3))
     args.warmup_ref = 1 if args.warmup > 0 else 0
     global DECODE_STEPS
     DECODE_STEPS = args.decode_steps
@@ -209,8 +209,9 @@ def main():
     # ---- lanes: independent GROUPS of batches in flight on their own streams; weights shared, workspaces private.
     # A group = G batches of 32 x 10 s: each batch is encoded on its own, the G*32 hypotheses are decoded together.
     G = max(1, min(args.group, K))
-    sizes = [G] * (K // G) + ([K % G] if K % G else [])  # exactly K batches are timed; the last group may be smaller
-    n_calls = len(sizes)
+    n_calls = -(-K // G)
+    sizes = [K // n_calls + (1 if i < K % n_calls else 0) for i in range(n_calls)]  # exactly K batches, balanced groups
+    G = max(sizes)
     NL = max(1, min(args.lanes, n_calls))
     lanes = [eng] + [eng.clone() for _ in range(NL - 1)]
     for e in lanes:
@@ -354,6 +355,8 @@ def main():
                                      f"on {NL} streams; max over ranks"},
                 "e2e": {"value": e2e, "unit": "audio-sec/sec", "ms_per_step": ms_host / K,
                         "h2d_bytes_per_step": BATCH * L * 4 + BATCH * 4, "d2h_bytes_per_step": BATCH * DECODE_STEPS * 4},
+                "single_batch": {"value": BATCH * UTT_SECONDS / (ms_single / 1e3), "unit": "audio-sec/sec", "ms_per_step": ms_single,
+                                 "note": "one batch in flight, no decode coalescing, L2 flushed before every step (latency view)"},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base}
         print(json.dumps(line))
     if world > 1:
