@@ -216,3 +216,47 @@ def test_beam_search_golden(dev, case):
     assert (scores.cpu() - gb["scores"]).abs().max() < 2e-2
     assert torch.allclose(lens.cpu(), gb["lens"])
     assert (lp.cpu() - gb["log_probs"]).abs().max() < 3e-2
+
+
+# ----------------------------------------------------------------------------------------- full-size properties
+def test_full_size_properties(dev):
+    """BASELINE full size (32 x 10 s, Conformer-L) is too slow for the CPU oracle, so parity is checked through
+    size-independent properties:
+      * Fbank: scaling the waveform by 10 adds exactly 20 dB everywhere (the top_db clip is relative to the maximum);
+      * batch invariance: utterance i of the 32-batch gets the same encoder states / tokens as when transcribed alone;
+      * determinism: two runs give identical token ids;
+      * decode coalescing: transcribing two batches as one group gives the same ids as two separate calls;
+      * ragged lengths: rows with wav_len < 1 only differ from the full-length run where the reference's masks act."""
+    from speechbrain_b200.lobes.features import Fbank
+    from speechbrain_b200.utils.seeded_init import CONFORMER_LARGE
+    g = torch.Generator().manual_seed(99)
+    B, L, steps = 32, 160000, 12
+    wav = torch.randn(B, L, generator=g).to(dev)
+    fb = Fbank(n_fft=512, n_mels=80, win_length=32)
+    f1, f10 = fb(wav), fb(wav * 10.0)
+    assert f1.shape == (B, 1001, 80)
+    assert (f10 - f1 - 20.0).abs().max().item() < 2e-3
+    eng, _ = _engine(dict(CONFORMER_LARGE), dev)
+    ones = torch.ones(B, device=dev)
+    pred, _, enc, _ = eng.transcribe_greedy_dev(wav, ones, steps, 1, 2, want_enc=True)
+    pred2, _, _, _ = eng.transcribe_greedy_dev(wav, ones, steps, 1, 2)
+    assert torch.equal(pred, pred2), "non-deterministic decode"
+    assert torch.isfinite(enc).all()
+    for i in (0, 17, 31):
+        p1, _, e1, _ = eng.transcribe_greedy_dev(wav[i:i + 1].contiguous(), ones[:1], steps, 1, 2, want_enc=True)
+        assert _rel(e1[0].cpu(), enc[i].cpu()) < 1e-5, f"encoder states of utterance {i} depend on the batch"
+        assert torch.equal(p1[0], pred[i]), f"tokens of utterance {i} depend on the batch"
+    # decode coalescing == separate calls
+    wav_b = torch.randn(B, L, generator=g).to(dev)
+    pb, _, _, _ = eng.transcribe_greedy_dev(wav_b, ones, steps, 1, 2)
+    outs = [torch.empty(B, steps, dtype=torch.int32, device=dev) for _ in range(2)]
+    eng.transcribe_greedy_group_dev([wav, wav_b], [ones, ones.clone()], steps, 1, 2, outs)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], pred) and torch.equal(outs[1], pb)
+    # ragged: shortening utterance 5 must not change any other utterance
+    lens = ones.clone()
+    lens[5] = 0.6
+    pr, _, er, _ = eng.transcribe_greedy_dev(wav, lens, steps, 1, 2, want_enc=True)
+    keep = [i for i in range(B) if i != 5]
+    assert torch.equal(pr[keep], pred[keep]) and torch.equal(er[keep], enc[keep])
+    assert not torch.equal(er[5], enc[5])
