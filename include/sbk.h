@@ -19,7 +19,7 @@ typedef struct sbk_asr sbk_asr;     /* opaque */
 
 enum { SBK_ATT_ROPE = 0, SBK_ATT_RELPOS = 1 };
 enum { SBK_ACT_RELU = 0, SBK_ACT_GELU = 1 };
-enum { SBK_PART_FBANK = 1, SBK_PART_CNN = 2, SBK_PART_ENCODER = 4, SBK_PART_DECODER = 8, SBK_PART_ALL = 15 };
+enum { SBK_PART_FBANK = 1, SBK_PART_CNN = 2, SBK_PART_ENCODER = 4, SBK_PART_DECODER = 8, SBK_PART_ALL = 15, SBK_PART_LM = 16 };
 
 typedef struct {
     const char* name;  /* reference state_dict key with recipe prefix, e.g. "Transformer.encoder.layers.0.norm1.norm.weight" */
@@ -38,6 +38,8 @@ typedef struct {
     int decoder_activation; /* SBK_ACT_RELU | SBK_ACT_GELU (the `activation` ctor kwarg) */
     int max_len;            /* positional tables (ctor kwarg max_length, default 2500) */
     int parts;              /* bitmask of SBK_PART_*: which sub-models the weight table carries */
+    /* TransformerLM used as a shallow-fusion scorer (lobes/models/transformer/TransformerLM.py; weights "lm.*") */
+    int lm_d_model, lm_nhead, lm_layers, lm_d_ffn, lm_activation;
 } sbk_asr_config;
 
 typedef struct {
@@ -48,6 +50,8 @@ typedef struct {
     float eos_threshold;
     int length_normalization;
     float minus_inf;
+    /* ScorerBuilder(full_scorers=[TransformerLMScorer]) (decoders/scorer.py:455-560,1221-1268): 0 weight = no scorer */
+    float lm_weight, lm_temperature;
 } sbk_beam_params;
 
 const char* sbk_last_error(void); /* thread-local message of the last failing call */

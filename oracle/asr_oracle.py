@@ -420,8 +420,10 @@ def full_pipeline_features(wav, wav_lens, sd, cfg):
 
 def beam_search(enc_states, wav_len, sd, cfg, seq_lin_w, seq_lin_b, bos_index=1, eos_index=2, beam_size=4,
                 min_decode_ratio=0.0, max_decode_ratio=1.0, temperature=1.0, using_eos_threshold=True,
-                eos_threshold=1.5, length_normalization=True, minus_inf=-1e20, topk=1, prefix="", return_history=False):
-    """S2STransformerBeamSearcher.forward with scorer=None, using_max_attn_shift=False.
+                eos_threshold=1.5, length_normalization=True, minus_inf=-1e20, topk=1, prefix="", return_history=False,
+                lm=None):
+    """S2STransformerBeamSearcher.forward, using_max_attn_shift=False; scorer=None, or (``lm`` = dict(sd, cfg, weight,
+    temperature, prefix)) a ScorerBuilder with one full scorer, TransformerLMScorer (scorer.py:1221-1268).
 
     Follows init_beam_search_data (:1267-1369), search_step (:1478-1598), _compute_scores_and_next_inp_tokens
     (:1204-1265), _update_sequences_and_log_probs (:1152-1202), _update_hyps_and_scores_if_eos_token (:1371-1416),
@@ -467,6 +469,9 @@ def beam_search(enc_states, wav_len, sd, cfg, seq_lin_w, seq_lin_b, bos_index=1,
             max_probs, _ = torch.max(log_probs, dim=-1)
             cond = log_probs[:, eos_index] > (eos_threshold * max_probs)
             log_probs[:, eos_index] = torch.where(cond, log_probs[:, eos_index], torch.tensor(minus_inf))
+        if lm is not None:  # _scorer_step: the LM sees the same token prefix as the decoder (memory incl. inp)
+            log_probs = log_probs + lm["weight"] * lm_scorer_log_probs(memory, lm["sd"], lm["cfg"], lm["temperature"],
+                                                                      lm.get("prefix", ""))
         sc = seq_scores.unsqueeze(1) + log_probs
         if length_normalization:
             sc = sc / (step + 1)
@@ -510,3 +515,40 @@ def finalize_beams(finished, beam_size, topk=1):
     best_hyps, best_lens = tk_hyps[:, 0, :], tk_len[:, 0]
     hyps = [best_hyps[b, : int(torch.round(best_lens[b] * best_hyps.shape[1]))].tolist() for b in range(B)]
     return hyps, best_lens, tk_scores[:, 0], tk_lp[:, 0, :]
+
+
+# --------------------------------------------------------------------------
+# TransformerLM + TransformerLMScorer (shallow fusion): TransformerLM.py:22-187, Transformer.py:331-481,597-660,
+# decoders/scorer.py:455-560 (score / permute_mem), :1221-1268 (ScorerBuilder.score, full scorers only)
+# --------------------------------------------------------------------------
+
+
+def transformer_lm_forward(tokens, sd, cfg, prefix=""):
+    """TransformerLM.forward(src) for the recipe's LM: 12 post-norm TransformerEncoder layers (normalize_before=False),
+    causal mask + key-padding mask on token id 0 (make_masks, pad_idx=0), final LayerNorm(1e-6), output_proj =
+    Linear(d,d) -> LayerNorm(1e-6) -> Linear(d,vocab).  tokens (n, s) -> logits (n, s, vocab)."""
+    n, s = tokens.shape
+    d, H = cfg["d_model"], cfg["nhead"]
+    x = F.embedding(tokens.long(), sd[prefix + "custom_src_module.emb.Embedding.weight"]) * math.sqrt(d)
+    x = x + sine_pe(s, d).unsqueeze(0)
+    causal = torch.triu(torch.full((s, s), float("-inf")), diagonal=1)
+    kpm = tokens.long() == 0
+    act = F.gelu if cfg.get("activation", "gelu") == "gelu" else F.relu
+    for i in range(cfg["num_encoder_layers"]):
+        p = f"{prefix}encoder.layers.{i}."
+        h, _ = _mha_regular(x, x, {k.replace("self_att.", "A."): v for k, v in sd.items() if k.startswith(p + "self_att.")},
+                            p + "A.", H, attn_mask=causal, key_padding_mask=kpm)
+        x = _ln(x + h, sd, p + "norm1.norm.", 1e-6)
+        h = F.linear(act(F.linear(x, sd[p + "pos_ffn.ffn.0.weight"], sd[p + "pos_ffn.ffn.0.bias"])),
+                     sd[p + "pos_ffn.ffn.3.weight"], sd[p + "pos_ffn.ffn.3.bias"])
+        x = _ln(x + h, sd, p + "norm2.norm.", 1e-6)
+    x = _ln(x, sd, prefix + "encoder.norm.norm.", 1e-6)
+    x = F.linear(x, sd[prefix + "output_proj.layers.0.w.weight"], sd[prefix + "output_proj.layers.0.w.bias"])
+    x = _ln(x, sd, prefix + "output_proj.layers.1.norm.", 1e-6)
+    return F.linear(x, sd[prefix + "output_proj.layers.2.w.weight"], sd[prefix + "output_proj.layers.2.w.bias"])
+
+
+def lm_scorer_log_probs(memory_tokens, sd_lm, cfg_lm, temperature, prefix=""):
+    """TransformerLMScorer.score (scorer.py:510-543): log_softmax(lm(memory) / temperature)[:, -1, :]."""
+    logits = transformer_lm_forward(memory_tokens, sd_lm, cfg_lm, prefix)
+    return F.log_softmax(logits / temperature, dim=-1)[:, -1, :]

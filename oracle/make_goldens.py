@@ -201,10 +201,56 @@ def beam_case(tag="beam_conformer_large_rope"):
     torch.save(out, os.path.join(OUT, f"{tag}.pt"))
 
 
+def beam_lm_case(tag="beam_lm_conformer_large_rope"):
+    """S2STransformerBeamSearcher + ScorerBuilder(full_scorers=[TransformerLMScorer]) -- shallow fusion with the recipe's
+    12 x 768 TransformerLM (conformer_large.yaml:160-170, 215-223), weight 0.6, temperature 1.15."""
+    from speechbrain.decoders.scorer import ScorerBuilder, TransformerLMScorer
+    from speechbrain.decoders.seq2seq import S2STransformerBeamSearcher
+    from speechbrain.lobes.models.transformer.TransformerLM import TransformerLM
+    from speechbrain_b200.utils.shapes import transformer_lm_shapes
+    fb, norm, mods, sd = build_reference(CFG_L, "RoPEMHA")
+    g = torch.load(os.path.join(OUT, "conformer_large_rope.pt"))
+    enc, wav_lens = g["enc_out"], g["wav_lens"]
+    T = enc.shape[1]
+    lm = TransformerLM(vocab=5000, d_model=768, nhead=12, num_encoder_layers=12, num_decoder_layers=0, d_ffn=3072,
+                       dropout=0.0, activation=torch.nn.GELU, normalize_before=False)
+    sd_lm = seeded_state_dict(lm, seed=1)
+    lm.load_state_dict(sd_lm)
+    lm.eval()
+    ours = {k: tuple(v) for k, v in transformer_lm_shapes(5000).items()}
+    ref_shapes = {k: tuple(v.shape) for k, v in lm.state_dict().items() if not k.endswith(".pe")}
+    assert ours == ref_shapes, (set(ours) ^ set(ref_shapes))
+    cfg_lm = dict(d_model=768, nhead=12, num_encoder_layers=12, d_ffn=3072, activation="gelu")
+    out = {}
+    for name, kw, eos_bias in [("lm_recipe", dict(beam_size=4, using_eos_threshold=False, temperature=1.15), 0.0),
+                               ("lm_eos", dict(beam_size=3, using_eos_threshold=True, temperature=1.0, min_decode_ratio=1.5 / T), 9.0)]:
+        with torch.no_grad():
+            bias = sd["seq_lin.w.bias"].clone()
+            bias[2] += eos_bias
+            mods["seq_lin"].w.bias.copy_(bias)
+            kwargs = dict(kw)
+            kwargs.setdefault("min_decode_ratio", 0.0)
+            scorer = ScorerBuilder(full_scorers=[TransformerLMScorer(language_model=lm, temperature=1.15)],
+                                   weights={"transformerlm": 0.6})
+            bs = S2STransformerBeamSearcher(modules=[mods["Transformer"], mods["seq_lin"]], bos_index=1, eos_index=2,
+                                            max_decode_ratio=6.5 / T, scorer=scorer, **kwargs)
+            hyps, lens, scores, lp = bs(enc, wav_lens)
+            ocfg = dict(CFG_L, attention_type="RoPEMHA")
+            ohyps, olens, oscores, olp = O.beam_search(
+                enc, wav_lens, sd, ocfg, sd["seq_lin.w.weight"], bias, 1, 2, max_decode_ratio=6.5 / T, prefix="Transformer.",
+                lm=dict(sd=sd_lm, cfg=cfg_lm, weight=0.6, temperature=1.15), **kwargs)
+        print(f"[beam+lm {name}] ref hyps {hyps} scores {scores.tolist()} | oracle equal: {ohyps == hyps} "
+              f"score err {(oscores - scores).abs().max():.2e}")
+        assert ohyps == hyps and (oscores - scores).abs().max() < 1e-4
+        out[name] = dict(kwargs=kwargs, eos_bias=eos_bias, max_decode_ratio=6.5 / T, lm_weight=0.6, lm_temperature=1.15,
+                         hyps=hyps, lens=lens, scores=scores, log_probs=lp)
+    torch.save(out, os.path.join(OUT, f"{tag}.pt"))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
-    which = sys.argv[1:] or ["fbank", "norm", "L_rope", "L_relpos", "S_relpos", "beam"]
+    which = sys.argv[1:] or ["fbank", "norm", "L_rope", "L_relpos", "S_relpos", "beam", "beam_lm"]
     if "fbank" in which:
         fbank_cases()
     if "norm" in which:
@@ -217,5 +263,7 @@ if __name__ == "__main__":
         model_case(CFG_S, "RelPosMHAXL", 2, 24000, [0.8, 1.0], 6, "conformer_small_relpos")
     if "beam" in which:
         beam_case()
+    if "beam_lm" in which:
+        beam_lm_case()
     for fn in sorted(os.listdir(OUT)):
         print(fn, os.path.getsize(os.path.join(OUT, fn)))

@@ -22,19 +22,20 @@ class sbk_asr_config(ctypes.Structure):
     _fields_ = [(k, ctypes.c_int) for k in (
         "n_fft", "hop", "n_mels", "cnn_c1", "cnn_c2", "input_size", "d_model", "nhead", "num_encoder_layers",
         "num_decoder_layers", "d_ffn", "vocab", "kernel_size", "attention_type", "decoder_activation", "max_len",
-        "parts")]
+        "parts", "lm_d_model", "lm_nhead", "lm_layers", "lm_d_ffn", "lm_activation")]
 
 
 class sbk_beam_params(ctypes.Structure):
     _fields_ = [("beam_size", ctypes.c_int), ("max_steps", ctypes.c_int), ("min_steps", ctypes.c_int),
                 ("bos", ctypes.c_int), ("eos", ctypes.c_int), ("temperature", ctypes.c_float),
                 ("using_eos_threshold", ctypes.c_int), ("eos_threshold", ctypes.c_float),
-                ("length_normalization", ctypes.c_int), ("minus_inf", ctypes.c_float)]
+                ("length_normalization", ctypes.c_int), ("minus_inf", ctypes.c_float),
+                ("lm_weight", ctypes.c_float), ("lm_temperature", ctypes.c_float)]
 
 
 SBK_ATT_ROPE, SBK_ATT_RELPOS = 0, 1
 SBK_ACT_RELU, SBK_ACT_GELU = 0, 1
-SBK_PARTS = {"fbank": 1, "cnn": 2, "encoder": 4, "decoder": 8}
+SBK_PARTS = {"fbank": 1, "cnn": 2, "encoder": 4, "decoder": 8, "lm": 16}
 
 # every symbol include/sbk.h declares (tests check the library exports all of them)
 EXPORTS = [

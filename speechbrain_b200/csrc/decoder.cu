@@ -324,6 +324,7 @@ __global__ void __launch_bounds__(DA_WARPS * 32, 4) dec_attention_kernel(const D
     float o[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) o[e] = 0.0f;
+    const int* tokc = a.tok_cache;  // TransformerLM.make_masks: keys whose token id is pad_idx (0) are masked
     for (int c0 = kb; c0 < ke; c0 += DA_CHUNK) {
         // ---- issue every load of this chunk up front: 2 keys x 128 B (K) and 16 keys x 16 B (V) per lane
         uint4 kv[DA_KPL][8];
@@ -355,7 +356,9 @@ __global__ void __launch_bounds__(DA_WARPS * 32, 4) dec_attention_kernel(const D
         for (int t = 0; t < DA_KPL; ++t) {
             const int j = c0 + lane + 32 * t;
             float dot = -INFINITY;
-            if (j < ke) {
+            bool live = j < ke;
+            if (live && tokc) live = tokc[static_cast<size_t>(lin ? lin[j] : r) * a.lin_stride + j] != a.pad_tok;
+            if (live) {
                 dot = 0.0f;
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
@@ -542,6 +545,80 @@ int greedy_select(const float* logits, int n_rows, int V, int* step_arr, int eos
 }
 
 
+// --------------------------------------------------------------------------- post-norm helpers (TransformerLM)
+// x = LayerNorm(x) in place (fp32) + fp16 copy for the next projection: the post-norm residual stream of
+// TransformerEncoderLayer(normalize_before=False) (Transformer.py:466-481). One warp per row.
+__global__ void __launch_bounds__(256)
+layernorm_dual_kernel(float* __restrict__ x, __half* __restrict__ x16, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, int M, int D, float eps, int write_f32) {
+    pdl_trigger();
+    pdl_wait();
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const int lane = threadIdx.x & 31;
+    float* xr = x + static_cast<size_t>(row) * D;
+    float s = 0.0f;
+    for (int j = lane; j < D; j += 32) s += xr[j];
+    const float mean = warp_sum(s) / D;
+    float q = 0.0f;
+    for (int j = lane; j < D; j += 32) {
+        const float d0 = xr[j] - mean;
+        q += d0 * d0;
+    }
+    const float rstd = rsqrtf(warp_sum(q) / D + eps);
+    for (int j = lane; j < D; j += 32) {
+        const float y = (xr[j] - mean) * rstd * __ldg(gamma + j) + __ldg(beta + j);
+        if (write_f32) xr[j] = y;
+        x16[static_cast<size_t>(row) * D + j] = __float2half_rn(y);
+    }
+}
+
+int layernorm_dual(float* x, __half* x16, const float* gamma, const float* beta, int M, int D, float eps, bool write_f32,
+                   cudaStream_t stream) {
+    if (M == 0) return SBK_OK;
+    SBK_CUDA_CHECK(launch_k(layernorm_dual_kernel, dim3(ceil_div(M, 8)), dim3(256), 0, stream, x, x16, gamma, beta, M, D, eps,
+                            write_f32 ? 1 : 0));
+    SBK_LAUNCH_CHECK();
+    return SBK_OK;
+}
+
+// out[r][j] = weight * log_softmax(logits[r] / temperature)[j]   (TransformerLMScorer.score scorer.py:532-543 times
+// ScorerBuilder's weight :1252).  One CTA per row.
+__global__ void __launch_bounds__(256)
+weighted_log_softmax_kernel(const float* __restrict__ logits, float* __restrict__ out, int V, float inv_temp, float weight) {
+    __shared__ float s_red[8];
+    pdl_trigger();
+    pdl_wait();
+    const int r = blockIdx.x, tid = threadIdx.x;
+    const float* lg = logits + static_cast<size_t>(r) * V;
+    float mx = -INFINITY;
+    for (int j = tid; j < V; j += 256) mx = fmaxf(mx, lg[j] * inv_temp);
+    mx = warp_max(mx);
+    if ((tid & 31) == 0) s_red[tid >> 5] = mx;
+    __syncthreads();
+    mx = s_red[0];
+    for (int w = 1; w < 8; ++w) mx = fmaxf(mx, s_red[w]);
+    __syncthreads();
+    float sm = 0.0f;
+    for (int j = tid; j < V; j += 256) sm += expf(lg[j] * inv_temp - mx);
+    sm = warp_sum(sm);
+    if ((tid & 31) == 0) s_red[tid >> 5] = sm;
+    __syncthreads();
+    float tot = 0.0f;
+    for (int w = 0; w < 8; ++w) tot += s_red[w];
+    const float lse = mx + logf(tot);
+    for (int j = tid; j < V; j += 256) out[static_cast<size_t>(r) * V + j] = weight * (lg[j] * inv_temp - lse);
+}
+
+int weighted_log_softmax(const float* logits, float* out, int rows, int V, float temperature, float weight,
+                         cudaStream_t stream) {
+    if (rows == 0) return SBK_OK;
+    SBK_CUDA_CHECK(launch_k(weighted_log_softmax_kernel, dim3(rows), dim3(256), 0, stream, logits, out, V, 1.0f / temperature,
+                            weight));
+    SBK_LAUNCH_CHECK();
+    return SBK_OK;
+}
+
 // --------------------------------------------------------------------------- beam search step
 // decoders/seq2seq.py search_step (:1478-1598) for one utterance per CTA, scorer-less path:
 //   log_probs = log_softmax(logits / temperature)                                   (:1929-1934)
@@ -565,6 +642,10 @@ struct BeamArgs {
     float inv_temp, eos_threshold, minus_inf;
     int min_steps, eos, use_eos_threshold, length_norm;
     const float* emb; const float* pe; int d; float sqrt_d; float* x_next;
+    // optional shallow-fusion scorer (TransformerLMScorer): pre-weighted scores added to the (masked) log-probs,
+    // and the LM's own next input (embedding + PE in fp32 and fp16) and token cache (pad-mask on id 0)
+    const float* add_scores;
+    const float* lm_emb; const float* lm_pe; int lm_d; float lm_sqrt_d; float* lm_x_next; __half* lm_x16_next; int* tok_cache;
 };
 
 __global__ void __launch_bounds__(BS_THREADS) beam_step_kernel(const BeamArgs a) {
@@ -614,6 +695,7 @@ __global__ void __launch_bounds__(BS_THREADS) beam_step_kernel(const BeamArgs a)
                 const float max_lp = fmaxf(mne - lse, eos_lp);
                 if (!(eos_lp > a.eos_threshold * max_lp)) eos_lp = a.minus_inf;
             }
+            if (a.add_scores) eos_lp += a.add_scores[static_cast<size_t>(row0 + k) * V + a.eos];  // ScorerBuilder.score
             s_lse[k] = lse;
             s_eos[k] = eos_lp;
         }
@@ -628,7 +710,8 @@ __global__ void __launch_bounds__(BS_THREADS) beam_step_kernel(const BeamArgs a)
     const int n_cand = beam * V;
     for (int cidx = tid; cidx < n_cand; cidx += BS_THREADS) {
         const int k = cidx / V, j = cidx - k * V;
-        const float lp = (j == a.eos) ? s_eos[k] : a.logits[static_cast<size_t>(row0 + k) * V + j] * a.inv_temp - s_lse[k];
+        float lp = (j == a.eos) ? s_eos[k] : a.logits[static_cast<size_t>(row0 + k) * V + j] * a.inv_temp - s_lse[k];
+        if (a.add_scores && j != a.eos) lp += a.add_scores[static_cast<size_t>(row0 + k) * V + j];
         const float sc = (seq_in[row0 + k] + lp) * inv_len;
         if (sc > bv[BS_MAXB - 1] && sc > -INFINITY) {  // insert (list sorted descending; only the first `beam` matter)
             float v = sc;
@@ -714,6 +797,16 @@ __global__ void __launch_bounds__(BS_THREADS) beam_step_kernel(const BeamArgs a)
         a.x_next[static_cast<size_t>(row0 + k) * a.d + c] =
             a.emb[static_cast<size_t>(s_wtok[k]) * a.d + c] * a.sqrt_d + a.pe[static_cast<size_t>(step + 1) * a.d + c];
     }
+    if (a.lm_emb) {
+        for (int i = tid; i < beam * a.lm_d; i += BS_THREADS) {
+            const int k = i / a.lm_d, c = i - k * a.lm_d;
+            const float v = a.lm_emb[static_cast<size_t>(s_wtok[k]) * a.lm_d + c] * a.lm_sqrt_d +
+                            a.lm_pe[static_cast<size_t>(step + 1) * a.lm_d + c];
+            a.lm_x_next[static_cast<size_t>(row0 + k) * a.lm_d + c] = v;
+            a.lm_x16_next[static_cast<size_t>(row0 + k) * a.lm_d + c] = __float2half_rn(v);
+        }
+        if (tid < beam) a.tok_cache[static_cast<size_t>(row0 + tid) * a.S_max + step + 1] = s_wtok[tid];
+    }
     __syncthreads();
     if (tid < beam) a.step_arr[row0 + tid] = step + 1;
 }
@@ -721,7 +814,9 @@ __global__ void __launch_bounds__(BS_THREADS) beam_step_kernel(const BeamArgs a)
 // step = 0 state: x = emb[bos] * sqrt(d) + pe[0]; beam 0 alive (score 0), others -inf; identity lineage.
 __global__ void beam_reset_kernel(int n_bh, int beam, int S_max, int bos, int* step_arr, float* seq_scores, int* lineage,
                                   int* finished, int* n_full, const float* __restrict__ emb, const float* __restrict__ pe,
-                                  int d, float sqrt_d, float* __restrict__ x) {
+                                  int d, float sqrt_d, float* __restrict__ x, const float* __restrict__ lm_emb,
+                                  const float* __restrict__ lm_pe, int lm_d, float lm_sqrt_d, float* __restrict__ lm_x,
+                                  __half* __restrict__ lm_x16, int* __restrict__ tok_cache) {
     const int r = blockIdx.x;
     if (threadIdx.x == 0) {
         step_arr[r] = 0;
@@ -733,12 +828,22 @@ __global__ void beam_reset_kernel(int n_bh, int beam, int S_max, int bos, int* s
     }
     const float* e = emb + static_cast<size_t>(bos) * d;
     for (int i = threadIdx.x; i < d; i += blockDim.x) x[static_cast<size_t>(r) * d + i] = e[i] * sqrt_d + pe[i];
+    if (lm_emb) {
+        for (int i = threadIdx.x; i < lm_d; i += blockDim.x) {
+            const float v = lm_emb[static_cast<size_t>(bos) * lm_d + i] * lm_sqrt_d + lm_pe[i];
+            lm_x[static_cast<size_t>(r) * lm_d + i] = v;
+            lm_x16[static_cast<size_t>(r) * lm_d + i] = __float2half_rn(v);
+        }
+        if (threadIdx.x == 0) tok_cache[static_cast<size_t>(r) * S_max] = bos;
+    }
 }
 
 int beam_reset(int n_bh, int beam, int S_max, int bos, int* step_arr, float* seq_scores, int* lineage, int* finished,
-               int* n_full, const float* emb, const float* pe, int d, float* x, cudaStream_t stream) {
+               int* n_full, const float* emb, const float* pe, int d, float* x, const BeamLm* lm, cudaStream_t stream) {
     beam_reset_kernel<<<n_bh, 128, 0, stream>>>(n_bh, beam, S_max, bos, step_arr, seq_scores, lineage, finished, n_full, emb,
-                                                pe, d, sqrtf(static_cast<float>(d)), x);
+                                                pe, d, sqrtf(static_cast<float>(d)), x, lm ? lm->emb : nullptr,
+                                                lm ? lm->pe : nullptr, lm ? lm->d : 0, lm ? sqrtf(static_cast<float>(lm->d)) : 0.f,
+                                                lm ? lm->x : nullptr, lm ? lm->x16 : nullptr, lm ? lm->tok_cache : nullptr);
     SBK_LAUNCH_CHECK();
     return SBK_OK;
 }
@@ -752,6 +857,9 @@ int beam_step(const BeamStepArgs& p, int B, cudaStream_t stream) {
     a.inv_temp = 1.0f / p.temperature; a.eos_threshold = p.eos_threshold; a.minus_inf = p.minus_inf;
     a.min_steps = p.min_steps; a.eos = p.eos; a.use_eos_threshold = p.use_eos_threshold; a.length_norm = p.length_norm;
     a.emb = p.emb; a.pe = p.pe; a.d = p.d; a.sqrt_d = sqrtf(static_cast<float>(p.d)); a.x_next = p.x_next;
+    a.add_scores = p.add_scores;
+    a.lm_emb = p.lm.emb; a.lm_pe = p.lm.pe; a.lm_d = p.lm.d; a.lm_sqrt_d = p.lm.d ? sqrtf(static_cast<float>(p.lm.d)) : 0.f;
+    a.lm_x_next = p.lm.x; a.lm_x16_next = p.lm.x16; a.tok_cache = p.lm.tok_cache;
     SBK_CUDA_CHECK(launch_k(beam_step_kernel, dim3(B), dim3(BS_THREADS), 0, stream, a));
     SBK_LAUNCH_CHECK();
     return SBK_OK;

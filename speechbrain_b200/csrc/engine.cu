@@ -47,6 +47,11 @@ struct DecLayerW {
     const float *b_self_in, *b_self_out, *b_cross_q, *b_cross_out, *b_ffn1, *b_ffn2;
 };
 
+struct LmLayerW {
+    const __half *w_in, *w_out, *w1, *w2;
+    const float *b_in, *b_out, *b1, *b2, *n1g, *n1b, *n2g, *n2b;
+};
+
 struct Arena {
     uint8_t* base = nullptr;
     size_t cap = 0, used = 0;
@@ -81,12 +86,21 @@ struct AsrModel {
     const float *dec_norm_g, *dec_norm_b;
     const __half* w_lin; const float* b_lin;
     const __half* w_ctc = nullptr; const float* b_ctc = nullptr;
+    // TransformerLM scorer (optional part)
+    bool has_lm = false;
+    const float *lm_emb = nullptr, *lm_pe = nullptr;
+    std::vector<LmLayerW> lm;
+    const float *lm_norm_g, *lm_norm_b, *lm_bp0, *lm_lnp_g, *lm_lnp_b, *lm_bp2;
+    const __half *lm_wp0, *lm_wp2;
     // shapes the workspace is carved for
     int wsB = 0, wsL = 0, ws_rows = 0, ws_steps = 0;
     struct Buf {
         float *wav, *feats, *x, *glu, *enc_out, *act1_f, *cnn_f, *dx, *logits, *score, *seq_scores;
         int *utt_max, *enc_len, *tokens, *step, *has_ended, *ended_count, *pred, *lineage, *finished;
         float* rel_len;
+        float *lx, *lh32, *lm_logits, *lm_extra;
+        __half *lx16, *lq16, *latt16, *lf16, *lh16, *lkc, *lvc;
+        int* tok_cache;
         __half *act1, *a_in, *h16, *f16, *qkv16, *att16, *P16, *enc16, *ckv16, *kcache, *vcache, *dh16, *dq16, *datt16, *df16;
     } b;
     cudaGraphExec_t step_graph = nullptr;
@@ -159,7 +173,13 @@ static size_t weight_arena_bytes(const sbk_asr_config& c) {
     size_t enc = (size_t)c.num_encoder_layers * (4 * d * f + 3 * d * d + d * d + d * d + 2 * d * d + d * d) * 2;
     size_t dec = (size_t)c.num_decoder_layers * (3 * d * d + d * d + 3 * d * d + d * d + 2 * d * f) * 2;
     size_t misc = (size_t)c.vocab * d * (4 + 2 + 2) + (size_t)c.max_len * d * (4 + 2) + (size_t)c.input_size * d * 2;
-    return enc + dec + misc + (64u << 20);
+    size_t lm = 0;
+    if (c.parts & SBK_PART_LM) {
+        const size_t dl = c.lm_d_model, fl = c.lm_d_ffn;
+        lm = (size_t)c.lm_layers * (4 * dl * dl + 2 * dl * fl) * 2 + (size_t)c.vocab * dl * (4 + 2) + dl * dl * 2 +
+             (size_t)c.max_len * dl * 4 + (8u << 20);
+    }
+    return enc + dec + misc + lm + (64u << 20);
 }
 
 int asr_create(const sbk_asr_config* cfg, const sbk_tensor* weights, int n_weights, AsrModel** out) {
@@ -353,6 +373,47 @@ int asr_create(const sbk_asr_config* cfg, const sbk_tensor* weights, int n_weigh
         m->w_lin = p.f16("seq_lin.w.weight", (int64_t)c.vocab * d);
         m->b_lin = p.f32("seq_lin.w.bias", c.vocab);
     }
+    if ((c.parts & SBK_PART_LM) && c.lm_layers > 0) {
+        const int dl = c.lm_d_model, Fl = c.lm_d_ffn, dhl = dl / c.lm_nhead;
+        if (dhl != 64 || dl % 128 != 0) { set_error("asr_create: LM head_dim must be 64 and d_model %% 128 == 0"); rc = SBK_ERR_UNSUPPORTED; goto fail; }
+        m->has_lm = true;
+        m->lm_emb = p.f32("lm.custom_src_module.emb.Embedding.weight", (int64_t)c.vocab * dl);
+        {
+            std::vector<float> pe((size_t)c.max_len * dl);
+            for (int i = 0; i < dl / 2; ++i) {
+                const float den = expf((float)(2 * i) * -(logf(10000.0f) / (float)dl));
+                for (int t = 0; t < c.max_len; ++t) {
+                    pe[(size_t)t * dl + 2 * i] = sinf((float)t * den);
+                    pe[(size_t)t * dl + 2 * i + 1] = cosf((float)t * den);
+                }
+            }
+            m->lm_pe = p.f32_raw(pe.data(), pe.size());
+        }
+        m->lm.resize(c.lm_layers);
+        const float qs = 1.0f / sqrtf((float)dhl);
+        for (int l = 0; l < c.lm_layers && p.ok; ++l) {
+            const std::string q = "lm.encoder.layers." + std::to_string(l) + ".";
+            LmLayerW& e = m->lm[l];
+            const float* wi = find(w, q + "self_att.att.in_proj_weight", (int64_t)3 * dl * dl);
+            const float* bi = find(w, q + "self_att.att.in_proj_bias", 3 * dl);
+            if (!wi || !bi) { p.ok = false; break; }
+            std::vector<float> ws(wi, wi + (size_t)3 * dl * dl), bs(bi, bi + 3 * dl);
+            for (size_t i = 0; i < (size_t)dl * dl; ++i) ws[i] *= qs;  // fold 1/sqrt(d_h) into the query rows
+            for (int i = 0; i < dl; ++i) bs[i] *= qs;
+            e.w_in = p.f16_raw(ws.data(), ws.size());
+            e.b_in = p.f32_raw(bs.data(), bs.size());
+            e.w_out = p.f16(q + "self_att.att.out_proj.weight", (int64_t)dl * dl); e.b_out = p.f32(q + "self_att.att.out_proj.bias", dl);
+            e.w1 = p.f16(q + "pos_ffn.ffn.0.weight", (int64_t)Fl * dl); e.b1 = p.f32(q + "pos_ffn.ffn.0.bias", Fl);
+            e.w2 = p.f16(q + "pos_ffn.ffn.3.weight", (int64_t)dl * Fl); e.b2 = p.f32(q + "pos_ffn.ffn.3.bias", dl);
+            e.n1g = p.f32(q + "norm1.norm.weight", dl); e.n1b = p.f32(q + "norm1.norm.bias", dl);
+            e.n2g = p.f32(q + "norm2.norm.weight", dl); e.n2b = p.f32(q + "norm2.norm.bias", dl);
+        }
+        m->lm_norm_g = p.f32("lm.encoder.norm.norm.weight", dl); m->lm_norm_b = p.f32("lm.encoder.norm.norm.bias", dl);
+        m->lm_wp0 = p.f16("lm.output_proj.layers.0.w.weight", (int64_t)dl * dl); m->lm_bp0 = p.f32("lm.output_proj.layers.0.w.bias", dl);
+        m->lm_lnp_g = p.f32("lm.output_proj.layers.1.norm.weight", dl); m->lm_lnp_b = p.f32("lm.output_proj.layers.1.norm.bias", dl);
+        m->lm_wp2 = p.f16("lm.output_proj.layers.2.w.weight", (int64_t)c.vocab * dl); m->lm_bp2 = p.f32("lm.output_proj.layers.2.w.bias", c.vocab);
+        if (!p.ok) { rc = SBK_ERR_ARG; goto fail; }
+    }
     if (w.count("ctc_lin.w.weight")) {
         m->w_ctc = p.f16("ctc_lin.w.weight", (int64_t)c.vocab * d);
         m->b_ctc = p.f32("ctc_lin.w.bias", c.vocab);
@@ -438,6 +499,12 @@ static int ensure_workspace(AsrModel* m, int B, int L, int rows, int steps) {
     sz((size_t)Ld * rows * S * d * 2); sz((size_t)Ld * rows * S * d * 2);
     sz((size_t)rows * d * 2); sz((size_t)rows * d * 2); sz((size_t)rows * d * 2); sz((size_t)rows * F * 2);
     sz((size_t)2 * rows * S * 4); sz(B * 4 + 64); sz((size_t)2 * rows * 4);
+    const size_t dl = m->has_lm ? c.lm_d_model : 0, Fl = m->has_lm ? c.lm_d_ffn : 0, Ll = m->has_lm ? c.lm_layers : 0;
+    if (m->has_lm) {
+        sz(rows * dl * 4); sz(rows * dl * 4); sz((size_t)rows * c.vocab * 4); sz((size_t)rows * c.vocab * 4);
+        sz(rows * dl * 2); sz(rows * dl * 2); sz(rows * dl * 2); sz(rows * Fl * 2); sz(rows * dl * 2);
+        sz(Ll * rows * S * dl * 2); sz(Ll * rows * S * dl * 2); sz((size_t)rows * S * 4);
+    }
     need += 1 << 20;
     if (need > m->ws.cap) {
         if (m->ws.base) { cudaDeviceSynchronize(); cudaFree(m->ws.base); m->ws.base = nullptr; }
@@ -467,8 +534,16 @@ static int ensure_workspace(AsrModel* m, int B, int L, int rows, int steps) {
     TAKE(dh16, __half, (size_t)rows * d * 2); TAKE(dq16, __half, (size_t)rows * d * 2); TAKE(datt16, __half, (size_t)rows * d * 2);
     TAKE(df16, __half, (size_t)rows * F * 2);
     TAKE(lineage, int, (size_t)2 * rows * S * 4); TAKE(finished, int, B * 4 + 64); TAKE(seq_scores, float, (size_t)2 * rows * 4);
-#undef TAKE
+    if (m->has_lm) {
+        TAKE(lx, float, rows * dl * 4); TAKE(lh32, float, rows * dl * 4); TAKE(lm_logits, float, (size_t)rows * c.vocab * 4);
+        TAKE(lm_extra, float, (size_t)rows * c.vocab * 4);
+        TAKE(lx16, __half, rows * dl * 2); TAKE(lq16, __half, rows * dl * 2); TAKE(latt16, __half, rows * dl * 2);
+        TAKE(lf16, __half, rows * Fl * 2); TAKE(lh16, __half, rows * dl * 2);
+        TAKE(lkc, __half, Ll * rows * S * dl * 2); TAKE(lvc, __half, Ll * rows * S * dl * 2); TAKE(tok_cache, int, (size_t)rows * S * 4);
+        if (!b.tok_cache) { set_error("workspace carve failed (LM)"); return SBK_ERR_NOMEM; }
+    }
     if (!b.df16 || !b.seq_scores) { set_error("workspace carve failed"); return SBK_ERR_NOMEM; }
+#undef TAKE
     m->wsB = B; m->wsL = L; m->ws_rows = rows; m->ws_steps = steps;
     return SBK_OK;
 }
@@ -624,6 +699,52 @@ static int enqueue_decode_step(AsrModel* m, int rows, int rows_per_utt, int T, i
     return SBK_OK;
 }
 
+// One TransformerLM step over `rows` hypotheses (post-norm encoder layers with a lineage-indexed KV cache), ending in
+// b.lm_extra[rows, V] = weight * log_softmax(lm_logits / temperature): TransformerLMScorer.score (scorer.py:510-543)
+// scaled by ScorerBuilder's weight.  b.lx / b.lx16 hold emb[token] * sqrt(d) + pe[step] (beam_reset / beam_step).
+static int enqueue_lm_step(AsrModel* m, int rows, int S_max, float temperature, float weight, cudaStream_t st) {
+    const sbk_asr_config& c = m->cfg;
+    AsrModel::Buf& b = m->b;
+    const int dl = c.lm_d_model, Fl = c.lm_d_ffn, H = c.lm_nhead;
+    for (int l = 0; l < c.lm_layers; ++l) {
+        const LmLayerW& w = m->lm[l];
+        __half* kc = b.lkc + (size_t)l * rows * S_max * dl;
+        __half* vc = b.lvc + (size_t)l * rows * S_max * dl;
+        SkinnyArgs a{};
+        a.A = b.lx16; a.lda = dl; a.W = w.w_in; a.ldw = dl; a.bias = w.b_in; a.n_rows = rows; a.N = 3 * dl; a.K = dl;
+        a.epi = SK_QKV_CACHE; a.out = b.lq16; a.ldo = dl; a.kcache = kc; a.vcache = vc; a.step_ptr = b.step; a.S_max = S_max;
+        a.d = dl; a.q_scale = 1.0f;
+        RC(skinny_gemm(a, st));
+        DecAttnArgs t{};
+        t.q = b.lq16; t.ldq = dl; t.kbase = kc; t.vbase = vc; t.row_stride = (size_t)S_max * dl; t.key_stride = dl;
+        t.rows_per_block = 1; t.n_keys_ptr = b.step; t.H = H; t.dh = 64; t.out = b.latt16; t.ldo = dl;
+        t.lineage = b.lineage; t.lin_stride = S_max; t.tok_cache = b.tok_cache; t.pad_tok = 0;
+        RC(dec_attention(t, rows, S_max, st));
+        a = SkinnyArgs{}; a.A = b.latt16; a.lda = dl; a.W = w.w_out; a.ldw = dl; a.bias = w.b_out; a.n_rows = rows;
+        a.N = dl; a.K = dl; a.epi = SK_RESID; a.out = b.lx; a.ldo = dl;
+        RC(skinny_gemm(a, st));
+        RC(layernorm_dual(b.lx, b.lx16, w.n1g, w.n1b, rows, dl, 1e-6f, true, st));
+        a = SkinnyArgs{}; a.A = b.lx16; a.lda = dl; a.W = w.w1; a.ldw = dl; a.bias = w.b1; a.n_rows = rows;
+        a.N = Fl; a.K = dl; a.epi = c.lm_activation == SBK_ACT_GELU ? SK_F16_GELU : SK_F16_RELU; a.out = b.lf16; a.ldo = Fl;
+        RC(skinny_gemm(a, st));
+        a = SkinnyArgs{}; a.A = b.lf16; a.lda = Fl; a.W = w.w2; a.ldw = Fl; a.bias = w.b2; a.n_rows = rows;
+        a.N = dl; a.K = Fl; a.epi = SK_RESID; a.out = b.lx; a.ldo = dl;
+        RC(skinny_gemm(a, st));
+        RC(layernorm_dual(b.lx, b.lx16, w.n2g, w.n2b, rows, dl, 1e-6f, true, st));
+    }
+    RC(layernorm_dual(b.lx, b.lx16, m->lm_norm_g, m->lm_norm_b, rows, dl, 1e-6f, false, st));  // encoder.norm
+    SkinnyArgs a{};
+    a.A = b.lx16; a.lda = dl; a.W = m->lm_wp0; a.ldw = dl; a.bias = m->lm_bp0; a.n_rows = rows; a.N = dl; a.K = dl;
+    a.epi = SK_F32; a.out = b.lh32; a.ldo = dl;
+    RC(skinny_gemm(a, st));
+    RC(layernorm_dual(b.lh32, b.lh16, m->lm_lnp_g, m->lm_lnp_b, rows, dl, 1e-6f, false, st));
+    a = SkinnyArgs{}; a.A = b.lh16; a.lda = dl; a.W = m->lm_wp2; a.ldw = dl; a.bias = m->lm_bp2; a.n_rows = rows;
+    a.N = c.vocab; a.K = dl; a.epi = SK_F32; a.out = b.lm_logits; a.ldo = c.vocab;
+    RC(skinny_gemm(a, st));
+    RC(weighted_log_softmax(b.lm_logits, b.lm_extra, rows, c.vocab, temperature, weight, st));
+    return SBK_OK;
+}
+
 // Beam search (decoders/seq2seq.py:1632-1723 with scorer=None): the device runs decoder step + beam_step_kernel and
 // records the per-step (token, predecessor, normalised score, log-prob) history; hypothesis bookkeeping is replayed
 // on the host from that history (speechbrain_b200/decoders/seq2seq.py).
@@ -643,9 +764,15 @@ static int run_beam(AsrModel* m, int B, int T, const sbk_beam_params& p, int* hi
         RC(gemm_f16(b.enc16, d, m->w_ckv + (size_t)l * 2 * d * d, d, e, M, 2 * d, d, st));
     }
     set_pdl(getenv("SBK_PDL") != nullptr);
+    const bool use_lm = p.lm_weight != 0.0f;
+    SBK_REQUIRE(!use_lm || m->has_lm, "beam: lm_weight != 0 but this handle has no TransformerLM weights");
+    BeamLm lm;
+    if (use_lm) { lm.emb = m->lm_emb; lm.pe = m->lm_pe; lm.d = c.lm_d_model; lm.x = b.lx; lm.x16 = b.lx16; lm.tok_cache = b.tok_cache; }
     RC(beam_reset(rows, beam, S_max, p.bos, b.step, b.seq_scores, b.lineage, b.finished, b.ended_count, m->emb, m->dec_pe, d,
-                  b.dx, st));
+                  b.dx, use_lm ? &lm : nullptr, st));
     BeamStepArgs a{};
+    a.add_scores = use_lm ? b.lm_extra : nullptr;
+    a.lm = lm;
     a.logits = b.logits; a.V = c.vocab; a.beam = beam; a.S_max = S_max; a.seq_scores = b.seq_scores; a.lineage = b.lineage;
     a.step_arr = b.step; a.finished = b.finished; a.n_full = b.ended_count;
     a.hist_tok = hist_tok; a.hist_pred = hist_pred; a.hist_score = hist_score; a.hist_lp = hist_lp;
@@ -658,6 +785,7 @@ static int run_beam(AsrModel* m, int B, int T, const sbk_beam_params& p, int* hi
         const int chunk = std::min(check_every, p.max_steps - s);
         for (int i = 0; i < chunk; ++i) {
             RC(enqueue_decode_layers(m, rows, beam, T, S_max, b.lineage, st));
+            if (use_lm) RC(enqueue_lm_step(m, rows, S_max, p.lm_temperature, p.lm_weight, st));
             RC(beam_step(a, B, st));
         }
         s += chunk;

@@ -105,8 +105,13 @@ struct DecAttnArgs {
     int H, dh;
     __half* out; int ldo;
     const int* lineage; int lin_stride;  // beam search: [2][n_rows][lin_stride] cache-row table (null for greedy)
+    const int* tok_cache; int pad_tok;   // LM pad mask: keys whose token (tok_cache[phys_row][pos]) == pad_tok are masked
 };
 int dec_attention(const DecAttnArgs& a, int n_rows, int max_keys, cudaStream_t stream);
+struct BeamLm {  // TransformerLM scorer state the beam step feeds (all null/0 when there is no LM)
+    const float* emb = nullptr; const float* pe = nullptr; int d = 0;
+    float* x = nullptr; __half* x16 = nullptr; int* tok_cache = nullptr;
+};
 struct BeamStepArgs {
     const float* logits; int V; int beam; int S_max;
     float* seq_scores; int* lineage; int* step_arr; int* finished; int* n_full;
@@ -114,9 +119,15 @@ struct BeamStepArgs {
     float temperature, eos_threshold, minus_inf;
     int min_steps, eos, use_eos_threshold, length_norm;
     const float* emb; const float* pe; int d; float* x_next;
+    const float* add_scores;  // [n_bh, V] pre-weighted scorer scores or null
+    BeamLm lm;
 };
 int beam_reset(int n_bh, int beam, int S_max, int bos, int* step_arr, float* seq_scores, int* lineage, int* finished,
-               int* n_full, const float* emb, const float* pe, int d, float* x, cudaStream_t stream);
+               int* n_full, const float* emb, const float* pe, int d, float* x, const BeamLm* lm, cudaStream_t stream);
+int layernorm_dual(float* x, __half* x16, const float* gamma, const float* beta, int M, int D, float eps, bool write_f32,
+                   cudaStream_t stream);
+int weighted_log_softmax(const float* logits, float* out, int rows, int V, float temperature, float weight,
+                         cudaStream_t stream);
 int beam_step(const BeamStepArgs& p, int B, cudaStream_t stream);
 int greedy_reset(int* tokens, int tok_stride, int n_rows, int bos, int* step_arr, int* has_ended, int* ended_count,
                  const float* emb, const float* pe, int d, float* x, cudaStream_t stream);

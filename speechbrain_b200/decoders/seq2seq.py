@@ -61,8 +61,15 @@ class S2STransformerBeamSearcher(torch.nn.Module):
         super().__init__()
         if bos_index is None or eos_index is None or beam_size is None:
             raise TypeError("bos_index, eos_index and beam_size are required")
+        self.lm_scorer, self.lm_weight = None, 0.0
         if scorer is not None:
-            raise NotImplementedError("speechbrain_b200 beam searcher: scorers (CTC / TransformerLM / ...) are not built yet")
+            from .scorer import ScorerBuilder
+            if not isinstance(scorer, ScorerBuilder):
+                raise NotImplementedError("speechbrain_b200 beam searcher: scorer must be a speechbrain_b200 ScorerBuilder")
+            if length_normalization and scorer.weights["length"] > 0.0:
+                raise ValueError("Length normalization is not compatible with length rewarding.")
+            self.lm_scorer = scorer.full_scorers["transformerlm"]
+            self.lm_weight = scorer.weights["transformerlm"]
         if using_max_attn_shift:
             raise NotImplementedError("speechbrain_b200 beam searcher: using_max_attn_shift is not built")
         if topk > beam_size:
@@ -83,7 +90,12 @@ class S2STransformerBeamSearcher(torch.nn.Module):
             from ..engine import AsrEngine
             sd = self.model.prefixed_state("Transformer.")
             sd.update({"seq_lin." + k: v for k, v in self.fc.state_dict().items()})
-            self._engine = AsrEngine(self.model.engine_cfg(), sd, device=device, parts=("decoder",))
+            cfg, parts = self.model.engine_cfg(), ("decoder",)
+            if self.lm_scorer is not None:
+                sd.update({"lm." + k: v for k, v in self.lm_scorer.lm.state_dict().items()})
+                cfg["lm"] = self.lm_scorer.lm.engine_cfg()
+                parts = ("decoder", "lm")
+            self._engine = AsrEngine(cfg, sd, device=device, parts=parts)
         return self._engine
 
     @torch.no_grad()
@@ -95,7 +107,8 @@ class S2STransformerBeamSearcher(torch.nn.Module):
             raise ValueError("max_decode_ratio gives zero decoding steps")  # the reference fails on `scores` too
         hist = self._get_engine(enc_states.device).beam_from_enc(
             enc_states, wav_len, self.beam_size, max_steps, min_steps, self.bos_index, self.eos_index, self.temperature,
-            self.using_eos_threshold, self.eos_threshold, self.length_normalization, self.minus_inf)
+            self.using_eos_threshold, self.eos_threshold, self.length_normalization, self.minus_inf,
+            lm_weight=self.lm_weight, lm_temperature=self.lm_scorer.temperature if self.lm_scorer is not None else 1.0)
         out = replay_beam_history(hist, B, self.beam_size, self.eos_index, self.topk)
         topk_hyps, topk_lengths, topk_scores, topk_log_probs = (t.to(enc_states.device) for t in out)
         if self.return_topk:

@@ -90,6 +90,10 @@ class AsrEngine:
         c.attention_type = _lib.SBK_ATT_ROPE if att == "RoPEMHA" else _lib.SBK_ATT_RELPOS
         c.decoder_activation = _lib.SBK_ACT_GELU if cfg.get("decoder_activation", "gelu") == "gelu" else _lib.SBK_ACT_RELU
         c.max_len = cfg.get("max_length", 2500)
+        lm = cfg.get("lm")  # dict(d_model, nhead, num_encoder_layers, d_ffn, activation) of a TransformerLM scorer
+        if lm is not None:
+            c.lm_d_model, c.lm_nhead, c.lm_layers, c.lm_d_ffn = lm["d_model"], lm["nhead"], lm["num_encoder_layers"], lm["d_ffn"]
+            c.lm_activation = _lib.SBK_ACT_GELU if lm.get("activation", "gelu") == "gelu" else _lib.SBK_ACT_RELU
         c.parts = sum(_lib.SBK_PARTS[p] for p in self.parts)
         if cfg["num_decoder_layers"] == 0:
             c.parts &= ~_lib.SBK_PARTS["decoder"]
@@ -184,7 +188,8 @@ class AsrEngine:
         return pred, score, lp, done.value
 
     def beam_from_enc(self, enc, wav_lens, beam_size, max_steps, min_steps, bos, eos, temperature=1.0,
-                      using_eos_threshold=True, eos_threshold=1.5, length_normalization=True, minus_inf=-1e20):
+                      using_eos_threshold=True, eos_threshold=1.5, length_normalization=True, minus_inf=-1e20,
+                      lm_weight=0.0, lm_temperature=1.0):
         """Device part of the beam search: returns the per-step history (tok, pred, score, lp) [steps, B*beam] on CPU."""
         enc = enc.float().contiguous()
         B, T, _ = enc.shape
@@ -196,7 +201,7 @@ class AsrEngine:
         lp = torch.zeros(S, n_bh, device=enc.device, dtype=torch.float32)
         wl = wav_lens.float().contiguous().to(enc.device) if wav_lens is not None else None
         prm = _lib.sbk_beam_params(beam_size, max_steps, min_steps, bos, eos, temperature, int(bool(using_eos_threshold)),
-                                   eos_threshold, int(bool(length_normalization)), minus_inf)
+                                   eos_threshold, int(bool(length_normalization)), minus_inf, lm_weight, lm_temperature)
         done = ctypes.c_int()
         with torch.cuda.device(self.device):
             check(lib().sbk_asr_beam_from_enc(self._h, ptr(enc), ptr(wl), B, T, ctypes.byref(prm), ptr(tok), ptr(pred),

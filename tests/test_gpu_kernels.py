@@ -260,3 +260,38 @@ def test_full_size_properties(dev):
     keep = [i for i in range(B) if i != 5]
     assert torch.equal(pr[keep], pred[keep]) and torch.equal(er[keep], enc[keep])
     assert not torch.equal(er[5], enc[5])
+
+
+@pytest.mark.parametrize("case", ["lm_recipe", "lm_eos"])
+def test_beam_search_with_transformerlm_scorer_golden(dev, case):
+    """S2STransformerBeamSearcher + ScorerBuilder(full_scorers=[TransformerLMScorer], weight 0.6, temperature 1.15) with the
+    recipe's 12 x 768 TransformerLM vs the REFERENCE (shallow fusion, scorer.py:510-543,1221-1268)."""
+    from speechbrain_b200.decoders.scorer import ScorerBuilder, TransformerLMScorer
+    from speechbrain_b200.decoders.seq2seq import S2STransformerBeamSearcher
+    from speechbrain_b200.lobes.models.transformer.TransformerASR import TransformerASR
+    from speechbrain_b200.lobes.models.transformer.TransformerLM import TransformerLM
+    from speechbrain_b200.nnet.linear import Linear
+    from speechbrain_b200.utils.seeded_init import CONFORMER_LARGE, seeded_asr_state, seeded_state_dict
+    g = torch.load(os.path.join(GOLDEN, "conformer_large_rope.pt"))
+    gb = torch.load(os.path.join(GOLDEN, "beam_lm_conformer_large_rope.pt"))[case]
+    sd = seeded_asr_state(dict(CONFORMER_LARGE), 0)
+    tr = TransformerASR(input_size=640, tgt_vocab=5000, d_model=512, nhead=8, num_encoder_layers=12, num_decoder_layers=6,
+                        d_ffn=2048, activation=torch.nn.GELU, encoder_module="conformer", attention_type="RoPEMHA",
+                        normalize_before=True, causal=False)
+    tr.load_state_dict({k[len("Transformer."):]: v for k, v in sd.items() if k.startswith("Transformer.")}, strict=False)
+    lin = Linear(input_size=512, n_neurons=5000)
+    bias = sd["seq_lin.w.bias"].clone()
+    bias[2] += gb["eos_bias"]
+    lin.load_state_dict({"w.weight": sd["seq_lin.w.weight"], "w.bias": bias})
+    lm = TransformerLM(vocab=5000, d_model=768, nhead=12, num_encoder_layers=12, num_decoder_layers=0, d_ffn=3072, dropout=0.0,
+                       activation=torch.nn.GELU, normalize_before=False)
+    lm.load_state_dict(seeded_state_dict(lm, seed=1))
+    scorer = ScorerBuilder(full_scorers=[TransformerLMScorer(language_model=lm, temperature=gb["lm_temperature"])],
+                           weights={"transformerlm": gb["lm_weight"]})
+    bs = S2STransformerBeamSearcher(modules=[tr, lin], bos_index=1, eos_index=2, max_decode_ratio=gb["max_decode_ratio"],
+                                    scorer=scorer, **gb["kwargs"])
+    hyps, lens, scores, lp = bs(g["enc_out"].to(dev), g["wav_lens"].to(dev))
+    print(f"beam+lm[{case}] hyps {hyps} ref {gb['hyps']} scores {scores.tolist()} ref {gb['scores'].tolist()}")
+    assert hyps == gb["hyps"]
+    assert (scores.cpu() - gb["scores"]).abs().max() < 3e-2
+    assert (lp.cpu() - gb["log_probs"]).abs().max() < 3e-2
