@@ -52,6 +52,10 @@ typedef struct {
     float minus_inf;
     /* ScorerBuilder(full_scorers=[TransformerLMScorer]) (decoders/scorer.py:455-560,1221-1268): 0 weight = no scorer */
     float lm_weight, lm_temperature;
+    /* ... and CTCScorer (decoders/scorer.py:183-249, decoders/ctc.py:46-295) as a full scorer; needs "ctc_lin.w.*" weights.
+       ctc_weight != 0 also scales the decoder log-probs by 1 - ctc_weight (seq2seq.py:791-804,916-921). */
+    float ctc_weight;
+    int blank_index;
 } sbk_beam_params;
 
 const char* sbk_last_error(void); /* thread-local message of the last failing call */

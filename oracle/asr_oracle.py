@@ -421,9 +421,10 @@ def full_pipeline_features(wav, wav_lens, sd, cfg):
 def beam_search(enc_states, wav_len, sd, cfg, seq_lin_w, seq_lin_b, bos_index=1, eos_index=2, beam_size=4,
                 min_decode_ratio=0.0, max_decode_ratio=1.0, temperature=1.0, using_eos_threshold=True,
                 eos_threshold=1.5, length_normalization=True, minus_inf=-1e20, topk=1, prefix="", return_history=False,
-                lm=None):
-    """S2STransformerBeamSearcher.forward, using_max_attn_shift=False; scorer=None, or (``lm`` = dict(sd, cfg, weight,
-    temperature, prefix)) a ScorerBuilder with one full scorer, TransformerLMScorer (scorer.py:1221-1268).
+                lm=None, ctc=None):
+    """S2STransformerBeamSearcher.forward, using_max_attn_shift=False; scorer=None, or a ScorerBuilder with full scorers
+    TransformerLMScorer (``lm`` = dict(sd, cfg, weight, temperature, prefix)) and/or CTCScorer (``ctc`` = dict(w, b, weight,
+    blank_index)), in the recipe's order [transformerlm, ctc] (scorer.py:1221-1268; conformer_large.yaml:209-223).
 
     Follows init_beam_search_data (:1267-1369), search_step (:1478-1598), _compute_scores_and_next_inp_tokens
     (:1204-1265), _update_sequences_and_log_probs (:1152-1202), _update_hyps_and_scores_if_eos_token (:1371-1416),
@@ -446,6 +447,13 @@ def beam_search(enc_states, wav_len, sd, cfg, seq_lin_w, seq_lin_b, bos_index=1,
     memory = None
     scores = None
     history = []
+    attn_weight = 1.0
+    ctc_state = ctc_mem = None
+    if ctc is not None:  # seq2seq.py:791-804 (attn_weight = 1 - ctc_weight), scorer.py:243-249 (CTCScorer.reset_mem)
+        assert len({bos_index, eos_index, ctc["blank_index"]}) == 3
+        attn_weight = 1.0 - ctc["weight"]
+        ctc_state = ctc_prefix_reset(F.log_softmax(F.linear(enc_states, ctc["w"], ctc["b"]), dim=-1), enc_lens,
+                                     ctc["blank_index"], eos_index)
 
     def add_eos_hyps(tokens, scores_):
         is_eos = tokens.eq(eos_index)
@@ -462,6 +470,8 @@ def beam_search(enc_states, wav_len, sd, cfg, seq_lin_w, seq_lin_b, bos_index=1,
         memory = inp.unsqueeze(1) if memory is None else torch.cat([memory, inp.unsqueeze(1)], dim=-1)
         pred, _ = decode(memory, enc, enc_l, sd, cfg, prefix)
         log_probs = F.log_softmax(F.linear(pred, seq_lin_w, seq_lin_b) / temperature, dim=-1)[:, -1, :]
+        if ctc is not None:
+            log_probs = attn_weight * log_probs  # _attn_weight_step (:916-921)
         lp_clone = log_probs.clone().reshape(B, -1)
         if step < min_steps:
             log_probs[:, eos_index] = minus_inf
@@ -472,10 +482,16 @@ def beam_search(enc_states, wav_len, sd, cfg, seq_lin_w, seq_lin_b, bos_index=1,
         if lm is not None:  # _scorer_step: the LM sees the same token prefix as the decoder (memory incl. inp)
             log_probs = log_probs + lm["weight"] * lm_scorer_log_probs(memory, lm["sd"], lm["cfg"], lm["temperature"],
                                                                       lm.get("prefix", ""))
+        if ctc is not None:  # ScorerBuilder.score: block blank, add weight * (psi - psi_prev) over the full vocabulary
+            log_probs[:, ctc["blank_index"]] = ctc_state["minus_inf"]
+            ctc_score, ctc_mem = ctc_prefix_step(ctc_state, inp, ctc_mem, beam_size)
+            log_probs = log_probs + ctc["weight"] * ctc_score
         sc = seq_scores.unsqueeze(1) + log_probs
         if length_normalization:
             sc = sc / (step + 1)
         scores, cand = sc.view(B, -1).topk(beam_size, dim=-1)
+        if ctc is not None:  # permute_scorer_mem: the CTC memory follows ``candidates`` (scorer.py:1286-1290)
+            ctc_mem = ctc_prefix_permute(ctc_state, ctc_mem, cand)
         inp = (cand % V).view(n_bh)
         scores = scores.view(n_bh)
         seq_scores = scores * (step + 1) if length_normalization else scores.clone()
@@ -552,3 +568,73 @@ def lm_scorer_log_probs(memory_tokens, sd_lm, cfg_lm, temperature, prefix=""):
     """TransformerLMScorer.score (scorer.py:510-543): log_softmax(lm(memory) / temperature)[:, -1, :]."""
     logits = transformer_lm_forward(memory_tokens, sd_lm, cfg_lm, prefix)
     return F.log_softmax(logits / temperature, dim=-1)[:, -1, :]
+
+
+# --------------------------------------------------------------------------
+# CTC prefix scorer (joint CTC/attention decoding, full-vocabulary scoring): decoders/ctc.py:46-295 (CTCPrefixScore),
+# decoders/scorer.py:183-249 (CTCScorer); ctc_window_size = 0 and candidates = None (the recipe's full scorer).
+# --------------------------------------------------------------------------
+
+
+def ctc_prefix_reset(x, enc_lens, blank_index, eos_index, minus_inf=-1e20):
+    """CTCPrefixScore.__init__ (ctc.py:46-78): x = log_softmax(ctc_lin(enc)) (B, T, V); frames >= enc_len get minus_inf for
+    every non-blank token and 0 for the blank (x[:, :, 0] is hard-coded there, i.e. the blank must be index 0)."""
+    B, T, V = x.shape
+    x = x.clone()
+    pad = ~(torch.arange(T).unsqueeze(0) < enc_lens.unsqueeze(1))  # (B, T)
+    x.masked_fill_(pad.unsqueeze(-1), minus_inf)
+    x[:, :, 0] = x[:, :, 0].masked_fill(pad, 0.0)
+    return dict(x_nb=x.transpose(0, 1).contiguous(),  # (T, B, V)
+                x_b=x[:, :, blank_index].transpose(0, 1).contiguous(),  # (T, B)
+                last=(enc_lens - 1).long(), blank=blank_index, eos=eos_index, minus_inf=minus_inf, prefix_length=-1,
+                B=B, T=T, V=V)
+
+
+def ctc_prefix_step(st, last_char, states, beam_size):
+    """CTCPrefixScore.forward_step (ctc.py:80-249), candidates=None.  states = (r_prev (T, 2, n_bh), psi_prev (n_bh, V)) or
+    None.  Returns (psi - psi_prev, (r (T, 2, n_bh, V), psi (n_bh, V)))."""
+    T, B, V, NEG = st["T"], st["B"], st["V"], st["minus_inf"]
+    n_bh = last_char.shape[0]
+    st["prefix_length"] += 1
+    pl = st["prefix_length"]
+    if states is None:
+        r_prev = torch.full((T, 2, B, beam_size), NEG)
+        r_prev[:, 1] = torch.cumsum(st["x_nb"][:, :, st["blank"]], 0).unsqueeze(2)
+        r_prev = r_prev.view(T, 2, n_bh)
+        psi_prev = torch.zeros(n_bh, V)
+    else:
+        r_prev, psi_prev = states
+    x_nb = st["x_nb"].repeat_interleave(beam_size, dim=1)  # (T, n_bh, V)
+    x_b = st["x_b"].repeat_interleave(beam_size, dim=1).unsqueeze(-1)  # (T, n_bh, 1)
+    r = torch.full((T, 2, n_bh, V), NEG)
+    if pl == 0:
+        r[0, 0] = x_nb[0]
+    r_sum = torch.logsumexp(r_prev, 1)  # (T, n_bh)
+    phi = r_sum.unsqueeze(2).repeat(1, 1, V)
+    rows = torch.arange(n_bh)
+    phi[:, rows, last_char] = r_prev[:, 1, :]
+    start, end = max(1, pl), T
+    for t in range(start, end):
+        rnb, rb = r[t - 1, 0], r[t - 1, 1]
+        r[t, 0] = torch.logsumexp(torch.stack([rnb, phi[t - 1]]), 0) + x_nb[t]
+        r[t, 1] = torch.logsumexp(torch.stack([rnb, rb]), 0) + x_b[t]
+    psi_init = r[start - 1, 0].unsqueeze(0)
+    phix = torch.cat((phi[0].unsqueeze(0), phi[:-1]), dim=0) + x_nb
+    psi = torch.logsumexp(torch.cat((phix[start:end], psi_init), dim=0), dim=0)
+    psi[rows, st["eos"]] = r_sum[st["last"].repeat_interleave(beam_size), rows]
+    if st["eos"] != st["blank"]:
+        psi[:, st["blank"]] = NEG
+    return psi - psi_prev, (r, psi)
+
+
+def ctc_prefix_permute(st, memory, cand):
+    """CTCPrefixScore.permute_mem (ctc.py:251-295) for scoring_table=None: ``cand`` (B, beam) indexes beam*V per batch."""
+    r, psi = memory
+    V, T = st["V"], st["T"]
+    B, beam = cand.shape
+    n_bh = B * beam
+    off = (torch.arange(B) * beam).unsqueeze(1)
+    cand_index = (cand + off * V).view(n_bh)
+    psi_sel = psi.reshape(-1)[cand_index].view(-1, 1).repeat(1, V)
+    r_sel = r.reshape(T, 2, n_bh * V)[:, :, cand_index]
+    return r_sel, psi_sel

@@ -247,10 +247,59 @@ def beam_lm_case(tag="beam_lm_conformer_large_rope"):
     torch.save(out, os.path.join(OUT, f"{tag}.pt"))
 
 
+def beam_ctc_case(tag="beam_ctc_conformer_large_rope"):
+    """Joint CTC/attention decoding: ScorerBuilder(full_scorers=[TransformerLMScorer, CTCScorer]) (the recipe's test search,
+    conformer_large.yaml:209-223: lm 0.60, ctc 0.40) and full_scorers=[CTCScorer] (the valid search, :225-228)."""
+    from speechbrain.decoders.scorer import CTCScorer, ScorerBuilder, TransformerLMScorer
+    from speechbrain.decoders.seq2seq import S2STransformerBeamSearcher
+    from speechbrain.lobes.models.transformer.TransformerLM import TransformerLM
+    fb, norm, mods, sd = build_reference(CFG_L, "RoPEMHA")
+    g = torch.load(os.path.join(OUT, "conformer_large_rope.pt"))
+    enc, wav_lens = g["enc_out"], g["wav_lens"]
+    T = enc.shape[1]
+    lm = TransformerLM(vocab=5000, d_model=768, nhead=12, num_encoder_layers=12, num_decoder_layers=0, d_ffn=3072,
+                       dropout=0.0, activation=torch.nn.GELU, normalize_before=False)
+    sd_lm = seeded_state_dict(lm, seed=1)
+    lm.load_state_dict(sd_lm)
+    lm.eval()
+    cfg_lm = dict(d_model=768, nhead=12, num_encoder_layers=12, d_ffn=3072, activation="gelu")
+    out = {}
+    cases = [("ctc_lm_test", True, dict(beam_size=4, using_eos_threshold=False, temperature=1.15), 0.0, 10.5),
+             ("ctc_valid", False, dict(beam_size=5, using_eos_threshold=False, temperature=1.15), 0.0, 10.5),
+             ("ctc_eos", False, dict(beam_size=3, using_eos_threshold=True, temperature=1.0, min_decode_ratio=1.5 / T), 9.0, 8.5)]
+    for name, with_lm, kw, eos_bias, steps in cases:
+        with torch.no_grad():
+            bias = sd["seq_lin.w.bias"].clone()
+            bias[2] += eos_bias
+            mods["seq_lin"].w.bias.copy_(bias)
+            kwargs = dict(kw)
+            kwargs.setdefault("min_decode_ratio", 0.0)
+            ctc_scorer = CTCScorer(eos_index=2, blank_index=0, ctc_fc=mods["ctc_lin"])
+            if with_lm:
+                scorer = ScorerBuilder(full_scorers=[TransformerLMScorer(language_model=lm, temperature=1.15), ctc_scorer],
+                                       weights={"transformerlm": 0.6, "ctc": 0.4})
+            else:
+                scorer = ScorerBuilder(full_scorers=[ctc_scorer], weights={"ctc": 0.4})
+            bs = S2STransformerBeamSearcher(modules=[mods["Transformer"], mods["seq_lin"]], bos_index=1, eos_index=2,
+                                            max_decode_ratio=steps / T, scorer=scorer, **kwargs)
+            hyps, lens, scores, lp = bs(enc, wav_lens)
+            ocfg = dict(CFG_L, attention_type="RoPEMHA")
+            ohyps, olens, oscores, olp = O.beam_search(
+                enc, wav_lens, sd, ocfg, sd["seq_lin.w.weight"], bias, 1, 2, max_decode_ratio=steps / T, prefix="Transformer.",
+                lm=dict(sd=sd_lm, cfg=cfg_lm, weight=0.6, temperature=1.15) if with_lm else None,
+                ctc=dict(w=sd["ctc_lin.w.weight"], b=sd["ctc_lin.w.bias"], weight=0.4, blank_index=0), **kwargs)
+        print(f"[beam+ctc {name}] ref hyps {hyps} scores {scores.tolist()} | oracle equal: {ohyps == hyps} "
+              f"score err {(oscores - scores).abs().max():.2e} lp err {(olp - lp).abs().max():.2e}")
+        assert ohyps == hyps and (oscores - scores).abs().max() < 1e-3
+        out[name] = dict(kwargs=kwargs, eos_bias=eos_bias, max_decode_ratio=steps / T, with_lm=with_lm, lm_weight=0.6,
+                         lm_temperature=1.15, ctc_weight=0.4, hyps=hyps, lens=lens, scores=scores, log_probs=lp)
+    torch.save(out, os.path.join(OUT, f"{tag}.pt"))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
-    which = sys.argv[1:] or ["fbank", "norm", "L_rope", "L_relpos", "S_relpos", "beam", "beam_lm"]
+    which = sys.argv[1:] or ["fbank", "norm", "L_rope", "L_relpos", "S_relpos", "beam", "beam_lm", "beam_ctc"]
     if "fbank" in which:
         fbank_cases()
     if "norm" in which:
@@ -265,5 +314,7 @@ if __name__ == "__main__":
         beam_case()
     if "beam_lm" in which:
         beam_lm_case()
+    if "beam_ctc" in which:
+        beam_ctc_case()
     for fn in sorted(os.listdir(OUT)):
         print(fn, os.path.getsize(os.path.join(OUT, fn)))

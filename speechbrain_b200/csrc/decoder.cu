@@ -645,6 +645,7 @@ struct BeamArgs {
     // optional shallow-fusion scorer (TransformerLMScorer): pre-weighted scores added to the (masked) log-probs,
     // and the LM's own next input (embedding + PE in fp32 and fp16) and token cache (pad-mask on id 0)
     const float* add_scores;
+    float attn_weight; int blank;
     const float* lm_emb; const float* lm_pe; int lm_d; float lm_sqrt_d; float* lm_x_next; __half* lm_x16_next; int* tok_cache;
 };
 
@@ -689,10 +690,10 @@ __global__ void __launch_bounds__(BS_THREADS) beam_step_kernel(const BeamArgs a)
             float tot = 0.0f, mne = -INFINITY;
             for (int w = 0; w < BS_THREADS / 32; ++w) { tot += s_red[w]; mne = fmaxf(mne, __int_as_float(s_redi[w])); }
             const float lse = mx + logf(tot);
-            float eos_lp = lg[a.eos] * a.inv_temp - lse;
+            float eos_lp = a.attn_weight * (lg[a.eos] * a.inv_temp - lse);
             if (step < a.min_steps) eos_lp = a.minus_inf;
             if (a.use_eos_threshold) {
-                const float max_lp = fmaxf(mne - lse, eos_lp);
+                const float max_lp = fmaxf(a.attn_weight * (mne - lse), eos_lp);
                 if (!(eos_lp > a.eos_threshold * max_lp)) eos_lp = a.minus_inf;
             }
             if (a.add_scores) eos_lp += a.add_scores[static_cast<size_t>(row0 + k) * V + a.eos];  // ScorerBuilder.score
@@ -710,7 +711,9 @@ __global__ void __launch_bounds__(BS_THREADS) beam_step_kernel(const BeamArgs a)
     const int n_cand = beam * V;
     for (int cidx = tid; cidx < n_cand; cidx += BS_THREADS) {
         const int k = cidx / V, j = cidx - k * V;
-        float lp = (j == a.eos) ? s_eos[k] : a.logits[static_cast<size_t>(row0 + k) * V + j] * a.inv_temp - s_lse[k];
+        float lp = (j == a.eos) ? s_eos[k]
+                                : a.attn_weight * (a.logits[static_cast<size_t>(row0 + k) * V + j] * a.inv_temp - s_lse[k]);
+        if (j == a.blank) lp = a.minus_inf;
         if (a.add_scores && j != a.eos) lp += a.add_scores[static_cast<size_t>(row0 + k) * V + j];
         const float sc = (seq_in[row0 + k] + lp) * inv_len;
         if (sc > bv[BS_MAXB - 1] && sc > -INFINITY) {  // insert (list sorted descending; only the first `beam` matter)
@@ -761,7 +764,7 @@ __global__ void __launch_bounds__(BS_THREADS) beam_step_kernel(const BeamArgs a)
             int kk = 0, tok = 0;
             if (cand != 0x7fffffff) { kk = cand / V; tok = cand - kk * V; }
             const int row = row0 + k, prow = row0 + kk;
-            const float raw_lp = a.logits[static_cast<size_t>(prow) * V + tok] * a.inv_temp - s_lse[kk];
+            const float raw_lp = a.attn_weight * (a.logits[static_cast<size_t>(prow) * V + tok] * a.inv_temp - s_lse[kk]);
             const size_t h = static_cast<size_t>(step) * a.n_bh + row;
             a.hist_tok[h] = tok; a.hist_pred[h] = prow; a.hist_score[h] = sc; a.hist_lp[h] = raw_lp;
             float ns = a.length_norm ? sc * static_cast<float>(step + 1) : sc;
@@ -857,7 +860,7 @@ int beam_step(const BeamStepArgs& p, int B, cudaStream_t stream) {
     a.inv_temp = 1.0f / p.temperature; a.eos_threshold = p.eos_threshold; a.minus_inf = p.minus_inf;
     a.min_steps = p.min_steps; a.eos = p.eos; a.use_eos_threshold = p.use_eos_threshold; a.length_norm = p.length_norm;
     a.emb = p.emb; a.pe = p.pe; a.d = p.d; a.sqrt_d = sqrtf(static_cast<float>(p.d)); a.x_next = p.x_next;
-    a.add_scores = p.add_scores;
+    a.add_scores = p.add_scores; a.attn_weight = p.attn_weight; a.blank = p.blank;
     a.lm_emb = p.lm.emb; a.lm_pe = p.lm.pe; a.lm_d = p.lm.d; a.lm_sqrt_d = p.lm.d ? sqrtf(static_cast<float>(p.lm.d)) : 0.f;
     a.lm_x_next = p.lm.x; a.lm_x16_next = p.lm.x16; a.tok_cache = p.lm.tok_cache;
     SBK_CUDA_CHECK(launch_k(beam_step_kernel, dim3(B), dim3(BS_THREADS), 0, stream, a));

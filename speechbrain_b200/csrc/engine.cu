@@ -92,6 +92,9 @@ struct AsrModel {
     std::vector<LmLayerW> lm;
     const float *lm_norm_g, *lm_norm_b, *lm_bp0, *lm_lnp_g, *lm_lnp_b, *lm_bp2;
     const __half *lm_wp0, *lm_wp2;
+    // CTC prefix scorer state (allocated on the first beam search that uses it): x [B, T, V] masked log-posteriors,
+    // xb [B, T], rsum/rb [2][rows, T] and psi [2][rows] ping-pong by step parity, add [rows, V] when there is no LM buffer
+    struct CtcBuf { float* base = nullptr; size_t cap = 0; float *x, *xb, *rsum, *rb, *psi, *add; } ctc;
     // shapes the workspace is carved for
     int wsB = 0, wsL = 0, ws_rows = 0, ws_steps = 0;
     struct Buf {
@@ -440,6 +443,7 @@ int asr_clone(AsrModel* src, AsrModel** out) {
     m->ws = Arena();
     m->wsB = m->wsL = m->ws_rows = m->ws_steps = 0;
     m->b = AsrModel::Buf();
+    m->ctc = AsrModel::CtcBuf();
     m->step_graph = nullptr;
     m->pipe_graph = nullptr;
     m->group_graph = nullptr;
@@ -467,6 +471,7 @@ void asr_destroy(AsrModel* m) {
         delete m->weight_refs;
     }
     cudaFree(m->ws.base);
+    cudaFree(m->ctc.base);
     if (m->host_flag) cudaFreeHost(m->host_flag);
     if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
     delete m;
@@ -766,13 +771,44 @@ static int run_beam(AsrModel* m, int B, int T, const sbk_beam_params& p, int* hi
     set_pdl(getenv("SBK_PDL") != nullptr);
     const bool use_lm = p.lm_weight != 0.0f;
     SBK_REQUIRE(!use_lm || m->has_lm, "beam: lm_weight != 0 but this handle has no TransformerLM weights");
+    const bool use_ctc = p.ctc_weight != 0.0f;
+    CtcStep cs{};
+    if (use_ctc) {  // CTCScorer.reset_mem (scorer.py:243-249) + CTCPrefixScore.__init__ (ctc.py:46-78)
+        SBK_REQUIRE(m->w_ctc, "beam: ctc_weight != 0 but this handle has no ctc_lin weights");
+        SBK_REQUIRE(p.blank_index >= 0 && p.blank_index < c.vocab && p.blank_index != p.bos && p.blank_index != p.eos &&
+                    p.bos != p.eos, "Set blank, eos and bos to different indexes for joint ATT/CTC or CTC decoding");
+        const size_t V = c.vocab;
+        auto al = [](size_t n) { return (n * 4 + 255) & ~size_t(255); };
+        const size_t need = al((size_t)M * V) + al(M) + 2 * al((size_t)2 * rows * T) + al(2 * rows) + (use_lm ? 0 : al(rows * V));
+        AsrModel::CtcBuf& cb = m->ctc;
+        if (need > cb.cap) {
+            if (cb.base) { SBK_CUDA_CHECK(cudaStreamSynchronize(st)); cudaFree(cb.base); cb.base = nullptr; cb.cap = 0; }
+            if (cudaMalloc(&cb.base, need) != cudaSuccess) { set_error("beam: CTC scorer cudaMalloc(%zu) failed", need); return SBK_ERR_NOMEM; }
+            cb.cap = need;
+        }
+        char* q = reinterpret_cast<char*>(cb.base);
+        cb.x = reinterpret_cast<float*>(q); q += al((size_t)M * V);
+        cb.xb = reinterpret_cast<float*>(q); q += al(M);
+        cb.rsum = reinterpret_cast<float*>(q); q += al((size_t)2 * rows * T);
+        cb.rb = reinterpret_cast<float*>(q); q += al((size_t)2 * rows * T);
+        cb.psi = reinterpret_cast<float*>(q); q += al(2 * rows);
+        cb.add = use_lm ? b.lm_extra : reinterpret_cast<float*>(q);
+        GemmEpilogue e;
+        e.mode = EPI_F32; e.bias = m->b_ctc; e.out = cb.x; e.ldo = c.vocab;
+        RC(gemm_f16(b.enc16, d, m->w_ctc, d, e, M, c.vocab, d, st));
+        RC(ctc_prefix_reset(cb.x, cb.xb, b.enc_len, B, T, c.vocab, p.blank_index, beam, cb.rsum, cb.rb, cb.psi, st));
+        cs.x = cb.x; cs.xb = cb.xb; cs.enc_len = b.enc_len; cs.hist_tok = hist_tok; cs.hist_pred = hist_pred; cs.n_bh = rows;
+        cs.bos = p.bos; cs.T = T; cs.V = c.vocab; cs.beam = beam; cs.blank = p.blank_index; cs.eos = p.eos;
+        cs.weight = p.ctc_weight; cs.out = cb.add; cs.accumulate = use_lm ? 1 : 0;
+    }
     BeamLm lm;
     if (use_lm) { lm.emb = m->lm_emb; lm.pe = m->lm_pe; lm.d = c.lm_d_model; lm.x = b.lx; lm.x16 = b.lx16; lm.tok_cache = b.tok_cache; }
     RC(beam_reset(rows, beam, S_max, p.bos, b.step, b.seq_scores, b.lineage, b.finished, b.ended_count, m->emb, m->dec_pe, d,
                   b.dx, use_lm ? &lm : nullptr, st));
     BeamStepArgs a{};
-    a.add_scores = use_lm ? b.lm_extra : nullptr;
+    a.add_scores = use_lm ? b.lm_extra : (use_ctc ? m->ctc.add : nullptr);
     a.lm = lm;
+    if (use_ctc) { a.attn_weight = 1.0f - p.ctc_weight; a.blank = p.blank_index; }
     a.logits = b.logits; a.V = c.vocab; a.beam = beam; a.S_max = S_max; a.seq_scores = b.seq_scores; a.lineage = b.lineage;
     a.step_arr = b.step; a.finished = b.finished; a.n_full = b.ended_count;
     a.hist_tok = hist_tok; a.hist_pred = hist_pred; a.hist_score = hist_score; a.hist_lp = hist_lp;
@@ -786,7 +822,17 @@ static int run_beam(AsrModel* m, int B, int T, const sbk_beam_params& p, int* hi
         for (int i = 0; i < chunk; ++i) {
             RC(enqueue_decode_layers(m, rows, beam, T, S_max, b.lineage, st));
             if (use_lm) RC(enqueue_lm_step(m, rows, S_max, p.lm_temperature, p.lm_weight, st));
+            if (use_ctc) {  // ScorerBuilder.score (ctc after transformerlm), then permute_scorer_mem on the survivors
+                const int cur = (s + i) & 1;
+                const size_t rt = (size_t)rows * T;
+                cs.step = s + i;
+                cs.rsum = m->ctc.rsum + cur * rt; cs.rb = m->ctc.rb + cur * rt; cs.psi_prev = m->ctc.psi + cur * rows;
+                cs.rsum_out = m->ctc.rsum + (cur ^ 1) * rt; cs.rb_out = m->ctc.rb + (cur ^ 1) * rt;
+                cs.psi_out = m->ctc.psi + (cur ^ 1) * rows;
+                RC(ctc_prefix_score(cs, st));
+            }
             RC(beam_step(a, B, st));
+            if (use_ctc) RC(ctc_prefix_update(cs, st));
         }
         s += chunk;
         if (s < p.max_steps && m->poll_every > 0) {  // `_check_full_beams` (:806-822), polled once per chunk

@@ -121,7 +121,21 @@ struct BeamStepArgs {
     const float* emb; const float* pe; int d; float* x_next;
     const float* add_scores;  // [n_bh, V] pre-weighted scorer scores or null
     BeamLm lm;
+    float attn_weight = 1.0f;  // 1 - ctc_weight (seq2seq.py:803-804, _attn_weight_step)
+    int blank = -1;            // CTC blank index, blocked in the log-probs (scorer.py:1248-1250); -1 = no CTC scorer
 };
+// CTC prefix scorer (ctc_scorer.cu)
+struct CtcStep {
+    const float* x; const float* xb; const float* rsum; const float* rb; const float* psi_prev; const int* enc_len;
+    const int* hist_tok; const int* hist_pred;
+    int n_bh, step, bos, T, V, beam, blank, eos;
+    float weight; float* out; int accumulate;
+    float* rsum_out; float* rb_out; float* psi_out;
+};
+int ctc_prefix_reset(float* x, float* xb, const int* enc_len, int B, int T, int V, int blank, int beam, float* rsum, float* rb,
+                     float* psi_prev, cudaStream_t stream);
+int ctc_prefix_score(const CtcStep& p, cudaStream_t stream);
+int ctc_prefix_update(const CtcStep& p, cudaStream_t stream);
 int beam_reset(int n_bh, int beam, int S_max, int bos, int* step_arr, float* seq_scores, int* lineage, int* finished,
                int* n_full, const float* emb, const float* pe, int d, float* x, const BeamLm* lm, cudaStream_t stream);
 int layernorm_dual(float* x, __half* x16, const float* gamma, const float* beta, int M, int D, float eps, bool write_f32,

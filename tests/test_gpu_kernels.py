@@ -295,3 +295,45 @@ def test_beam_search_with_transformerlm_scorer_golden(dev, case):
     assert hyps == gb["hyps"]
     assert (scores.cpu() - gb["scores"]).abs().max() < 3e-2
     assert (lp.cpu() - gb["log_probs"]).abs().max() < 3e-2
+
+
+@pytest.mark.parametrize("case", ["ctc_lm_test", "ctc_valid", "ctc_eos"])
+def test_beam_search_with_ctc_scorer_golden(dev, case):
+    """Joint CTC/attention decoding: S2STransformerBeamSearcher + ScorerBuilder(full_scorers=[TransformerLMScorer, CTCScorer]
+    (test search) or [CTCScorer] (valid search), ctc 0.4 / lm 0.6) vs the REFERENCE: hypotheses identical, scores within
+    5e-2 (fp16 GEMM operands in the decoder, LM and CTC head; the prefix scores sum ~T log-posteriors)."""
+    from speechbrain_b200.decoders.scorer import CTCScorer, ScorerBuilder, TransformerLMScorer
+    from speechbrain_b200.decoders.seq2seq import S2STransformerBeamSearcher
+    from speechbrain_b200.lobes.models.transformer.TransformerASR import TransformerASR
+    from speechbrain_b200.lobes.models.transformer.TransformerLM import TransformerLM
+    from speechbrain_b200.nnet.linear import Linear
+    from speechbrain_b200.utils.seeded_init import CONFORMER_LARGE, seeded_asr_state, seeded_state_dict
+    g = torch.load(os.path.join(GOLDEN, "conformer_large_rope.pt"))
+    gb = torch.load(os.path.join(GOLDEN, "beam_ctc_conformer_large_rope.pt"))[case]
+    sd = seeded_asr_state(dict(CONFORMER_LARGE), 0)
+    tr = TransformerASR(input_size=640, tgt_vocab=5000, d_model=512, nhead=8, num_encoder_layers=12, num_decoder_layers=6,
+                        d_ffn=2048, activation=torch.nn.GELU, encoder_module="conformer", attention_type="RoPEMHA",
+                        normalize_before=True, causal=False)
+    tr.load_state_dict({k[len("Transformer."):]: v for k, v in sd.items() if k.startswith("Transformer.")}, strict=False)
+    lin = Linear(input_size=512, n_neurons=5000)
+    bias = sd["seq_lin.w.bias"].clone()
+    bias[2] += gb["eos_bias"]
+    lin.load_state_dict({"w.weight": sd["seq_lin.w.weight"], "w.bias": bias})
+    ctc_lin = Linear(input_size=512, n_neurons=5000)
+    ctc_lin.load_state_dict({"w.weight": sd["ctc_lin.w.weight"], "w.bias": sd["ctc_lin.w.bias"]})
+    ctc_scorer = CTCScorer(eos_index=2, blank_index=0, ctc_fc=ctc_lin)
+    if gb["with_lm"]:
+        lm = TransformerLM(vocab=5000, d_model=768, nhead=12, num_encoder_layers=12, num_decoder_layers=0, d_ffn=3072,
+                           dropout=0.0, activation=torch.nn.GELU, normalize_before=False)
+        lm.load_state_dict(seeded_state_dict(lm, seed=1))
+        scorer = ScorerBuilder(full_scorers=[TransformerLMScorer(language_model=lm, temperature=gb["lm_temperature"]), ctc_scorer],
+                               weights={"transformerlm": gb["lm_weight"], "ctc": gb["ctc_weight"]})
+    else:
+        scorer = ScorerBuilder(full_scorers=[ctc_scorer], weights={"ctc": gb["ctc_weight"]})
+    bs = S2STransformerBeamSearcher(modules=[tr, lin], bos_index=1, eos_index=2, max_decode_ratio=gb["max_decode_ratio"],
+                                    scorer=scorer, **gb["kwargs"])
+    hyps, lens, scores, lp = bs(g["enc_out"].to(dev), g["wav_lens"].to(dev))
+    print(f"beam+ctc[{case}] hyps {hyps} ref {gb['hyps']} scores {scores.tolist()} ref {gb['scores'].tolist()}")
+    assert hyps == gb["hyps"]
+    assert (scores.cpu() - gb["scores"]).abs().max() < 5e-2
+    assert (lp.cpu() - gb["log_probs"]).abs().max() < 5e-2
