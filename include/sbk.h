@@ -98,6 +98,9 @@ int sbk_asr_set_poll_interval(sbk_asr* m, int every_n_steps);
 /* Decoder pre-norms: 1 (default) = fused into the consuming projection kernel (best single-batch latency);
  * 0 = separate LayerNorm kernel (less total GPU time when several batches are in flight). Same numerics. */
 int sbk_asr_set_decoder_ln_fusion(sbk_asr* m, int on);
+/* Decode steps with at least `rows` live hypotheses (several batches decoded together, wide beams) run their projections
+ * on the tcgen05 GEMM instead of the weight-streaming kernel (default 64; a huge value = never, 1 = always). */
+int sbk_asr_set_decoder_tc_min_rows(sbk_asr* m, int rows);
 int sbk_asr_num_frames(const sbk_asr* m, int n_samples, int* T_feat, int* T_enc);
 
 /* ConvolutionFrontEnd.forward (lobes/models/convolution.py:116-320): feats [B,T0,n_mels] -> out [B,T2,F2*C2] fp32 */

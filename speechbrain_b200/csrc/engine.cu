@@ -119,6 +119,7 @@ struct AsrModel {
     cudaGraphExec_t pipe_graph = nullptr;
     long long pipe_nodes = 0;
     int* weight_refs = nullptr;  // weights (arena + fbank plan) are shared between a handle and its clones (lanes)
+    int dec_tc_rows = getenv("SBK_DEC_TC_ROWS") ? atoi(getenv("SBK_DEC_TC_ROWS")) : 64;  // >= this many live hypotheses: tcgen05 decode GEMMs
     int fuse_dec_ln = 1;         // 1: LayerNorm inside the projection kernel (latency); 0: separate LN kernel (throughput)
     int poll_every = 8;          // greedy early-exit poll interval in steps; 0 = never sync, run exactly max_steps
     bool has_fbank = false, has_cnn = false, has_enc = false, has_dec = false;
@@ -637,8 +638,58 @@ static int dec_ln(AsrModel* m, SkinnyArgs& a, const float* g, const float* bta, 
     return layernorm_rows(b.dx, b.dh16, true, g, bta, rows, d, 1e-6f, false, st);
 }
 
+// Decode step when many hypotheses are live (several batches decoded together, or a wide beam): the projections run on
+// the tcgen05 GEMM (128 x 32/64 tiles, a handful of CTAs each, so concurrent lanes share the GPU) instead of the
+// weight-streaming kernel whose cost grows with every 32 rows.  Same maths: fp16 operands, fp32 accumulate / residual.
+static int enqueue_decode_layers_tc(AsrModel* m, int rows, int rows_per_utt, int T, int S_max, const int* lineage,
+                                    cudaStream_t st) {
+    const sbk_asr_config& c = m->cfg;
+    AsrModel::Buf& b = m->b;
+    const int d = c.d_model, F = c.d_ffn, H = c.nhead, dh = d / H, Ld = c.num_decoder_layers;
+    const int n_utt = rows / rows_per_utt;
+    for (int l = 0; l < Ld; ++l) {
+        const DecLayerW& w = m->dec[l];
+        __half* kc = b.kcache + (size_t)l * rows * S_max * d;
+        __half* vc = b.vcache + (size_t)l * rows * S_max * d;
+        RC(layernorm_rows(b.dx, b.dh16, true, w.n1g, w.n1b, rows, d, 1e-6f, false, st));
+        GemmEpilogue e;
+        e.mode = EPI_QKV_CACHE; e.bias = w.b_self_in; e.out = b.dq16; e.ldo = d; e.kcache = kc; e.vcache = vc;
+        e.step_ptr = b.step; e.S_max = S_max; e.qkv_d = d;
+        RC(gemm_f16_small(b.dh16, d, w.w_self_in, d, e, rows, 3 * d, d, st));
+        DecAttnArgs t{};
+        t.q = b.dq16; t.ldq = d; t.kbase = kc; t.vbase = vc; t.row_stride = (size_t)S_max * d; t.key_stride = d;
+        t.rows_per_block = 1; t.n_keys_ptr = b.step; t.enc_len = nullptr; t.H = H; t.dh = dh; t.out = b.datt16; t.ldo = d;
+        t.lineage = lineage; t.lin_stride = S_max;
+        RC(dec_attention(t, rows, S_max, st));
+        e = GemmEpilogue(); e.mode = EPI_RESID; e.bias = w.b_self_out; e.out = b.dx; e.resid = b.dx; e.ldo = d;
+        RC(gemm_f16_small(b.datt16, d, w.w_self_out, d, e, rows, d, d, st));
+        RC(layernorm_rows(b.dx, b.dh16, true, w.n2g, w.n2b, rows, d, 1e-6f, false, st));
+        e = GemmEpilogue(); e.mode = EPI_F16; e.bias = w.b_cross_q; e.out = b.dq16; e.ldo = d;
+        RC(gemm_f16_small(b.dh16, d, w.w_cross_q, d, e, rows, d, d, st));
+        t = DecAttnArgs{};
+        t.q = b.dq16; t.ldq = d; t.kbase = b.ckv16 + (size_t)l * n_utt * T * 2 * d; t.vbase = t.kbase + d;
+        t.row_stride = (size_t)T * 2 * d; t.key_stride = 2 * d; t.rows_per_block = rows_per_utt;
+        t.n_keys_ptr = nullptr; t.enc_len = b.enc_len; t.H = H; t.dh = dh; t.out = b.datt16; t.ldo = d;
+        RC(dec_attention(t, rows, T, st));
+        e = GemmEpilogue(); e.mode = EPI_RESID; e.bias = w.b_cross_out; e.out = b.dx; e.resid = b.dx; e.ldo = d;
+        RC(gemm_f16_small(b.datt16, d, w.w_cross_out, d, e, rows, d, d, st));
+        RC(layernorm_rows(b.dx, b.dh16, true, w.n3g, w.n3b, rows, d, 1e-6f, false, st));
+        e = GemmEpilogue(); e.mode = EPI_F16; e.act = c.decoder_activation == SBK_ACT_GELU ? ACT_GELU : ACT_RELU;
+        e.bias = w.b_ffn1; e.out = b.df16; e.ldo = F;
+        RC(gemm_f16_small(b.dh16, d, w.w_ffn1, d, e, rows, F, d, st));
+        e = GemmEpilogue(); e.mode = EPI_RESID; e.bias = w.b_ffn2; e.out = b.dx; e.resid = b.dx; e.ldo = d;
+        RC(gemm_f16_small(b.df16, F, w.w_ffn2, F, e, rows, d, F, st));
+    }
+    RC(layernorm_rows(b.dx, b.dh16, true, m->dec_norm_g, m->dec_norm_b, rows, d, 1e-6f, false, st));
+    GemmEpilogue e;
+    e.mode = EPI_F32; e.bias = m->b_lin; e.out = b.logits; e.ldo = c.vocab;
+    RC(gemm_f16_small(b.dh16, d, m->w_lin, d, e, rows, c.vocab, d, st));
+    return SBK_OK;
+}
+
 static int enqueue_decode_layers(AsrModel* m, int rows, int rows_per_utt, int T, int S_max, const int* lineage,
                                  cudaStream_t st) {
+    if (rows >= m->dec_tc_rows) return enqueue_decode_layers_tc(m, rows, rows_per_utt, T, S_max, lineage, st);
     const sbk_asr_config& c = m->cfg;
     AsrModel::Buf& b = m->b;
     const int d = c.d_model, F = c.d_ffn, H = c.nhead, dh = d / H, Ld = c.num_decoder_layers;
@@ -995,6 +1046,16 @@ int sbk_asr_set_decoder_ln_fusion(sbk_asr* m, int on) {
         if (mm->group_graph) { cudaGraphExecDestroy(mm->group_graph); mm->group_graph = nullptr; }
     }
     mm->fuse_dec_ln = on != 0;
+    return SBK_OK;
+}
+int sbk_asr_set_decoder_tc_min_rows(sbk_asr* m, int rows) {
+    AsrModel* mm = reinterpret_cast<AsrModel*>(m);
+    if (mm->dec_tc_rows != rows) {
+        if (mm->step_graph) { cudaGraphExecDestroy(mm->step_graph); mm->step_graph = nullptr; mm->graph_rows = -1; }
+        if (mm->pipe_graph) { cudaGraphExecDestroy(mm->pipe_graph); mm->pipe_graph = nullptr; }
+        if (mm->group_graph) { cudaGraphExecDestroy(mm->group_graph); mm->group_graph = nullptr; }
+    }
+    mm->dec_tc_rows = rows;
     return SBK_OK;
 }
 int sbk_asr_set_poll_interval(sbk_asr* m, int every_n_steps) {

@@ -35,6 +35,9 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const uint
             } else if (e.act == ACT_GELU) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = gelu_erf_f(v[j]);
+            } else if (e.act == ACT_RELU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
             }
             __half* o = reinterpret_cast<__half*>(e.out) + static_cast<size_t>(row) * e.ldo + col0;
             if (full) {
@@ -86,6 +89,23 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const uint
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
                     if (col0 + j < N) o[j] = fmaf(alpha, v[j], r[j]);
+            }
+            break;
+        }
+        case EPI_QKV_CACHE: {  // qkv_d % 32 == 0, N == 3 * qkv_d: a 32-column chunk lies in exactly one of q / k / v
+            const int sect = col0 / e.qkv_d, c = col0 - sect * e.qkv_d;
+            __half* o;
+            if (sect == 0) o = reinterpret_cast<__half*>(e.out) + static_cast<size_t>(row) * e.ldo + c;
+            else o = (sect == 1 ? e.kcache : e.vcache) +
+                     (static_cast<size_t>(row) * e.S_max + __ldg(e.step_ptr + row)) * e.qkv_d + c;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+                __half2 h0 = __floats2half2_rn(v[j], v[j + 1]), h1 = __floats2half2_rn(v[j + 2], v[j + 3]);
+                __half2 h2 = __floats2half2_rn(v[j + 4], v[j + 5]), h3 = __floats2half2_rn(v[j + 6], v[j + 7]);
+                uint4 u;
+                u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+                u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+                *reinterpret_cast<uint4*>(o + j) = u;
             }
             break;
         }

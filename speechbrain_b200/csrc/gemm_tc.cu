@@ -144,6 +144,22 @@ static int launch_gemm(const void* A, int lda, const void* W, int ldw, const Gem
     return SBK_OK;
 }
 
+int gemm_f16_small(const void* A, int lda, const void* W, int ldw, const GemmEpilogue& epi, int M, int N, int K,
+                   cudaStream_t stream) {
+    SBK_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_f16_small: empty problem M=%d N=%d K=%d", M, N, K);
+    SBK_REQUIRE((K % 8) == 0 && (lda % 8) == 0 && (ldw % 8) == 0, "gemm_f16_small: K/lda/ldw must be multiples of 8");
+    SBK_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0,
+                "gemm_f16_small: operands must be 16-byte aligned");
+    SBK_REQUIRE(epi.mode == EPI_F16 || epi.mode == EPI_F32 || epi.mode == EPI_RESID || epi.mode == EPI_QKV_CACHE,
+                "gemm_f16_small: epilogue mode %d not supported", epi.mode);
+    if (epi.mode == EPI_QKV_CACHE)
+        SBK_REQUIRE(epi.qkv_d % 32 == 0 && N == 3 * epi.qkv_d && epi.kcache && epi.vcache && epi.step_ptr,
+                    "gemm_f16_small: bad EPI_QKV_CACHE arguments");
+    // few, latency-bound CTAs: narrow N tiles spread the weight stream over more SMs; the ring holds a whole K = 512 panel
+    if (N > 2048) return launch_gemm<64, 6>(A, lda, W, ldw, epi, M, N, K, stream);
+    return launch_gemm<32, 8>(A, lda, W, ldw, epi, M, N, K, stream);
+}
+
 int gemm_f16(const void* A, int lda, const void* W, int ldw, const GemmEpilogue& epi, int M, int N, int K,
              cudaStream_t stream) {
     SBK_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_f16: empty problem M=%d N=%d K=%d", M, N, K);

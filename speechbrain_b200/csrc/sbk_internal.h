@@ -8,8 +8,8 @@
 
 namespace sbk {
 
-enum GemmEpiMode { EPI_F16 = 0, EPI_F32 = 1, EPI_RESID = 2, EPI_GLU = 3, EPI_ROPE = 4 };
-enum GemmAct { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU = 2 };
+enum GemmEpiMode { EPI_F16 = 0, EPI_F32 = 1, EPI_RESID = 2, EPI_GLU = 3, EPI_ROPE = 4, EPI_QKV_CACHE = 5 };
+enum GemmAct { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU = 2, ACT_RELU = 3 };
 
 struct GemmEpilogue {
     int mode = EPI_F16;
@@ -24,11 +24,18 @@ struct GemmEpilogue {
     const float* rope_cos = nullptr;  // EPI_ROPE: [T, head_dim/2]
     const float* rope_sin = nullptr;
     int head_dim = 64;
+    // EPI_QKV_CACHE (decoder self-attention in_proj, columns [q | k | v] of width qkv_d): q -> out (fp16, ldo), k / v ->
+    // cache[(row * S_max + step_ptr[row]) * qkv_d + col]
+    __half* kcache = nullptr; __half* vcache = nullptr; const int* step_ptr = nullptr; int S_max = 0; int qkv_d = 0;
 };
 
 // out = epilogue(A[M,K] fp16 x W[N,K]^T fp16), tcgen05 tensor cores. gemm_tc.cu
 int gemm_f16(const void* A, int lda, const void* W, int ldw, const GemmEpilogue& epi, int M, int N, int K,
              cudaStream_t stream);
+// Small-M variant for the decode steps of several batches (M = live hypotheses, 64..512): 128 x 32/64 tiles, deep TMA
+// ring; any epilogue mode incl. EPI_QKV_CACHE. gemm_tc.cu
+int gemm_f16_small(const void* A, int lda, const void* W, int ldw, const GemmEpilogue& epi, int M, int N, int K,
+                   cudaStream_t stream);
 // 2-CTA (cta_group::2) persistent variant, N % 256 == 0. gemm_tc2.cu
 int gemm_f16_2cta(const void* A, int lda, const void* W, int ldw, const GemmEpilogue& epi, int M, int N, int K,
                   cudaStream_t stream);

@@ -130,6 +130,10 @@ class AsrEngine:
     def set_poll_interval(self, every_n_steps):
         check(lib().sbk_asr_set_poll_interval(self._h, int(every_n_steps)), "sbk_asr_set_poll_interval")
 
+    def set_decoder_tc_min_rows(self, rows):
+        """Decode steps with >= rows live hypotheses use the tcgen05 GEMM for the decoder projections (default 64)."""
+        check(lib().sbk_asr_set_decoder_tc_min_rows(self._h, int(rows)), "sbk_asr_set_decoder_tc_min_rows")
+
     def set_decoder_ln_fusion(self, on):
         check(lib().sbk_asr_set_decoder_ln_fusion(self._h, int(bool(on))), "sbk_asr_set_decoder_ln_fusion")
 
