@@ -286,21 +286,25 @@ int skinny_gemm(const SkinnyArgs& a, cudaStream_t stream) {
 }
 
 // --------------------------------------------------------------------------- decode-time attention (1 query / row)
-// One CTA per (row, head), 4 warps split the keys (flash-decoding style): each warp scores its key slice with
-// lanes parallel over keys, then accumulates p.V with 4 lane-groups over keys x 8 lanes over 16-byte dim chunks;
-// the 4 partial (max, sum, out) triples are merged through shared memory.
+// One CTA per (row, head), 4 warps split the keys (flash-decoding style).  Within a warp, lane group g = lane / 8 owns
+// keys c0 + g + 4 i (i < 8) of a 32-key chunk and lane % 8 owns 8 of the 64 head dims, for BOTH q.k and p.V: every
+// 16-byte load instruction of the warp covers 4 whole 128-byte key rows (4 cache lines -- a lane-per-key layout costs
+// 32 L1 tag lookups per instruction and bounded the kernel), q.k partials are reduced over the 8 lanes of a group with
+// 3 shuffles, and the probabilities stay in registers for p.V.  The 4 warps' (max, sum, out) triples are merged
+// through shared memory.
 // Self-attention: keys = cache positions [0, step]; cross-attention: keys = encoder frames [0, enc_len[utt]).
 // (nn.MultiheadAttention semantics, scale 1/sqrt(d_h) already folded into q.)  head_dim == 64.
 constexpr int DA_WARPS = 4;
-constexpr int DA_CHUNK = 32;  // keys a warp scores per round: 1 per lane for q.k, 8 per lane-group for p.V
-constexpr int DA_KPL = DA_CHUNK / 32, DA_VPL = DA_CHUNK / 4;
+constexpr int DA_CHUNK = 32;  // keys a warp handles per round (8 per lane group)
+constexpr int DA_KPG = DA_CHUNK / 4;
 
 __global__ void __launch_bounds__(DA_WARPS * 32, 4) dec_attention_kernel(const DecAttnArgs a) {
-    __shared__ float s_p[DA_WARPS][DA_CHUNK];
     __shared__ float part_o[DA_WARPS][64];
     __shared__ float part_m[DA_WARPS], part_l[DA_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int r = blockIdx.x, h = blockIdx.y;
+    // heads on the fast grid axis: the 8 CTAs that share an utterance's K/V rows (2 KB per frame, 128 B per head) are
+    // co-scheduled, so each DRAM page / L2 line set is consumed while it is open
+    const int r = blockIdx.y, h = blockIdx.x;
     const int blk = r / a.rows_per_block;
     pdl_trigger();
     pdl_wait();
@@ -309,92 +313,79 @@ __global__ void __launch_bounds__(DA_WARPS * 32, 4) dec_attention_kernel(const D
     else n_keys = a.enc_len ? min(a.enc_len[blk], a.n_keys_fixed) : a.n_keys_fixed;
     const int per = (n_keys + DA_WARPS - 1) / DA_WARPS;
     const int kb = warp * per, ke = min(n_keys, kb + per);
-    const __half* q = a.q + static_cast<size_t>(r) * a.ldq + h * 64;
-    const __half* kbase = a.kbase + static_cast<size_t>(blk) * a.row_stride + h * 64;
-    const __half* vbase = a.vbase + static_cast<size_t>(blk) * a.row_stride + h * 64;
+    const int gq = lane >> 3, dl = (lane & 7) * 8;
+    const __half* kbase = a.kbase + static_cast<size_t>(blk) * a.row_stride + h * 64 + dl;
+    const __half* vbase = a.vbase + static_cast<size_t>(blk) * a.row_stride + h * 64 + dl;
     // beam search: position j of hypothesis r lives in the cache row of the ancestor that wrote it
     const int* lin = nullptr;
-    if (a.lineage) lin = a.lineage + static_cast<size_t>((n_keys - 1) & 1) * gridDim.x * a.lin_stride + static_cast<size_t>(r) * a.lin_stride;
-    // query vector (every lane holds all 64 dims as half2 pairs)
-    uint4 qv[8];
+    if (a.lineage) lin = a.lineage + static_cast<size_t>((n_keys - 1) & 1) * gridDim.y * a.lin_stride + static_cast<size_t>(r) * a.lin_stride;
+    const int* tokc = a.tok_cache;  // TransformerLM.make_masks: keys whose token id is pad_idx (0) are masked
+    // this lane's 8 dims of the query
+    float qf[8];
+    {
+        const uint4 qv = *reinterpret_cast<const uint4*>(a.q + static_cast<size_t>(r) * a.ldq + h * 64 + dl);
+        const __half2* q2 = reinterpret_cast<const __half2*>(&qv);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) qv[e] = *reinterpret_cast<const uint4*>(q + e * 8);
-    const int gq = lane >> 3, dl = (lane & 7) * 8;
+        for (int u = 0; u < 4; ++u) {
+            const float2 f = __half22float2(q2[u]);
+            qf[2 * u] = f.x; qf[2 * u + 1] = f.y;
+        }
+    }
     float m_run = -INFINITY, l_run = 0.0f;
     float o[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) o[e] = 0.0f;
-    const int* tokc = a.tok_cache;  // TransformerLM.make_masks: keys whose token id is pad_idx (0) are masked
     for (int c0 = kb; c0 < ke; c0 += DA_CHUNK) {
-        // ---- issue every load of this chunk up front: 2 keys x 128 B (K) and 16 keys x 16 B (V) per lane
-        uint4 kv[DA_KPL][8];
-        uint4 vv[DA_VPL];
+        // ---- issue every load of this chunk up front: 8 keys x (16 B of K + 16 B of V) per lane
+        uint4 kv[DA_KPG], vv[DA_KPG];
+        bool live[DA_KPG];
 #pragma unroll
-        for (int t = 0; t < DA_KPL; ++t) {
-            const int j = c0 + lane + 32 * t;
-            if (j < ke) {
-                const __half* kr = kbase + static_cast<size_t>(j) * a.key_stride;
-                if (lin) kr += (static_cast<ptrdiff_t>(lin[j]) - r) * static_cast<ptrdiff_t>(a.row_stride);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) kv[t][e] = *reinterpret_cast<const uint4*>(kr + e * 8);
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < DA_VPL; ++i) {
+        for (int i = 0; i < DA_KPG; ++i) {
             const int j = c0 + gq + 4 * i;
-            if (j < ke) {
-                const __half* vr = vbase + static_cast<size_t>(j) * a.key_stride + dl;
-                if (lin) vr += (static_cast<ptrdiff_t>(lin[j]) - r) * static_cast<ptrdiff_t>(a.row_stride);
-                vv[i] = *reinterpret_cast<const uint4*>(vr);
+            live[i] = j < ke;
+            if (live[i]) {
+                ptrdiff_t off = static_cast<ptrdiff_t>(j) * a.key_stride;
+                int src_row = r;
+                if (lin) { src_row = lin[j]; off += (static_cast<ptrdiff_t>(src_row) - r) * static_cast<ptrdiff_t>(a.row_stride); }
+                kv[i] = *reinterpret_cast<const uint4*>(kbase + off);
+                vv[i] = *reinterpret_cast<const uint4*>(vbase + off);
+                if (tokc) live[i] = tokc[static_cast<size_t>(src_row) * a.lin_stride + j] != a.pad_tok;
             } else {
+                kv[i] = make_uint4(0u, 0u, 0u, 0u);
                 vv[i] = make_uint4(0u, 0u, 0u, 0u);
             }
         }
-        // ---- scores
-        float sc[DA_KPL];
+        // ---- scores: 8-dim partial dot per lane, summed over the 8 lanes of the key's group
+        float sc[DA_KPG];
+        float cm = -INFINITY;
 #pragma unroll
-        for (int t = 0; t < DA_KPL; ++t) {
-            const int j = c0 + lane + 32 * t;
-            float dot = -INFINITY;
-            bool live = j < ke;
-            if (live && tokc) live = tokc[static_cast<size_t>(lin ? lin[j] : r) * a.lin_stride + j] != a.pad_tok;
-            if (live) {
-                dot = 0.0f;
+        for (int i = 0; i < DA_KPG; ++i) {
+            const __half2* k2 = reinterpret_cast<const __half2*>(&kv[i]);
+            float dot = 0.0f;
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const __half2* k2 = reinterpret_cast<const __half2*>(&kv[t][e]);
-                    const __half2* q2 = reinterpret_cast<const __half2*>(&qv[e]);
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const float2 kf = __half22float2(k2[u]), qf = __half22float2(q2[u]);
-                        dot = fmaf(kf.x, qf.x, dot);
-                        dot = fmaf(kf.y, qf.y, dot);
-                    }
-                }
+            for (int u = 0; u < 4; ++u) {
+                const float2 kf = __half22float2(k2[u]);
+                dot = fmaf(kf.x, qf[2 * u], dot);
+                dot = fmaf(kf.y, qf[2 * u + 1], dot);
             }
-            sc[t] = dot;
+            dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+            dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+            dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+            sc[i] = live[i] ? dot : -INFINITY;
+            cm = fmaxf(cm, sc[i]);
         }
-        float cm = sc[0];
-#pragma unroll
-        for (int t = 1; t < DA_KPL; ++t) cm = fmaxf(cm, sc[t]);
-        const float m_new = fmaxf(m_run, warp_max(cm));
+        cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 8));
+        cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 16));
+        const float m_new = fmaxf(m_run, cm);
         const float alpha = (m_run == -INFINITY) ? 0.0f : __expf(m_run - m_new);
+        // ---- p.V with the probabilities still in registers
         float psum = 0.0f;
-#pragma unroll
-        for (int t = 0; t < DA_KPL; ++t) {
-            const float p = (sc[t] == -INFINITY) ? 0.0f : __expf(sc[t] - m_new);
-            s_p[warp][lane + 32 * t] = p;
-            psum += p;
-        }
-        l_run = l_run * alpha + warp_sum(psum);
-        m_run = m_new;
-        __syncwarp();
-        // ---- p.V : lane group gq owns keys c0 + gq + 4 i; lane % 8 owns dims [dl, dl + 8)
 #pragma unroll
         for (int e = 0; e < 8; ++e) o[e] *= alpha;
 #pragma unroll
-        for (int i = 0; i < DA_VPL; ++i) {
-            const float p = s_p[warp][gq + 4 * i];
+        for (int i = 0; i < DA_KPG; ++i) {
+            const float p = (sc[i] == -INFINITY) ? 0.0f : __expf(sc[i] - m_new);
+            psum += p;
             const __half2* v2 = reinterpret_cast<const __half2*>(&vv[i]);
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -403,7 +394,10 @@ __global__ void __launch_bounds__(DA_WARPS * 32, 4) dec_attention_kernel(const D
                 o[2 * u + 1] = fmaf(p, vf.y, o[2 * u + 1]);
             }
         }
-        __syncwarp();
+        psum += __shfl_xor_sync(0xffffffffu, psum, 8);
+        psum += __shfl_xor_sync(0xffffffffu, psum, 16);
+        l_run = l_run * alpha + psum;
+        m_run = m_new;
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -437,7 +431,7 @@ int dec_attention(const DecAttnArgs& a, int n_rows, int max_keys, cudaStream_t s
     const size_t smem = 0;
     DecAttnArgs b = a;
     b.n_keys_fixed = max_keys;
-    SBK_CUDA_CHECK(launch_k(dec_attention_kernel, dim3(n_rows, a.H), dim3(DA_WARPS * 32), smem, stream, b));
+    SBK_CUDA_CHECK(launch_k(dec_attention_kernel, dim3(a.H, n_rows), dim3(DA_WARPS * 32), smem, stream, b));
     SBK_LAUNCH_CHECK();
     return SBK_OK;
 }

@@ -161,22 +161,50 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const uint
 constexpr int EPI_STG_PITCH = 144;                 // bytes per staged row (32 fp32 + 16 B pad)
 constexpr int EPI_STG_BYTES = 32 * EPI_STG_PITCH;  // per warp
 
-template <int MODE, int ACT>
-__device__ __forceinline__ void epilogue_chunk_coalesced(const GemmEpilogue& e, const uint32_t (&acc)[32], uint8_t* stg,
-                                                         int row_base, int col0, int M, int lane) {
-    float4 res[8];
-    if constexpr (MODE == EPI_RESID) {
-        // out aliases resid (x += ...): issue all 8 residual loads up front -- before the epilogue math and before the
-        // first store (otherwise the compiler must order load i after store i-1 and every iteration eats a full
-        // L2/HBM round trip; measured as the dominant long-scoreboard stall of the N=512 GEMMs)
-        const int seg = lane & 7, rsub = lane >> 3;
+// staging pitch per mode: 32 fp32 (+16 B pad) for fp32 outputs, 64 B of payload (+16 B pad) for fp16 / GLU outputs
+template <int MODE>
+__host__ __device__ constexpr int epi_stg_pitch() { return (MODE == EPI_F32 || MODE == EPI_RESID) ? EPI_STG_PITCH : 80; }
+
+// EPI_RESID: out aliases resid (x += ...).  The 8 residual loads of a chunk are issued through this helper one chunk AHEAD
+// of the epilogue math (the first one before the accumulator is even complete), so their L2/HBM round trip hides behind
+// the main loop / the previous chunk instead of being eaten once per chunk (measured as the dominant long-scoreboard
+// stall of the N=512 GEMMs); they must also precede the first store or the compiler serialises load i after store i-1.
+__device__ __forceinline__ void epilogue_resid_prefetch(const GemmEpilogue& e, float4 (&res)[8], int row_base, int col0, int M,
+                                                        int lane) {
+    const int seg = lane & 7, rsub = lane >> 3;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int row = row_base + i * 4 + rsub;
-            res[i] = row < M ? __ldcg(reinterpret_cast<const float4*>(e.resid + static_cast<size_t>(row) * e.ldo + col0 + seg * 4))
-                             : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < 8; ++i) {
+        const int row = row_base + i * 4 + rsub;
+        res[i] = row < M ? __ldcg(reinterpret_cast<const float4*>(e.resid + static_cast<size_t>(row) * e.ldo + col0 + seg * 4))
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+// EPI_ROPE: the cos / sin of a chunk (16 rotation pairs of this lane's row; q and k sections only) are fetched one chunk
+// ahead as well: with ~200 KB of the SM carved out as shared memory the tables do not survive in L1, so every chunk's
+// rotation would otherwise wait for an L2 round trip (measured: tensor pipe 18 %, issue slots 12 % busy).
+__device__ __forceinline__ void epilogue_rope_prefetch(const GemmEpilogue& e, float2 (&cs)[8], float2 (&sn)[8], int my_row,
+                                                       int col0) {
+    const int dh = e.head_dim;
+    const int within = col0 % (3 * dh);
+    const int sect = within / dh;  // 0 q, 1 k, 2 v
+    if (sect < 2) {
+        const int t = my_row % e.T;
+        const int p0 = (within - sect * dh) >> 1;
+        const float* c = e.rope_cos + static_cast<size_t>(t) * (dh >> 1) + p0;
+        const float* s = e.rope_sin + static_cast<size_t>(t) * (dh >> 1) + p0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            cs[j] = __ldg(reinterpret_cast<const float2*>(c + 2 * j));
+            sn[j] = __ldg(reinterpret_cast<const float2*>(s + 2 * j));
         }
     }
+}
+
+template <int MODE, int ACT, int PITCH = EPI_STG_PITCH>
+__device__ __forceinline__ void epilogue_chunk_coalesced(const GemmEpilogue& e, const uint32_t (&acc)[32], uint8_t* stg,
+                                                         int row_base, int col0, int M, int lane, float4 (&res)[8],
+                                                         int next_col0, float2 (&rcs)[8], float2 (&rsn)[8]) {
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
@@ -188,7 +216,7 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmEpilogue& e, 
         }
     }
     const int my_row = row_base + lane;
-    uint8_t* my = stg + lane * EPI_STG_PITCH;
+    uint8_t* my = stg + lane * PITCH;
     constexpr int out_bytes_per_row = (MODE == EPI_F32 || MODE == EPI_RESID) ? 128 : 64;  // 32 fp32 | 32 fp16 / 16 fp32
     {
         if constexpr (MODE == EPI_F32 || MODE == EPI_RESID) {
@@ -216,15 +244,10 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmEpilogue& e, 
                 const int within = col0 % (3 * dh);
                 const int sect = within / dh;  // 0 q, 1 k, 2 v
                 if (sect < 2) {
-                    const int t = my_row % e.T;
-                    const int p0 = (within - sect * dh) >> 1;
-                    const float* cs = e.rope_cos + static_cast<size_t>(t) * (dh >> 1) + p0;
-                    const float* sn = e.rope_sin + static_cast<size_t>(t) * (dh >> 1) + p0;
                     const float sc = sect == 0 ? e.alpha : 1.0f;
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
-                        const float2 c2 = __ldg(reinterpret_cast<const float2*>(cs + (j >> 1)));
-                        const float2 s2 = __ldg(reinterpret_cast<const float2*>(sn + (j >> 1)));
+                        const float2 c2 = rcs[j >> 2], s2 = rsn[j >> 2];
                         const float x0 = v[j], x1 = v[j + 1], x2 = v[j + 2], x3 = v[j + 3];
                         v[j] = (x0 * c2.x - x1 * s2.x) * sc;
                         v[j + 1] = (x1 * c2.x + x0 * s2.x) * sc;
@@ -232,6 +255,7 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmEpilogue& e, 
                         v[j + 3] = (x3 * c2.y + x2 * s2.y) * sc;
                     }
                 }
+                if (next_col0 >= 0) epilogue_rope_prefetch(e, rcs, rsn, my_row, next_col0);
             } else if constexpr (ACT == ACT_SILU) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
@@ -259,13 +283,15 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmEpilogue& e, 
             const int r = i * 4 + rsub;
             const int row = row_base + r;
             if (row < M) {
-                float4 val = *reinterpret_cast<const float4*>(stg + r * EPI_STG_PITCH + seg * 16);
+                float4 val = *reinterpret_cast<const float4*>(stg + r * PITCH + seg * 16);
                 if constexpr (MODE == EPI_RESID) {
                     val.x += res[i].x; val.y += res[i].y; val.z += res[i].z; val.w += res[i].w;
                 }
                 *reinterpret_cast<float4*>(outp + static_cast<size_t>(row) * e.ldo + col0 + seg * 4) = val;
             }
         }
+        if constexpr (MODE == EPI_RESID)
+            if (next_col0 >= 0) epilogue_resid_prefetch(e, res, row_base, next_col0, M, lane);
     } else {
         const int seg = lane & 3, rsub = lane >> 2;  // 4 lanes x 16 B per row, 8 rows per instruction
         uint8_t* outp = reinterpret_cast<uint8_t*>(e.out);
@@ -278,7 +304,7 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmEpilogue& e, 
             const int row = row_base + r;
             if (row < M)
                 *reinterpret_cast<uint4*>(outp + static_cast<size_t>(row) * row_pitch + col_off + seg * 16) =
-                    *reinterpret_cast<const uint4*>(stg + r * EPI_STG_PITCH + seg * 16);
+                    *reinterpret_cast<const uint4*>(stg + r * PITCH + seg * 16);
         }
     }
     __syncwarp();  // staging tile is reused by the next chunk

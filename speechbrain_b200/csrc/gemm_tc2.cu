@@ -25,14 +25,18 @@ constexpr int G2_BM = 128;        // rows per CTA (256 per pair)
 constexpr int G2_BN = 256;        // columns per pair tile
 constexpr int G2_BK = 64;
 constexpr int G2_STAGES = 5;
-constexpr int G2_EPI_WARPS = 8;      // two warps per TMEM lane quarter, each drains half of the columns
-constexpr int G2_THREADS = 64 + 32 * G2_EPI_WARPS;
+// epilogue warps: EW / 4 warps per TMEM lane quarter, each drains 1 / (EW / 4) of the tile's columns.  The modes that
+// prefetch per-chunk operands (residual, RoPE tables: 32 more registers) keep 8; the MUFU/ALU-heavy fp16 modes (SiLU, GLU)
+// use 16 so every scheduler has 4 epilogue warps to hide latencies behind.
+template <int MODE>
+constexpr int g2_epi_warps() { return (MODE == EPI_F32 || MODE == EPI_RESID || MODE == EPI_ROPE) ? 8 : 16; }
 constexpr int G2_A_BYTES = G2_BM * G2_BK * 2;            // 16 KB
 constexpr int G2_B_BYTES = (G2_BN / 2) * G2_BK * 2;      // 16 KB (this CTA's half of W's tile rows)
 constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
 constexpr int G2_BAR_OFFSET = G2_STAGES * G2_STAGE_BYTES;
-constexpr int G2_STG_OFFSET = G2_BAR_OFFSET + 256;   // 4 epilogue warps x EPI_STG_BYTES staging tiles
-constexpr int G2_SMEM = G2_STG_OFFSET + G2_EPI_WARPS * EPI_STG_BYTES + 1024;
+constexpr int G2_STG_OFFSET = G2_BAR_OFFSET + 256;   // per-epilogue-warp staging tiles (32 rows x pitch)
+template <int MODE, int EW>
+constexpr int g2_smem() { return G2_STG_OFFSET + EW * 32 * epi_stg_pitch<MODE>() + 1024; }
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -93,8 +97,8 @@ __device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols)
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
-template <int MODE, int ACT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
+template <int MODE, int ACT, int EW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EW, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 const GemmEpilogue epi, int M, int N, int K) {
     extern __shared__ uint8_t smem_raw[];
@@ -180,32 +184,40 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         }
     } else {
         const int q = warp & 3;             // TMEM lane quarter this warp may access
-        const int half = (warp - 2) >> 2;   // which half of the tile's columns this warp drains
-        constexpr int CHUNKS = G2_BN / 32 / 2;
-        uint8_t* stg = smem + G2_STG_OFFSET + (warp - 2) * EPI_STG_BYTES;
+        constexpr int PARTS = EW / 4, PART_COLS = G2_BN / PARTS, PITCH = epi_stg_pitch<MODE>();
+        const int part = (warp - 2) >> 2;   // which slice of the tile's columns this warp drains
+        constexpr int CHUNKS = PART_COLS / 32;
+        static_assert(CHUNKS % 2 == 0, "epilogue double buffer needs an even chunk count");
+        uint8_t* stg = smem + G2_STG_OFFSET + (warp - 2) * 32 * PITCH;
         int local_tile = 0;
         for (int tile = pair; tile < total_tiles; tile += num_pairs, ++local_tile) {
             const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
             const int buf = local_tile & 1;
             const uint32_t acc_ph = (local_tile >> 1) & 1;
+            const int row_base = mt * 2 * G2_BM + static_cast<int>(rank) * G2_BM + q * 32;
+            const int n0 = nt * G2_BN + part * PART_COLS;
+            float4 res[8];
+            float2 rcs[8], rsn[8];
+            if constexpr (MODE == EPI_RESID) epilogue_resid_prefetch(epi, res, row_base, n0, M, lane);
+            if constexpr (MODE == EPI_ROPE) epilogue_rope_prefetch(epi, rcs, rsn, row_base + lane, n0);
             mbar_wait_b(&tmem_full_bar[buf], acc_ph, 4);
             tc_fence_after();
-            const int row_base = mt * 2 * G2_BM + static_cast<int>(rank) * G2_BM + q * 32;
-            const int n0 = nt * G2_BN + half * (G2_BN / 2);
-            const uint32_t t0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * G2_BN + half * (G2_BN / 2);
+            const uint32_t t0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * G2_BN + part * PART_COLS;
             uint32_t acc[2][32];
             tmem_ld_32x32(t0, acc[0]);
 #pragma unroll 1
-            for (int c = 0; c < CHUNKS; c += 2) {  // two chunks per iteration keep the double buffer statically indexed
+            for (int c = 0; c < CHUNKS; c += 2) {  // two chunks per iteration keep the double buffers statically indexed
                 tmem_ld_wait();
                 tmem_ld_32x32(t0 + (c + 1) * 32, acc[1]);  // next chunk in flight
-                epilogue_chunk_coalesced<MODE, ACT>(epi, acc[0], stg, row_base, n0 + c * 32, M, lane);
+                epilogue_chunk_coalesced<MODE, ACT, PITCH>(epi, acc[0], stg, row_base, n0 + c * 32, M, lane, res,
+                                                           n0 + (c + 1) * 32, rcs, rsn);
                 tmem_ld_wait();
                 if (c + 2 < CHUNKS) tmem_ld_32x32(t0 + (c + 2) * 32, acc[0]);
-                epilogue_chunk_coalesced<MODE, ACT>(epi, acc[1], stg, row_base, n0 + (c + 1) * 32, M, lane);
+                epilogue_chunk_coalesced<MODE, ACT, PITCH>(epi, acc[1], stg, row_base, n0 + (c + 1) * 32, M, lane, res,
+                                                           c + 2 < CHUNKS ? n0 + (c + 2) * 32 : -1, rcs, rsn);
             }
             tc_fence_before();
-            asm volatile("bar.sync 1, %0;" ::"n"(32 * G2_EPI_WARPS) : "memory");  // all epilogue warps are done with `buf`
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");  // all epilogue warps are done with `buf`
             if (warp == 2 && lane == 0) {
                 if (leader) mbar_arrive(&tmem_empty_bar[buf]);
                 else mbar_arrive_remote(&tmem_empty_bar[buf], 0);
@@ -225,18 +237,29 @@ int gemm_f16_2cta(const void* A, int lda, const void* W, int ldw, const GemmEpil
     rc = make_tmap_2d_f16(&tb, W, N, K, ldw, G2_BN / 2, G2_BK);
     if (rc) return rc;
     void (*kern)(const CUtensorMap, const CUtensorMap, const GemmEpilogue, int, int, int) = nullptr;
+    int smem = 0, threads = 0;
+#define G2_PICK(MODE, ACT)                                                        \
+    do {                                                                          \
+        constexpr int EW = g2_epi_warps<MODE>();                                  \
+        kern = gemm_tc2_kernel<MODE, ACT, EW>;                                    \
+        smem = g2_smem<MODE, EW>();                                               \
+        threads = 64 + 32 * EW;                                                   \
+    } while (0)
     switch (epi.mode) {
         case EPI_F16:
-            kern = epi.act == ACT_SILU ? gemm_tc2_kernel<EPI_F16, ACT_SILU>
-                 : epi.act == ACT_GELU ? gemm_tc2_kernel<EPI_F16, ACT_GELU> : gemm_tc2_kernel<EPI_F16, ACT_NONE>;
+            if (epi.act == ACT_SILU) G2_PICK(EPI_F16, ACT_SILU);
+            else if (epi.act == ACT_GELU) G2_PICK(EPI_F16, ACT_GELU);
+            else if (epi.act == ACT_NONE) G2_PICK(EPI_F16, ACT_NONE);
+            else { set_error("gemm_f16_2cta: activation %d not built", epi.act); return SBK_ERR_ARG; }
             break;
-        case EPI_F32: kern = gemm_tc2_kernel<EPI_F32, ACT_NONE>; break;
-        case EPI_RESID: kern = gemm_tc2_kernel<EPI_RESID, ACT_NONE>; break;
-        case EPI_GLU: kern = gemm_tc2_kernel<EPI_GLU, ACT_NONE>; break;
-        case EPI_ROPE: kern = gemm_tc2_kernel<EPI_ROPE, ACT_NONE>; break;
+        case EPI_F32: G2_PICK(EPI_F32, ACT_NONE); break;
+        case EPI_RESID: G2_PICK(EPI_RESID, ACT_NONE); break;
+        case EPI_GLU: G2_PICK(EPI_GLU, ACT_NONE); break;
+        case EPI_ROPE: G2_PICK(EPI_ROPE, ACT_NONE); break;
         default: set_error("gemm_f16_2cta: bad epilogue mode %d", epi.mode); return SBK_ERR_ARG;
     }
-    SBK_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM));
+#undef G2_PICK
+    SBK_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     static int num_sms = 0;
     if (num_sms == 0) {
         int dev = 0;
@@ -252,7 +275,7 @@ int gemm_f16_2cta(const void* A, int lda, const void* W, int ldw, const GemmEpil
         cudaEventCreate(&e1);
         cudaEventRecord(e0, stream);
     }
-    kern<<<2 * pairs, G2_THREADS, G2_SMEM, stream>>>(ta, tb, epi, M, N, K);
+    kern<<<2 * pairs, threads, smem, stream>>>(ta, tb, epi, M, N, K);
     if (prof->enabled) {
         cudaEventRecord(e1, stream);
         prof->ev.push_back(e0);
