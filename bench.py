@@ -14,7 +14,7 @@ region).  One "step" = one pass of the whole path over one batch.
 
 value  : device-timed throughput, wav already resident in HBM (per-step CUDA events, L2 flushed between steps).
 e2e    : the same through the host-buffer C-ABI call (pinned host wav -> H2D -> ... -> D2H token ids).
-roofline: the dominant kernel (gemm_tc_kernel, tcgen05) timed live with CUDA events in a separate pass.
+roofline: the dominant kernel (gemm_tc2_kernel, 2-CTA tcgen05) timed live with CUDA events in a separate pass.
 cpu_baseline: the CPU oracle (a restatement of the reference algorithm, no KV cache) on a bounded sample.
 """
 import argparse
@@ -158,13 +158,13 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=32)
+    ap.add_argument("--steps", type=int, default=64)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--attention", default="RoPEMHA", choices=["RoPEMHA", "RelPosMHAXL"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lanes", type=int, default=4, help="batches in flight per GPU (engine clones on their own streams)")
-    ap.add_argument("--group", type=int, default=8, help="batches whose decode is coalesced into one greedy loop (engine-level)")
+    ap.add_argument("--group", type=int, default=16, help="batches whose decode is coalesced into one greedy loop (engine-level)")
     ap.add_argument("--decode-steps", type=int, default=48, help="diagnostic: override the pinned 48 greedy steps")
     ap.add_argument("--fuse-dec-ln", type=int, default=1, help="1: decoder LayerNorm fused into projections (latency mode)")
     args = ap.parse_args()
@@ -208,7 +208,7 @@ def main():
 
     # ---- lanes: independent GROUPS of batches in flight on their own streams; weights shared, workspaces private.
     # A group = G batches of 32 x 10 s: each batch is encoded on its own, the G*32 hypotheses are decoded together.
-    G = max(1, min(args.group, K))
+    G = max(1, min(args.group, -(-K // max(1, args.lanes))))  # keep every lane busy when K is small
     n_calls = -(-K // G)
     sizes = [K // n_calls + (1 if i < K % n_calls else 0) for i in range(n_calls)]  # exactly K batches, balanced groups
     G = max(sizes)
@@ -325,8 +325,15 @@ def main():
         lib.sbk_gemm_profile_enable(0)
         ach = fl.value / (ms.value * 1e-3) / 1e12 if ms.value > 0 else 0.0
         enc_fl = BATCH * encoder_flops_per_utt(cfg, T)
-        roof = {"bound": "tensor", "kernel": "gemm_tc_kernel<128,3> (tcgen05.mma kind::f16, fp16 in / fp32 acc)",
-                "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s", "frac": ach / tf_sus, "traffic": None,
+        roof = {"bound": "tensor",
+                "kernel": "gemm_tc2_kernel<MODE,ACT,EW> (2-CTA tcgen05.mma cta_group::2 kind::f16, 256x256x64 tiles, fp16 in / "
+                          "fp32 acc in TMEM) -- all encoder / cross-K,V GEMM launches of one 32 x 10 s batch",
+                "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s", "frac": ach / tf_sus,
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the 6 GEMMs of one encoder layer in
+                # the `ncu --set full` capture profiles/r1f_gemm_ncu_full_summary.csv (reads 21.9 MB, writes 0.03 MB: the
+                # outputs stay in the 126 MB L2 for the next kernel; algorithmic operand + output bytes of the same 6
+                # launches average 42.4 MB)
+                "traffic": 21.9e6,
                 "peak_source": f"{src} bf16_tflops_sustained (kernel timed inside a long step)",
                 "launches_per_step": n.value, "gemm_ms_per_step": ms.value, "gemm_flops_per_step": fl.value,
                 "gemm_share_of_gpu_time_per_step": ms.value / (ms_dev / K),
@@ -336,9 +343,9 @@ def main():
     cpu_base = None
     if rank == 0 and not args.no_cpu_baseline:
         cores = usable_threads()
-        v, dt = cpu_oracle_rtfx(cfg, sd, 2, DECODE_STEPS, threads=cores)
+        v, dt = cpu_oracle_rtfx(cfg, sd, 16, DECODE_STEPS, threads=cores)
         cpu_base = {"value": v, "unit": "audio-sec/sec", "cores": cores, "kind": "port",
-                    "sample": f"2 x 10 s utterances, encode + {DECODE_STEPS} greedy steps, {dt:.1f} s wall"}
+                    "sample": f"16 x 10 s utterances (half a batch), encode + {DECODE_STEPS} greedy steps, {dt:.1f} s wall"}
     if rank == 0:
         line = {"metric": "audio-sec/sec (RTFx) Conformer-L ASR, batch=32x10s@16kHz", "value": value, "unit": "audio-sec/sec",
                 "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_dev / K, "higher_is_better": True,

@@ -7,14 +7,40 @@
 namespace sbk {
 
 // Apply the epilogue to 32 consecutive accumulator columns of one row.
+// `pre`: bias (and, for EPI_RESID, residual) values of this full, in-range chunk were fetched by the caller before the
+// accumulator was ready (the latency-bound decode-step GEMMs hide two L2 round trips that way).
+struct EpiPrefetch {
+    float4 bias[8];
+    float4 res[8];
+    bool on = false;
+};
+__device__ __forceinline__ void epilogue_prefetch(const GemmEpilogue& e, EpiPrefetch& p, int row, int col0, int M, int N) {
+    p.on = row < M && col0 + 32 <= N;
+    if (!p.on) return;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        p.bias[j] = e.bias != nullptr ? __ldg(reinterpret_cast<const float4*>(e.bias + col0) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (e.mode == EPI_RESID) {
+        const float4* r = reinterpret_cast<const float4*>(e.resid + static_cast<size_t>(row) * e.ldo + col0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) p.res[j] = __ldcg(r + j);
+    }
+}
+
 __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const uint32_t (&acc)[32], int row, int col0,
-                                               int M, int N) {
+                                               int M, int N, const EpiPrefetch& pre) {
     if (row >= M || col0 >= N) return;
     const bool full = (col0 + 32 <= N);
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-    if (e.bias != nullptr) {
+    if (pre.on) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const float4 b = pre.bias[j >> 2];
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+        }
+    } else if (e.bias != nullptr) {
         if (full) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -81,7 +107,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const uint
             if (full) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
-                    const float4 x = *reinterpret_cast<const float4*>(r + j);
+                    const float4 x = pre.on ? pre.res[j >> 2] : *reinterpret_cast<const float4*>(r + j);
                     *reinterpret_cast<float4*>(o + j) = make_float4(fmaf(alpha, v[j], x.x), fmaf(alpha, v[j + 1], x.y),
                                                                     fmaf(alpha, v[j + 2], x.z), fmaf(alpha, v[j + 3], x.w));
                 }
@@ -163,7 +189,7 @@ constexpr int EPI_STG_BYTES = 32 * EPI_STG_PITCH;  // per warp
 
 // staging pitch per mode: 32 fp32 (+16 B pad) for fp32 outputs, 64 B of payload (+16 B pad) for fp16 / GLU outputs
 template <int MODE>
-__host__ __device__ constexpr int epi_stg_pitch() { return (MODE == EPI_F32 || MODE == EPI_RESID) ? EPI_STG_PITCH : 80; }
+__host__ __device__ constexpr int epi_stg_pitch() { return (MODE == EPI_F32 || MODE == EPI_RESID || MODE == EPI_ROPE) ? EPI_STG_PITCH : 80; }
 
 // EPI_RESID: out aliases resid (x += ...).  The 8 residual loads of a chunk are issued through this helper one chunk AHEAD
 // of the epilogue math (the first one before the accumulator is even complete), so their L2/HBM round trip hides behind
@@ -180,23 +206,23 @@ __device__ __forceinline__ void epilogue_resid_prefetch(const GemmEpilogue& e, f
     }
 }
 
-// EPI_ROPE: the cos / sin of a chunk (16 rotation pairs of this lane's row; q and k sections only) are fetched one chunk
-// ahead as well: with ~200 KB of the SM carved out as shared memory the tables do not survive in L1, so every chunk's
-// rotation would otherwise wait for an L2 round trip (measured: tensor pipe 18 %, issue slots 12 % busy).
-__device__ __forceinline__ void epilogue_rope_prefetch(const GemmEpilogue& e, float2 (&cs)[8], float2 (&sn)[8], int my_row,
-                                                       int col0) {
+// EPI_ROPE: the rotation is applied in the write-back phase, where 4 lanes cover 32 consecutive columns of a row (8 rows
+// per instruction): each lane needs 4 cos + 4 sin of its row -- one 16-byte load each, 64 contiguous bytes per row.  (With
+// one row per lane, as after tcgen05.ld, every table load touched 32 different lines and the L1 tag stage, not the tensor
+// pipe, bounded the QKV GEMM: tensor pipe 18 %, issue slots 12 % busy.)  The 8 loads of a chunk are fetched one chunk
+// ahead: with ~200 KB of the SM carved out as shared memory the tables do not survive in L1.
+__device__ __forceinline__ void epilogue_rope_prefetch(const GemmEpilogue& e, float4 (&rc)[4], float4 (&rs)[4], int row_base,
+                                                       int col0, int lane) {
     const int dh = e.head_dim;
     const int within = col0 % (3 * dh);
     const int sect = within / dh;  // 0 q, 1 k, 2 v
     if (sect < 2) {
-        const int t = my_row % e.T;
-        const int p0 = (within - sect * dh) >> 1;
-        const float* c = e.rope_cos + static_cast<size_t>(t) * (dh >> 1) + p0;
-        const float* s = e.rope_sin + static_cast<size_t>(t) * (dh >> 1) + p0;
+        const int p = ((within - sect * dh) >> 1) + (lane & 3) * 4;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            cs[j] = __ldg(reinterpret_cast<const float2*>(c + 2 * j));
-            sn[j] = __ldg(reinterpret_cast<const float2*>(s + 2 * j));
+        for (int i = 0; i < 4; ++i) {
+            const int t = (row_base + i * 8 + (lane >> 2)) % e.T;
+            rc[i] = __ldg(reinterpret_cast<const float4*>(e.rope_cos + static_cast<size_t>(t) * (dh >> 1) + p));
+            rs[i] = __ldg(reinterpret_cast<const float4*>(e.rope_sin + static_cast<size_t>(t) * (dh >> 1) + p));
         }
     }
 }
@@ -204,7 +230,7 @@ __device__ __forceinline__ void epilogue_rope_prefetch(const GemmEpilogue& e, fl
 template <int MODE, int ACT, int PITCH = EPI_STG_PITCH>
 __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmEpilogue& e, const uint32_t (&acc)[32], uint8_t* stg,
                                                          int row_base, int col0, int M, int lane, float4 (&res)[8],
-                                                         int next_col0, float2 (&rcs)[8], float2 (&rsn)[8]) {
+                                                         int next_col0, float4 (&rc)[4], float4 (&rs)[4]) {
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
@@ -219,7 +245,7 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmEpilogue& e, 
     uint8_t* my = stg + lane * PITCH;
     constexpr int out_bytes_per_row = (MODE == EPI_F32 || MODE == EPI_RESID) ? 128 : 64;  // 32 fp32 | 32 fp16 / 16 fp32
     {
-        if constexpr (MODE == EPI_F32 || MODE == EPI_RESID) {
+        if constexpr (MODE == EPI_F32 || MODE == EPI_RESID || MODE == EPI_ROPE) {  // staged as fp32
             if constexpr (MODE == EPI_RESID) {
                 float alpha = e.alpha;
                 if (e.row_lens != nullptr && my_row < M) {
@@ -238,25 +264,8 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmEpilogue& e, 
                 *reinterpret_cast<float4*>(my + j * 4) =
                     make_float4(v[j] * sigmoid_f(v[j + 16]), v[j + 1] * sigmoid_f(v[j + 17]),
                                 v[j + 2] * sigmoid_f(v[j + 18]), v[j + 3] * sigmoid_f(v[j + 19]));
-        } else {  // EPI_F16, EPI_ROPE -> 32 halfs
-            if constexpr (MODE == EPI_ROPE) {
-                const int dh = e.head_dim;
-                const int within = col0 % (3 * dh);
-                const int sect = within / dh;  // 0 q, 1 k, 2 v
-                if (sect < 2) {
-                    const float sc = sect == 0 ? e.alpha : 1.0f;
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float2 c2 = rcs[j >> 2], s2 = rsn[j >> 2];
-                        const float x0 = v[j], x1 = v[j + 1], x2 = v[j + 2], x3 = v[j + 3];
-                        v[j] = (x0 * c2.x - x1 * s2.x) * sc;
-                        v[j + 1] = (x1 * c2.x + x0 * s2.x) * sc;
-                        v[j + 2] = (x2 * c2.y - x3 * s2.y) * sc;
-                        v[j + 3] = (x3 * c2.y + x2 * s2.y) * sc;
-                    }
-                }
-                if (next_col0 >= 0) epilogue_rope_prefetch(e, rcs, rsn, my_row, next_col0);
-            } else if constexpr (ACT == ACT_SILU) {
+        } else {  // EPI_F16 -> 32 halfs
+            if constexpr (ACT == ACT_SILU) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
             } else if constexpr (ACT == ACT_GELU) {
@@ -292,6 +301,37 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmEpilogue& e, 
         }
         if constexpr (MODE == EPI_RESID)
             if (next_col0 >= 0) epilogue_resid_prefetch(e, res, row_base, next_col0, M, lane);
+    } else if constexpr (MODE == EPI_ROPE) {
+        const int seg = lane & 3, rsub = lane >> 2;  // 4 lanes x 8 columns (4 rotation pairs) per row, 8 rows per instruction
+        const int dh = e.head_dim;
+        const int sect = (col0 % (3 * dh)) / dh;     // 0 q (rotated, scaled), 1 k (rotated), 2 v
+        const float sc = sect == 0 ? e.alpha : 1.0f;
+        __half* outp = reinterpret_cast<__half*>(e.out);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = i * 8 + rsub;
+            const int row = row_base + r;
+            float4 x0 = *reinterpret_cast<const float4*>(stg + r * PITCH + seg * 32);
+            float4 x1 = *reinterpret_cast<const float4*>(stg + r * PITCH + seg * 32 + 16);
+            if (sect < 2) {
+                const float4 c = rc[i], s4 = rs[i];
+                const float a0 = (x0.x * c.x - x0.y * s4.x) * sc, a1 = (x0.y * c.x + x0.x * s4.x) * sc;
+                const float a2 = (x0.z * c.y - x0.w * s4.y) * sc, a3 = (x0.w * c.y + x0.z * s4.y) * sc;
+                const float b0 = (x1.x * c.z - x1.y * s4.z) * sc, b1 = (x1.y * c.z + x1.x * s4.z) * sc;
+                const float b2 = (x1.z * c.w - x1.w * s4.w) * sc, b3 = (x1.w * c.w + x1.z * s4.w) * sc;
+                x0 = make_float4(a0, a1, a2, a3);
+                x1 = make_float4(b0, b1, b2, b3);
+            }
+            if (row < M) {
+                __half2 h0 = __floats2half2_rn(x0.x, x0.y), h1 = __floats2half2_rn(x0.z, x0.w);
+                __half2 h2 = __floats2half2_rn(x1.x, x1.y), h3 = __floats2half2_rn(x1.z, x1.w);
+                uint4 u;
+                u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+                u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+                *reinterpret_cast<uint4*>(outp + static_cast<size_t>(row) * e.ldo + col0 + seg * 8) = u;
+            }
+        }
+        if (next_col0 >= 0) epilogue_rope_prefetch(e, rc, rs, row_base, next_col0, lane);
     } else {
         const int seg = lane & 3, rsub = lane >> 2;  // 4 lanes x 16 B per row, 8 rows per instruction
         uint8_t* outp = reinterpret_cast<uint8_t*>(e.out);

@@ -121,16 +121,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
     } else {
         const int q = warp & 3;  // TMEM lane quarter this warp may access
+        const int row = m0 + q * 32 + lane;
+        EpiPrefetch pre;
+        if constexpr (BN == 32 && SPLIT == 1) epilogue_prefetch(epi, pre, row, n0, M, N);  // while the main loop runs
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
-        const int row = m0 + q * 32 + lane;
         if constexpr (SPLIT == 1) {
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
                 uint32_t acc[32];
                 tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, acc);
                 tmem_ld_wait();
-                epilogue_chunk(epi, acc, row, n0 + c * 32, M, N);
+                epilogue_chunk(epi, acc, row, n0 + c * 32, M, N, pre);
             }
         } else if (rank != 0) {
             float* part = reinterpret_cast<float*>(smem + S::PART_OFFSET) +
@@ -172,7 +174,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         acc[j + 3] = __float_as_uint(__uint_as_float(acc[j + 3]) + p4.w);
                     }
                 }
-                epilogue_chunk(epi, acc, row, n0 + c * 32, M, N);
+                epilogue_chunk(epi, acc, row, n0 + c * 32, M, N, EpiPrefetch());
             }
         }
     }

@@ -197,9 +197,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             const int row_base = mt * 2 * G2_BM + static_cast<int>(rank) * G2_BM + q * 32;
             const int n0 = nt * G2_BN + part * PART_COLS;
             float4 res[8];
-            float2 rcs[8], rsn[8];
+            float4 rcs[4], rsn[4];
             if constexpr (MODE == EPI_RESID) epilogue_resid_prefetch(epi, res, row_base, n0, M, lane);
-            if constexpr (MODE == EPI_ROPE) epilogue_rope_prefetch(epi, rcs, rsn, row_base + lane, n0);
+            if constexpr (MODE == EPI_ROPE) epilogue_rope_prefetch(epi, rcs, rsn, row_base, n0, lane);
             mbar_wait_b(&tmem_full_bar[buf], acc_ph, 4);
             tc_fence_after();
             const uint32_t t0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * G2_BN + part * PART_COLS;
