@@ -179,7 +179,29 @@ __device__ __forceinline__ float rcp_approx(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-__device__ __forceinline__ float sigmoid_f(float x) { return rcp_approx(1.0f + __expf(-x)); }
+// exp(x) = 2^(x log2 e) on the SFU, flush-to-zero: without -use_fast_math `__expf` wraps ex2.approx in a denormal
+// range check + two scalings (5 instructions); results below 1.2e-38 are irrelevant for sigmoid / softmax weights
+__device__ __forceinline__ float exp_ftz(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+    return y;
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return rcp_approx(1.0f + exp_ftz(-x)); }
+// explicit shared-space 16-byte accesses (a generic pointer makes the compiler emit LD.E / ST.E with 64-bit addressing)
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint4 f4_as_u4(float4 f) {
+    return make_uint4(__float_as_uint(f.x), __float_as_uint(f.y), __float_as_uint(f.z), __float_as_uint(f.w));
+}
+__device__ __forceinline__ float4 u4_as_f4(uint4 u) {
+    return make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
+}
 __device__ __forceinline__ float silu_f(float x) { return x * sigmoid_f(x); }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 

@@ -134,8 +134,12 @@ dwconv_ln_swish_kernel(const float* __restrict__ glu, int T, int D, int K, const
     if (threadIdx.x == 0) {
         const uint32_t row_bytes = static_cast<uint32_t>(D) * 4;
         mbar_arrive_expect_tx(&bar, row_bytes * static_cast<uint32_t>(r_hi - r_lo));
-        for (int r = r_lo; r < r_hi; ++r)
-            bulk_load_1d(slab + r * D, src + static_cast<size_t>(t0 - halo + r) * D, row_bytes, &bar);
+        // the valid rows are contiguous on both sides: a few large bulk copies instead of one 2 KB copy per row (whose
+        // serial issue by this one thread was a visible part of the CTA's life)
+        for (int r = r_lo; r < r_hi; r += 8) {
+            const int nr = min(8, r_hi - r);
+            bulk_load_1d(slab + r * D, src + static_cast<size_t>(t0 - halo + r) * D, row_bytes * nr, &bar);
+        }
     }
     // zero rows outside the utterance (Conv1d zero padding)
     for (int i = threadIdx.x; i < (r_lo + rows_in - r_hi) * D; i += blockDim.x) {

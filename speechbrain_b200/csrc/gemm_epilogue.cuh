@@ -242,7 +242,8 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmEpilogue& e, 
         }
     }
     const int my_row = row_base + lane;
-    uint8_t* my = stg + lane * PITCH;
+    const uint32_t stg_s = smem_u32(stg);
+    const uint32_t my = stg_s + lane * PITCH;
     constexpr int out_bytes_per_row = (MODE == EPI_F32 || MODE == EPI_RESID) ? 128 : 64;  // 32 fp32 | 32 fp16 / 16 fp32
     {
         if constexpr (MODE == EPI_F32 || MODE == EPI_RESID || MODE == EPI_ROPE) {  // staged as fp32
@@ -257,13 +258,12 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmEpilogue& e, 
             }
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(my + j * 4) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                sts128(my + j * 4, f4_as_u4(make_float4(v[j], v[j + 1], v[j + 2], v[j + 3])));
         } else if constexpr (MODE == EPI_GLU) {
 #pragma unroll
             for (int j = 0; j < 16; j += 4)
-                *reinterpret_cast<float4*>(my + j * 4) =
-                    make_float4(v[j] * sigmoid_f(v[j + 16]), v[j + 1] * sigmoid_f(v[j + 17]),
-                                v[j + 2] * sigmoid_f(v[j + 18]), v[j + 3] * sigmoid_f(v[j + 19]));
+                sts128(my + j * 4, f4_as_u4(make_float4(v[j] * sigmoid_f(v[j + 16]), v[j + 1] * sigmoid_f(v[j + 17]),
+                                                        v[j + 2] * sigmoid_f(v[j + 18]), v[j + 3] * sigmoid_f(v[j + 19]))));
         } else {  // EPI_F16 -> 32 halfs
             if constexpr (ACT == ACT_SILU) {
 #pragma unroll
@@ -279,7 +279,7 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmEpilogue& e, 
                 uint4 u;
                 u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
                 u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
-                *reinterpret_cast<uint4*>(my + j * 2) = u;
+                sts128(my + j * 2, u);
             }
         }
     }
@@ -292,7 +292,7 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmEpilogue& e, 
             const int r = i * 4 + rsub;
             const int row = row_base + r;
             if (row < M) {
-                float4 val = *reinterpret_cast<const float4*>(stg + r * PITCH + seg * 16);
+                float4 val = u4_as_f4(lds128(stg_s + r * PITCH + seg * 16));
                 if constexpr (MODE == EPI_RESID) {
                     val.x += res[i].x; val.y += res[i].y; val.z += res[i].z; val.w += res[i].w;
                 }
@@ -311,8 +311,8 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmEpilogue& e, 
         for (int i = 0; i < 4; ++i) {
             const int r = i * 8 + rsub;
             const int row = row_base + r;
-            float4 x0 = *reinterpret_cast<const float4*>(stg + r * PITCH + seg * 32);
-            float4 x1 = *reinterpret_cast<const float4*>(stg + r * PITCH + seg * 32 + 16);
+            float4 x0 = u4_as_f4(lds128(stg_s + r * PITCH + seg * 32));
+            float4 x1 = u4_as_f4(lds128(stg_s + r * PITCH + seg * 32 + 16));
             if (sect < 2) {
                 const float4 c = rc[i], s4 = rs[i];
                 const float a0 = (x0.x * c.x - x0.y * s4.x) * sc, a1 = (x0.y * c.x + x0.x * s4.x) * sc;
@@ -344,7 +344,7 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmEpilogue& e, 
             const int row = row_base + r;
             if (row < M)
                 *reinterpret_cast<uint4*>(outp + static_cast<size_t>(row) * row_pitch + col_off + seg * 16) =
-                    *reinterpret_cast<const uint4*>(stg + r * PITCH + seg * 16);
+                    lds128(stg_s + r * PITCH + seg * 16);
         }
     }
     __syncwarp();  // staging tile is reused by the next chunk
