@@ -275,6 +275,10 @@ encoder_attention_kernel(const __half* __restrict__ qkv, int ld, int T, const in
     __half* Qv = Vs + ATT_BK * STR;                    // RELPOS: [64][STR]
     __half* Ps = Qv + ATT_BQ * STR;                    // RELPOS: [T][STR]
     float* Gs = reinterpret_cast<float*>(Ps + (RELPOS ? T : 0) * STR);  // RELPOS: [4 warps][16][GW+1]
+    // head dims that are whole 16-byte vectors: K/V blocks are double-buffered with cp.async (block jb+1 streams in while
+    // block jb is multiplied); the second buffer pair sits behind everything else
+    constexpr bool ASYNC = (DH % 8 == 0) && (DHP == DH);
+    __half* KV1 = reinterpret_cast<__half*>(Gs + (RELPOS ? 4 * 16 * (GW + 1) : 0));  // [2][64][STR] when ASYNC
 
     const int b = blockIdx.z, h = blockIdx.y, i0 = blockIdx.x * ATT_BQ;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
@@ -348,27 +352,58 @@ encoder_attention_kernel(const __half* __restrict__ qkv, int ld, int T, const in
     const float LOG2E = 1.4426950408889634f;
     const int n_blk = (len + ATT_BK - 1) / ATT_BK;
 
+    auto stage_async = [&](int jb, __half* kd, __half* vd) {  // 16-byte cp.async, rows >= T zero-filled
+        const int j0 = jb * ATT_BK;
+        constexpr int V8 = DH / 8;
+        for (int i = threadIdx.x; i < ATT_BK * V8; i += blockDim.x) {
+            const int r = i / V8, v8 = i - r * V8;
+            const bool ok = j0 + r < T;
+            const __half* rowp = base + static_cast<size_t>(ok ? j0 + r : 0) * ld + v8 * 8;
+            const uint32_t nbytes = ok ? 16u : 0u;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(kd + r * STR + v8 * 8)),
+                         "l"(rowp + DH), "r"(nbytes) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(vd + r * STR + v8 * 8)),
+                         "l"(rowp + 2 * DH), "r"(nbytes) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if constexpr (ASYNC) {
+        if (n_blk > 0) stage_async(0, Ks, Vs);
+    }
+
     for (int jb = 0; jb < n_blk; ++jb) {
         const int j0 = jb * ATT_BK;
-        __syncthreads();  // previous block's K/V fully consumed
-        for (int i = threadIdx.x; i < ATT_BK * VPR; i += blockDim.x) {
-            const int r = i / VPR, v4 = i - r * VPR;
-            uint2 kv = make_uint2(0, 0), vv = make_uint2(0, 0);
-            if (j0 + r < T) {
-                const __half* rowp = base + static_cast<size_t>(j0 + r) * ld + v4 * 4;
-                kv = *reinterpret_cast<const uint2*>(rowp + DH);
-                vv = *reinterpret_cast<const uint2*>(rowp + 2 * DH);
+        const __half* Kc = Ks;
+        const __half* Vc = Vs;
+        if constexpr (ASYNC) {
+            if (jb & 1) { Kc = KV1; Vc = KV1 + ATT_BK * STR; }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();  // block jb has landed for everyone; block jb-1 (the other buffer) is fully consumed
+            if (jb + 1 < n_blk) {
+                if (jb & 1) stage_async(jb + 1, Ks, Vs);
+                else stage_async(jb + 1, KV1, KV1 + ATT_BK * STR);
             }
-            *reinterpret_cast<uint2*>(Ks + r * STR + v4 * 4) = kv;
-            *reinterpret_cast<uint2*>(Vs + r * STR + v4 * 4) = vv;
+        } else {
+            __syncthreads();  // previous block's K/V fully consumed
+            for (int i = threadIdx.x; i < ATT_BK * VPR; i += blockDim.x) {
+                const int r = i / VPR, v4 = i - r * VPR;
+                uint2 kv = make_uint2(0, 0), vv = make_uint2(0, 0);
+                if (j0 + r < T) {
+                    const __half* rowp = base + static_cast<size_t>(j0 + r) * ld + v4 * 4;
+                    kv = *reinterpret_cast<const uint2*>(rowp + DH);
+                    vv = *reinterpret_cast<const uint2*>(rowp + 2 * DH);
+                }
+                *reinterpret_cast<uint2*>(Ks + r * STR + v4 * 4) = kv;
+                *reinterpret_cast<uint2*>(Vs + r * STR + v4 * 4) = vv;
+            }
+            __syncthreads();
         }
-        __syncthreads();
 
         float s[ATT_BK / 8][4];
 #pragma unroll
         for (int nt = 0; nt < ATT_BK / 8; ++nt) {
             s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.0f;
-            const __half* kp = Ks + (nt * 8 + g) * STR + 2 * c;
+            const __half* kp = Kc + (nt * 8 + g) * STR + 2 * c;
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks)
                 mma16816(s[nt], qa[ks], *reinterpret_cast<const uint32_t*>(kp + ks * 16),
@@ -453,7 +488,7 @@ encoder_attention_kernel(const __half* __restrict__ qkv, int ld, int T, const in
 #pragma unroll
             for (int nt = 0; nt < DHP / 8; ++nt) {
                 uint32_t b0, b1;
-                ldmatrix_x2_trans(b0, b1, Vs + (kk * 16 + (lane & 15)) * STR + nt * 8);
+                ldmatrix_x2_trans(b0, b1, Vc + (kk * 16 + (lane & 15)) * STR + nt * 8);
                 mma16816(o[nt], pa[kk], b0, b1);
             }
         }
@@ -478,13 +513,14 @@ static int launch_encoder_attention(const __half* qkv, int ld, int B, int T, int
     constexpr int STR = DHP + 8;
     dim3 grid(ceil_div(T, ATT_BQ), H, B);
     if (!relpos) {
-        const size_t smem = 4ull * ATT_BQ * STR * 2;
+        const size_t smem = 4ull * ATT_BQ * STR * 2 + 2ull * ATT_BK * STR * 2;  // + second K/V buffer pair
         auto kern = encoder_attention_kernel<DH, DHP, false>;
         SBK_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, 128, smem, stream>>>(qkv, ld, T, lens, nullptr, nullptr, nullptr, 0, scale, out, ldo);
     } else {
         SBK_REQUIRE(ldp % 4 == 0, "encoder_attention: bad ldp");
-        const size_t smem = 4ull * ATT_BQ * STR * 2 + static_cast<size_t>(T) * STR * 2 + 4ull * 16 * 81 * 4;
+        const size_t smem = 4ull * ATT_BQ * STR * 2 + static_cast<size_t>(T) * STR * 2 + 4ull * 16 * 81 * 4 +
+                            2ull * ATT_BK * STR * 2;
         SBK_REQUIRE(smem <= 220 * 1024, "encoder_attention(RelPos): T=%d too long for the shared-memory table", T);
         auto kern = encoder_attention_kernel<DH, DHP, true>;
         SBK_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -499,6 +535,8 @@ int encoder_attention(const __half* qkv, int ld, int B, int T, int H, int head_d
                       const float* pos_u, const float* pos_v, const __half* P, int ldp, float scale, __half* out,
                       int ldo, cudaStream_t stream) {
     SBK_REQUIRE(ld % 4 == 0 && ldo % 2 == 0, "encoder_attention: bad leading dims");
+    if (head_dim % 8 == 0)  // cp.async 16-byte K/V staging
+        SBK_REQUIRE(ld % 8 == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0, "encoder_attention: qkv must be 16-byte aligned");
     if (head_dim == 64)
         return launch_encoder_attention<64, 64>(qkv, ld, B, T, H, lens, relpos, pos_u, pos_v, P, ldp, scale, out, ldo, stream);
     if (head_dim == 36)  // conformer_small: 144 / 4 heads, zero-padded to 48 for the k16 steps

@@ -115,6 +115,8 @@ struct DecAttnArgs {
     const int* tok_cache; int pad_tok;   // LM pad mask: keys whose token (tok_cache[phys_row][pos]) == pad_tok are masked
 };
 int dec_attention(const DecAttnArgs& a, int n_rows, int max_keys, cudaStream_t stream);
+int make_tmap_kv_f16(CUtensorMap* out, const void* base, int n_utt, int T, int H, uint64_t key_stride_elems,
+                     uint64_t utt_stride_elems, int box_T);
 struct BeamLm {  // TransformerLM scorer state the beam step feeds (all null/0 when there is no LM)
     const float* emb = nullptr; const float* pe = nullptr; int d = 0;
     float* x = nullptr; __half* x16 = nullptr; int* tok_cache = nullptr;
