@@ -248,6 +248,22 @@ constexpr int ATT_BK = 64;
 __device__ __forceinline__ void ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, const void* p) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(smem_u32(p)));
 }
+__device__ __forceinline__ void ldmatrix_x4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, const void* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldmatrix_x2(uint32_t& r0, uint32_t& r1, const void* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, const void* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ float ex2_ftz(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile(
         "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -403,11 +419,20 @@ encoder_attention_kernel(const __half* __restrict__ qkv, int ld, int T, const in
 #pragma unroll
         for (int nt = 0; nt < ATT_BK / 8; ++nt) {
             s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.0f;
-            const __half* kp = Kc + (nt * 8 + g) * STR + 2 * c;
+            // B fragments of K[key][dim] for two k16 steps per ldmatrix.x4 (lanes 8m..8m+7 address matrix m = dims 8m..)
+            const __half* kp = Kc + (nt * 8 + (lane & 7)) * STR + (lane >> 3) * 8;
 #pragma unroll
-            for (int ks = 0; ks < KS; ++ks)
-                mma16816(s[nt], qa[ks], *reinterpret_cast<const uint32_t*>(kp + ks * 16),
-                         *reinterpret_cast<const uint32_t*>(kp + ks * 16 + 8));
+            for (int ks = 0; ks + 1 < KS; ks += 2) {
+                uint32_t b0, b1, b2, b3;
+                ldmatrix_x4(b0, b1, b2, b3, kp + ks * 16);
+                mma16816(s[nt], qa[ks], b0, b1);
+                mma16816(s[nt], qa[ks + 1], b2, b3);
+            }
+            if constexpr (KS & 1) {
+                uint32_t b0, b1;
+                ldmatrix_x2(b0, b1, Kc + (nt * 8 + (lane & 7)) * STR + ((lane >> 3) & 1) * 8 + (KS - 1) * 16);
+                mma16816(s[nt], qa[KS - 1], b0, b1);
+            }
         }
         if constexpr (RELPOS) {
             // band G[li][rr] = Qv[li] . P[|rmin + rr|], rr in [0, 80): rmin = iw - j0 - 63
@@ -443,29 +468,33 @@ encoder_attention_kernel(const __half* __restrict__ qkv, int ld, int T, const in
         }
         // ---- key padding mask + online softmax (rows g and g+8 of this warp's 16)
         float mx[2] = {-INFINITY, -INFINITY};
+        if (j0 + ATT_BK > len) {  // only the last key block holds masked keys
+#pragma unroll
+            for (int nt = 0; nt < ATT_BK / 8; ++nt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (j0 + nt * 8 + 2 * c + (e & 1) >= len) s[nt][e] = -INFINITY;
+        }
 #pragma unroll
         for (int nt = 0; nt < ATT_BK / 8; ++nt)
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int j = j0 + nt * 8 + 2 * c + (e & 1);
-                if (j >= len) s[nt][e] = -INFINITY;
-                mx[e >> 1] = fmaxf(mx[e >> 1], s[nt][e]);
-            }
+            for (int e = 0; e < 4; ++e) mx[e >> 1] = fmaxf(mx[e >> 1], s[nt][e]);
         float alpha[2];
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
             mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
             const float m_new = fmaxf(m_run[r], mx[r]);
-            alpha[r] = exp2f((m_run[r] - m_new) * LOG2E);
+            alpha[r] = ex2_ftz((m_run[r] - m_new) * LOG2E);
             m_run[r] = m_new;
         }
         float rs[2] = {0.0f, 0.0f};
         uint32_t pa[ATT_BK / 16][4];
 #pragma unroll
         for (int nt = 0; nt < ATT_BK / 8; ++nt) {
-            const float p0 = exp2f((s[nt][0] - m_run[0]) * LOG2E), p1 = exp2f((s[nt][1] - m_run[0]) * LOG2E);
-            const float p2 = exp2f((s[nt][2] - m_run[1]) * LOG2E), p3 = exp2f((s[nt][3] - m_run[1]) * LOG2E);
+            const float ms0 = m_run[0] * LOG2E, ms1 = m_run[1] * LOG2E;
+            const float p0 = ex2_ftz(fmaf(s[nt][0], LOG2E, -ms0)), p1 = ex2_ftz(fmaf(s[nt][1], LOG2E, -ms0));
+            const float p2 = ex2_ftz(fmaf(s[nt][2], LOG2E, -ms1)), p3 = ex2_ftz(fmaf(s[nt][3], LOG2E, -ms1));
             rs[0] += p0 + p1;
             rs[1] += p2 + p3;
             pa[nt >> 1][(nt & 1) * 2 + 0] = pack_half2(p0, p1);
@@ -486,10 +515,16 @@ encoder_attention_kernel(const __half* __restrict__ qkv, int ld, int T, const in
 #pragma unroll
         for (int kk = 0; kk < ATT_BK / 16; ++kk) {
 #pragma unroll
-            for (int nt = 0; nt < DHP / 8; ++nt) {
-                uint32_t b0, b1;
-                ldmatrix_x2_trans(b0, b1, Vc + (kk * 16 + (lane & 15)) * STR + nt * 8);
+            for (int nt = 0; nt + 1 < DHP / 8; nt += 2) {  // two 8-wide dim tiles per ldmatrix.x4.trans
+                uint32_t b0, b1, b2, b3;
+                ldmatrix_x4_trans(b0, b1, b2, b3, Vc + (kk * 16 + (lane & 15)) * STR + nt * 8 + (lane >> 4) * 8);
                 mma16816(o[nt], pa[kk], b0, b1);
+                mma16816(o[nt + 1], pa[kk], b2, b3);
+            }
+            if constexpr ((DHP / 8) & 1) {
+                uint32_t b0, b1;
+                ldmatrix_x2_trans(b0, b1, Vc + (kk * 16 + (lane & 15)) * STR + (DHP / 8 - 1) * 8);
+                mma16816(o[DHP / 8 - 1], pa[kk], b0, b1);
             }
         }
     }
