@@ -277,7 +277,7 @@ def main():
     launches0 = lib.sbk_launch_count()
     ms_dev = timed(step_dev, n_calls)
     host_enqueue_ms = timed.host_ms * n_calls / K
-    launches = (lib.sbk_launch_count() - launches0) // max(K, 1)
+    launches = lib.sbk_launch_count() - launches0  # kernels of libsbk.so inside the K-step timed region (graph nodes included)
     barrier()
     for i in range(n_calls):
         step_host(i)
@@ -364,7 +364,7 @@ def main():
                         "h2d_bytes_per_step": BATCH * L * 4 + BATCH * 4, "d2h_bytes_per_step": BATCH * DECODE_STEPS * 4},
                 "single_batch": {"value": BATCH * UTT_SECONDS / (ms_single / 1e3), "unit": "audio-sec/sec", "ms_per_step": ms_single,
                                  "note": "one batch in flight, no decode coalescing, L2 flushed before every step (latency view)"},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base}
+                "gpu_launches": int(launches), "gpu_launches_per_step": int(launches) // max(K, 1), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
