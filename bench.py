@@ -232,12 +232,19 @@ def main():
                 for g_ in range(g):
                     dist.all_gather(gathered, preds[ln][g_])  # the path's only collective: final hypothesis gather
 
+    # host->device copies go through ONE copy stream in call order (a FIFO over PCIe): the first group's 16 batches arrive
+    # after 1/4 of the time it takes when the 4 lanes' copies share the link, so the pipeline fills 3 groups earlier
+    h2d_stream = torch.cuda.Stream(device=dev)
+
     def step_host(i):
         ln, g = i % NL, sizes[i % n_calls]
-        with torch.cuda.stream(streams[ln]):
+        with torch.cuda.stream(h2d_stream):
+            h2d_stream.wait_stream(streams[ln])  # the lane's previous group no longer reads these buffers
             for g_ in range(g):  # H2D of every batch's wav / lengths from pinned host memory, inside the timed region
                 wavs[ln][g_].copy_(wav_host, non_blocking=True)
                 lens[ln][g_].copy_(lens_host, non_blocking=True)
+        with torch.cuda.stream(streams[ln]):
+            streams[ln].wait_stream(h2d_stream)
             lanes[ln].transcribe_greedy_group_dev(wavs[ln][:g], lens[ln][:g], DECODE_STEPS, BOS, EOS, preds[ln][:g])
             for g_ in range(g):  # D2H of every batch's token ids
                 preds_host[ln][g_].copy_(preds[ln][g_], non_blocking=True)
@@ -250,7 +257,7 @@ def main():
         cur = torch.cuda.current_stream(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(cur)
-        for s_ in streams:
+        for s_ in streams + [h2d_stream]:
             s_.wait_event(e0)
         t_host = time.perf_counter()
         for i in range(n):
