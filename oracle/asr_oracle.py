@@ -421,7 +421,7 @@ def full_pipeline_features(wav, wav_lens, sd, cfg):
 def beam_search(enc_states, wav_len, sd, cfg, seq_lin_w, seq_lin_b, bos_index=1, eos_index=2, beam_size=4,
                 min_decode_ratio=0.0, max_decode_ratio=1.0, temperature=1.0, using_eos_threshold=True,
                 eos_threshold=1.5, length_normalization=True, minus_inf=-1e20, topk=1, prefix="", return_history=False,
-                lm=None, ctc=None):
+                lm=None, ctc=None, return_topk=False):
     """S2STransformerBeamSearcher.forward, using_max_attn_shift=False; scorer=None, or a ScorerBuilder with full scorers
     TransformerLMScorer (``lm`` = dict(sd, cfg, weight, temperature, prefix)) and/or CTCScorer (``ctc`` = dict(w, b, weight,
     blank_index)), in the recipe's order [transformerlm, ctc] (scorer.py:1221-1268; conformer_large.yaml:209-223).
@@ -505,12 +505,13 @@ def beam_search(enc_states, wav_len, sd, cfg, seq_lin_w, seq_lin_b, bos_index=1,
         seq_scores = seq_scores.masked_fill(is_eos, float("-inf"))
     if [len(f) for f in finished] != [beam_size] * B:
         add_eos_hyps(torch.full((n_bh,), eos_index, dtype=torch.long), scores)
-    out = finalize_beams(finished, beam_size, topk)
+    out = finalize_beams(finished, beam_size, topk, return_topk)
     return out + (history,) if return_history else out
 
 
-def finalize_beams(finished, beam_size, topk=1):
-    """_get_topk_prediction (:1418-1476) + the return_topk=False tail of forward (:1709-1723)."""
+def finalize_beams(finished, beam_size, topk=1, return_topk=False):
+    """_get_topk_prediction (:1418-1476) + the tail of forward (:1709-1723): return_topk=True gives the padded
+    (topk_hyps, topk_lengths, topk_scores, topk_log_probs), else (hyps, best_lens, best_scores, best_log_probs)."""
     B = len(finished)
     top_hyps, top_lp, top_scores, top_len = [], [], [], []
     for i in range(B):
@@ -528,6 +529,8 @@ def finalize_beams(finished, beam_size, topk=1):
     tk_hyps = torch.index_select(top_hyps, 0, idx).view(B, topk, -1)
     tk_len = torch.index_select(top_len, 0, idx).view(B, topk)
     tk_lp = torch.index_select(top_lp, 0, idx).view(B, topk, -1)
+    if return_topk:
+        return tk_hyps, tk_len, tk_scores, tk_lp
     best_hyps, best_lens = tk_hyps[:, 0, :], tk_len[:, 0]
     hyps = [best_hyps[b, : int(torch.round(best_lens[b] * best_hyps.shape[1]))].tolist() for b in range(B)]
     return hyps, best_lens, tk_scores[:, 0], tk_lp[:, 0, :]

@@ -201,6 +201,34 @@ def beam_case(tag="beam_conformer_large_rope"):
     torch.save(out, os.path.join(OUT, f"{tag}.pt"))
 
 
+def beam_topk_case(tag="beam_topk_conformer_large_rope"):
+    """return_topk=True, topk=3 (the n-best output the rescorers consume): padded (B, topk, L) hypotheses, lengths, scores and
+    log-probs of the reference vs the oracle."""
+    from speechbrain.decoders.seq2seq import S2STransformerBeamSearcher
+    fb, norm, mods, sd = build_reference(CFG_L, "RoPEMHA")
+    g = torch.load(os.path.join(OUT, "conformer_large_rope.pt"))
+    enc, wav_lens = g["enc_out"], g["wav_lens"]
+    T = enc.shape[1]
+    kwargs = dict(beam_size=5, using_eos_threshold=False, temperature=1.15, min_decode_ratio=2.5 / T)
+    eos_bias = 5.5
+    with torch.no_grad():
+        bias = sd["seq_lin.w.bias"].clone()
+        bias[2] += eos_bias
+        mods["seq_lin"].w.bias.copy_(bias)
+        bs = S2STransformerBeamSearcher(modules=[mods["Transformer"], mods["seq_lin"]], bos_index=1, eos_index=2,
+                                        max_decode_ratio=8.5 / T, return_topk=True, topk=3, **kwargs)
+        tk_hyps, tk_len, tk_scores, tk_lp = bs(enc, wav_lens)
+        ocfg = dict(CFG_L, attention_type="RoPEMHA")
+        o_hyps, o_len, o_scores, o_lp = O.beam_search(enc, wav_lens, sd, ocfg, sd["seq_lin.w.weight"], bias, 1, 2,
+                                                      max_decode_ratio=8.5 / T, prefix="Transformer.", topk=3,
+                                                      return_topk=True, **kwargs)
+    print(f"[beam topk] ref hyps {tk_hyps.tolist()} scores {tk_scores.tolist()} | oracle equal: {torch.equal(o_hyps, tk_hyps)} "
+          f"score err {(o_scores - tk_scores).abs().max():.2e}")
+    assert torch.equal(o_hyps, tk_hyps) and torch.allclose(o_len, tk_len) and (o_scores - tk_scores).abs().max() < 1e-4
+    torch.save(dict(kwargs=kwargs, eos_bias=eos_bias, max_decode_ratio=8.5 / T, topk=3, hyps=tk_hyps, lens=tk_len,
+                    scores=tk_scores, log_probs=tk_lp), os.path.join(OUT, f"{tag}.pt"))
+
+
 def beam_lm_case(tag="beam_lm_conformer_large_rope"):
     """S2STransformerBeamSearcher + ScorerBuilder(full_scorers=[TransformerLMScorer]) -- shallow fusion with the recipe's
     12 x 768 TransformerLM (conformer_large.yaml:160-170, 215-223), weight 0.6, temperature 1.15."""
@@ -299,7 +327,7 @@ def beam_ctc_case(tag="beam_ctc_conformer_large_rope"):
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
-    which = sys.argv[1:] or ["fbank", "norm", "L_rope", "L_relpos", "S_relpos", "beam", "beam_lm", "beam_ctc"]
+    which = sys.argv[1:] or ["fbank", "norm", "L_rope", "L_relpos", "S_relpos", "beam", "beam_topk", "beam_lm", "beam_ctc"]
     if "fbank" in which:
         fbank_cases()
     if "norm" in which:
@@ -312,6 +340,8 @@ if __name__ == "__main__":
         model_case(CFG_S, "RelPosMHAXL", 2, 24000, [0.8, 1.0], 6, "conformer_small_relpos")
     if "beam" in which:
         beam_case()
+    if "beam_topk" in which:
+        beam_topk_case()
     if "beam_lm" in which:
         beam_lm_case()
     if "beam_ctc" in which:

@@ -355,3 +355,28 @@ def test_beam_search_with_ctc_scorer_golden(dev, case):
     assert hyps == gb["hyps"]
     assert (scores.cpu() - gb["scores"]).abs().max() < 5e-2
     assert (lp.cpu() - gb["log_probs"]).abs().max() < 5e-2
+
+
+def test_beam_search_return_topk_golden(dev):
+    """return_topk=True, topk=3: padded n-best hypotheses, lengths, scores and log-probs vs the REFERENCE."""
+    from speechbrain_b200.decoders.seq2seq import S2STransformerBeamSearcher
+    from speechbrain_b200.lobes.models.transformer.TransformerASR import TransformerASR
+    from speechbrain_b200.nnet.linear import Linear
+    from speechbrain_b200.utils.seeded_init import CONFORMER_LARGE, seeded_asr_state
+    g = torch.load(os.path.join(GOLDEN, "conformer_large_rope.pt"))
+    gb = torch.load(os.path.join(GOLDEN, "beam_topk_conformer_large_rope.pt"))
+    sd = seeded_asr_state(dict(CONFORMER_LARGE), 0)
+    tr = TransformerASR(input_size=640, tgt_vocab=5000, d_model=512, nhead=8, num_encoder_layers=12, num_decoder_layers=6,
+                        d_ffn=2048, activation=torch.nn.GELU, encoder_module="conformer", attention_type="RoPEMHA",
+                        normalize_before=True, causal=False)
+    tr.load_state_dict({k[len("Transformer."):]: v for k, v in sd.items() if k.startswith("Transformer.")}, strict=False)
+    lin = Linear(input_size=512, n_neurons=5000)
+    bias = sd["seq_lin.w.bias"].clone()
+    bias[2] += gb["eos_bias"]
+    lin.load_state_dict({"w.weight": sd["seq_lin.w.weight"], "w.bias": bias})
+    bs = S2STransformerBeamSearcher(modules=[tr, lin], bos_index=1, eos_index=2, max_decode_ratio=gb["max_decode_ratio"],
+                                    return_topk=True, topk=gb["topk"], **gb["kwargs"])
+    hyps, lens, scores, lp = bs(g["enc_out"].to(dev), g["wav_lens"].to(dev))
+    print(f"beam topk hyps {hyps.tolist()} ref {gb['hyps'].tolist()} scores {scores.tolist()} ref {gb['scores'].tolist()}")
+    assert torch.equal(hyps.cpu(), gb["hyps"]) and torch.allclose(lens.cpu(), gb["lens"])
+    assert (scores.cpu() - gb["scores"]).abs().max() < 2e-2 and (lp.cpu() - gb["log_probs"]).abs().max() < 3e-2

@@ -89,3 +89,40 @@ def test_seeded_weights_are_order_independent():
     a = seeded_tensor(0, "Transformer.encoder.layers.3.norm1.norm.weight", (512,))
     b = seeded_tensor(0, "Transformer.encoder.layers.3.norm1.norm.weight", (512,))
     assert torch.equal(a, b) and abs(float(a.mean()) - 1.0) < 0.05
+
+
+def test_scorer_builder_mirrors_reference_validation():
+    """ScorerBuilder / CTCScorer / beam searcher argument checks raise like the reference (scorer.py:1186-1218,1317-1341;
+    seq2seq.py:785-804) or with NotImplementedError for what is not built -- never a silent fallback."""
+    import pytest
+    import torch
+
+    from speechbrain_b200.decoders.scorer import CTCScorer, ScorerBuilder, TransformerLMScorer
+    from speechbrain_b200.decoders.seq2seq import S2STransformerBeamSearcher
+    from speechbrain_b200.lobes.models.transformer.TransformerLM import TransformerLM
+    from speechbrain_b200.nnet.linear import Linear
+    ctc = CTCScorer(ctc_fc=Linear(input_size=16, n_neurons=8), blank_index=0, eos_index=2)
+    with pytest.raises(AssertionError):  # "Weights and scorers are not matched."
+        ScorerBuilder(full_scorers=[ctc], weights={})
+    with pytest.raises(ValueError):
+        ScorerBuilder(full_scorers=[ctc], weights={"transformerlm": 1.0})
+    with pytest.raises(NotImplementedError):
+        ScorerBuilder(full_scorers=[], partial_scorers=[ctc], weights={"ctc": 1.0})
+    with pytest.raises(NotImplementedError):
+        CTCScorer(ctc_fc=None, blank_index=0, eos_index=2, ctc_window_size=10)
+    with pytest.raises(NotImplementedError):  # post-norm LM only (the recipe's), head_dim 64
+        TransformerLM(vocab=100, d_model=128, nhead=4, num_encoder_layers=1, d_ffn=256, normalize_before=True)
+    sb = ScorerBuilder(full_scorers=[ctc], weights={"ctc": 0.4})
+    assert sb.weights["ctc"] == 0.4 and sb.weights["transformerlm"] == 0.0 and sb.weights["length"] == 0.0
+    # blank / bos / eos must differ for joint CTC/attention decoding (seq2seq.py:797-801)
+    with pytest.raises(ValueError):
+        S2STransformerBeamSearcher(modules=[torch.nn.Identity(), Linear(input_size=16, n_neurons=8)], bos_index=0, eos_index=2,
+                                   beam_size=2, scorer=sb)
+    with pytest.raises(ValueError):
+        S2STransformerBeamSearcher(modules=[torch.nn.Identity(), Linear(input_size=16, n_neurons=8)], bos_index=1, eos_index=2,
+                                   beam_size=2, topk=3)
+    lm = TransformerLM(vocab=100, d_model=128, nhead=2, num_encoder_layers=2, d_ffn=256, activation=torch.nn.GELU)
+    keys = set(lm.state_dict().keys())
+    assert "custom_src_module.emb.Embedding.weight" in keys and "output_proj.layers.2.w.bias" in keys
+    assert "encoder.layers.1.self_att.att.in_proj_weight" in keys and "positional_encoding.pe" in keys
+    TransformerLMScorer(language_model=lm, temperature=1.15)
