@@ -101,6 +101,11 @@ int sbk_asr_set_decoder_ln_fusion(sbk_asr* m, int on);
 /* Decode steps with at least `rows` live hypotheses (several batches decoded together, wide beams) run their projections
  * on the tcgen05 GEMM instead of the weight-streaming kernel (default 64; a huge value = never, 1 = always). */
 int sbk_asr_set_decoder_tc_min_rows(sbk_asr* m, int rows);
+/* TransformerLMRescorer.rescore_hyps (decoders/scorer.py:1835-1882), device part: tokens_dev [n, L] int32 rows
+ * "bos ... eos pad pad", lens_dev [n] int32 (tokens incl. bos/eos) -> scores_dev [n] fp32 = sum of log p(token | prefix) at
+ * `temperature` with the pad column excluded from the normalisation.  Needs a handle created with SBK_PART_LM. */
+int sbk_asr_lm_rescore(sbk_asr* m, const int* tokens_dev, const int* lens_dev, int n, int L, float temperature, int pad_index,
+                       float* scores_dev, void* stream);
 int sbk_asr_num_frames(const sbk_asr* m, int n_samples, int* T_feat, int* T_enc);
 
 /* ConvolutionFrontEnd.forward (lobes/models/convolution.py:116-320): feats [B,T0,n_mels] -> out [B,T2,F2*C2] fp32 */

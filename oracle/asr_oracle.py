@@ -641,3 +641,47 @@ def ctc_prefix_permute(st, memory, cand):
     psi_sel = psi.reshape(-1)[cand_index].view(-1, 1).repeat(1, V)
     r_sel = r.reshape(T, 2, n_bh * V)[:, :, cand_index]
     return r_sel, psi_sel
+
+
+# --------------------------------------------------------------------------
+# TransformerLMRescorer.rescore_hyps (decoders/scorer.py:1793-1882) + RescorerBuilder.rescore (:2113-2162)
+# --------------------------------------------------------------------------
+
+
+class StubTokenizer:
+    """Stands in for the sentencepiece processor the recipes pass (only ``encode_as_ids`` is called, scorer.py:1817):
+    one id per character, ids in [3, 4993), deterministic."""
+
+    def encode_as_ids(self, text):
+        return [3 + (ord(ch) * 131) % 4990 for ch in text]
+
+
+def lm_rescore_hyps(topk_hyps, tokenizer, sd_lm, cfg_lm, temperature=1.0, bos_index=0, eos_index=0, pad_index=0, prefix=""):
+    """preprocess_func (:1793-1833: upper-case, bos + ids + eos, pad) then rescore_hyps (:1835-1882): one LM forward over the
+    padded batch, log-softmax(logits / T) with the pad column at -inf and renormalised, sum of the target log-probs over the
+    valid positions (nansum)."""
+    enc = [torch.tensor([bos_index] + tokenizer.encode_as_ids(seq.upper()) + [eos_index]) for batch in topk_hyps for seq in batch]
+    lengths = torch.tensor([e.shape[0] for e in enc])
+    padded = torch.nn.utils.rnn.pad_sequence(enc, batch_first=True, padding_value=pad_index)
+    logits = transformer_lm_forward(padded, sd_lm, cfg_lm, prefix)
+    log_probs = F.log_softmax(logits / temperature, dim=-1)
+    log_probs[:, :, pad_index] = float("-inf")
+    tgt = log_probs[:, :-1].gather(2, padded[:, 1:].unsqueeze(2)).squeeze(2)
+    tgt = tgt - log_probs[:, :-1].logsumexp(dim=-1)
+    mask = torch.arange(padded.shape[1]).unsqueeze(0) < lengths.unsqueeze(1)
+    return torch.nansum(tgt * mask[:, 1:], dim=-1)
+
+
+def rescorer_builder_rescore(topk_candidates, topk_scores, lm_scores, weight):
+    """RescorerBuilder.rescore (:2113-2162) with one rescorer: add weight * score, sort each utterance's candidates."""
+    new_scores = [list(r) for r in topk_scores]
+    it = iter(lm_scores.tolist())
+    for i in range(len(new_scores)):
+        for j in range(len(new_scores[i])):
+            new_scores[i][j] += weight * next(it)
+    out_c, out_s = [], []
+    for cands, scs in zip(topk_candidates, new_scores):
+        order = sorted(zip(cands, scs), key=lambda x: x[1], reverse=True)
+        out_c.append([c for c, _ in order])
+        out_s.append([s_ for _, s_ in order])
+    return out_c, out_s

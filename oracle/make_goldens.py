@@ -229,6 +229,36 @@ def beam_topk_case(tag="beam_topk_conformer_large_rope"):
                     scores=tk_scores, log_probs=tk_lp), os.path.join(OUT, f"{tag}.pt"))
 
 
+def rescore_case(tag="lm_rescore"):
+    """TransformerLMRescorer.rescore_hyps + RescorerBuilder.rescore of the reference (n-best rescoring of text hypotheses) with
+    the recipe-size TransformerLM (seed 1) and a stub tokenizer."""
+    import copy
+
+    from speechbrain.decoders.scorer import RescorerBuilder, TransformerLMRescorer
+    from speechbrain.lobes.models.transformer.TransformerLM import TransformerLM
+    lm = TransformerLM(vocab=5000, d_model=768, nhead=12, num_encoder_layers=12, num_decoder_layers=0, d_ffn=3072,
+                       dropout=0.0, activation=torch.nn.GELU, normalize_before=False)
+    sd_lm = seeded_state_dict(lm, seed=1)
+    lm.load_state_dict(sd_lm)
+    lm.eval()
+    cfg_lm = dict(d_model=768, nhead=12, num_encoder_layers=12, d_ffn=3072, activation="gelu")
+    tok = O.StubTokenizer()
+    hyps = [["hello world", "hello word", "yellow world peace"], ["a b", "abc", "the cat sat on the mat"]]
+    scores = [[-1.0, -1.2, -1.5], [-0.3, -0.35, -0.4]]
+    resc = TransformerLMRescorer(language_model=lm, tokenizer=tok, device="cpu", temperature=1.15, bos_index=1, eos_index=2,
+                                 pad_index=0)
+    with torch.no_grad():
+        ref = resc.rescore_hyps(hyps)
+        ours = O.lm_rescore_hyps(hyps, tok, sd_lm, cfg_lm, 1.15, 1, 2, 0)
+        rb = RescorerBuilder(weights={"transformerlm": 0.5}, rescorers=[resc])
+        out_c, out_s = rb.rescore(hyps, copy.deepcopy(scores))
+    o_c, o_s = O.rescorer_builder_rescore(hyps, scores, ours, 0.5)
+    print(f"[rescore] ref {ref.tolist()} oracle err {(ours - ref).abs().max():.2e}; reranked {out_c} equal: {o_c == out_c}")
+    assert (ours - ref).abs().max() < 1e-3 and o_c == out_c
+    torch.save(dict(hyps=hyps, scores=scores, temperature=1.15, weight=0.5, lm_scores=ref, out_candidates=out_c, out_scores=out_s),
+               os.path.join(OUT, f"{tag}.pt"))
+
+
 def beam_lm_case(tag="beam_lm_conformer_large_rope"):
     """S2STransformerBeamSearcher + ScorerBuilder(full_scorers=[TransformerLMScorer]) -- shallow fusion with the recipe's
     12 x 768 TransformerLM (conformer_large.yaml:160-170, 215-223), weight 0.6, temperature 1.15."""
@@ -327,7 +357,7 @@ def beam_ctc_case(tag="beam_ctc_conformer_large_rope"):
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
-    which = sys.argv[1:] or ["fbank", "norm", "L_rope", "L_relpos", "S_relpos", "beam", "beam_topk", "beam_lm", "beam_ctc"]
+    which = sys.argv[1:] or ["fbank", "norm", "L_rope", "L_relpos", "S_relpos", "beam", "beam_topk", "beam_lm", "beam_ctc", "rescore"]
     if "fbank" in which:
         fbank_cases()
     if "norm" in which:
@@ -344,6 +374,8 @@ if __name__ == "__main__":
         beam_topk_case()
     if "beam_lm" in which:
         beam_lm_case()
+    if "rescore" in which:
+        rescore_case()
     if "beam_ctc" in which:
         beam_ctc_case()
     for fn in sorted(os.listdir(OUT)):

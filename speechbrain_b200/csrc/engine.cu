@@ -956,6 +956,58 @@ static int run_greedy(AsrModel* m, int B, int T, int max_steps, int bos, int eos
     return SBK_OK;
 }
 
+// ---------------------------------------------------------------------------- TransformerLMRescorer (scorer.py:1835-1882)
+// Teacher-forced scoring of n padded token sequences with the KV-cached LM step: position s feeds tokens[:, s] and adds
+// log p(tokens[:, s+1]) -- renormalised without the pad column like the reference -- for the rows whose sequence is longer.
+__global__ void lm_teacher_reset_kernel(const int* __restrict__ tokens, int n, int L, int S_max, int pad, int* __restrict__ lineage,
+                                        int* __restrict__ tok_cache, float* __restrict__ scores) {
+    const int r = blockIdx.x;
+    for (int p = threadIdx.x; p < S_max; p += blockDim.x) {
+        lineage[static_cast<size_t>(r) * S_max + p] = r;                                   // parity 0
+        lineage[static_cast<size_t>(n) * S_max + static_cast<size_t>(r) * S_max + p] = r;  // parity 1
+        tok_cache[static_cast<size_t>(r) * S_max + p] = p < L ? tokens[static_cast<size_t>(r) * L + p] : pad;
+    }
+    if (threadIdx.x == 0) scores[r] = 0.0f;
+}
+__global__ void lm_teacher_embed_kernel(const int* __restrict__ tokens, int L, int s, const float* __restrict__ emb,
+                                        const float* __restrict__ pe, int d, float sqrt_d, float* __restrict__ x,
+                                        __half* __restrict__ x16, int* __restrict__ step_arr) {
+    const int r = blockIdx.x;
+    const int tok = tokens[static_cast<size_t>(r) * L + s];
+    for (int i = threadIdx.x; i < d; i += blockDim.x) {
+        const float v = emb[static_cast<size_t>(tok) * d + i] * sqrt_d + pe[static_cast<size_t>(s) * d + i];
+        x[static_cast<size_t>(r) * d + i] = v;
+        x16[static_cast<size_t>(r) * d + i] = __float2half_rn(v);
+    }
+    if (threadIdx.x == 0) step_arr[r] = s;
+}
+__global__ void lm_teacher_score_kernel(const float* __restrict__ log_probs, int V, const int* __restrict__ tokens, int L, int s,
+                                        const int* __restrict__ lens, int pad, float* __restrict__ scores, int n) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n || s + 1 >= lens[r]) return;
+    const float* lp = log_probs + static_cast<size_t>(r) * V;
+    const int tgt = tokens[static_cast<size_t>(r) * L + s + 1];
+    const float v = (tgt == pad ? -INFINITY : lp[tgt]) - log1pf(-expf(lp[pad]));  // log_softmax over the non-pad entries
+    if (v == v) scores[r] += v;  // torch.nansum
+}
+
+static int run_lm_rescore(AsrModel* m, const int* tokens, const int* lens, int n, int L, float temperature, int pad,
+                          float* scores, cudaStream_t st) {
+    const sbk_asr_config& c = m->cfg;
+    AsrModel::Buf& b = m->b;
+    const int S_max = m->ws_steps + 1, dl = c.lm_d_model;
+    lm_teacher_reset_kernel<<<n, 128, 0, st>>>(tokens, n, L, S_max, pad, b.lineage, b.tok_cache, scores);
+    SBK_LAUNCH_CHECK();
+    for (int s = 0; s + 1 < L; ++s) {
+        lm_teacher_embed_kernel<<<n, 128, 0, st>>>(tokens, L, s, m->lm_emb, m->lm_pe, dl, sqrtf((float)dl), b.lx, b.lx16, b.step);
+        SBK_LAUNCH_CHECK();
+        RC(enqueue_lm_step(m, n, S_max, temperature, 1.0f, st));
+        lm_teacher_score_kernel<<<ceil_div(n, 128), 128, 0, st>>>(b.lm_extra, c.vocab, tokens, L, s, lens, pad, scores, n);
+        SBK_LAUNCH_CHECK();
+    }
+    return SBK_OK;
+}
+
 }  // namespace sbk
 
 // ============================================================================ C ABI
@@ -1366,6 +1418,20 @@ int sbk_asr_transcribe_greedy_host_async(sbk_asr* mm, const float* wav_host, con
                                          int* steps_done, void* stream) {
     return transcribe_greedy_host_impl(mm, wav_host, rel_len_host, B, L, max_steps, bos, eos, pred_host, score_host,
                                        steps_done, stream, false);
+}
+
+// TransformerLMRescorer.rescore_hyps device part: tokens [n, L] int32 (bos ... eos, pad-filled), lens [n] int32 (device) ->
+// scores [n] fp32 (device) = sum over the sequence of log p(token | prefix) at `temperature`, pad column excluded.
+int sbk_asr_lm_rescore(sbk_asr* mm, const int* tokens_dev, const int* lens_dev, int n, int L, float temperature, int pad_index,
+                       float* scores_dev, void* stream) {
+    AsrModel* m = reinterpret_cast<AsrModel*>(mm);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    SBK_REQUIRE(m->has_lm, "lm_rescore: this handle was created without TransformerLM weights");
+    SBK_REQUIRE(n >= 1 && L >= 2 && L <= m->cfg.max_len && pad_index >= 0 && pad_index < m->cfg.vocab && temperature > 0.0f,
+                "lm_rescore: bad arguments (n=%d L=%d pad=%d)", n, L, pad_index);
+    SBK_REQUIRE(pad_index == 0, "lm_rescore: pad_index must be 0 (TransformerLM.make_masks pads with index 0)");
+    RC(ensure_workspace(m, std::max(1, m->wsB), std::max(m->wsL, 4 * m->cfg.hop), std::max(n, m->ws_rows), std::max(L, m->ws_steps)));
+    return run_lm_rescore(m, tokens_dev, lens_dev, n, L, temperature, pad_index, scores_dev, st);
 }
 
 }  // extern "C"

@@ -130,6 +130,19 @@ class AsrEngine:
     def set_poll_interval(self, every_n_steps):
         check(lib().sbk_asr_set_poll_interval(self._h, int(every_n_steps)), "sbk_asr_set_poll_interval")
 
+    def lm_rescore(self, tokens, lens, temperature=1.0, pad_index=0):
+        """TransformerLMRescorer.rescore_hyps device part: ``tokens`` [n, L] int32 CUDA (bos ... eos, pad-filled), ``lens`` [n]
+        int32 CUDA -> [n] fp32 CUDA scores (sum of log p(token | prefix), pad column excluded from the normalisation)."""
+        _lib.require_cuda(tokens, "AsrEngine.lm_rescore")
+        tokens = tokens.to(torch.int32).contiguous()
+        lens = lens.to(device=tokens.device, dtype=torch.int32).contiguous()
+        n, L = tokens.shape
+        scores = torch.empty(n, device=tokens.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            check(lib().sbk_asr_lm_rescore(self._h, ptr(tokens), ptr(lens), n, L, ctypes.c_float(temperature), int(pad_index),
+                                           ptr(scores), self._sp()), "sbk_asr_lm_rescore")
+        return scores
+
     def set_decoder_tc_min_rows(self, rows):
         """Decode steps with >= rows live hypotheses use the tcgen05 GEMM for the decoder projections (default 64)."""
         check(lib().sbk_asr_set_decoder_tc_min_rows(self._h, int(rows)), "sbk_asr_set_decoder_tc_min_rows")

@@ -380,3 +380,26 @@ def test_beam_search_return_topk_golden(dev):
     print(f"beam topk hyps {hyps.tolist()} ref {gb['hyps'].tolist()} scores {scores.tolist()} ref {gb['scores'].tolist()}")
     assert torch.equal(hyps.cpu(), gb["hyps"]) and torch.allclose(lens.cpu(), gb["lens"])
     assert (scores.cpu() - gb["scores"]).abs().max() < 2e-2 and (lp.cpu() - gb["log_probs"]).abs().max() < 3e-2
+
+
+def test_lm_rescorer_golden(dev):
+    """TransformerLMRescorer + RescorerBuilder mirrors (teacher-forced KV-cached LM on the device) vs the REFERENCE's n-best
+    rescoring: LM scores within 5e-2 of sums of up to 24 log-probs (|score| ~ 35..200), identical re-ranking."""
+    from oracle.asr_oracle import StubTokenizer
+    from speechbrain_b200.decoders.scorer import RescorerBuilder, TransformerLMRescorer
+    from speechbrain_b200.lobes.models.transformer.TransformerLM import TransformerLM
+    from speechbrain_b200.utils.seeded_init import seeded_state_dict
+    gb = torch.load(os.path.join(GOLDEN, "lm_rescore.pt"))
+    lm = TransformerLM(vocab=5000, d_model=768, nhead=12, num_encoder_layers=12, num_decoder_layers=0, d_ffn=3072, dropout=0.0,
+                       activation=torch.nn.GELU, normalize_before=False)
+    lm.load_state_dict(seeded_state_dict(lm, seed=1))
+    resc = TransformerLMRescorer(language_model=lm, tokenizer=StubTokenizer(), device=dev, temperature=gb["temperature"],
+                                 bos_index=1, eos_index=2, pad_index=0)
+    scores = resc.rescore_hyps(gb["hyps"]).cpu()
+    print("lm rescore", scores.tolist(), "ref", gb["lm_scores"].tolist())
+    assert (scores - gb["lm_scores"]).abs().max() < 5e-2
+    import copy
+    rb = RescorerBuilder(weights={"transformerlm": gb["weight"]}, rescorers=[resc])
+    out_c, out_s = rb.rescore(gb["hyps"], copy.deepcopy(gb["scores"]))
+    assert out_c == gb["out_candidates"]
+    assert max(abs(a - b) for ra, rb_ in zip(out_s, gb["out_scores"]) for a, b in zip(ra, rb_)) < 5e-2

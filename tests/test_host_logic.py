@@ -126,3 +126,34 @@ def test_scorer_builder_mirrors_reference_validation():
     assert "custom_src_module.emb.Embedding.weight" in keys and "output_proj.layers.2.w.bias" in keys
     assert "encoder.layers.1.self_att.att.in_proj_weight" in keys and "positional_encoding.pe" in keys
     TransformerLMScorer(language_model=lm, temperature=1.15)
+
+
+def test_no_undefined_names_in_package():
+    """Static check (the GPU-only code paths cannot run on the CPU box): every name loaded in speechbrain_b200/*.py, bench.py
+    and __graft_entry__.py is defined somewhere in its module (imports, defs, assignments, arguments, comprehensions)."""
+    import ast
+    import builtins
+    import glob
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = glob.glob(os.path.join(root, "speechbrain_b200", "**", "*.py"), recursive=True)
+    files += [os.path.join(root, "bench.py"), os.path.join(root, "__graft_entry__.py")]
+    bad = {}
+    for f in files:
+        tree = ast.parse(open(f).read())
+        defined = set(dir(builtins)) | {"__file__", "__name__"}
+        for n in ast.walk(tree):
+            if isinstance(n, (ast.Import, ast.ImportFrom)):
+                defined.update((a.asname or a.name).split(".")[0] for a in n.names)
+            elif isinstance(n, (ast.FunctionDef, ast.ClassDef, ast.AsyncFunctionDef)):
+                defined.add(n.name)
+            elif isinstance(n, ast.Name) and isinstance(n.ctx, (ast.Store, ast.Del)):
+                defined.add(n.id)
+            elif isinstance(n, ast.arg):
+                defined.add(n.arg)
+            elif isinstance(n, ast.ExceptHandler) and n.name:
+                defined.add(n.name)
+        und = {n.id for n in ast.walk(tree) if isinstance(n, ast.Name) and isinstance(n.ctx, ast.Load) and n.id not in defined}
+        if und:
+            bad[os.path.relpath(f, root)] = sorted(und)
+    assert not bad, bad
