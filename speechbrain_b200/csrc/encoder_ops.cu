@@ -112,7 +112,8 @@ int cast_f32_f16(const float* in, __half* out, size_t n, cudaStream_t stream) {
 // input slab is staged in shared memory once.
 constexpr int DW_TT = 16;
 
-template <int KT>  // KT > 0: compile-time kernel size (taps held in registers); KT == 0: runtime K
+// KT > 0: compile-time kernel size (taps held in registers); KT == 0: runtime K.  MAXC: channels per thread (D <= 256 * MAXC)
+template <int KT, int MAXC>
 __global__ void __launch_bounds__(256, 2)
 dwconv_ln_swish_kernel(const float* __restrict__ glu, int T, int D, int K, const float* __restrict__ wdw /*[D,K]*/,
                        const float* __restrict__ bdw, const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -148,28 +149,39 @@ dwconv_ln_swish_kernel(const float* __restrict__ glu, int T, int D, int K, const
         if (r >= r_lo) r += r_hi - r_lo;
         slab[r * D + ch] = 0.0f;
     }
+    // tap weights and biases of this thread's channels: fetched while the slab is still in flight
+    float wreg[KT > 0 ? MAXC : 1][KT > 0 ? KT : 1];
+    float breg[MAXC];
+#pragma unroll
+    for (int cc = 0; cc < MAXC; ++cc) {
+        const int ch = threadIdx.x + cc * 256;
+        breg[cc] = 0.0f;
+        if (ch < D) {
+            breg[cc] = __ldg(bdw + ch);
+            if constexpr (KT > 0) {
+#pragma unroll
+                for (int k = 0; k < KT; ++k) wreg[cc][k] = __ldg(wdw + static_cast<size_t>(ch) * K + k);
+            }
+        }
+    }
     mbar_wait(&bar, 0);
     __syncthreads();
-    constexpr int MAXC = 4;  // channels per thread: D <= 256 * MAXC
     float acc[MAXC][DW_TT];
 #pragma unroll
     for (int cc = 0; cc < MAXC; ++cc) {
         const int ch = threadIdx.x + cc * 256;
         if (ch < D) {
-            const float bz = __ldg(bdw + ch);
+            const float bz = breg[cc];
 #pragma unroll
             for (int i = 0; i < DW_TT; ++i) acc[cc][i] = bz;
             const float* w = wdw + static_cast<size_t>(ch) * K;
             if constexpr (KT > 0) {
-                float wr[KT];
-#pragma unroll
-                for (int k = 0; k < KT; ++k) wr[k] = __ldg(w + k);
 #pragma unroll
                 for (int r = 0; r < DW_TT + KT - 1; ++r) {
                     const float xv = slab[r * D + ch];
 #pragma unroll
                     for (int i = 0; i < DW_TT; ++i)
-                        if (r - i >= 0 && r - i < KT) acc[cc][i] = fmaf(xv, wr[r - i], acc[cc][i]);
+                        if (r - i >= 0 && r - i < KT) acc[cc][i] = fmaf(xv, wreg[cc][r - i], acc[cc][i]);
                 }
             } else {
                 for (int r = 0; r < rows_in; ++r) {
@@ -194,6 +206,16 @@ dwconv_ln_swish_kernel(const float* __restrict__ glu, int T, int D, int K, const
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int MAXP = MAXC * 4;  // channel pairs per lane (D <= 256 * MAXC): LayerNorm scale / shift held in registers
+    float2 g2[MAXP], b2[MAXP];
+#pragma unroll
+    for (int p = 0; p < MAXP; ++p) {
+        const int j = 2 * lane + 64 * p;
+        if (j < D) {
+            g2[p] = __ldg(reinterpret_cast<const float2*>(gamma + j));
+            b2[p] = __ldg(reinterpret_cast<const float2*>(beta + j));
+        }
+    }
     for (int i = warp; i < DW_TT; i += (blockDim.x >> 5)) {
         const int t = t0 + i;
         if (t >= T) continue;
@@ -208,10 +230,15 @@ dwconv_ln_swish_kernel(const float* __restrict__ glu, int T, int D, int K, const
         }
         const float rstd = rsqrtf(warp_sum(q) / D + eps);
         __half* o = out + (static_cast<size_t>(b) * T + t) * D;
-        for (int j = 2 * lane; j < D; j += 64) {
-            const float y0 = silu_f((c[j] - mean) * rstd * __ldg(gamma + j) + __ldg(beta + j));
-            const float y1 = silu_f((c[j + 1] - mean) * rstd * __ldg(gamma + j + 1) + __ldg(beta + j + 1));
-            *reinterpret_cast<__half2*>(o + j) = __floats2half2_rn(y0, y1);
+#pragma unroll
+        for (int p = 0; p < MAXP; ++p) {
+            const int j = 2 * lane + 64 * p;
+            if (j < D) {
+                const float2 cv = *reinterpret_cast<const float2*>(c + j);
+                const float y0 = silu_f((cv.x - mean) * rstd * g2[p].x + b2[p].x);
+                const float y1 = silu_f((cv.y - mean) * rstd * g2[p].y + b2[p].y);
+                *reinterpret_cast<__half2*>(o + j) = __floats2half2_rn(y0, y1);
+            }
         }
     }
 }
@@ -222,7 +249,8 @@ int dwconv_ln_swish(const float* glu, int B, int T, int D, int K, const float* w
     SBK_REQUIRE((reinterpret_cast<uintptr_t>(glu) & 15) == 0, "dwconv_ln_swish: input must be 16-byte aligned");
     const size_t smem = static_cast<size_t>(DW_TT + K - 1) * D * sizeof(float);
     SBK_REQUIRE(smem <= 200 * 1024, "dwconv_ln_swish: tile too large for shared memory (D=%d K=%d)", D, K);
-    auto kern = (K == 31) ? dwconv_ln_swish_kernel<31> : dwconv_ln_swish_kernel<0>;
+    auto kern = dwconv_ln_swish_kernel<0, 4>;
+    if (K == 31) kern = D <= 256 ? dwconv_ln_swish_kernel<31, 1> : D <= 512 ? dwconv_ln_swish_kernel<31, 2> : dwconv_ln_swish_kernel<31, 4>;
     SBK_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<dim3(ceil_div(T, DW_TT), B), 256, smem, stream>>>(glu, T, D, K, wdw, bdw, gamma, beta, eps, out);
     SBK_LAUNCH_CHECK();
