@@ -56,6 +56,8 @@ typedef struct {
        ctc_weight != 0 also scales the decoder log-probs by 1 - ctc_weight (seq2seq.py:791-804,916-921). */
     float ctc_weight;
     int blank_index;
+    /* LengthScorer (decoders/scorer.py:956-1072): this constant is added to every token's log-prob at every step */
+    float length_weight;
 } sbk_beam_params;
 
 const char* sbk_last_error(void); /* thread-local message of the last failing call */

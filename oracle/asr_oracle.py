@@ -421,7 +421,7 @@ def full_pipeline_features(wav, wav_lens, sd, cfg):
 def beam_search(enc_states, wav_len, sd, cfg, seq_lin_w, seq_lin_b, bos_index=1, eos_index=2, beam_size=4,
                 min_decode_ratio=0.0, max_decode_ratio=1.0, temperature=1.0, using_eos_threshold=True,
                 eos_threshold=1.5, length_normalization=True, minus_inf=-1e20, topk=1, prefix="", return_history=False,
-                lm=None, ctc=None, return_topk=False):
+                lm=None, ctc=None, return_topk=False, length_weight=0.0):
     """S2STransformerBeamSearcher.forward, using_max_attn_shift=False; scorer=None, or a ScorerBuilder with full scorers
     TransformerLMScorer (``lm`` = dict(sd, cfg, weight, temperature, prefix)) and/or CTCScorer (``ctc`` = dict(w, b, weight,
     blank_index)), in the recipe's order [transformerlm, ctc] (scorer.py:1221-1268; conformer_large.yaml:209-223).
@@ -486,6 +486,8 @@ def beam_search(enc_states, wav_len, sd, cfg, seq_lin_w, seq_lin_b, bos_index=1,
             log_probs[:, ctc["blank_index"]] = ctc_state["minus_inf"]
             ctc_score, ctc_mem = ctc_prefix_step(ctc_state, inp, ctc_mem, beam_size)
             log_probs = log_probs + ctc["weight"] * ctc_score
+        if length_weight != 0.0:  # LengthScorer.score (scorer.py:1043-1071): ones * weight on every token
+            log_probs = log_probs + length_weight
         sc = seq_scores.unsqueeze(1) + log_probs
         if length_normalization:
             sc = sc / (step + 1)

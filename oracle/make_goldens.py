@@ -259,6 +259,37 @@ def rescore_case(tag="lm_rescore"):
                os.path.join(OUT, f"{tag}.pt"))
 
 
+def beam_len_case(tag="beam_len_conformer_large_rope"):
+    """ScorerBuilder(full_scorers=[LengthScorer]) (length reward, no length normalisation): with the reward the search keeps
+    longer hypotheses than without it."""
+    from speechbrain.decoders.scorer import LengthScorer, ScorerBuilder
+    from speechbrain.decoders.seq2seq import S2STransformerBeamSearcher
+    fb, norm, mods, sd = build_reference(CFG_L, "RoPEMHA")
+    g = torch.load(os.path.join(OUT, "conformer_large_rope.pt"))
+    enc, wav_lens = g["enc_out"], g["wav_lens"]
+    T = enc.shape[1]
+    kwargs = dict(beam_size=4, using_eos_threshold=False, temperature=1.0, min_decode_ratio=0.0, length_normalization=False)
+    eos_bias, w_len = 4.0, 8.3
+    with torch.no_grad():
+        bias = sd["seq_lin.w.bias"].clone()
+        bias[2] += eos_bias
+        mods["seq_lin"].w.bias.copy_(bias)
+        res = {}
+        for name, scorer in (("off", None), ("on", ScorerBuilder(full_scorers=[LengthScorer(5000)], weights={"length": w_len}))):
+            bs = S2STransformerBeamSearcher(modules=[mods["Transformer"], mods["seq_lin"]], bos_index=1, eos_index=2,
+                                            max_decode_ratio=8.5 / T, scorer=scorer, **kwargs)
+            res[name] = bs(enc, wav_lens)
+        ocfg = dict(CFG_L, attention_type="RoPEMHA")
+        ohyps, olens, oscores, olp = O.beam_search(enc, wav_lens, sd, ocfg, sd["seq_lin.w.weight"], bias, 1, 2,
+                                                   max_decode_ratio=8.5 / T, prefix="Transformer.", length_weight=w_len, **kwargs)
+    hyps, lens, scores, lp = res["on"]
+    print(f"[beam len] without {res['off'][0]} with {hyps} scores {scores.tolist()} | oracle equal: {ohyps == hyps} "
+          f"score err {(oscores - scores).abs().max():.2e}")
+    assert ohyps == hyps and (oscores - scores).abs().max() < 1e-4 and res["off"][0] != hyps
+    torch.save(dict(kwargs=kwargs, eos_bias=eos_bias, length_weight=w_len, max_decode_ratio=8.5 / T, hyps=hyps, lens=lens,
+                    scores=scores, log_probs=lp, hyps_without=res["off"][0]), os.path.join(OUT, f"{tag}.pt"))
+
+
 def beam_lm_case(tag="beam_lm_conformer_large_rope"):
     """S2STransformerBeamSearcher + ScorerBuilder(full_scorers=[TransformerLMScorer]) -- shallow fusion with the recipe's
     12 x 768 TransformerLM (conformer_large.yaml:160-170, 215-223), weight 0.6, temperature 1.15."""
@@ -357,7 +388,7 @@ def beam_ctc_case(tag="beam_ctc_conformer_large_rope"):
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
-    which = sys.argv[1:] or ["fbank", "norm", "L_rope", "L_relpos", "S_relpos", "beam", "beam_topk", "beam_lm", "beam_ctc", "rescore"]
+    which = sys.argv[1:] or ["fbank", "norm", "L_rope", "L_relpos", "S_relpos", "beam", "beam_topk", "beam_lm", "beam_ctc", "rescore", "beam_len"]
     if "fbank" in which:
         fbank_cases()
     if "norm" in which:
@@ -376,6 +407,8 @@ if __name__ == "__main__":
         beam_lm_case()
     if "rescore" in which:
         rescore_case()
+    if "beam_len" in which:
+        beam_len_case()
     if "beam_ctc" in which:
         beam_ctc_case()
     for fn in sorted(os.listdir(OUT)):

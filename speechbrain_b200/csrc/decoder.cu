@@ -935,7 +935,7 @@ struct BeamArgs {
     // optional shallow-fusion scorer (TransformerLMScorer): pre-weighted scores added to the (masked) log-probs,
     // and the LM's own next input (embedding + PE in fp32 and fp16) and token cache (pad-mask on id 0)
     const float* add_scores;
-    float attn_weight; int blank;
+    float attn_weight; int blank; float add_const;
     const float* lm_emb; const float* lm_pe; int lm_d; float lm_sqrt_d; float* lm_x_next; __half* lm_x16_next; int* tok_cache;
 };
 
@@ -987,6 +987,7 @@ __global__ void __launch_bounds__(BS_THREADS) beam_step_kernel(const BeamArgs a)
                 if (!(eos_lp > a.eos_threshold * max_lp)) eos_lp = a.minus_inf;
             }
             if (a.add_scores) eos_lp += a.add_scores[static_cast<size_t>(row0 + k) * V + a.eos];  // ScorerBuilder.score
+            eos_lp += a.add_const;
             s_lse[k] = lse;
             s_eos[k] = eos_lp;
         }
@@ -1005,6 +1006,7 @@ __global__ void __launch_bounds__(BS_THREADS) beam_step_kernel(const BeamArgs a)
                                 : a.attn_weight * (a.logits[static_cast<size_t>(row0 + k) * V + j] * a.inv_temp - s_lse[k]);
         if (j == a.blank) lp = a.minus_inf;
         if (a.add_scores && j != a.eos) lp += a.add_scores[static_cast<size_t>(row0 + k) * V + j];
+        if (j != a.eos) lp += a.add_const;
         const float sc = (seq_in[row0 + k] + lp) * inv_len;
         if (sc > bv[BS_MAXB - 1] && sc > -INFINITY) {  // insert (list sorted descending; only the first `beam` matter)
             float v = sc;
@@ -1150,7 +1152,7 @@ int beam_step(const BeamStepArgs& p, int B, cudaStream_t stream) {
     a.inv_temp = 1.0f / p.temperature; a.eos_threshold = p.eos_threshold; a.minus_inf = p.minus_inf;
     a.min_steps = p.min_steps; a.eos = p.eos; a.use_eos_threshold = p.use_eos_threshold; a.length_norm = p.length_norm;
     a.emb = p.emb; a.pe = p.pe; a.d = p.d; a.sqrt_d = sqrtf(static_cast<float>(p.d)); a.x_next = p.x_next;
-    a.add_scores = p.add_scores; a.attn_weight = p.attn_weight; a.blank = p.blank;
+    a.add_scores = p.add_scores; a.attn_weight = p.attn_weight; a.blank = p.blank; a.add_const = p.add_const;
     a.lm_emb = p.lm.emb; a.lm_pe = p.lm.pe; a.lm_d = p.lm.d; a.lm_sqrt_d = p.lm.d ? sqrtf(static_cast<float>(p.lm.d)) : 0.f;
     a.lm_x_next = p.lm.x; a.lm_x16_next = p.lm.x16; a.tok_cache = p.lm.tok_cache;
     SBK_CUDA_CHECK(launch_k(beam_step_kernel, dim3(B), dim3(BS_THREADS), 0, stream, a));

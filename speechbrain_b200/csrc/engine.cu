@@ -860,6 +860,7 @@ static int run_beam(AsrModel* m, int B, int T, const sbk_beam_params& p, int* hi
     a.add_scores = use_lm ? b.lm_extra : (use_ctc ? m->ctc.add : nullptr);
     a.lm = lm;
     if (use_ctc) { a.attn_weight = 1.0f - p.ctc_weight; a.blank = p.blank_index; }
+    a.add_const = p.length_weight;
     a.logits = b.logits; a.V = c.vocab; a.beam = beam; a.S_max = S_max; a.seq_scores = b.seq_scores; a.lineage = b.lineage;
     a.step_arr = b.step; a.finished = b.finished; a.n_full = b.ended_count;
     a.hist_tok = hist_tok; a.hist_pred = hist_pred; a.hist_score = hist_score; a.hist_lp = hist_lp;

@@ -132,6 +132,7 @@ struct BeamStepArgs {
     BeamLm lm;
     float attn_weight = 1.0f;  // 1 - ctc_weight (seq2seq.py:803-804, _attn_weight_step)
     int blank = -1;            // CTC blank index, blocked in the log-probs (scorer.py:1248-1250); -1 = no CTC scorer
+    float add_const = 0.0f;    // LengthScorer: weight * 1 added to every token (scorer.py:1043-1071)
 };
 // CTC prefix scorer (ctc_scorer.cu)
 struct CtcStep {

@@ -26,7 +26,14 @@ class CTCScorer:
         self.ctc_window_size = ctc_window_size
 
 
-_NAMES = {TransformerLMScorer: "transformerlm", CTCScorer: "ctc"}
+class LengthScorer:
+    """Length reward (scorer.py:956-1072): +weight on every token at every step; not compatible with length normalisation."""
+
+    def __init__(self, vocab_size):
+        self.vocab_size = vocab_size
+
+
+_NAMES = {TransformerLMScorer: "transformerlm", CTCScorer: "ctc", LengthScorer: "length"}
 _ALL = ("ctc", "rnnlm", "transformerlm", "kenlm", "coverage", "length")
 
 
@@ -39,7 +46,7 @@ class ScorerBuilder:
         for impl in full_scorers:
             if type(impl) not in _NAMES:
                 raise NotImplementedError(f"speechbrain_b200.ScorerBuilder: {type(impl).__name__} is not built "
-                                          "(TransformerLMScorer and CTCScorer are)")
+                                          "(TransformerLMScorer, CTCScorer and LengthScorer are)")
             names.append(_NAMES[type(impl)])
         if len(set(names)) != len(names):
             raise ValueError("ScorerBuilder: duplicate scorers")

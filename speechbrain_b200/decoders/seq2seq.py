@@ -61,13 +61,15 @@ class S2STransformerBeamSearcher(torch.nn.Module):
         super().__init__()
         if bos_index is None or eos_index is None or beam_size is None:
             raise TypeError("bos_index, eos_index and beam_size are required")
-        self.lm_scorer, self.lm_weight, self.ctc_scorer, self.ctc_weight = None, 0.0, None, 0.0
+        self.lm_scorer, self.lm_weight, self.ctc_scorer, self.ctc_weight, self.length_weight = None, 0.0, None, 0.0, 0.0
         if scorer is not None:
             from .scorer import ScorerBuilder
             if not isinstance(scorer, ScorerBuilder):
                 raise NotImplementedError("speechbrain_b200 beam searcher: scorer must be a speechbrain_b200 ScorerBuilder")
             if length_normalization and scorer.weights["length"] > 0.0:
                 raise ValueError("Length normalization is not compatible with length rewarding.")
+            if "length" in scorer.full_scorers:
+                self.length_weight = scorer.weights["length"]
             self.lm_scorer = scorer.full_scorers.get("transformerlm")
             self.lm_weight = scorer.weights["transformerlm"] if self.lm_scorer is not None else 0.0
             self.ctc_scorer = scorer.full_scorers.get("ctc")
@@ -116,7 +118,8 @@ class S2STransformerBeamSearcher(torch.nn.Module):
             enc_states, wav_len, self.beam_size, max_steps, min_steps, self.bos_index, self.eos_index, self.temperature,
             self.using_eos_threshold, self.eos_threshold, self.length_normalization, self.minus_inf,
             lm_weight=self.lm_weight, lm_temperature=self.lm_scorer.temperature if self.lm_scorer is not None else 1.0,
-            ctc_weight=self.ctc_weight, blank_index=self.ctc_scorer.blank_index if self.ctc_scorer is not None else -1)
+            ctc_weight=self.ctc_weight, blank_index=self.ctc_scorer.blank_index if self.ctc_scorer is not None else -1,
+            length_weight=self.length_weight)
         out = replay_beam_history(hist, B, self.beam_size, self.eos_index, self.topk)
         topk_hyps, topk_lengths, topk_scores, topk_log_probs = (t.to(enc_states.device) for t in out)
         if self.return_topk:

@@ -403,3 +403,32 @@ def test_lm_rescorer_golden(dev):
     out_c, out_s = rb.rescore(gb["hyps"], copy.deepcopy(gb["scores"]))
     assert out_c == gb["out_candidates"]
     assert max(abs(a - b) for ra, rb_ in zip(out_s, gb["out_scores"]) for a, b in zip(ra, rb_)) < 5e-2
+
+
+def test_beam_search_with_length_scorer_golden(dev):
+    """ScorerBuilder(full_scorers=[LengthScorer], weights={"length": w}) with length_normalization=False vs the REFERENCE."""
+    from speechbrain_b200.decoders.scorer import LengthScorer, ScorerBuilder
+    from speechbrain_b200.decoders.seq2seq import S2STransformerBeamSearcher
+    from speechbrain_b200.lobes.models.transformer.TransformerASR import TransformerASR
+    from speechbrain_b200.nnet.linear import Linear
+    from speechbrain_b200.utils.seeded_init import CONFORMER_LARGE, seeded_asr_state
+    g = torch.load(os.path.join(GOLDEN, "conformer_large_rope.pt"))
+    gb = torch.load(os.path.join(GOLDEN, "beam_len_conformer_large_rope.pt"))
+    sd = seeded_asr_state(dict(CONFORMER_LARGE), 0)
+    tr = TransformerASR(input_size=640, tgt_vocab=5000, d_model=512, nhead=8, num_encoder_layers=12, num_decoder_layers=6,
+                        d_ffn=2048, activation=torch.nn.GELU, encoder_module="conformer", attention_type="RoPEMHA",
+                        normalize_before=True, causal=False)
+    tr.load_state_dict({k[len("Transformer."):]: v for k, v in sd.items() if k.startswith("Transformer.")}, strict=False)
+    lin = Linear(input_size=512, n_neurons=5000)
+    bias = sd["seq_lin.w.bias"].clone()
+    bias[2] += gb["eos_bias"]
+    lin.load_state_dict({"w.weight": sd["seq_lin.w.weight"], "w.bias": bias})
+    scorer = ScorerBuilder(full_scorers=[LengthScorer(5000)], weights={"length": gb["length_weight"]})
+    with pytest.raises(ValueError):  # "Length normalization is not compatible with length rewarding."
+        S2STransformerBeamSearcher(modules=[tr, lin], bos_index=1, eos_index=2, beam_size=4, scorer=scorer)
+    bs = S2STransformerBeamSearcher(modules=[tr, lin], bos_index=1, eos_index=2, max_decode_ratio=gb["max_decode_ratio"],
+                                    scorer=scorer, **gb["kwargs"])
+    hyps, lens, scores, lp = bs(g["enc_out"].to(dev), g["wav_lens"].to(dev))
+    print(f"beam+length hyps {hyps} ref {gb['hyps']} scores {scores.tolist()} ref {gb['scores'].tolist()}")
+    assert hyps == gb["hyps"]
+    assert (scores.cpu() - gb["scores"]).abs().max() < 2e-2 and (lp.cpu() - gb["log_probs"]).abs().max() < 3e-2
