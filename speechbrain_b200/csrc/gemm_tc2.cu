@@ -22,7 +22,7 @@
 namespace sbk {
 
 constexpr int G2_BM = 128;        // rows per CTA (256 per pair)
-constexpr int G2_BN = 256;        // columns per pair tile
+constexpr int G2_BN = 256;        // columns per pair tile (default; template parameter BN of the kernel)
 constexpr int G2_BK = 64;
 constexpr int G2_STAGES = 5;
 // epilogue warps: EW / 4 warps per TMEM lane quarter, each drains 1 / (EW / 4) of the tile's columns.  The modes that
@@ -31,12 +31,19 @@ constexpr int G2_STAGES = 5;
 template <int MODE>
 constexpr int g2_epi_warps() { return (MODE == EPI_F32 || MODE == EPI_RESID || MODE == EPI_ROPE) ? 8 : 16; }
 constexpr int G2_A_BYTES = G2_BM * G2_BK * 2;            // 16 KB
-constexpr int G2_B_BYTES = (G2_BN / 2) * G2_BK * 2;      // 16 KB (this CTA's half of W's tile rows)
-constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
-constexpr int G2_BAR_OFFSET = G2_STAGES * G2_STAGE_BYTES;
-constexpr int G2_STG_OFFSET = G2_BAR_OFFSET + 256;   // per-epilogue-warp staging tiles (32 rows x pitch)
-template <int MODE, int EW>
-constexpr int g2_smem() { return G2_STG_OFFSET + EW * 32 * epi_stg_pitch<MODE>() + 1024; }
+// shared-memory map for a tile width BN and a ring of ST stages: [ST x (A 16 KB | this CTA's BN/2 rows of W)] [barriers]
+// [per-epilogue-warp staging tiles (32 rows x pitch)]
+template <int BN, int ST>
+struct G2Cfg {
+    static constexpr int B_BYTES = (BN / 2) * G2_BK * 2;
+    static constexpr int STAGE_BYTES = G2_A_BYTES + B_BYTES;
+    static constexpr int BAR_OFFSET = ST * STAGE_BYTES;
+    static constexpr int STG_OFFSET = BAR_OFFSET + 256;
+    static_assert(STAGE_BYTES % 1024 == 0, "128B-swizzled stages must stay 1 KB aligned");
+    static_assert((2 * ST + 4) * 8 + 4 <= 256, "barrier block");
+};
+template <int MODE, int EW, int BN, int ST>
+constexpr int g2_smem() { return G2Cfg<BN, ST>::STG_OFFSET + EW * 32 * epi_stg_pitch<MODE>() + 1024; }
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -97,15 +104,16 @@ __device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols)
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
-template <int MODE, int ACT, int EW>
+template <int MODE, int ACT, int EW, int BN = G2_BN, int ST = G2_STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EW, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 const GemmEpilogue epi, int M, int N, int K) {
+    using C = G2Cfg<BN, ST>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + G2_BAR_OFFSET);   // [STAGES]  (used on the leader)
-    uint64_t* empty_bar = full_bar + G2_STAGES;                               // [STAGES]  (each CTA its own)
-    uint64_t* tmem_full_bar = empty_bar + G2_STAGES;                          // [2]       (each CTA its own)
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::BAR_OFFSET);   // [STAGES]  (used on the leader)
+    uint64_t* empty_bar = full_bar + ST;                               // [STAGES]  (each CTA its own)
+    uint64_t* tmem_full_bar = empty_bar + ST;                          // [2]       (each CTA its own)
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;                             // [2]       (used on the leader)
     uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
@@ -113,14 +121,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
     const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
-    const int n_tiles = (N + G2_BN - 1) / G2_BN, m_tiles = (M + 2 * G2_BM - 1) / (2 * G2_BM);
+    const int n_tiles = (N + BN - 1) / BN, m_tiles = (M + 2 * G2_BM - 1) / (2 * G2_BM);
     const int total_tiles = n_tiles * m_tiles;
     const int num_kb = (K + G2_BK - 1) / G2_BK;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
-        for (int s = 0; s < G2_STAGES; ++s) {
+        for (int s = 0; s < ST; ++s) {
             mbar_init(&full_bar[s], 2);   // leader's expect_tx arrive + the peer's remote arrive
             mbar_init(&empty_bar[s], 1);  // multicast tcgen05.commit
         }
@@ -143,35 +151,35 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             for (int tile = pair; tile < total_tiles; tile += num_pairs) {
                 const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
                 const int m_row = mt * 2 * G2_BM + static_cast<int>(rank) * G2_BM;
-                const int n_row = nt * G2_BN + static_cast<int>(rank) * (G2_BN / 2);
+                const int n_row = nt * BN + static_cast<int>(rank) * (BN / 2);
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                    const int s = it % G2_STAGES;
-                    const uint32_t ph = (it / G2_STAGES) & 1;
+                    const int s = it % ST;
+                    const uint32_t ph = (it / ST) & 1;
                     mbar_wait_b(&empty_bar[s], ph ^ 1, 1);
-                    uint8_t* a_dst = smem + s * G2_STAGE_BYTES;
+                    uint8_t* a_dst = smem + s * C::STAGE_BYTES;
                     tma_load_2d_2sm(a_dst, &tmap_a, &full_bar[s], kb * G2_BK, m_row);
                     tma_load_2d_2sm(a_dst + G2_A_BYTES, &tmap_b, &full_bar[s], kb * G2_BK, n_row);
-                    if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * G2_STAGE_BYTES);
+                    if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * C::STAGE_BYTES);
                     else mbar_arrive_remote(&full_bar[s], 0);
                 }
             }
         }
     } else if (warp == 1) {
         if (leader && lane == 0) {
-            const uint32_t idesc = make_idesc_f16(2 * G2_BM, G2_BN, 0);
+            const uint32_t idesc = make_idesc_f16(2 * G2_BM, BN, 0);
             int it = 0, local_tile = 0;
             for (int tile = pair; tile < total_tiles; tile += num_pairs, ++local_tile) {
                 const int buf = local_tile & 1;
                 const uint32_t acc_ph = (local_tile >> 1) & 1;
                 mbar_wait_b(&tmem_empty_bar[buf], acc_ph ^ 1, 2);  // epilogues of both CTAs drained this buffer
                 tc_fence_after();
-                const uint32_t d_addr = tmem_base + buf * G2_BN;
+                const uint32_t d_addr = tmem_base + buf * BN;
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                    const int s = it % G2_STAGES;
-                    const uint32_t ph = (it / G2_STAGES) & 1;
+                    const int s = it % ST;
+                    const uint32_t ph = (it / ST) & 1;
                     mbar_wait_b(&full_bar[s], ph, 3);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem + s * G2_STAGE_BYTES);
+                    const uint32_t a_addr = smem_u32(smem + s * C::STAGE_BYTES);
                     const uint64_t da = make_kmajor_sw128_desc(a_addr);
                     const uint64_t db = make_kmajor_sw128_desc(a_addr + G2_A_BYTES);
 #pragma unroll
@@ -184,25 +192,25 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         }
     } else {
         const int q = warp & 3;             // TMEM lane quarter this warp may access
-        constexpr int PARTS = EW / 4, PART_COLS = G2_BN / PARTS, PITCH = epi_stg_pitch<MODE>();
+        constexpr int PARTS = EW / 4, PART_COLS = BN / PARTS, PITCH = epi_stg_pitch<MODE>();
         const int part = (warp - 2) >> 2;   // which slice of the tile's columns this warp drains
         constexpr int CHUNKS = PART_COLS / 32;
         static_assert(CHUNKS % 2 == 0, "epilogue double buffer needs an even chunk count");
-        uint8_t* stg = smem + G2_STG_OFFSET + (warp - 2) * 32 * PITCH;
+        uint8_t* stg = smem + C::STG_OFFSET + (warp - 2) * 32 * PITCH;
         int local_tile = 0;
         for (int tile = pair; tile < total_tiles; tile += num_pairs, ++local_tile) {
             const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
             const int buf = local_tile & 1;
             const uint32_t acc_ph = (local_tile >> 1) & 1;
             const int row_base = mt * 2 * G2_BM + static_cast<int>(rank) * G2_BM + q * 32;
-            const int n0 = nt * G2_BN + part * PART_COLS;
+            const int n0 = nt * BN + part * PART_COLS;
             float4 res[8];
             float4 rcs[4], rsn[4];
             if constexpr (MODE == EPI_RESID) epilogue_resid_prefetch(epi, res, row_base, n0, M, lane);
             if constexpr (MODE == EPI_ROPE) epilogue_rope_prefetch(epi, rcs, rsn, row_base, n0, lane);
             mbar_wait_b(&tmem_full_bar[buf], acc_ph, 4);
             tc_fence_after();
-            const uint32_t t0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * G2_BN + part * PART_COLS;
+            const uint32_t t0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + part * PART_COLS;
             uint32_t acc[2][32];
             tmem_ld_32x32(t0, acc[0]);
 #pragma unroll 1
@@ -234,7 +242,12 @@ int gemm_f16_2cta(const void* A, int lda, const void* W, int ldw, const GemmEpil
     CUtensorMap ta, tb;
     int rc = make_tmap_2d_f16(&ta, A, M, K, lda, G2_BM, G2_BK);
     if (rc) return rc;
-    rc = make_tmap_2d_f16(&tb, W, N, K, ldw, G2_BN / 2, G2_BK);
+    // optional 256 x 128 tiles with a 7-stage ring for the fp32-output modes (N = 512 GEMMs: two rounds of tiles so the
+    // epilogue of the first overlaps the main loop of the second).  NOT YET MEASURED on hardware: opt-in only.
+    static const bool bn128_env = getenv("SBK_GEMM_BN128") != nullptr;
+    const bool bn128 = bn128_env && (epi.mode == EPI_RESID || epi.mode == EPI_F32) && N % 128 == 0 && N <= 1024;
+    const int bn = bn128 ? 128 : G2_BN;
+    rc = make_tmap_2d_f16(&tb, W, N, K, ldw, bn / 2, G2_BK);
     if (rc) return rc;
     void (*kern)(const CUtensorMap, const CUtensorMap, const GemmEpilogue, int, int, int) = nullptr;
     int smem = 0, threads = 0;
@@ -242,8 +255,14 @@ int gemm_f16_2cta(const void* A, int lda, const void* W, int ldw, const GemmEpil
     do {                                                                          \
         constexpr int EW = g2_epi_warps<MODE>();                                  \
         kern = gemm_tc2_kernel<MODE, ACT, EW>;                                    \
-        smem = g2_smem<MODE, EW>();                                               \
+        smem = g2_smem<MODE, EW, G2_BN, G2_STAGES>();                             \
         threads = 64 + 32 * EW;                                                   \
+    } while (0)
+#define G2_PICK_BN128(MODE)                                                       \
+    do {                                                                          \
+        kern = gemm_tc2_kernel<MODE, ACT_NONE, 8, 128, 7>;                        \
+        smem = g2_smem<MODE, 8, 128, 7>();                                        \
+        threads = 64 + 32 * 8;                                                    \
     } while (0)
     switch (epi.mode) {
         case EPI_F16:
@@ -252,13 +271,20 @@ int gemm_f16_2cta(const void* A, int lda, const void* W, int ldw, const GemmEpil
             else if (epi.act == ACT_NONE) G2_PICK(EPI_F16, ACT_NONE);
             else { set_error("gemm_f16_2cta: activation %d not built", epi.act); return SBK_ERR_ARG; }
             break;
-        case EPI_F32: G2_PICK(EPI_F32, ACT_NONE); break;
-        case EPI_RESID: G2_PICK(EPI_RESID, ACT_NONE); break;
+        case EPI_F32:
+            if (bn128) G2_PICK_BN128(EPI_F32);
+            else G2_PICK(EPI_F32, ACT_NONE);
+            break;
+        case EPI_RESID:
+            if (bn128) G2_PICK_BN128(EPI_RESID);
+            else G2_PICK(EPI_RESID, ACT_NONE);
+            break;
         case EPI_GLU: G2_PICK(EPI_GLU, ACT_NONE); break;
         case EPI_ROPE: G2_PICK(EPI_ROPE, ACT_NONE); break;
         default: set_error("gemm_f16_2cta: bad epilogue mode %d", epi.mode); return SBK_ERR_ARG;
     }
 #undef G2_PICK
+#undef G2_PICK_BN128
     SBK_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     static int num_sms = 0;
     if (num_sms == 0) {
@@ -266,7 +292,7 @@ int gemm_f16_2cta(const void* A, int lda, const void* W, int ldw, const GemmEpil
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    const int n_tiles = ceil_div(N, G2_BN), m_tiles = ceil_div(M, 2 * G2_BM);
+    const int n_tiles = ceil_div(N, bn), m_tiles = ceil_div(M, 2 * G2_BM);
     int pairs = std::min(num_sms / 2, n_tiles * m_tiles);
     GemmProfile* prof = gemm_profile();
     cudaEvent_t e0 = nullptr, e1 = nullptr;
