@@ -40,6 +40,9 @@ typedef struct {
     int parts;              /* bitmask of SBK_PART_*: which sub-models the weight table carries */
     /* TransformerLM used as a shallow-fusion scorer (lobes/models/transformer/TransformerLM.py; weights "lm.*") */
     int lm_d_model, lm_nhead, lm_layers, lm_d_ffn, lm_activation;
+    /* Filterbank amin / top_db (processing/features.py:437-475) and InputNormalization epsilon (:1360-1455) of the fused
+       wav -> features front end; 0 = the reference defaults (1e-10, 80 dB, 1e-10) */
+    float fbank_amin, fbank_top_db, norm_eps;
 } sbk_asr_config;
 
 typedef struct {
@@ -124,6 +127,12 @@ int sbk_asr_encode_feats(sbk_asr* m, const float* feats_dev, const float* rel_le
 int sbk_asr_greedy_from_enc(sbk_asr* m, const float* enc_dev, const float* rel_len_dev, int B, int T, int max_steps,
                             int bos, int eos, int* pred_dev, float* score_dev, float* log_probs_dev, int* steps_done,
                             void* stream);
+/* TransformerASR.decode(tgt, encoder_out, enc_len) (lobes/models/transformer/TransformerASR.py:426-473), teacher-forced on the
+ * KV-cached decoder step: tgt_dev [n, S] int32 (bos first), enc_dev [n, T, d_model] fp32, enc_len_dev [n] int32 ABSOLUTE
+ * frame counts or NULL -> out_dev [n, S, d_model] fp32 = decoder.norm(decoder(...)) (the input of seq_lin).  The reference's
+ * second return value (last layer's head-averaged cross-attention weights) is not produced. */
+int sbk_asr_decode_teacher_forced(sbk_asr* m, const int* tgt_dev, const float* enc_dev, const int* enc_len_dev, int n, int S,
+                                  int T, float* out_dev, void* stream);
 /* S2STransformerBeamSearcher.forward, scorer=None (decoders/seq2seq.py:1632-1723,1853-1934), KV-cached with a
  * cache-row lineage table instead of index_select copies.  Writes the per-step search history
  * hist_*[max_steps, B * beam_size]: token, predecessor row, length-normalised score, raw log-prob; the host replays
@@ -144,6 +153,14 @@ int sbk_asr_transcribe_greedy_group_dev(sbk_asr* m, int G, const float* const* w
 int sbk_asr_transcribe_greedy_host(sbk_asr* m, const float* wav_host, const float* rel_len_host, int B, int L,
                                    int max_steps, int bos, int eos, int* pred_host, float* score_host,
                                    int* steps_done, void* stream);
+
+/* The group call from HOST buffers (pinned): per batch g, wav_host[g] [B, L] fp32 and rel_len_host[g] [B] are copied to the
+ * device on an internal copy stream (batch g+1's copy overlaps batch g's encoder), pred_host[g] [B, max_steps] receives the
+ * token ids; pred_dev (NULL, or an array whose entries may be NULL) additionally keeps them on the device.  Enqueue only:
+ * the caller synchronises `stream`.  With poll interval 0 the whole call (copies included) replays one CUDA graph. */
+int sbk_asr_transcribe_greedy_group_host_async(sbk_asr* m, int G, const float* const* wav_host,
+                                               const float* const* rel_len_host, int B, int L, int max_steps, int bos, int eos,
+                                               int* const* pred_host, int* const* pred_dev, int* steps_done, void* stream);
 
 /* as _host, but only enqueues (pinned host buffers required); the caller synchronises the stream */
 int sbk_asr_transcribe_greedy_host_async(sbk_asr* m, const float* wav_host, const float* rel_len_host, int B, int L,

@@ -421,7 +421,7 @@ def full_pipeline_features(wav, wav_lens, sd, cfg):
 def beam_search(enc_states, wav_len, sd, cfg, seq_lin_w, seq_lin_b, bos_index=1, eos_index=2, beam_size=4,
                 min_decode_ratio=0.0, max_decode_ratio=1.0, temperature=1.0, using_eos_threshold=True,
                 eos_threshold=1.5, length_normalization=True, minus_inf=-1e20, topk=1, prefix="", return_history=False,
-                lm=None, ctc=None, return_topk=False, length_weight=0.0):
+                lm=None, ctc=None, return_topk=False, length_weight=0.0, forced=None):
     """S2STransformerBeamSearcher.forward, using_max_attn_shift=False; scorer=None, or a ScorerBuilder with full scorers
     TransformerLMScorer (``lm`` = dict(sd, cfg, weight, temperature, prefix)) and/or CTCScorer (``ctc`` = dict(w, b, weight,
     blank_index)), in the recipe's order [transformerlm, ctc] (scorer.py:1221-1268; conformer_large.yaml:209-223).
@@ -429,7 +429,16 @@ def beam_search(enc_states, wav_len, sd, cfg, seq_lin_w, seq_lin_b, bos_index=1,
     Follows init_beam_search_data (:1267-1369), search_step (:1478-1598), _compute_scores_and_next_inp_tokens
     (:1204-1265), _update_sequences_and_log_probs (:1152-1202), _update_hyps_and_scores_if_eos_token (:1371-1416),
     _fill_alived_hyps_with_eos_token (:1600-1630), _get_topk_prediction (:1418-1476) -- whole-prefix decode, no cache.
-    Returns (hyps, best_lens, best_scores, best_log_probs) like return_topk=False."""
+    Returns (hyps, best_lens, best_scores, best_log_probs) like return_topk=False.
+
+    ``forced`` (test helper, needs beam_size=1): a list of B token lists.  The search is walked along exactly these tokens
+    (candidate = forced token instead of the top-1) and the function returns a (B,) tensor with the search score the
+    reference assigns to each path at its last token -- used to judge a hypothesis the CUDA search found when fp16 rounding
+    made it pick another near-tied hypothesis than the fp32 reference."""
+    if forced is not None:
+        assert beam_size == 1 and len(forced) == enc_states.shape[0]
+        max_decode_ratio = (max(len(f) for f in forced) + 0.5) / enc_states.shape[1]
+        forced_scores = torch.zeros(len(forced))
     B, T, _ = enc_states.shape
     V = seq_lin_w.shape[0]
     n_bh = B * beam_size
@@ -465,7 +474,7 @@ def beam_search(enc_states, wav_len, sd, cfg, seq_lin_w, seq_lin_b, bos_index=1,
         return is_eos
 
     for step in range(max_steps):
-        if [len(f) for f in finished] == [beam_size] * B:
+        if forced is None and [len(f) for f in finished] == [beam_size] * B:
             break
         memory = inp.unsqueeze(1) if memory is None else torch.cat([memory, inp.unsqueeze(1)], dim=-1)
         pred, _ = decode(memory, enc, enc_l, sd, cfg, prefix)
@@ -492,6 +501,12 @@ def beam_search(enc_states, wav_len, sd, cfg, seq_lin_w, seq_lin_b, bos_index=1,
         if length_normalization:
             sc = sc / (step + 1)
         scores, cand = sc.view(B, -1).topk(beam_size, dim=-1)
+        if forced is not None:
+            cand = torch.tensor([[f[step] if step < len(f) else eos_index] for f in forced])
+            scores = sc.view(B, -1).gather(1, cand)
+            for b_, f in enumerate(forced):
+                if step == len(f) - 1:
+                    forced_scores[b_] = scores[b_, 0]
         if ctc is not None:  # permute_scorer_mem: the CTC memory follows ``candidates`` (scorer.py:1286-1290)
             ctc_mem = ctc_prefix_permute(ctc_state, ctc_mem, cand)
         inp = (cand % V).view(n_bh)
@@ -503,8 +518,12 @@ def beam_search(enc_states, wav_len, sd, cfg, seq_lin_w, seq_lin_b, bos_index=1,
         alived_seq = torch.cat([torch.index_select(alived_seq, 0, predecessors), inp.unsqueeze(1)], dim=-1)
         alived_lp = torch.cat([torch.index_select(alived_lp, 0, predecessors), beam_lp.unsqueeze(1)], dim=-1)
         history.append((inp.clone(), predecessors.clone(), scores.clone(), beam_lp.clone()))
+        if forced is not None:
+            continue
         is_eos = add_eos_hyps(inp, scores)
         seq_scores = seq_scores.masked_fill(is_eos, float("-inf"))
+    if forced is not None:
+        return forced_scores
     if [len(f) for f in finished] != [beam_size] * B:
         add_eos_hyps(torch.full((n_bh,), eos_index, dtype=torch.long), scores)
     out = finalize_beams(finished, beam_size, topk, return_topk)

@@ -385,6 +385,148 @@ def beam_ctc_case(tag="beam_ctc_conformer_large_rope"):
     torch.save(out, os.path.join(OUT, f"{tag}.pt"))
 
 
+def bench_shape_case(cfg, attention_type, B, L, lens, n_greedy, tag, beams=(), seed=4321):
+    """Goldens at the shapes bench.py runs: 10 s utterances -> T = 251 = four 64-key attention blocks, ragged
+    lengths so that one trailing key block is partially and one fully masked, 48 greedy steps (KV-cache positions 0..47),
+    beam = 10 with the recipe's scorers.  The waveform is regenerated from ``seed`` by the test (a checksum pins it); stored:
+    reference enc_out (fp32), greedy tokens / chosen log-probs / top-2 margins, beam n-best (all `beam` hypotheses + scores)."""
+    from speechbrain.decoders.scorer import CTCScorer, ScorerBuilder, TransformerLMScorer
+    from speechbrain.decoders.seq2seq import S2STransformerBeamSearcher, S2STransformerGreedySearcher
+    from speechbrain.lobes.models.transformer.TransformerLM import TransformerLM
+    import time
+    fb, norm, mods, sd = build_reference(cfg, attention_type)
+    g = torch.Generator().manual_seed(seed)
+    wav = torch.randn(B, L, generator=g)
+    wav_lens = torch.tensor(lens)
+    for b in range(B):
+        wav[b, int(round(lens[b] * L)):] = 0
+    ocfg = dict(cfg, attention_type=attention_type)
+    gold = dict(cfg=ocfg, wav_seed=seed, wav_shape=(B, L), wav_lens=wav_lens, wav_checksum=float(wav.double().abs().sum()),
+                weight_checksum=float(sum(v.double().abs().sum() for k, v in sorted(seeded_asr_state(_product_cfg(cfg, attention_type), 0).items()))))
+    with torch.no_grad():
+        t0 = time.time()
+        fn = norm(fb(wav), wav_lens)
+        c = mods["CNN"](fn)
+        enc = mods["Transformer"].encode(c, wav_lens)
+        T = enc.shape[1]
+        oc = O.full_pipeline_features(wav, wav_lens, sd, dict(cfg))
+        oenc = O.encode(oc, wav_lens, sd, ocfg, "Transformer.")
+        print(f"[{tag}] T={T} encoder: reference {time.time() - t0:.1f}s; oracle rel {rel(oenc, enc):.2e}")
+        assert rel(oenc, enc) < 1e-5
+        gold["enc_out"] = enc.clone()
+        gold["abs_len"] = torch.round(wav_lens * T).int()
+        if n_greedy > 0:
+            t0 = time.time()
+            gs = S2STransformerGreedySearcher(modules=[mods["Transformer"], mods["seq_lin"]], bos_index=1, eos_index=2,
+                                              min_decode_ratio=0.0, max_decode_ratio=(n_greedy + 0.5) / T)
+            hyps, top_len, top_scores, top_lp = gs(enc, wav_lens)
+            ohyps, olen, oscores, olp, ologits = O.greedy_search(
+                enc, wav_lens, sd, ocfg, sd["seq_lin.w.weight"], sd["seq_lin.w.bias"], 1, 2, 0.0,
+                (n_greedy + 0.5) / T, "Transformer.", return_logits=True)
+            assert ohyps == hyps, "oracle greedy != reference greedy"
+            top2 = ologits.topk(2, dim=-1).values
+            lp = torch.log_softmax(ologits, -1)
+            tok = ologits.argmax(-1)
+            gold.update(greedy_hyps=hyps, greedy_tokens=tok.int(), greedy_margin=(top2[..., 0] - top2[..., 1]).clone(),
+                        greedy_chosen_lp=lp.gather(-1, tok.unsqueeze(-1)).squeeze(-1).clone(),
+                        greedy_lp_sample=lp[:, :, :128].clone().half())
+            print(f"[{tag}] greedy {n_greedy} steps {time.time() - t0:.1f}s  min margin {float(gold['greedy_margin'].min()):.4f} "
+                  f"lens {[len(h) for h in hyps]}")
+        lm = None
+        for name, kw in beams:
+            kw = dict(kw)
+            t0 = time.time()
+            with_lm, with_ctc, eos_bias, steps = kw.pop("with_lm"), kw.pop("with_ctc"), kw.pop("eos_bias"), kw.pop("steps")
+            if with_lm and lm is None:
+                lm = TransformerLM(vocab=5000, d_model=768, nhead=12, num_encoder_layers=12, num_decoder_layers=0, d_ffn=3072,
+                                   dropout=0.0, activation=torch.nn.GELU, normalize_before=False)
+                sd_lm = seeded_state_dict(lm, seed=1)
+                lm.load_state_dict(sd_lm)
+                lm.eval()
+            cfg_lm = dict(d_model=768, nhead=12, num_encoder_layers=12, d_ffn=3072, activation="gelu")
+            bias = sd["seq_lin.w.bias"].clone()
+            bias[2] += eos_bias
+            mods["seq_lin"].w.bias.copy_(bias)
+            full, weights = [], {}
+            if with_lm:
+                full.append(TransformerLMScorer(language_model=lm, temperature=1.15)); weights["transformerlm"] = 0.6
+            if with_ctc:
+                full.append(CTCScorer(eos_index=2, blank_index=0, ctc_fc=mods["ctc_lin"])); weights["ctc"] = 0.4
+            scorer = ScorerBuilder(full_scorers=full, weights=weights) if full else None
+            kw.setdefault("min_decode_ratio", 0.0)
+            beam = kw["beam_size"]
+            bs = S2STransformerBeamSearcher(modules=[mods["Transformer"], mods["seq_lin"]], bos_index=1, eos_index=2,
+                                            max_decode_ratio=(steps + 0.5) / T, scorer=scorer, return_topk=True, topk=beam, **kw)
+            tk_hyps, tk_len, tk_scores, tk_lp = bs(enc, wav_lens)
+            t_ref = time.time() - t0
+            o_hyps, o_len, o_scores, o_lp = O.beam_search(
+                enc, wav_lens, sd, ocfg, sd["seq_lin.w.weight"], bias, 1, 2, max_decode_ratio=(steps + 0.5) / T,
+                prefix="Transformer.", topk=beam, return_topk=True,
+                lm=dict(sd=sd_lm, cfg=cfg_lm, weight=0.6, temperature=1.15) if with_lm else None,
+                ctc=dict(w=sd["ctc_lin.w.weight"], b=sd["ctc_lin.w.bias"], weight=0.4, blank_index=0) if with_ctc else None, **kw)
+            print(f"[{tag} beam {name}] reference {t_ref:.1f}s; best lens {(tk_len[:, 0] * tk_hyps.shape[2]).round().int().tolist()} "
+                  f"scores {tk_scores[:, 0].tolist()}; oracle hyps equal {torch.equal(o_hyps, tk_hyps)} "
+                  f"score err {(o_scores - tk_scores).abs().max():.2e}; top1-top2 score gap {(tk_scores[:, 0] - tk_scores[:, 1]).tolist()}")
+            assert torch.equal(o_hyps[:, 0], tk_hyps[:, 0]) and (o_scores - tk_scores).abs().max() < 1e-3
+            gold["beam_" + name] = dict(kwargs=kw, with_lm=with_lm, with_ctc=with_ctc, eos_bias=eos_bias,
+                                        max_decode_ratio=(steps + 0.5) / T, lm_weight=0.6, lm_temperature=1.15, ctc_weight=0.4,
+                                        hyps=tk_hyps.int(), lens=tk_len, scores=tk_scores, log_probs=tk_lp)
+        mods["seq_lin"].w.bias.copy_(sd["seq_lin.w.bias"])
+    torch.save(gold, os.path.join(OUT, f"{tag}.pt"))
+    print(tag, os.path.getsize(os.path.join(OUT, f"{tag}.pt")))
+
+
+def bench_extra_case(tag="bench_decode_conformer_large_rope_10s"):
+    """On the encoder states of the bench-shape RoPE golden: (1) TransformerASR.decode(tgt, enc, enc_len) of the reference,
+    teacher-forced on the greedy tokens (48 positions, ragged memory lengths) -> decoder outputs [4, 48, 512];
+    (2) beam = 10 without scorers, EOS bias chosen so that hypotheses finish gradually over many steps."""
+    from speechbrain.decoders.seq2seq import S2STransformerBeamSearcher
+    import time
+    fb, norm, mods, sd = build_reference(CFG_L, "RoPEMHA")
+    g = torch.load(os.path.join(OUT, "bench_conformer_large_rope_10s.pt"))
+    enc, wav_lens = g["enc_out"], g["wav_lens"]
+    T = enc.shape[1]
+    ocfg = dict(CFG_L, attention_type="RoPEMHA")
+    out = {}
+    with torch.no_grad():
+        tgt = torch.cat([torch.full((enc.shape[0], 1), 1, dtype=torch.long), g["greedy_tokens"].long()[:, :-1]], 1)
+        enc_len = torch.round(wav_lens * T).int()
+        pred, attn = mods["Transformer"].decode(tgt, enc, enc_len)
+        opred, _ = O.decode(tgt, enc, enc_len, sd, ocfg, "Transformer.")
+        print(f"[decode] pred {tuple(pred.shape)} oracle rel {rel(opred, pred):.2e}")
+        assert rel(opred, pred) < 1e-5
+        out["decode"] = dict(tgt=tgt.int(), enc_len=enc_len, pred=pred.clone())
+        for name, eos_bias, steps in (("b10_plain_eos12", 1.2, 48), ("b10_plain_eos16", 1.6, 48)):
+            t0 = time.time()
+            kw = dict(beam_size=10, using_eos_threshold=False, temperature=1.15, min_decode_ratio=3.5 / T)
+            bias = sd["seq_lin.w.bias"].clone()
+            bias[2] += eos_bias
+            mods["seq_lin"].w.bias.copy_(bias)
+            bs = S2STransformerBeamSearcher(modules=[mods["Transformer"], mods["seq_lin"]], bos_index=1, eos_index=2,
+                                            max_decode_ratio=(steps + 0.5) / T, return_topk=True, topk=10, **kw)
+            tk_hyps, tk_len, tk_scores, tk_lp = bs(enc, wav_lens)
+            o_hyps, o_len, o_scores, o_lp = O.beam_search(enc, wav_lens, sd, ocfg, sd["seq_lin.w.weight"], bias, 1, 2,
+                                                          max_decode_ratio=(steps + 0.5) / T, prefix="Transformer.", topk=10,
+                                                          return_topk=True, **kw)
+            print(f"[beam {name}] reference {time.time() - t0:.1f}s; best lens {(tk_len[:, 0] * tk_hyps.shape[2]).round().int().tolist()} "
+                  f"max len {tk_hyps.shape[2]} scores {tk_scores[:, 0].tolist()} oracle equal {torch.equal(o_hyps, tk_hyps)} "
+                  f"gap {(tk_scores[:, 0] - tk_scores[:, 1]).tolist()}")
+            assert torch.equal(o_hyps[:, 0], tk_hyps[:, 0]) and (o_scores - tk_scores).abs().max() < 1e-3
+            out["beam_" + name] = dict(kwargs=kw, with_lm=False, with_ctc=False, eos_bias=eos_bias, max_decode_ratio=(steps + 0.5) / T,
+                                       hyps=tk_hyps.int(), lens=tk_len, scores=tk_scores, log_probs=tk_lp)
+        mods["seq_lin"].w.bias.copy_(sd["seq_lin.w.bias"])
+    torch.save(out, os.path.join(OUT, f"{tag}.pt"))
+    print(tag, os.path.getsize(os.path.join(OUT, f"{tag}.pt")))
+
+
+BEAMS_10S = (
+    ("b10_lm_ctc", dict(beam_size=10, using_eos_threshold=False, temperature=1.15, with_lm=True, with_ctc=True, eos_bias=0.0, steps=24)),
+    ("b10_ctc_valid", dict(beam_size=10, using_eos_threshold=False, temperature=1.15, with_lm=False, with_ctc=True, eos_bias=0.0, steps=24)),
+    ("b10_plain_eos", dict(beam_size=10, using_eos_threshold=False, temperature=1.15, min_decode_ratio=3.5 / 251, with_lm=False,
+                           with_ctc=False, eos_bias=6.0, steps=48)),
+)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
@@ -411,5 +553,15 @@ if __name__ == "__main__":
         beam_len_case()
     if "beam_ctc" in which:
         beam_ctc_case()
+    # ---- bench-shape goldens (not in the default list: minutes of CPU time each)
+    if "bench_L_rope" in which:
+        bench_shape_case(CFG_L, "RoPEMHA", 4, 160000, [1.0, 0.9, 0.6, 0.3], 48, "bench_conformer_large_rope_10s", BEAMS_10S)
+    if "bench_L_relpos" in which:
+        bench_shape_case(CFG_L, "RelPosMHAXL", 4, 160000, [1.0, 0.9, 0.6, 0.3], 48, "bench_conformer_large_relpos_10s")
+    if "bench_extra" in which:
+        bench_extra_case()
+    if "bench_S_relpos" in which:
+        bench_shape_case(CFG_S, "RelPosMHAXL", 8, 80000, [1.0, 0.95, 0.9, 0.8, 0.7, 0.55, 0.4, 0.25], 0,
+                         "bench_conformer_small_relpos_5s")
     for fn in sorted(os.listdir(OUT)):
         print(fn, os.path.getsize(os.path.join(OUT, fn)))

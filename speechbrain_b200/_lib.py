@@ -22,7 +22,8 @@ class sbk_asr_config(ctypes.Structure):
     _fields_ = [(k, ctypes.c_int) for k in (
         "n_fft", "hop", "n_mels", "cnn_c1", "cnn_c2", "input_size", "d_model", "nhead", "num_encoder_layers",
         "num_decoder_layers", "d_ffn", "vocab", "kernel_size", "attention_type", "decoder_activation", "max_len",
-        "parts", "lm_d_model", "lm_nhead", "lm_layers", "lm_d_ffn", "lm_activation")]
+        "parts", "lm_d_model", "lm_nhead", "lm_layers", "lm_d_ffn", "lm_activation")] + [
+        (k, ctypes.c_float) for k in ("fbank_amin", "fbank_top_db", "norm_eps")]
 
 
 class sbk_beam_params(ctypes.Structure):
@@ -46,7 +47,7 @@ EXPORTS = [
     "sbk_asr_encode_feats", "sbk_asr_greedy_from_enc", "sbk_asr_transcribe_greedy_dev",
     "sbk_asr_transcribe_greedy_host", "sbk_asr_transcribe_greedy_host_async", "sbk_asr_clone",
     "sbk_asr_set_poll_interval", "sbk_asr_beam_from_enc", "sbk_asr_set_decoder_ln_fusion", "sbk_asr_transcribe_greedy_group_dev",
-    "sbk_asr_set_decoder_tc_min_rows", "sbk_asr_lm_rescore",
+    "sbk_asr_set_decoder_tc_min_rows", "sbk_asr_lm_rescore", "sbk_asr_transcribe_greedy_group_host_async", "sbk_asr_decode_teacher_forced",
 ]
 
 

@@ -98,7 +98,7 @@ struct AsrModel {
     // shapes the workspace is carved for
     int wsB = 0, wsL = 0, ws_rows = 0, ws_steps = 0;
     struct Buf {
-        float *wav, *feats, *x, *glu, *enc_out, *act1_f, *cnn_f, *dx, *logits, *score, *seq_scores;
+        float *wav, *feats, *x, *glu, *enc_out, *act1_f, *cnn_f, *dx, *logits, *score, *seq_scores, *lnout;
         int *utt_max, *enc_len, *tokens, *step, *has_ended, *ended_count, *pred, *lineage, *finished;
         float* rel_len;
         float *lx, *lh32, *lm_logits, *lm_extra;
@@ -107,13 +107,22 @@ struct AsrModel {
         __half *act1, *a_in, *h16, *f16, *qkv16, *att16, *P16, *enc16, *ckv16, *kcache, *vcache, *dh16, *dq16, *datt16, *df16;
     } b;
     cudaGraphExec_t step_graph = nullptr;
-    int graph_rows = -1, graph_T = -1, graph_B = -1;
+    int graph_rows = -1, graph_T = -1, graph_B = -1, graph_eos = -1, graph_S = -1;
     long long graph_nodes = 0;
     int* host_flag = nullptr;  // pinned
     struct GroupKey { const void *wav[16], *rel[16], *pred[16]; int G, B, L, steps, bos, eos; };
     GroupKey group_key{};
     cudaGraphExec_t group_graph = nullptr;
     long long group_nodes = 0;
+    // host-buffer group entry point: device staging of the G batches' wav / lengths, a copy stream forked from the caller's
+    // stream (so batch g+1's H2D overlaps batch g's encoder) and its own graph (H2D / D2H memcpy nodes included)
+    float* gwav = nullptr; float* grel = nullptr; size_t gwav_cap = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_ready[16] = {};
+    struct HostGroupKey { const void *wav[16], *rel[16], *pred[16], *pred_dev[16]; int G, B, L, steps, bos, eos; };
+    HostGroupKey hgroup_key{};
+    cudaGraphExec_t hgroup_graph = nullptr;
+    long long hgroup_nodes = 0;
     struct PipeKey { const void *wav, *rel, *enc, *pred, *score; int B, L, steps, bos, eos; };
     PipeKey pipe_key{};
     cudaGraphExec_t pipe_graph = nullptr;
@@ -219,7 +228,8 @@ int asr_create(const sbk_asr_config* cfg, const sbk_tensor* weights, int n_weigh
         const float* win = find(w, "fbank.window", c.n_fft);
         const float* mel = find(w, "fbank.mel_matrix", (int64_t)(c.n_fft / 2 + 1) * c.n_mels);
         if (!win || !mel) { rc = SBK_ERR_ARG; goto fail; }
-        rc = fbank_create(&m->fbank, c.n_fft, c.hop, c.n_mels, win, mel, 1e-10f, 80.0f);
+        rc = fbank_create(&m->fbank, c.n_fft, c.hop, c.n_mels, win, mel, c.fbank_amin > 0.0f ? c.fbank_amin : 1e-10f,
+                          c.fbank_top_db > 0.0f ? c.fbank_top_db : 80.0f);
         if (rc) goto fail;
         if (w.count("normalize.glob_mean")) {
             m->glob_mean = p.f32("normalize.glob_mean", c.n_mels);
@@ -448,6 +458,10 @@ int asr_clone(AsrModel* src, AsrModel** out) {
     m->step_graph = nullptr;
     m->pipe_graph = nullptr;
     m->group_graph = nullptr;
+    m->hgroup_graph = nullptr;
+    m->gwav = m->grel = nullptr; m->gwav_cap = 0;
+    m->copy_stream = nullptr; m->ev_fork = nullptr;
+    for (auto& e : m->ev_ready) e = nullptr;
     m->graph_rows = m->graph_T = m->graph_B = -1;
     m->cap_stream = nullptr;
     m->host_flag = nullptr;
@@ -466,6 +480,11 @@ void asr_destroy(AsrModel* m) {
     if (m->step_graph) cudaGraphExecDestroy(m->step_graph);
     if (m->pipe_graph) cudaGraphExecDestroy(m->pipe_graph);
     if (m->group_graph) cudaGraphExecDestroy(m->group_graph);
+    if (m->hgroup_graph) cudaGraphExecDestroy(m->hgroup_graph);
+    cudaFree(m->gwav);
+    if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
+    if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+    for (auto e : m->ev_ready) if (e) cudaEventDestroy(e);
     if (m->weight_refs && --*m->weight_refs == 0) {
         if (m->fbank) fbank_destroy(m->fbank);
         cudaFree(m->warena.base);
@@ -476,6 +495,14 @@ void asr_destroy(AsrModel* m) {
     if (m->host_flag) cudaFreeHost(m->host_flag);
     if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
     delete m;
+}
+
+// cached graphs bake in workspace pointers / kernel choices: drop them whenever either changes
+static void drop_graphs(AsrModel* m) {
+    if (m->step_graph) { cudaGraphExecDestroy(m->step_graph); m->step_graph = nullptr; m->graph_rows = -1; }
+    if (m->pipe_graph) { cudaGraphExecDestroy(m->pipe_graph); m->pipe_graph = nullptr; }
+    if (m->group_graph) { cudaGraphExecDestroy(m->group_graph); m->group_graph = nullptr; }
+    if (m->hgroup_graph) { cudaGraphExecDestroy(m->hgroup_graph); m->hgroup_graph = nullptr; }
 }
 
 static void frames(const sbk_asr_config& c, int L, int* T0, int* T1, int* T2) {
@@ -504,7 +531,7 @@ static int ensure_workspace(AsrModel* m, int B, int L, int rows, int steps) {
     sz(M * d * 2); sz((size_t)T2 * d * 2); sz(Md * d * 2); sz(Md * Ld * 2 * d * 2);
     sz((size_t)Ld * rows * S * d * 2); sz((size_t)Ld * rows * S * d * 2);
     sz((size_t)rows * d * 2); sz((size_t)rows * d * 2); sz((size_t)rows * d * 2); sz((size_t)rows * F * 2);
-    sz((size_t)2 * rows * S * 4); sz(B * 4 + 64); sz((size_t)2 * rows * 4);
+    sz((size_t)2 * rows * S * 4); sz(B * 4 + 64); sz((size_t)2 * rows * 4); sz((size_t)rows * d * 4);
     const size_t dl = m->has_lm ? c.lm_d_model : 0, Fl = m->has_lm ? c.lm_d_ffn : 0, Ll = m->has_lm ? c.lm_layers : 0;
     if (m->has_lm) {
         sz(rows * dl * 4); sz(rows * dl * 4); sz((size_t)rows * c.vocab * 4); sz((size_t)rows * c.vocab * 4);
@@ -521,9 +548,7 @@ static int ensure_workspace(AsrModel* m, int B, int L, int rows, int steps) {
         }
         m->ws.cap = need;
     }
-    if (m->step_graph) { cudaGraphExecDestroy(m->step_graph); m->step_graph = nullptr; m->graph_rows = -1; }
-    if (m->pipe_graph) { cudaGraphExecDestroy(m->pipe_graph); m->pipe_graph = nullptr; }
-    if (m->group_graph) { cudaGraphExecDestroy(m->group_graph); m->group_graph = nullptr; }
+    drop_graphs(m);
     m->ws.used = 0;
     AsrModel::Buf& b = m->b;
 #define TAKE(field, type, bytes) b.field = reinterpret_cast<type*>(m->ws.take(bytes))
@@ -540,6 +565,7 @@ static int ensure_workspace(AsrModel* m, int B, int L, int rows, int steps) {
     TAKE(dh16, __half, (size_t)rows * d * 2); TAKE(dq16, __half, (size_t)rows * d * 2); TAKE(datt16, __half, (size_t)rows * d * 2);
     TAKE(df16, __half, (size_t)rows * F * 2);
     TAKE(lineage, int, (size_t)2 * rows * S * 4); TAKE(finished, int, B * 4 + 64); TAKE(seq_scores, float, (size_t)2 * rows * 4);
+    TAKE(lnout, float, (size_t)rows * d * 4);
     if (m->has_lm) {
         TAKE(lx, float, rows * dl * 4); TAKE(lh32, float, rows * dl * 4); TAKE(lm_logits, float, (size_t)rows * c.vocab * 4);
         TAKE(lm_extra, float, (size_t)rows * c.vocab * 4);
@@ -548,7 +574,7 @@ static int ensure_workspace(AsrModel* m, int B, int L, int rows, int steps) {
         TAKE(lkc, __half, Ll * rows * S * dl * 2); TAKE(lvc, __half, Ll * rows * S * dl * 2); TAKE(tok_cache, int, (size_t)rows * S * 4);
         if (!b.tok_cache) { set_error("workspace carve failed (LM)"); return SBK_ERR_NOMEM; }
     }
-    if (!b.df16 || !b.seq_scores) { set_error("workspace carve failed"); return SBK_ERR_NOMEM; }
+    if (!b.df16 || !b.seq_scores || !b.lnout) { set_error("workspace carve failed"); return SBK_ERR_NOMEM; }
 #undef TAKE
     m->wsB = B; m->wsL = L; m->ws_rows = rows; m->ws_steps = steps;
     return SBK_OK;
@@ -642,7 +668,7 @@ static int dec_ln(AsrModel* m, SkinnyArgs& a, const float* g, const float* bta, 
 // the tcgen05 GEMM (128 x 32/64 tiles, a handful of CTAs each, so concurrent lanes share the GPU) instead of the
 // weight-streaming kernel whose cost grows with every 32 rows.  Same maths: fp16 operands, fp32 accumulate / residual.
 static int enqueue_decode_layers_tc(AsrModel* m, int rows, int rows_per_utt, int T, int S_max, const int* lineage,
-                                    cudaStream_t st) {
+                                    cudaStream_t st, bool with_head) {
     const sbk_asr_config& c = m->cfg;
     AsrModel::Buf& b = m->b;
     const int d = c.d_model, F = c.d_ffn, H = c.nhead, dh = d / H, Ld = c.num_decoder_layers;
@@ -680,6 +706,7 @@ static int enqueue_decode_layers_tc(AsrModel* m, int rows, int rows_per_utt, int
         e = GemmEpilogue(); e.mode = EPI_RESID; e.bias = w.b_ffn2; e.out = b.dx; e.resid = b.dx; e.ldo = d;
         RC(gemm_f16_small(b.df16, F, w.w_ffn2, F, e, rows, d, F, st));
     }
+    if (!with_head) return SBK_OK;
     RC(layernorm_rows(b.dx, b.dh16, true, m->dec_norm_g, m->dec_norm_b, rows, d, 1e-6f, false, st));
     GemmEpilogue e;
     e.mode = EPI_F32; e.bias = m->b_lin; e.out = b.logits; e.ldo = c.vocab;
@@ -688,8 +715,8 @@ static int enqueue_decode_layers_tc(AsrModel* m, int rows, int rows_per_utt, int
 }
 
 static int enqueue_decode_layers(AsrModel* m, int rows, int rows_per_utt, int T, int S_max, const int* lineage,
-                                 cudaStream_t st) {
-    if (rows >= m->dec_tc_rows) return enqueue_decode_layers_tc(m, rows, rows_per_utt, T, S_max, lineage, st);
+                                 cudaStream_t st, bool with_head = true) {
+    if (rows >= m->dec_tc_rows) return enqueue_decode_layers_tc(m, rows, rows_per_utt, T, S_max, lineage, st, with_head);
     const sbk_asr_config& c = m->cfg;
     AsrModel::Buf& b = m->b;
     const int d = c.d_model, F = c.d_ffn, H = c.nhead, dh = d / H, Ld = c.num_decoder_layers;
@@ -738,6 +765,7 @@ static int enqueue_decode_layers(AsrModel* m, int rows, int rows_per_utt, int T,
         a.N = d; a.K = F; a.epi = SK_RESID; a.out = b.dx; a.ldo = d;
         RC(skinny_gemm(a, st));
     }
+    if (!with_head) return SBK_OK;
     SkinnyArgs a{};  // final LayerNorm + seq_lin
     RC(dec_ln(m, a, m->dec_norm_g, m->dec_norm_b, rows, st));
     a.W = m->w_lin; a.ldw = d; a.bias = m->b_lin; a.n_rows = rows; a.N = c.vocab; a.K = d;
@@ -923,7 +951,8 @@ static int run_greedy(AsrModel* m, int B, int T, int max_steps, int bos, int eos
         *steps_done = max_steps;
         return SBK_OK;
     }
-    if (use_graph && (m->step_graph == nullptr || m->graph_rows != rows || m->graph_T != T || m->graph_B != B)) {
+    if (use_graph && (m->step_graph == nullptr || m->graph_rows != rows || m->graph_T != T || m->graph_B != B ||
+                      m->graph_eos != eos || m->graph_S != S_max)) {
         if (m->step_graph) { cudaGraphExecDestroy(m->step_graph); m->step_graph = nullptr; }
         cudaGraph_t g;
         if (!m->cap_stream) SBK_CUDA_CHECK(cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
@@ -936,7 +965,7 @@ static int run_greedy(AsrModel* m, int B, int T, int max_steps, int bos, int eos
         SBK_CUDA_CHECK(ce);
         SBK_CUDA_CHECK(cudaGraphInstantiate(&m->step_graph, g, 0));
         cudaGraphDestroy(g);
-        m->graph_rows = rows; m->graph_T = T; m->graph_B = B;
+        m->graph_rows = rows; m->graph_T = T; m->graph_B = B; m->graph_eos = eos; m->graph_S = S_max;
     }
     const int check_every = m->poll_every > 0 ? m->poll_every : max_steps;
     int s = 0;
@@ -990,6 +1019,42 @@ __global__ void lm_teacher_score_kernel(const float* __restrict__ log_probs, int
     const int tgt = tokens[static_cast<size_t>(r) * L + s + 1];
     const float v = (tgt == pad ? -INFINITY : lp[tgt]) - log1pf(-expf(lp[pad]));  // log_softmax over the non-pad entries
     if (v == v) scores[r] += v;  // torch.nansum
+}
+
+// ---------------------------------------------------------------------------- TransformerASR.decode (TransformerASR.py:426-473)
+// Teacher-forced: position s feeds tgt[:, s] through the KV-cached decoder layers and writes decoder.norm(x) to
+// out[:, s, :] -- the same numbers the reference gets from one whole-prefix pass with the causal mask.
+__global__ void dec_teacher_embed_kernel(const int* __restrict__ tokens, int S, int s, const float* __restrict__ emb,
+                                         const float* __restrict__ pe, int d, float sqrt_d, float* __restrict__ x,
+                                         int* __restrict__ step_arr) {
+    const int r = blockIdx.x;
+    const int tok = tokens[static_cast<size_t>(r) * S + s];
+    for (int i = threadIdx.x; i < d; i += blockDim.x)
+        x[static_cast<size_t>(r) * d + i] = emb[static_cast<size_t>(tok) * d + i] * sqrt_d + pe[static_cast<size_t>(s) * d + i];
+    if (threadIdx.x == 0) step_arr[r] = s;
+}
+
+static int run_decode_teacher(AsrModel* m, const int* tokens, int n, int S, int T, float* out, cudaStream_t st) {
+    const sbk_asr_config& c = m->cfg;
+    AsrModel::Buf& b = m->b;
+    const int d = c.d_model, Ld = c.num_decoder_layers, M = n * T, S_max = m->ws_steps + 1;
+    SBK_REQUIRE(m->has_dec, "decode: this handle was created without decoder weights");
+    SBK_REQUIRE(S <= m->ws_steps && S <= c.max_len, "decode: %d target positions exceed the workspace / max_len", S);
+    RC(cast_f32_f16(b.enc_out, b.enc16, (size_t)M * d, st));
+    for (int l = 0; l < Ld; ++l) {
+        GemmEpilogue e;
+        e.mode = EPI_F16; e.bias = m->b_ckv + (size_t)l * 2 * d; e.out = b.ckv16 + (size_t)l * M * 2 * d; e.ldo = 2 * d;
+        RC(gemm_f16(b.enc16, d, m->w_ckv + (size_t)l * 2 * d * d, d, e, M, 2 * d, d, st));
+    }
+    for (int s = 0; s < S; ++s) {
+        dec_teacher_embed_kernel<<<n, 128, 0, st>>>(tokens, S, s, m->emb, m->dec_pe, d, sqrtf((float)d), b.dx, b.step);
+        SBK_LAUNCH_CHECK();
+        RC(enqueue_decode_layers(m, n, 1, T, S_max, nullptr, st, false));
+        RC(layernorm_rows(b.dx, b.lnout, false, m->dec_norm_g, m->dec_norm_b, n, d, 1e-6f, false, st));
+        SBK_CUDA_CHECK(cudaMemcpy2DAsync(out + (size_t)s * d, (size_t)S * d * 4, b.lnout, (size_t)d * 4, (size_t)d * 4, n,
+                                         cudaMemcpyDeviceToDevice, st));
+    }
+    return SBK_OK;
 }
 
 static int run_lm_rescore(AsrModel* m, const int* tokens, const int* lens, int n, int L, float temperature, int pad,
@@ -1093,21 +1158,13 @@ int sbk_asr_clone(sbk_asr* src, sbk_asr** out) {
 }
 int sbk_asr_set_decoder_ln_fusion(sbk_asr* m, int on) {
     AsrModel* mm = reinterpret_cast<AsrModel*>(m);
-    if (mm->fuse_dec_ln != (on != 0)) {  // cached graphs were captured with the other kernel sequence
-        if (mm->step_graph) { cudaGraphExecDestroy(mm->step_graph); mm->step_graph = nullptr; mm->graph_rows = -1; }
-        if (mm->pipe_graph) { cudaGraphExecDestroy(mm->pipe_graph); mm->pipe_graph = nullptr; }
-        if (mm->group_graph) { cudaGraphExecDestroy(mm->group_graph); mm->group_graph = nullptr; }
-    }
+    if (mm->fuse_dec_ln != (on != 0)) drop_graphs(mm);  // cached graphs were captured with the other kernel sequence
     mm->fuse_dec_ln = on != 0;
     return SBK_OK;
 }
 int sbk_asr_set_decoder_tc_min_rows(sbk_asr* m, int rows) {
     AsrModel* mm = reinterpret_cast<AsrModel*>(m);
-    if (mm->dec_tc_rows != rows) {
-        if (mm->step_graph) { cudaGraphExecDestroy(mm->step_graph); mm->step_graph = nullptr; mm->graph_rows = -1; }
-        if (mm->pipe_graph) { cudaGraphExecDestroy(mm->pipe_graph); mm->pipe_graph = nullptr; }
-        if (mm->group_graph) { cudaGraphExecDestroy(mm->group_graph); mm->group_graph = nullptr; }
-    }
+    if (mm->dec_tc_rows != rows) drop_graphs(mm);
     mm->dec_tc_rows = rows;
     return SBK_OK;
 }
@@ -1180,7 +1237,7 @@ static int transcribe_enqueue(AsrModel* m, const float* wav_dev, const float* re
     int T0, T1, T;
     frames(c, L, &T0, &T1, &T);
     AsrModel::Buf& b = m->b;
-    RC(fbank_forward(m->fbank, wav_dev, B, L, b.feats, b.utt_max, m->glob_mean, m->glob_std, 1e-10f, st));
+    RC(fbank_forward(m->fbank, wav_dev, B, L, b.feats, b.utt_max, m->glob_mean, m->glob_std, c.norm_eps > 0.0f ? c.norm_eps : 1e-10f, st));
     const int* enc_len = nullptr;
     if (rel_len_dev) {
         abs_len_kernel<<<ceil_div(B, 128), 128, 0, st>>>(rel_len_dev, B, T, b.enc_len);
@@ -1216,13 +1273,14 @@ static int transcribe_enqueue(AsrModel* m, const float* wav_dev, const float* re
 // batches in flight amortises it G-fold; per-utterance results are unchanged (rows are independent).
 static int transcribe_group_enqueue(AsrModel* m, int G, const float* const* wav_dev, const float* const* rel_dev, int B, int L,
                                     int max_steps, int bos, int eos, int* const* pred_dev, int* steps_done, cudaStream_t st,
-                                    bool in_capture) {
+                                    bool in_capture, const cudaEvent_t* ready = nullptr, int* const* pred_host = nullptr) {
     const sbk_asr_config& c = m->cfg;
     int T0, T1, T;
     frames(c, L, &T0, &T1, &T);
     AsrModel::Buf& b = m->b;
     for (int g = 0; g < G; ++g) {
-        RC(fbank_forward(m->fbank, wav_dev[g], B, L, b.feats, b.utt_max, m->glob_mean, m->glob_std, 1e-10f, st));
+        if (ready) SBK_CUDA_CHECK(cudaStreamWaitEvent(st, ready[g], 0));  // batch g's wav has landed in the staging buffer
+        RC(fbank_forward(m->fbank, wav_dev[g], B, L, b.feats, b.utt_max, m->glob_mean, m->glob_std, c.norm_eps > 0.0f ? c.norm_eps : 1e-10f, st));
         int* enc_len = b.enc_len + (size_t)g * B;
         abs_len_kernel<<<ceil_div(B, 128), 128, 0, st>>>(rel_dev[g], B, T, enc_len);
         SBK_LAUNCH_CHECK();
@@ -1231,12 +1289,38 @@ static int transcribe_group_enqueue(AsrModel* m, int G, const float* const* wav_
     int done = 0;
     RC(run_greedy(m, G * B, T, max_steps, bos, eos, nullptr, &done, st, in_capture));
     const int S_max = m->ws_steps + 1;
-    for (int g = 0; g < G; ++g)
-        if (pred_dev[g])
+    for (int g = 0; g < G; ++g) {
+        if (pred_dev && pred_dev[g])
             SBK_CUDA_CHECK(cudaMemcpy2DAsync(pred_dev[g], (size_t)max_steps * 4, b.pred + (size_t)g * B * S_max, (size_t)S_max * 4,
                                              (size_t)done * 4, B, cudaMemcpyDeviceToDevice, st));
+        if (pred_host && pred_host[g])
+            SBK_CUDA_CHECK(cudaMemcpy2DAsync(pred_host[g], (size_t)max_steps * 4, b.pred + (size_t)g * B * S_max, (size_t)S_max * 4,
+                                             (size_t)done * 4, B, cudaMemcpyDeviceToHost, st));
+    }
     if (steps_done) *steps_done = done;
     return SBK_OK;
+}
+
+// Host-buffer form of the group call: H2D of every batch on a copy stream forked from `st` (batch g+1's copy overlaps
+// batch g's encoder), the group pipeline, D2H of the token ids.  Works both eagerly and under stream capture (the fork /
+// join events become graph edges, the copies memcpy nodes).
+static int transcribe_group_host_enqueue(AsrModel* m, int G, const float* const* wav_host, const float* const* rel_host, int B,
+                                         int L, int max_steps, int bos, int eos, int* const* pred_host, int* const* pred_dev,
+                                         int* steps_done, cudaStream_t st, bool in_capture) {
+    SBK_CUDA_CHECK(cudaEventRecord(m->ev_fork, st));
+    SBK_CUDA_CHECK(cudaStreamWaitEvent(m->copy_stream, m->ev_fork, 0));  // the previous call no longer reads the staging buffers
+    const float* wav_dev[16];
+    const float* rel_dev[16];
+    for (int g = 0; g < G; ++g) {
+        float* w = m->gwav + (size_t)g * B * L;
+        float* r = m->grel + (size_t)g * B;
+        SBK_CUDA_CHECK(cudaMemcpyAsync(w, wav_host[g], (size_t)B * L * 4, cudaMemcpyHostToDevice, m->copy_stream));
+        SBK_CUDA_CHECK(cudaMemcpyAsync(r, rel_host[g], (size_t)B * 4, cudaMemcpyHostToDevice, m->copy_stream));
+        SBK_CUDA_CHECK(cudaEventRecord(m->ev_ready[g], m->copy_stream));
+        wav_dev[g] = w; rel_dev[g] = r;
+    }
+    return transcribe_group_enqueue(m, G, wav_dev, rel_dev, B, L, max_steps, bos, eos, pred_dev, steps_done, st, in_capture,
+                                    m->ev_ready, pred_host);
 }
 
 int sbk_asr_transcribe_greedy_group_dev(sbk_asr* mm, int G, const float* const* wav_dev, const float* const* rel_len_dev,
@@ -1251,7 +1335,8 @@ int sbk_asr_transcribe_greedy_group_dev(sbk_asr* mm, int G, const float* const* 
     RC(ensure_workspace(m, B, L, std::max(G * B, m->ws_rows), std::max(max_steps, m->ws_steps)));
     const bool whole_graph = m->poll_every == 0 && getenv("SBK_NO_GRAPH") == nullptr && max_steps > 0;
     if (!whole_graph) return transcribe_group_enqueue(m, G, wav_dev, rel_len_dev, B, L, max_steps, bos, eos, pred_dev, steps_done, st, false);
-    AsrModel::GroupKey key{};
+    AsrModel::GroupKey key;
+    memset(&key, 0, sizeof(key));
     key.G = G; key.B = B; key.L = L; key.steps = max_steps; key.bos = bos; key.eos = eos;
     for (int g = 0; g < G; ++g) { key.wav[g] = wav_dev[g]; key.rel[g] = rel_len_dev[g]; key.pred[g] = pred_dev[g]; }
     if (m->group_graph == nullptr || memcmp(&key, &m->group_key, sizeof(key)) != 0) {
@@ -1276,6 +1361,67 @@ int sbk_asr_transcribe_greedy_group_dev(sbk_asr* mm, int G, const float* const* 
     return SBK_OK;
 }
 
+// Same pipeline from HOST buffers (pinned): the call EncoderDecoderASR.transcribe_batch makes, for G batches at once.
+// Enqueue only; the caller synchronises `stream`.  pred_dev (optional, may be NULL or hold NULLs) also keeps the ids on the
+// device (multi-GPU: the hypothesis all-gather reads them).
+int sbk_asr_transcribe_greedy_group_host_async(sbk_asr* mm, int G, const float* const* wav_host,
+                                               const float* const* rel_len_host, int B, int L, int max_steps, int bos, int eos,
+                                               int* const* pred_host, int* const* pred_dev, int* steps_done, void* stream) {
+    AsrModel* m = reinterpret_cast<AsrModel*>(mm);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    SBK_REQUIRE(G >= 1 && G <= 16, "transcribe_group_host: G=%d not in [1, 16]", G);
+    SBK_REQUIRE(m->has_fbank && m->has_cnn && m->has_enc && m->has_dec, "transcribe_group_host: handle lacks model parts");
+    SBK_REQUIRE(m->glob_mean != nullptr, "transcribe_group_host: model has no normalize.glob_mean/std weights");
+    SBK_REQUIRE(wav_host && rel_len_host && pred_host, "transcribe_group_host: null argument");
+    for (int g = 0; g < G; ++g) SBK_REQUIRE(wav_host[g] && rel_len_host[g] && pred_host[g], "transcribe_group_host: null batch pointer");
+    RC(ensure_workspace(m, B, L, std::max(G * B, m->ws_rows), std::max(max_steps, m->ws_steps)));
+    const size_t need = (size_t)G * B * L * 4 + (size_t)G * B * 4 + 256;
+    if (need > m->gwav_cap) {
+        if (m->gwav) { SBK_CUDA_CHECK(cudaDeviceSynchronize()); cudaFree(m->gwav); m->gwav = nullptr; m->gwav_cap = 0; }
+        if (m->hgroup_graph) { cudaGraphExecDestroy(m->hgroup_graph); m->hgroup_graph = nullptr; }
+        if (cudaMalloc(&m->gwav, need) != cudaSuccess) { set_error("transcribe_group_host: cudaMalloc(%zu) failed", need); return SBK_ERR_NOMEM; }
+        m->gwav_cap = need;
+    }
+    m->grel = m->gwav + (size_t)G * B * L;  // lengths behind the G waveforms
+    if (!m->copy_stream) {
+        SBK_CUDA_CHECK(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+        SBK_CUDA_CHECK(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+        for (auto& e : m->ev_ready) SBK_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    const bool whole_graph = m->poll_every == 0 && getenv("SBK_NO_GRAPH") == nullptr && max_steps > 0;
+    if (!whole_graph)
+        return transcribe_group_host_enqueue(m, G, wav_host, rel_len_host, B, L, max_steps, bos, eos, pred_host, pred_dev,
+                                             steps_done, st, false);
+    AsrModel::HostGroupKey key;
+    memset(&key, 0, sizeof(key));
+    key.G = G; key.B = B; key.L = L; key.steps = max_steps; key.bos = bos; key.eos = eos;
+    for (int g = 0; g < G; ++g) {
+        key.wav[g] = wav_host[g]; key.rel[g] = rel_len_host[g]; key.pred[g] = pred_host[g];
+        key.pred_dev[g] = pred_dev ? pred_dev[g] : nullptr;
+    }
+    if (m->hgroup_graph == nullptr || memcmp(&key, &m->hgroup_key, sizeof(key)) != 0) {
+        if (m->hgroup_graph) { cudaGraphExecDestroy(m->hgroup_graph); m->hgroup_graph = nullptr; }
+        if (!m->cap_stream) SBK_CUDA_CHECK(cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
+        cudaGraph_t gr;
+        SBK_CUDA_CHECK(cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal));
+        launch_count_begin_capture();
+        int done = 0;
+        int rc = transcribe_group_host_enqueue(m, G, wav_host, rel_len_host, B, L, max_steps, bos, eos, pred_host, pred_dev, &done,
+                                               m->cap_stream, true);
+        m->hgroup_nodes = launch_count_end_capture();
+        cudaError_t ce = cudaStreamEndCapture(m->cap_stream, &gr);
+        if (rc) return rc;
+        SBK_CUDA_CHECK(ce);
+        SBK_CUDA_CHECK(cudaGraphInstantiate(&m->hgroup_graph, gr, 0));
+        cudaGraphDestroy(gr);
+        m->hgroup_key = key;
+    }
+    SBK_CUDA_CHECK(cudaGraphLaunch(m->hgroup_graph, st));
+    launch_count_add(m->hgroup_nodes);
+    if (steps_done) *steps_done = max_steps;
+    return SBK_OK;
+}
+
 int sbk_asr_transcribe_greedy_dev(sbk_asr* mm, const float* wav_dev, const float* rel_len_dev, int B, int L,
                                   int max_steps, int bos, int eos, float* enc_out_dev, int* pred_dev, float* score_dev,
                                   float* log_probs_dev, int* steps_done, void* stream) {
@@ -1287,11 +1433,14 @@ int sbk_asr_transcribe_greedy_dev(sbk_asr* mm, const float* wav_dev, const float
     // Fixed-length runs (poll interval 0) replay ONE CUDA graph of the whole pipeline (Fbank .. last decode step):
     // ~2.6k kernel nodes, a single host-side launch per batch.
     const bool whole_graph = m->poll_every == 0 && rel_len_dev != nullptr && log_probs_dev == nullptr &&
-                             getenv("SBK_NO_GRAPH") == nullptr && max_steps > 0 && m->has_dec;
+                             getenv("SBK_NO_GRAPH") == nullptr && (max_steps == 0 || m->has_dec);
     if (!whole_graph)
         return transcribe_enqueue(m, wav_dev, rel_len_dev, B, L, max_steps, bos, eos, enc_out_dev, pred_dev, score_dev,
                                   log_probs_dev, steps_done, st, false);
-    AsrModel::PipeKey key{wav_dev, rel_len_dev, enc_out_dev, pred_dev, score_dev, B, L, max_steps, bos, eos};
+    AsrModel::PipeKey key;
+    memset(&key, 0, sizeof(key));  // the struct has tail padding and is compared with memcmp
+    key.wav = wav_dev; key.rel = rel_len_dev; key.enc = enc_out_dev; key.pred = pred_dev; key.score = score_dev;
+    key.B = B; key.L = L; key.steps = max_steps; key.bos = bos; key.eos = eos;
     if (m->pipe_graph == nullptr || memcmp(&key, &m->pipe_key, sizeof(key)) != 0) {
         if (m->pipe_graph) { cudaGraphExecDestroy(m->pipe_graph); m->pipe_graph = nullptr; }
         if (!m->cap_stream) SBK_CUDA_CHECK(cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
@@ -1419,6 +1568,29 @@ int sbk_asr_transcribe_greedy_host_async(sbk_asr* mm, const float* wav_host, con
                                          int* steps_done, void* stream) {
     return transcribe_greedy_host_impl(mm, wav_host, rel_len_host, B, L, max_steps, bos, eos, pred_host, score_host,
                                        steps_done, stream, false);
+}
+
+// TransformerASR.decode(tgt, encoder_out, enc_len) (TransformerASR.py:426-473): tgt_dev [n, S] int32 token ids (teacher
+// forcing, bos first), enc_dev [n, T, d] fp32, enc_len_dev [n] int32 ABSOLUTE frame counts (or NULL = all T) ->
+// out_dev [n, S, d] fp32 = decoder.norm(decoder(...)).  The attention-weight output of the reference is not produced.
+int sbk_asr_decode_teacher_forced(sbk_asr* mm, const int* tgt_dev, const float* enc_dev, const int* enc_len_dev, int n, int S,
+                                  int T, float* out_dev, void* stream) {
+    AsrModel* m = reinterpret_cast<AsrModel*>(mm);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const sbk_asr_config& c = m->cfg;
+    SBK_REQUIRE(tgt_dev && enc_dev && out_dev && n >= 1 && S >= 1 && T >= 1, "decode: bad arguments");
+    const int L = std::max(m->wsL, ((T - 1) * 4) * c.hop);
+    RC(ensure_workspace(m, std::max(n, m->wsB), L, std::max(n, m->ws_rows), std::max(S, m->ws_steps)));
+    AsrModel::Buf& b = m->b;
+    SBK_CUDA_CHECK(cudaMemcpyAsync(b.enc_out, enc_dev, (size_t)n * T * c.d_model * 4, cudaMemcpyDeviceToDevice, st));
+    if (enc_len_dev) {
+        SBK_CUDA_CHECK(cudaMemcpyAsync(b.enc_len, enc_len_dev, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+    } else {
+        std::vector<int> full(n, T);
+        SBK_CUDA_CHECK(cudaMemcpyAsync(b.enc_len, full.data(), n * 4, cudaMemcpyHostToDevice, st));
+        SBK_CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    return run_decode_teacher(m, tgt_dev, n, S, T, out_dev, st);
 }
 
 // TransformerLMRescorer.rescore_hyps device part: tokens [n, L] int32 (bos ... eos, pad-filled), lens [n] int32 (device) ->

@@ -72,7 +72,7 @@ class TransformerLMRescorer:
         self.device = device
         self.temperature = temperature
         self.bos_index, self.eos_index, self.pad_index = bos_index, eos_index, pad_index
-        self._engine = None
+        self._slot = None
 
     def normalize_text(self, text):
         """scorer.py:1754-1771: the LM was trained on upper-case LibriSpeech text."""
@@ -90,15 +90,15 @@ class TransformerLMRescorer:
         padded = torch.nn.utils.rnn.pad_sequence(enc, batch_first=True, padding_value=self.pad_index)
         return padded, lengths
 
+    def _engine_cfg(self):
+        return dict(n_fft=400, hop=160, n_mels=80, cnn_channels=(64, 32), input_size=640, d_model=512, nhead=8,
+                    num_encoder_layers=0, num_decoder_layers=0, d_ffn=2048, vocab=self.lm.vocab, attention_type="RoPEMHA")
+
     def _get_engine(self):
-        if self._engine is None:
-            from ..engine import AsrEngine
-            cfg = dict(n_fft=400, hop=160, n_mels=80, cnn_channels=(64, 32), input_size=640, d_model=512, nhead=8,
-                       num_encoder_layers=0, num_decoder_layers=0, d_ffn=2048, vocab=self.lm.vocab, attention_type="RoPEMHA",
-                       lm=self.lm.engine_cfg())
-            sd = {"lm." + k: v for k, v in self.lm.state_dict().items()}
-            self._engine = AsrEngine(cfg, sd, device=self.device, parts=("lm",))
-        return self._engine
+        if self._slot is None:
+            from ..engine_cache import EngineSlot
+            self._slot = EngineSlot(self._engine_cfg)
+        return self._slot.get(self.device, ("lm",), {"lm.": self.lm})
 
     @torch.no_grad()
     def rescore_hyps(self, topk_hyps):

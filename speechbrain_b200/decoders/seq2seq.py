@@ -18,18 +18,21 @@ class S2STransformerGreedySearcher(torch.nn.Module):
         self.bos_index, self.eos_index = bos_index, eos_index
         self.min_decode_ratio, self.max_decode_ratio = min_decode_ratio, max_decode_ratio
         self.return_log_probs = return_log_probs  # extension: skip the (B,1,L,V) log-prob tensor when False
-        self._engine = None
 
     def set_n_out(self):
         return self.fc.w.out_features
 
-    def _get_engine(self, device):
-        if self._engine is None or self._engine.device != torch.device(device):
-            from ..engine import AsrEngine
-            sd = self.model.prefixed_state("Transformer.")
-            sd.update({"seq_lin." + k: v for k, v in self.fc.state_dict().items()})
-            self._engine = AsrEngine(self.model.engine_cfg(), sd, device=device, parts=("decoder",))
-        return self._engine
+    def engine_key(self):
+        return (id(self.fc), 0, 0)
+
+    def engine_sources(self):
+        return {"seq_lin.": self.fc}
+
+    def _get_engine(self, device, parts=(), extra_sources=None):
+        """The device engine shared with every other mirror wired to the same model / output head (engine_cache.py)."""
+        src = self.engine_sources()
+        src.update(extra_sources or {})
+        return self.model.engine_slot(self.engine_key()).get(device, tuple(parts) + ("decoder",), src)
 
     @torch.no_grad()
     def forward(self, enc_states, wav_len):
@@ -42,6 +45,9 @@ class S2STransformerGreedySearcher(torch.nn.Module):
         eng = self._get_engine(enc_states.device)
         pred, score, lp, done = eng.greedy_from_enc(enc_states, wav_len, n, self.bos_index, self.eos_index,
                                                     want_log_probs=self.return_log_probs)
+        # the device polls `has_ended.all()` only every few steps: cut back to the step at which the reference's loop
+        # breaks (seq2seq.py:256), i.e. one column past the last row's first EOS
+        done = greedy_exit_step(pred[:, :done], self.eos_index)
         return greedy_outputs(pred[:, :done], score[:, :done], lp[:, :done] if lp is not None else None, self.eos_index)
 
 
@@ -87,25 +93,28 @@ class S2STransformerBeamSearcher(torch.nn.Module):
         self.beam_size, self.return_topk, self.topk = beam_size, return_topk, topk
         self.using_eos_threshold, self.eos_threshold = using_eos_threshold, eos_threshold
         self.length_normalization, self.minus_inf = length_normalization, minus_inf
-        self._engine = None
 
     def set_n_out(self):
         return self.fc.w.out_features
 
-    def _get_engine(self, device):
-        if self._engine is None or self._engine.device != torch.device(device):
-            from ..engine import AsrEngine
-            sd = self.model.prefixed_state("Transformer.")
-            sd.update({"seq_lin." + k: v for k, v in self.fc.state_dict().items()})
-            cfg, parts = self.model.engine_cfg(), ("decoder",)
-            if self.lm_scorer is not None:
-                sd.update({"lm." + k: v for k, v in self.lm_scorer.lm.state_dict().items()})
-                cfg["lm"] = self.lm_scorer.lm.engine_cfg()
-                parts = ("decoder", "lm")
-            if self.ctc_weight > 0.0:
-                sd.update({"ctc_lin." + k: v for k, v in self.ctc_scorer.ctc_fc.state_dict().items()})
-            self._engine = AsrEngine(cfg, sd, device=device, parts=parts)
-        return self._engine
+    def engine_key(self):
+        return (id(self.fc), id(self.lm_scorer.lm) if self.lm_scorer is not None else 0,
+                id(self.ctc_scorer.ctc_fc) if self.ctc_weight > 0.0 else 0)
+
+    def engine_sources(self):
+        src = {"seq_lin.": self.fc}
+        if self.lm_scorer is not None:
+            src["lm."] = self.lm_scorer.lm
+        if self.ctc_weight > 0.0:
+            src["ctc_lin."] = self.ctc_scorer.ctc_fc
+        return src
+
+    def _get_engine(self, device, parts=(), extra_sources=None):
+        """The device engine shared with every other mirror wired to the same model / heads / LM (engine_cache.py)."""
+        src = self.engine_sources()
+        src.update(extra_sources or {})
+        parts = tuple(parts) + (("decoder", "lm") if self.lm_scorer is not None else ("decoder",))
+        return self.model.engine_slot(self.engine_key()).get(device, parts, src)
 
     @torch.no_grad()
     def forward(self, enc_states, wav_len):
@@ -171,6 +180,18 @@ def replay_beam_history(hist, B, beam_size, eos_index, topk=1):
     idx = (idx + (torch.arange(B) * beam_size).unsqueeze(1)).view(B * topk)
     return (top_hyps.index_select(0, idx).view(B, topk, -1), top_len.index_select(0, idx).view(B, topk), tk_scores,
             top_lp.index_select(0, idx).view(B, topk, -1))
+
+
+def greedy_exit_step(pred, eos_index):
+    """Number of steps the reference's greedy loop executes for these predictions: it breaks right after the step at which
+    every row has produced EOS (decoders/seq2seq.py:249-257); without that, all of them."""
+    B, L = pred.shape
+    if L == 0:
+        return 0
+    is_eos = pred == eos_index
+    if not bool(is_eos.any(1).all()):
+        return L
+    return int(is_eos.float().argmax(1).max()) + 1
 
 
 def greedy_outputs(pred, score, log_probs, eos_index):

@@ -1,6 +1,7 @@
 """Python handle on the C-ABI model engine (sbk_asr_*): repacks a reference-keyed state_dict once and
 runs the fused device pipeline.  Used by the nn.Module mirrors and by EncoderDecoderASR."""
 import ctypes
+import itertools
 import math
 
 import torch
@@ -98,9 +99,14 @@ class AsrEngine:
         if cfg["num_decoder_layers"] == 0:
             c.parts &= ~_lib.SBK_PARTS["decoder"]
         st = {k: v.detach().float().contiguous().cpu() for k, v in state.items() if torch.is_tensor(v) and v.is_floating_point()}
-        if "fbank" in self.parts:
-            st["fbank.window"] = stft_window(cfg["n_fft"], cfg["win"])
-            st["fbank.mel_matrix"] = mel_filter_matrix(cfg["n_mels"], cfg["n_fft"], cfg.get("sample_rate", 16000))
+        c.fbank_amin, c.fbank_top_db = float(cfg.get("fbank_amin", 0.0)), float(cfg.get("fbank_top_db", 0.0))  # 0 = defaults
+        c.norm_eps = float(cfg.get("norm_eps", 0.0))
+        if "fbank" in self.parts:  # a Fbank module's own tables when the caller passes them, else the recipe defaults
+            if "fbank.window" not in st:
+                st["fbank.window"] = stft_window(cfg["n_fft"], cfg["win"])
+            if "fbank.mel_matrix" not in st:
+                st["fbank.mel_matrix"] = mel_filter_matrix(cfg["n_mels"], cfg["n_fft"], cfg.get("sample_rate", 16000),
+                                                           cfg.get("f_min", 0), cfg.get("f_max"))
         names = [k.encode() for k in st]
         arr = (_lib.sbk_tensor * len(st))()
         for i, (k, v) in enumerate(st.items()):
@@ -204,6 +210,19 @@ class AsrEngine:
                                                 ptr(lp), ctypes.byref(done), self._sp()), "sbk_asr_greedy_from_enc")
         return pred, score, lp, done.value
 
+    def decode_teacher_forced(self, tgt, enc, enc_len=None):
+        """TransformerASR.decode device part: tgt [n, S] token ids, enc [n, T, d], enc_len [n] absolute -> [n, S, d] fp32."""
+        enc = enc.float().contiguous()
+        n, T, d = enc.shape
+        tgt = tgt.to(device=enc.device, dtype=torch.int32).contiguous()
+        S = tgt.shape[1]
+        el = enc_len.to(device=enc.device, dtype=torch.int32).contiguous() if enc_len is not None else None
+        out = torch.empty(n, S, d, device=enc.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            check(lib().sbk_asr_decode_teacher_forced(self._h, ptr(tgt), ptr(enc), ptr(el), n, S, T, ptr(out), self._sp()),
+                  "sbk_asr_decode_teacher_forced")
+        return out
+
     def beam_from_enc(self, enc, wav_lens, beam_size, max_steps, min_steps, bos, eos, temperature=1.0,
                       using_eos_threshold=True, eos_threshold=1.5, length_normalization=True, minus_inf=-1e20,
                       lm_weight=0.0, lm_temperature=1.0, ctc_weight=0.0, blank_index=-1, length_weight=0.0):
@@ -244,6 +263,20 @@ class AsrEngine:
                   "sbk_asr_transcribe_greedy_dev")
         return pred, score, enc, done.value
 
+    def encode_wav(self, wav, wav_lens, out=None):
+        """Fbank -> CMVN -> CNN -> encoder on device-resident wav (EncoderDecoderASR.encode_batch): [B, L] -> [B, T, d]."""
+        wav = wav.float().contiguous()
+        B, L = wav.shape
+        _, T = self.num_frames(L)
+        if out is None:
+            out = torch.empty(B, T, self.cfg["d_model"], device=wav.device, dtype=torch.float32)
+        wl = wav_lens.float().contiguous().to(wav.device)
+        done = ctypes.c_int()
+        with torch.cuda.device(self.device):
+            check(lib().sbk_asr_transcribe_greedy_dev(self._h, ptr(wav), ptr(wl), B, L, 0, 0, 0, ptr(out), None, None, None,
+                                                      ctypes.byref(done), self._sp()), "sbk_asr_transcribe_greedy_dev (encode)")
+        return out
+
     def transcribe_greedy_group_dev(self, wavs, lens, max_steps, bos, eos, preds):
         """Decode coalescing: ``wavs`` / ``lens`` / ``preds`` are lists of G per-batch device tensors ([B, L] fp32,
         [B] fp32, [B, max_steps] int32).  Each batch is encoded on its own, all G*B hypotheses are decoded together."""
@@ -257,6 +290,27 @@ class AsrEngine:
         with torch.cuda.device(self.device):
             check(lib().sbk_asr_transcribe_greedy_group_dev(self._h, G, w, r, B, L, max_steps, bos, eos, p, ctypes.byref(done),
                                                             self._sp()), "sbk_asr_transcribe_greedy_group_dev")
+        return done.value
+
+    def transcribe_greedy_group_host_async(self, wavs_host, lens_host, max_steps, bos, eos, preds_host, preds_dev=None):
+        """The group call from pinned HOST tensors (lists of G per-batch tensors): H2D copies, pipeline and D2H of the ids are
+        enqueued on the current stream (copies on the engine's copy stream); the caller synchronises.  ``preds_dev``
+        (optional list of device tensors) also keeps the ids on the device."""
+        G = len(wavs_host)
+        B, L = wavs_host[0].shape
+        for t in itertools.chain(wavs_host, lens_host, preds_host):
+            if t.is_cuda or not t.is_pinned() or not t.is_contiguous():
+                raise RuntimeError("transcribe_greedy_group_host_async: host tensors must be pinned and contiguous")
+        VP = ctypes.c_void_p * G
+        w = VP(*[t.data_ptr() for t in wavs_host])
+        r = VP(*[t.data_ptr() for t in lens_host])
+        p = VP(*[t.data_ptr() for t in preds_host])
+        pd = VP(*[t.data_ptr() for t in preds_dev]) if preds_dev is not None else None
+        done = ctypes.c_int()
+        with torch.cuda.device(self.device):
+            check(lib().sbk_asr_transcribe_greedy_group_host_async(self._h, G, w, r, B, L, max_steps, bos, eos, p, pd,
+                                                                   ctypes.byref(done), self._sp()),
+                  "sbk_asr_transcribe_greedy_group_host_async")
         return done.value
 
     def transcribe_greedy_host_async(self, wav_host, lens_host, max_steps, bos, eos, pred_host):
@@ -274,8 +328,12 @@ class AsrEngine:
         assert not wav_host.is_cuda
         wav_host = wav_host.float().contiguous()
         B, L = wav_host.shape
-        if pred_host is None:
-            pred_host = torch.empty(B, max(max_steps, 1), dtype=torch.int32).pin_memory()
+        if pred_host is None:  # pinned result buffer, cached per shape (pin_memory() costs more than the copy)
+            cache = self.__dict__.setdefault("_pinned_pred", {})
+            key = (B, max(max_steps, 1))
+            if key not in cache:
+                cache[key] = torch.empty(*key, dtype=torch.int32).pin_memory()
+            pred_host = cache[key]
         pred_host.fill_(eos)
         lh = lens_host.float().contiguous() if lens_host is not None else None
         done = ctypes.c_int()

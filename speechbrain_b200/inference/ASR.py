@@ -1,65 +1,101 @@
-"""EncoderDecoderASR -- drop-in for speechbrain.inference.ASR.EncoderDecoderASR (inference/ASR.py:35-173)
-for the Conformer encoder-decoder recipes: ``encode_batch`` / ``transcribe_batch`` with the same signatures,
-running wav -> token ids as ONE fused device pipeline (C ABI sbk_asr_transcribe_greedy_*).
+"""EncoderDecoderASR -- drop-in for speechbrain.inference.ASR.EncoderDecoderASR (inference/ASR.py:35-173) for the
+Conformer encoder-decoder recipes: ``encode_batch`` / ``transcribe_batch`` / ``forward`` with the reference's signatures.
 
-The reference builds its modules from a HyperPyYAML file (``from_hparams``); hyperpyyaml is not available
-offline, so this class is constructed from module objects:
+Two module layouts are accepted:
 
-    asr = EncoderDecoderASR(modules=dict(compute_features=Fbank(...), normalize=InputNormalization(...),
-                                         CNN=ConvolutionFrontEnd(...), Transformer=TransformerASR(...),
-                                         seq_lin=Linear(...), decoder=S2STransformerGreedySearcher(...)),
-                            hparams=dict(tokenizer=sentencepiece_processor_or_None))
-"""
+* the reference's (``MODULES_NEEDED = ["encoder", "decoder"]``): ``encoder`` is a ``LengthsCapableSequential`` of
+  Fbank -> InputNormalization -> ConvolutionFrontEnd [-> EncoderWrapper(TransformerASR)], ``decoder`` a
+  ``S2STransformerGreedySearcher`` or ``S2STransformerBeamSearcher`` (+ ``ScorerBuilder``), and with
+  ``hparams["transformer_beam_search"]`` the model itself sits under ``modules["transformer"]`` -- i.e. what
+  ``speechbrain/asr-conformer-transformerlm-librispeech``'s hyperparams.yaml builds (``from_hparams`` loads such a file
+  from a local directory, see ``speechbrain_b200.utils.hparams``);
+* the flat layout the recipes' training YAML uses (compute_features, normalize, CNN, Transformer, seq_lin, decoder).
+
+The waveform -> encoder states part runs as ONE fused device pipeline (Fbank + CMVN + CNN + Conformer encoder, C ABI
+``sbk_asr_transcribe_greedy_*`` / ``sbk_asr_encode``); a greedy decoder stays inside the same call (one CUDA-graph-able
+pipeline wav -> token ids), a beam decoder runs ``sbk_asr_beam_from_enc`` on the states.  One repacked engine is shared
+by every mirror involved (engine_cache.py)."""
 import torch
 
-from ..decoders.seq2seq import S2STransformerGreedySearcher, greedy_outputs
+from ..decoders.seq2seq import (S2STransformerBeamSearcher, S2STransformerGreedySearcher, greedy_exit_step, greedy_outputs)
+from ..lobes.features import Fbank
+from ..lobes.models.convolution import ConvolutionFrontEnd
+from ..lobes.models.transformer.TransformerASR import EncoderWrapper, TransformerASR
+from ..processing.features import InputNormalization
+
+
+def _find(mods, cls):
+    """First module of type ``cls`` among ``mods`` and their direct children (the reference nests the front end in a
+    LengthsCapableSequential)."""
+    for m in mods:
+        if isinstance(m, cls):
+            return m
+    for m in mods:
+        if isinstance(m, torch.nn.Module):
+            for c in m.children():
+                if isinstance(c, cls):
+                    return c
+    return None
 
 
 class EncoderDecoderASR(torch.nn.Module):
     HPARAMS_NEEDED = ["tokenizer"]
-    MODULES_NEEDED = ["compute_features", "normalize", "CNN", "Transformer", "seq_lin", "decoder"]
+    MODULES_NEEDED = ["encoder", "decoder"]
 
-    def __init__(self, modules, hparams=None, run_opts=None):
+    def __init__(self, modules=None, hparams=None, run_opts=None, freeze_params=True):
         super().__init__()
-        for k in self.MODULES_NEEDED:
-            if k not in modules:
-                raise ValueError(f"Need modules['{k}']")
+        modules = dict(modules or {})
+        if "decoder" not in modules:
+            raise ValueError("Need modules['decoder']")
+        if "encoder" not in modules and not {"compute_features", "normalize", "CNN", "Transformer"} <= set(modules):
+            raise ValueError("Need modules['encoder'] (or the flat compute_features / normalize / CNN / Transformer layout)")
         self.mods = torch.nn.ModuleDict(modules)
-        self.hparams = dict(hparams or {})
+        self.hparams = dict(hparams) if isinstance(hparams, dict) else (dict(vars(hparams)) if hparams is not None else {})
         self.tokenizer = self.hparams.get("tokenizer")
+        self.transformer_beam_search = bool(self.hparams.get("transformer_beam_search", False))
+        if self.hparams.get("transducer_beam_search", False):
+            raise NotImplementedError("speechbrain_b200.EncoderDecoderASR: transducer decoding is not on the B200 hot path")
         self.device = torch.device((run_opts or {}).get("device", "cuda:0"))
-        self._engine = None
-        if not isinstance(self.mods["decoder"], S2STransformerGreedySearcher):
-            raise NotImplementedError("EncoderDecoderASR: the fused pipeline takes a S2STransformerGreedySearcher decoder")
-        if self.mods["normalize"].norm_type != "global":
+        dec = self.mods["decoder"]
+        if not isinstance(dec, (S2STransformerGreedySearcher, S2STransformerBeamSearcher)):
+            raise NotImplementedError("EncoderDecoderASR: the decoder must be a speechbrain_b200 S2STransformerGreedySearcher "
+                                      "or S2STransformerBeamSearcher")
+        vals = list(self.mods.values())
+        wrap = _find(vals, EncoderWrapper)
+        # plain attributes (not sub-modules: they already live under self.mods)
+        for name, m in (("fbank", _find(vals, Fbank)), ("normalize", _find(vals, InputNormalization)),
+                        ("cnn", _find(vals, ConvolutionFrontEnd)),
+                        ("transformer", _find(vals, TransformerASR) or (wrap.transformer if wrap is not None else None) or dec.model)):
+            object.__setattr__(self, name, m)
+        if self.transformer is not dec.model:
+            raise ValueError("EncoderDecoderASR: the decoder's model is not the encoder's TransformerASR")
+        missing = [n for n, m in (("Fbank", self.fbank), ("InputNormalization", self.normalize), ("ConvolutionFrontEnd", self.cnn))
+                   if m is None]
+        if missing:
+            raise ValueError(f"EncoderDecoderASR: could not find {missing} among the modules")
+        if self.normalize.norm_type != "global":
             raise NotImplementedError("EncoderDecoderASR: fused pipeline needs InputNormalization(norm_type='global')")
 
     @classmethod
-    def from_hparams(cls, *args, **kwargs):
-        raise NotImplementedError("speechbrain_b200.EncoderDecoderASR.from_hparams needs hyperpyyaml + network access; "
-                                  "construct from module objects instead (see class docstring)")
+    def from_hparams(cls, source, hparams_file="hyperparams.yaml", overrides=None, savedir=None, run_opts=None, **kwargs):
+        """inference/interfaces.py:385-489 for a LOCAL directory: loads ``source/hparams_file`` with the HyperPyYAML-subset
+        loader (speechbrain.* dotted names are mapped onto this package), runs the ``pretrainer`` parameter transfer on the
+        checkpoint files found in ``source`` and builds the interface.  There is no hub download (no network)."""
+        from ..utils.hparams import load_pretrained_interface
+        return load_pretrained_interface(cls, source, hparams_file, overrides or {}, run_opts or {})
 
+    # ------------------------------------------------------------------ engine
     def engine(self):
-        if self._engine is None:
-            from ..engine import AsrEngine
-            fb, tr = self.mods["compute_features"], self.mods["Transformer"]
-            cfg = tr.engine_cfg()
-            cfg.update(n_fft=fb.n_fft, hop=fb.hop_length, win=fb.win_length, n_mels=fb.n_mels, sample_rate=fb.sample_rate,
-                       cnn_channels=self.mods["CNN"].out_channels)
-            sd = tr.prefixed_state("Transformer.")
-            sd.update({"CNN." + k: v for k, v in self.mods["CNN"].state_dict().items()})
-            sd.update({"seq_lin." + k: v for k, v in self.mods["seq_lin"].state_dict().items()})
-            n = self.mods["normalize"]
-            sd["normalize.glob_mean"] = n.glob_mean.float().cpu()
-            sd["normalize.glob_std"] = (n.glob_std if n.std_norm else torch.ones_like(n.glob_mean)).float().cpu()
-            self._engine = AsrEngine(cfg, sd, device=self.device)
-        return self._engine
+        dec = self.mods["decoder"]
+        src = {"fbank": self.fbank, "normalize": self.normalize, "CNN.": self.cnn}
+        return dec._get_engine(self.device, parts=("fbank", "cnn", "encoder"), extra_sources=src)
 
     def _steps(self, n_samples):
         dec = self.mods["decoder"]
         _, T = self.engine().num_frames(n_samples)
         return max(0, int(T * dec.max_decode_ratio) - int(T * dec.min_decode_ratio))
 
+    # ------------------------------------------------------------------ reference API
     @torch.no_grad()
     def encode_batch(self, wavs, wav_lens):
         """inference/ASR.py:100-128: wavs [B, L] (+ relative lengths) -> encoder states [B, T, d]."""
@@ -73,15 +109,22 @@ class EncoderDecoderASR(torch.nn.Module):
     def transcribe_batch(self, wavs, wav_lens):
         """inference/ASR.py:131-169: -> (predicted_words list[str], predicted_tokens list[list[int]])."""
         dec = self.mods["decoder"]
-        n = self._steps(wavs.shape[1])
-        if wavs.is_cuda:
-            pred, score, _, done = self.engine().transcribe_greedy_dev(wavs, wav_lens.to(wavs.device), n, dec.bos_index,
+        if isinstance(dec, S2STransformerBeamSearcher):
+            enc = self.encode_batch(wavs, wav_lens)
+            hyps = dec(enc, wav_lens.to(self.device))[0]
+            if dec.return_topk:  # padded (B, topk, L) tensor: the best hypothesis of every utterance, like hyps[0]
+                raise NotImplementedError("EncoderDecoderASR.transcribe_batch: build the searcher with return_topk=False")
+        else:
+            n = self._steps(wavs.shape[1])
+            if wavs.is_cuda:
+                pred, _, _, done = self.engine().transcribe_greedy_dev(wavs, wav_lens.to(wavs.device), n, dec.bos_index,
                                                                        dec.eos_index)
-            pred = pred[:, :done].cpu()
-        else:  # host buffers: H2D / D2H inside the C-ABI call
-            pred, done = self.engine().transcribe_greedy_host(wavs, wav_lens, n, dec.bos_index, dec.eos_index)
-            pred = pred[:, :done]
-        hyps, _, _, _ = greedy_outputs(pred, torch.zeros_like(pred, dtype=torch.float32), None, dec.eos_index)
+                pred = pred[:, :done].cpu()
+            else:  # host buffers: H2D / D2H inside the C-ABI call
+                pred, done = self.engine().transcribe_greedy_host(wavs, wav_lens, n, dec.bos_index, dec.eos_index)
+                pred = pred[:, :done]
+            pred = pred[:, :greedy_exit_step(pred, dec.eos_index)]
+            hyps, _, _, _ = greedy_outputs(pred, torch.zeros_like(pred, dtype=torch.float32), None, dec.eos_index)
         if self.tokenizer is not None:
             words = [self.tokenizer.decode_ids(h) for h in hyps]
         else:
@@ -90,3 +133,26 @@ class EncoderDecoderASR(torch.nn.Module):
 
     def forward(self, wavs, wav_lens):
         return self.transcribe_batch(wavs, wav_lens)
+
+    # ------------------------------------------------------------------ extension: several batches per call
+    @torch.no_grad()
+    def transcribe_batches_async(self, wavs_host, lens_host, preds_host, preds_dev=None):
+        """Throughput form of ``transcribe_batch`` for a greedy decoder: G pinned host batches ([B, L] fp32, [B] fp32) are
+        copied, encoded batch by batch and decoded together (one greedy loop over G*B rows); token ids land in the pinned
+        ``preds_host`` [B, steps] int32 tensors.  Only enqueues on the current stream -- synchronise it, then pass each
+        ``preds_host[g]`` to ``tokens_to_words``."""
+        dec = self.mods["decoder"]
+        if not isinstance(dec, S2STransformerGreedySearcher):
+            raise NotImplementedError("transcribe_batches_async needs a greedy decoder")
+        n = self._steps(wavs_host[0].shape[1])
+        if any(p.shape[1] != n for p in preds_host):
+            raise ValueError(f"preds_host tensors must be [B, {n}]")
+        return self.engine().transcribe_greedy_group_host_async(wavs_host, lens_host, n, dec.bos_index, dec.eos_index,
+                                                                preds_host, preds_dev)
+
+    def tokens_to_words(self, pred):
+        dec = self.mods["decoder"]
+        pred = pred[:, :greedy_exit_step(pred, dec.eos_index)]
+        hyps, _, _, _ = greedy_outputs(pred, torch.zeros_like(pred, dtype=torch.float32), None, dec.eos_index)
+        words = [self.tokenizer.decode_ids(h) for h in hyps] if self.tokenizer is not None else [" ".join(map(str, h)) for h in hyps]
+        return words, hyps

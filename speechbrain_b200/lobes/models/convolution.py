@@ -26,18 +26,20 @@ class ConvolutionFrontEnd(torch.nn.Module):
         self.n_mels = int(input_shape[-1])
         self.out_channels = tuple(out_channels[:2])
         build_param_tree(self, cnn_frontend_shapes(self.n_mels, self.out_channels), default_init)
-        self._engine = None
+        object.__setattr__(self, "_slot", None)
+
+    def _engine_cfg(self):
+        f2 = ((self.n_mels - 1) // 2 + 1 - 1) // 2 + 1
+        return dict(n_fft=400, hop=160, win=400, n_mels=self.n_mels, cnn_channels=self.out_channels,
+                    input_size=f2 * self.out_channels[1], d_model=64, nhead=1, num_encoder_layers=0,
+                    num_decoder_layers=0, d_ffn=64, vocab=8, attention_type="RoPEMHA")
 
     def _get_engine(self, device):
-        if self._engine is None or self._engine.device != torch.device(device):
-            from ...engine import AsrEngine
-            f2 = ((self.n_mels - 1) // 2 + 1 - 1) // 2 + 1
-            cfg = dict(n_fft=400, hop=160, win=400, n_mels=self.n_mels, cnn_channels=self.out_channels,
-                       input_size=f2 * self.out_channels[1], d_model=64, nhead=1, num_encoder_layers=0,
-                       num_decoder_layers=0, d_ffn=64, vocab=8, attention_type="RoPEMHA")
-            sd = {"CNN." + k: v for k, v in self.state_dict().items()}
-            self._engine = AsrEngine(cfg, sd, device=device, parts=("cnn",))
-        return self._engine
+        """Stand-alone use (module-by-module pipelines): a CNN-only engine, rebuilt when the parameters change."""
+        if self._slot is None:
+            from ...engine_cache import EngineSlot
+            object.__setattr__(self, "_slot", EngineSlot(self._engine_cfg))
+        return self._slot.get(device, ("cnn",), {"CNN.": self})
 
     @torch.no_grad()
     def forward(self, x):

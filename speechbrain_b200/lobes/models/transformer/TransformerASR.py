@@ -3,8 +3,8 @@
 encoder_module="conformer", attention_type in {"RoPEMHA", "RelPosMHAXL"}, normalize_before=True, causal=False.
 
 Same constructor kwargs, same state_dict keys (incl. the positional buffers), ``encode()`` on the sm_100a
-kernels.  ``decode()``/``forward()`` (teacher-forced training-style calls) are not part of the inference hot
-path: the searchers in speechbrain_b200.decoders run the KV-cached decoder directly.
+kernels.  ``decode()`` / ``forward()`` run teacher-forced on the KV-cached decoder step (the searchers in
+speechbrain_b200.decoders drive the same step one token at a time).
 """
 import math
 
@@ -79,7 +79,8 @@ class TransformerASR(torch.nn.Module):
             self.positional_encoding.register_buffer("pe", _sine_table(max_length, d_model))
         self.positional_encoding_decoder = _Node()
         self.positional_encoding_decoder.register_buffer("pe", _sine_table(max_length, d_model))
-        self._engine = None
+        # engine slots (plain dict, not sub-modules): one shared device engine per set of modules wired to this model
+        object.__setattr__(self, "_slots", {})
 
     def engine_cfg(self):
         return dict(n_fft=400, hop=160, win=400, n_mels=80, cnn_channels=(64, 32), input_size=self.input_size,
@@ -91,11 +92,29 @@ class TransformerASR(torch.nn.Module):
     def prefixed_state(self, prefix="Transformer."):
         return {prefix + k: v for k, v in self.state_dict().items()}
 
+    def engine_slot(self, key=()):
+        """The shared ``EngineSlot`` for the modules identified by ``key`` (ids of the output head / LM / CTC head wired to
+        this model by a searcher); every mirror using the same modules gets the same repacked device engine."""
+        from ....engine_cache import EngineSlot
+        if key not in self._slots:
+            slot = EngineSlot(self.engine_cfg)
+            slot.sources["Transformer."] = self
+            self._slots[key] = slot
+        return self._slots[key]
+
+    def invalidate_engines(self):
+        """Drop every cached device engine (needed only after edits through ``param.data``; ``load_state_dict``, ``.to()``
+        and in-place ops on the parameters are detected)."""
+        for slot in self._slots.values():
+            slot.invalidate()
+
     def _get_engine(self, device):
-        if self._engine is None or self._engine.device != torch.device(device):
-            from ....engine import AsrEngine
-            self._engine = AsrEngine(self.engine_cfg(), self.prefixed_state(), device=device, parts=("encoder",))
-        return self._engine
+        """Engine for ``encode``: any slot that already holds the encoder (e.g. the one EncoderDecoderASR or a searcher
+        built), else an encoder-only one."""
+        for slot in self._slots.values():
+            if "encoder" in slot.parts and slot.engine is not None:
+                return slot.get(device, ("encoder",))
+        return self.engine_slot().get(device, ("encoder",))
 
     @torch.no_grad()
     def encode(self, src, wav_len=None, pad_idx=0, dynchunktrain_config=None):
@@ -111,13 +130,35 @@ class TransformerASR(torch.nn.Module):
             raise ValueError("wav_len: the longest utterance must have relative length 1.0")
         return self._get_engine(src.device).encode_from_cnn(src, wav_len)
 
-    def decode(self, tgt, encoder_out, enc_len=None):
-        raise NotImplementedError("speechbrain_b200.TransformerASR.decode: use S2STransformer{Greedy,Beam}Searcher "
-                                  "(the KV-cached decoder step replaces the reference's whole-prefix decode)")
+    def _decoder_engine(self, device):
+        for slot in self._slots.values():
+            if "decoder" in slot.parts and slot.engine is not None:
+                return slot.get(device, ("decoder",))
+        return self.engine_slot().get(device, ("decoder",))
 
+    @torch.no_grad()
+    def decode(self, tgt, encoder_out, enc_len=None):
+        """TransformerASR.py:426-473: tgt [n, s] token ids (bos first), encoder_out [n, T, d], enc_len [n] ABSOLUTE frame
+        counts -> (prediction [n, s, d] = decoder.norm(decoder(...)), None).
+
+        Runs teacher-forced on the KV-cached decoder step: position s attends to positions <= s (the reference's causal
+        mask) and to the first enc_len frames of the memory.  The reference's second value (last layer's head-averaged
+        cross-attention weights [n, s, T]) is not produced by the device decoder and is returned as None."""
+        require_cuda(encoder_out, "TransformerASR.decode")
+        if self.num_decoder_layers == 0:
+            raise ValueError("TransformerASR.decode: the model has no decoder layers")
+        out = self._decoder_engine(encoder_out.device).decode_teacher_forced(tgt.long(), encoder_out, enc_len)
+        return out, None
+
+    @torch.no_grad()
     def forward(self, src, tgt, wav_len=None, pad_idx=0):
-        raise NotImplementedError("speechbrain_b200.TransformerASR.forward (teacher-forced training pass) is out of scope; "
-                                  "use encode() + a searcher")
+        """TransformerASR.py:326-424 for inference: (encoder_out, decoder_out).  Target positions holding ``pad_idx`` lie
+        behind every real token of their row, so the causal decoder gives the real positions the reference's values; the
+        padded positions (ignored by every consumer) are computed as if the pads were tokens."""
+        enc = self.encode(src, wav_len, pad_idx)
+        enc_len = torch.round(wav_len.to(enc.device).float() * enc.shape[1]).int() if wav_len is not None else None
+        dec, _ = self.decode(tgt, enc, enc_len)
+        return enc, dec
 
 
 class EncoderWrapper(torch.nn.Module):

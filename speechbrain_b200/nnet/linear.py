@@ -21,6 +21,7 @@ class Linear(torch.nn.Module):
         for p in self.parameters():
             p.requires_grad_(False)
         self._w16 = None
+        self._fp = None
 
     @torch.no_grad()
     def forward(self, x):
@@ -30,9 +31,12 @@ class Linear(torch.nn.Module):
         K, N = self.w.in_features, self.w.out_features
         if K % 8 != 0:
             raise NotImplementedError("speechbrain_b200.Linear: input_size must be a multiple of 8 (TMA row pitch)")
-        if self._w16 is None or self._w16.device != x.device:
+        # fp16 operand snapshot, refreshed whenever the parameters change (load_state_dict / .to() / in-place ops)
+        fp = tuple((t.data_ptr(), t._version) for t in self.w.parameters()) + (str(x.device),)
+        if self._w16 is None or self._fp != fp:
             self._w16 = self.w.weight.detach().to(x.device, torch.float16).contiguous()
             self._b32 = self.w.bias.detach().to(x.device, torch.float32).contiguous() if self.w.bias is not None else None
+            self._fp = fp
         a = x.reshape(-1, K).to(torch.float16).contiguous()
         out = torch.empty(a.shape[0], N, device=x.device, dtype=torch.float32)
         with torch.cuda.device(x.device):

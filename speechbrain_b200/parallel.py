@@ -20,14 +20,30 @@ def shard_batch(wavs, wav_lens, rank, world):
     return wavs[lo:hi], wav_lens[lo:hi], (lo, hi)
 
 
-def gather_hypotheses(tokens, n_total, world, pad=-1):
-    """tokens [n_local, L] int32 (pad = -1) -> [n_total, L] on every rank with one all_gather."""
+def gather_hypotheses(tokens, n_total, world, pad=-1, max_len=None, out=None):
+    """tokens [n_local, L_local] int32 -> [n_total, L] on every rank with ONE collective (``all_gather_into_tensor`` on a
+    preallocated [world, per, L] buffer).
+
+    Ranks may hold different numbers of rows (the last shards of ``shard_bounds`` can be short) and different widths
+    (greedy early exit and beam search stop at rank-dependent steps), while a collective needs identical shapes: rows are
+    padded to ceil(n_total / world) and columns to ``max_len`` -- pass the decode limit (max_decode_steps) to skip the
+    extra all-reduce(MAX) that otherwise agrees on the width.  ``pad`` fills both."""
     if world == 1:
         return tokens
     per = (n_total + world - 1) // world
     L = tokens.shape[1]
-    buf = torch.full((per, L), pad, dtype=tokens.dtype, device=tokens.device)
-    buf[: tokens.shape[0]] = tokens
-    out = [torch.empty_like(buf) for _ in range(world)]
-    dist.all_gather(out, buf)
-    return torch.cat(out, 0)[:n_total]
+    if max_len is None:
+        width = torch.tensor([L], device=tokens.device, dtype=torch.int64)
+        dist.all_reduce(width, op=dist.ReduceOp.MAX)
+        max_len = int(width.item())
+    if L > max_len or tokens.shape[0] > per:
+        raise ValueError(f"gather_hypotheses: local block {tuple(tokens.shape)} exceeds the agreed [{per}, {max_len}]")
+    if tokens.shape[0] == per and L == max_len and tokens.is_contiguous():
+        buf = tokens
+    else:
+        buf = torch.full((per, max_len), pad, dtype=tokens.dtype, device=tokens.device)
+        buf[: tokens.shape[0], :L] = tokens
+    if out is None or out.shape != (world * per, max_len) or out.dtype != tokens.dtype or out.device != tokens.device:
+        out = torch.empty(world * per, max_len, dtype=tokens.dtype, device=tokens.device)
+    dist.all_gather_into_tensor(out, buf)
+    return out[:n_total]

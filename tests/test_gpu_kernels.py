@@ -217,7 +217,7 @@ def test_beam_search_golden(dev, case):
                                     **gb["kwargs"])
     for name, tc_rows in (("skinny", None), ("tcgen05", 1)):  # both decode-step projection implementations
         if tc_rows is not None:
-            bs._engine.set_decoder_tc_min_rows(tc_rows)
+            bs._get_engine(dev).set_decoder_tc_min_rows(tc_rows)
         hyps, lens, scores, lp = bs(g["enc_out"].to(dev), g["wav_lens"].to(dev))
         print(f"beam[{case}/{name}] hyps {hyps} ref {gb['hyps']} scores {scores.tolist()} ref {gb['scores'].tolist()}")
         assert hyps == gb["hyps"]

@@ -24,8 +24,16 @@ def _worker(rank, world, sync_file, out):
     for i in range(hi - lo):
         n = 1 + int(w[i, 0].item()) % L
         tok[i, :n] = int(w[i, 0].item())
-    full = gather_hypotheses(tok, B, world)
+    full = gather_hypotheses(tok, B, world, max_len=L)
     assert full.shape == (B, L)
+    # rank-dependent widths (greedy early exit / beam search stop at different steps on different ranks): the helper agrees
+    # on the width itself (one all-reduce MAX) and pads
+    w_local = L - rank  # rank 0: 5 columns, rank 1: 4
+    ragged = gather_hypotheses(tok[:, :w_local].contiguous(), B, world)
+    assert ragged.shape == (B, L)
+    lo1 = 4  # rows of rank 1 (ceil(7 / 2) = 4 rows on rank 0)
+    assert torch.equal(ragged[:lo1], full[:lo1]) and torch.equal(ragged[lo1:, : L - 1], full[lo1:, : L - 1])
+    assert (ragged[lo1:, L - 1] == -1).all()
     for b in range(B):
         n = 1 + int(wav[b, 0].item()) % L
         assert full[b, :n].tolist() == [int(wav[b, 0].item())] * n and (full[b, n:] == -1).all()
