@@ -384,8 +384,11 @@ int asr_create(const sbk_asr_config* cfg, const sbk_tensor* weights, int n_weigh
         m->b_ckv = p.f32_raw(bckv.data(), bckv.size());
         m->dec_norm_g = p.f32("Transformer.decoder.norm.norm.weight", d);
         m->dec_norm_b = p.f32("Transformer.decoder.norm.norm.bias", d);
-        m->w_lin = p.f16("seq_lin.w.weight", (int64_t)c.vocab * d);
-        m->b_lin = p.f32("seq_lin.w.bias", c.vocab);
+        m->w_lin = nullptr; m->b_lin = nullptr;
+        if (w.count("seq_lin.w.weight")) {  // the output head belongs to the searchers; TransformerASR.decode runs without it
+            m->w_lin = p.f16("seq_lin.w.weight", (int64_t)c.vocab * d);
+            m->b_lin = p.f32("seq_lin.w.bias", c.vocab);
+        }
     }
     if ((c.parts & SBK_PART_LM) && c.lm_layers > 0) {
         const int dl = c.lm_d_model, Fl = c.lm_d_ffn, dhl = dl / c.lm_nhead;
@@ -707,6 +710,7 @@ static int enqueue_decode_layers_tc(AsrModel* m, int rows, int rows_per_utt, int
         RC(gemm_f16_small(b.df16, F, w.w_ffn2, F, e, rows, d, F, st));
     }
     if (!with_head) return SBK_OK;
+    SBK_REQUIRE(m->w_lin != nullptr, "decode step: this handle was created without the output head (seq_lin.w.*)");
     RC(layernorm_rows(b.dx, b.dh16, true, m->dec_norm_g, m->dec_norm_b, rows, d, 1e-6f, false, st));
     GemmEpilogue e;
     e.mode = EPI_F32; e.bias = m->b_lin; e.out = b.logits; e.ldo = c.vocab;
@@ -766,6 +770,7 @@ static int enqueue_decode_layers(AsrModel* m, int rows, int rows_per_utt, int T,
         RC(skinny_gemm(a, st));
     }
     if (!with_head) return SBK_OK;
+    SBK_REQUIRE(m->w_lin != nullptr, "decode step: this handle was created without the output head (seq_lin.w.*)");
     SkinnyArgs a{};  // final LayerNorm + seq_lin
     RC(dec_ln(m, a, m->dec_norm_g, m->dec_norm_b, rows, st));
     a.W = m->w_lin; a.ldw = d; a.bias = m->b_lin; a.n_rows = rows; a.N = c.vocab; a.K = d;

@@ -260,14 +260,24 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmEpilogue& e, 
             for (int j = 0; j < 32; j += 4)
                 sts128(my + j * 4, f4_as_u4(make_float4(v[j], v[j + 1], v[j + 2], v[j + 3])));
         } else if constexpr (MODE == EPI_GLU) {
+            if constexpr (ACT == ACT_SILU_FAST) {
 #pragma unroll
-            for (int j = 0; j < 16; j += 4)
-                sts128(my + j * 4, f4_as_u4(make_float4(v[j] * sigmoid_f(v[j + 16]), v[j + 1] * sigmoid_f(v[j + 17]),
-                                                        v[j + 2] * sigmoid_f(v[j + 18]), v[j + 3] * sigmoid_f(v[j + 19]))));
+                for (int j = 0; j < 16; j += 4)
+                    sts128(my + j * 4, f4_as_u4(make_float4(v[j] * sigmoid_fast(v[j + 16]), v[j + 1] * sigmoid_fast(v[j + 17]),
+                                                            v[j + 2] * sigmoid_fast(v[j + 18]), v[j + 3] * sigmoid_fast(v[j + 19]))));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    sts128(my + j * 4, f4_as_u4(make_float4(v[j] * sigmoid_f(v[j + 16]), v[j + 1] * sigmoid_f(v[j + 17]),
+                                                            v[j + 2] * sigmoid_f(v[j + 18]), v[j + 3] * sigmoid_f(v[j + 19]))));
+            }
         } else {  // EPI_F16 -> 32 halfs
             if constexpr (ACT == ACT_SILU) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+            } else if constexpr (ACT == ACT_SILU_FAST) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = silu_fast(v[j]);
             } else if constexpr (ACT == ACT_GELU) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = gelu_erf_f(v[j]);

@@ -265,9 +265,12 @@ int gemm_f16_2cta(const void* A, int lda, const void* W, int ldw, const GemmEpil
         smem = g2_smem<MODE, 8, 128, 7>();                                        \
         threads = 64 + 32 * 8;                                                    \
     } while (0)
+    // SiLU / GLU-gate sigmoid through one tanh.approx MUFU per element (default) or the exact-form EX2 + RCP (SBK_SILU_EXACT=1)
+    static const bool fast_act = getenv("SBK_SILU_EXACT") == nullptr;
     switch (epi.mode) {
         case EPI_F16:
-            if (epi.act == ACT_SILU) G2_PICK(EPI_F16, ACT_SILU);
+            if (epi.act == ACT_SILU && fast_act) G2_PICK(EPI_F16, ACT_SILU_FAST);
+            else if (epi.act == ACT_SILU) G2_PICK(EPI_F16, ACT_SILU);
             else if (epi.act == ACT_GELU) G2_PICK(EPI_F16, ACT_GELU);
             else if (epi.act == ACT_NONE) G2_PICK(EPI_F16, ACT_NONE);
             else { set_error("gemm_f16_2cta: activation %d not built", epi.act); return SBK_ERR_ARG; }
@@ -280,7 +283,10 @@ int gemm_f16_2cta(const void* A, int lda, const void* W, int ldw, const GemmEpil
             if (bn128) G2_PICK_BN128(EPI_RESID);
             else G2_PICK(EPI_RESID, ACT_NONE);
             break;
-        case EPI_GLU: G2_PICK(EPI_GLU, ACT_NONE); break;
+        case EPI_GLU:
+            if (fast_act) G2_PICK(EPI_GLU, ACT_SILU_FAST);
+            else G2_PICK(EPI_GLU, ACT_NONE);
+            break;
         case EPI_ROPE: G2_PICK(EPI_ROPE, ACT_NONE); break;
         default: set_error("gemm_f16_2cta: bad epilogue mode %d", epi.mode); return SBK_ERR_ARG;
     }

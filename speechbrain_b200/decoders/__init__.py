@@ -1,0 +1,4 @@
+"""speechbrain.decoders namespace: the names the recipes' YAML files reach through the package (decoders/__init__.py)."""
+from .scorer import (CTCScorer, LengthScorer, RescorerBuilder, ScorerBuilder, TransformerLMRescorer,  # noqa: F401
+                     TransformerLMScorer)
+from .seq2seq import S2STransformerBeamSearcher, S2STransformerGreedySearcher  # noqa: F401

@@ -131,8 +131,10 @@ class TransformerASR(torch.nn.Module):
         return self._get_engine(src.device).encode_from_cnn(src, wav_len)
 
     def _decoder_engine(self, device):
+        """Engine for ``decode``: a searcher's slot when one is wired to this model (its engine already holds the decoder),
+        else a decoder-only engine without the output head."""
         for slot in self._slots.values():
-            if "decoder" in slot.parts and slot.engine is not None:
+            if "seq_lin." in slot.sources:
                 return slot.get(device, ("decoder",))
         return self.engine_slot().get(device, ("decoder",))
 
