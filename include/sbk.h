@@ -127,6 +127,13 @@ int sbk_asr_encode_feats(sbk_asr* m, const float* feats_dev, const float* rel_le
 int sbk_asr_greedy_from_enc(sbk_asr* m, const float* enc_dev, const float* rel_len_dev, int B, int T, int max_steps,
                             int bos, int eos, int* pred_dev, float* score_dev, float* log_probs_dev, int* steps_done,
                             void* stream);
+/* torch.max(x, dim=-1).indices of a [rows, V] fp32 device matrix (ctc_greedy_decode, decoders/ctc.py:375) */
+int sbk_rows_argmax_f32(const float* x_dev, int rows, int V, int* idx_dev, void* stream);
+/* CTC head of an encoder-only recogniser (EncoderASR.transcribe_batch, inference/ASR.py:325-373; ctc_greedy_decode,
+ * decoders/ctc.py:335-378): enc_dev [B, T, d_model] fp32, or NULL for the encoder states the previous encode / transcribe
+ * call on this handle left in its workspace -> log_probs_dev [B, T, vocab] fp32 = log_softmax(ctc_lin(enc)) (optional) and
+ * argmax_dev [B, T] int32 per-frame arg-max (optional; first index on ties like torch.max).  Needs "ctc_lin.w.*" weights. */
+int sbk_asr_ctc_head(sbk_asr* m, const float* enc_dev, int B, int T, float* log_probs_dev, int* argmax_dev, void* stream);
 /* TransformerASR.decode(tgt, encoder_out, enc_len) (lobes/models/transformer/TransformerASR.py:426-473), teacher-forced on the
  * KV-cached decoder step: tgt_dev [n, S] int32 (bos first), enc_dev [n, T, d_model] fp32, enc_len_dev [n] int32 ABSOLUTE
  * frame counts or NULL -> out_dev [n, S, d_model] fp32 = decoder.norm(decoder(...)) (the input of seq_lin).  The reference's

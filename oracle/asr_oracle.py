@@ -706,3 +706,26 @@ def rescorer_builder_rescore(topk_candidates, topk_scores, lm_scores, weight):
         out_c.append([c for c, _ in order])
         out_s.append([s_ for _, s_ in order])
     return out_c, out_s
+
+
+# --------------------------------------------------------------------------
+# EncoderASR CTC greedy decoding: inference/ASR.py:325-373, decoders/ctc.py:298-378
+# --------------------------------------------------------------------------
+
+
+def ctc_log_probs(enc, w, b):
+    """The tail of the recipe's encoder Sequential: log_softmax(ctc_lin(enc)) (B, T, V)."""
+    return F.log_softmax(F.linear(enc, w, b), dim=-1)
+
+
+def ctc_greedy_decode(log_probs, seq_lens, blank_id):
+    """decoders/ctc.py:335-378 + filter_ctc_output (:298-332): per-frame arg-max over the first round(len * T) frames, merge
+    repetitions, drop blanks."""
+    T = log_probs.shape[1]
+    out = []
+    for seq, rel in zip(log_probs, seq_lens):
+        n = int(torch.round(rel * T))
+        pred = seq[:n].argmax(-1).tolist()
+        merged = [t for i, t in enumerate(pred) if i == 0 or t != pred[i - 1]]
+        out.append([t for t in merged if t != blank_id])
+    return out

@@ -519,6 +519,76 @@ def bench_extra_case(tag="bench_decode_conformer_large_rope_10s"):
     print(tag, os.path.getsize(os.path.join(OUT, f"{tag}.pt")))
 
 
+def ctc_greedy_case(tag="ctc_greedy_conformer_large_rope"):
+    """EncoderASR-style CTC greedy decoding (inference/ASR.py:325-373, decoders/ctc.py:335-378) of the reference on the golden
+    encoder states: log_softmax(ctc_lin(enc)) -> ctc_greedy_decode(blank 0).  Random-init posteriors almost never repeat, so a
+    second case adds a bias to the blank and to one token to exercise the merge / blank-filter rules."""
+    from speechbrain.decoders.ctc import ctc_greedy_decode
+    fb, norm, mods, sd = build_reference(CFG_L, "RoPEMHA")
+    g = torch.load(os.path.join(OUT, "conformer_large_rope.pt"))
+    enc, wav_lens = g["enc_out"], g["wav_lens"]
+    out = {}
+    for name, bias_blank, bias_tok in (("plain", 0.0, 0.0), ("merge", 1.2, 1.1)):
+        with torch.no_grad():
+            bias = sd["ctc_lin.w.bias"].clone()
+            bias[0] += bias_blank
+            bias[17] += bias_tok
+            mods["ctc_lin"].w.bias.copy_(bias)
+            lp = torch.log_softmax(mods["ctc_lin"](enc), dim=-1)
+            hyps = ctc_greedy_decode(lp, wav_lens, blank_id=0)
+            olp = O.ctc_log_probs(enc, sd["ctc_lin.w.weight"], bias)
+            ohyps = O.ctc_greedy_decode(olp, wav_lens, 0)
+        top2 = lp.topk(2, -1).values
+        print(f"[ctc greedy {name}] hyps lens {[len(h) for h in hyps]} of T={enc.shape[1]}; oracle equal {ohyps == hyps}; "
+              f"min margin {float((top2[..., 0] - top2[..., 1]).min()):.4f}")
+        assert ohyps == hyps and (olp - lp).abs().max() < 1e-4
+        out[name] = dict(bias_blank=bias_blank, bias_tok=bias_tok, hyps=hyps, argmax=lp.argmax(-1).int(),
+                         margin=(top2[..., 0] - top2[..., 1]).clone(), log_probs_head=lp[:, :, :64].clone())
+    with torch.no_grad():
+        mods["ctc_lin"].w.bias.copy_(sd["ctc_lin.w.bias"])
+    torch.save(out, os.path.join(OUT, f"{tag}.pt"))
+
+
+SCALES = {"ffn_w1": 200.0, "qkv": 3.0, "pw1": 4.0}
+
+
+def scale_state(sd, scales):
+    """Seeded weights with selected matrices scaled up (fp16-range test): FFN first layers, attention in_proj, conv pw1."""
+    out = dict(sd)
+    for k, v in sd.items():
+        if ".ffn_module" in k and k.endswith("ffn.0.weight"):
+            out[k] = v * scales["ffn_w1"]
+        elif k.endswith("mha_layer.in_proj_weight"):
+            out[k] = v * scales["qkv"]
+        elif k.endswith("convolution_module.bottleneck.0.weight"):
+            out[k] = v * scales["pw1"]
+    return out
+
+
+def scaled_case(tag="conformer_large_rope_scaled"):
+    """fp16 range: the 2 s RoPE golden re-run by the reference with FFN-hidden / attention-logit / GLU
+    pre-activations pushed far above what random init gives (max |FFN hidden| in the thousands, attention logits x9)."""
+    fb, norm, mods, sd = build_reference(CFG_L, "RoPEMHA")
+    g = torch.load(os.path.join(OUT, "conformer_large_rope.pt"))
+    sds = scale_state(sd, SCALES)
+    mods.load_state_dict({k: v for k, v in sds.items() if not k.startswith("normalize.")})
+    stats = {"ffn_hidden_absmax": 0.0, "qkv_absmax": 0.0}
+
+    def hook_ffn(m, i, o):
+        stats["ffn_hidden_absmax"] = max(stats["ffn_hidden_absmax"], float(o.abs().max()))
+    for layer in mods["Transformer"].encoder.layers:
+        layer.ffn_module1[1].ffn[0].register_forward_hook(hook_ffn)
+        layer.ffn_module2[1].ffn[0].register_forward_hook(hook_ffn)
+    with torch.no_grad():
+        enc = mods["Transformer"].encode(g["cnn_out"], g["wav_lens"])
+        oenc = O.encode(g["cnn_out"].reshape(g["cnn_out"].shape[0], g["cnn_out"].shape[1], -1), g["wav_lens"], sds,
+                        dict(CFG_L, attention_type="RoPEMHA"), "Transformer.")
+    print(f"[scaled] enc finite {bool(torch.isfinite(enc).all())} oracle rel {rel(oenc, enc):.2e} max |FFN pre-activation| "
+          f"{stats['ffn_hidden_absmax']:.1f} enc absmax {float(enc.abs().max()):.2f}")
+    assert rel(oenc, enc) < 1e-5
+    torch.save(dict(scales=SCALES, enc_out=enc, ffn_hidden_absmax=stats["ffn_hidden_absmax"]), os.path.join(OUT, f"{tag}.pt"))
+
+
 BEAMS_10S = (
     ("b10_lm_ctc", dict(beam_size=10, using_eos_threshold=False, temperature=1.15, with_lm=True, with_ctc=True, eos_bias=0.0, steps=24)),
     ("b10_ctc_valid", dict(beam_size=10, using_eos_threshold=False, temperature=1.15, with_lm=False, with_ctc=True, eos_bias=0.0, steps=24)),
@@ -558,6 +628,10 @@ if __name__ == "__main__":
         bench_shape_case(CFG_L, "RoPEMHA", 4, 160000, [1.0, 0.9, 0.6, 0.3], 48, "bench_conformer_large_rope_10s", BEAMS_10S)
     if "bench_L_relpos" in which:
         bench_shape_case(CFG_L, "RelPosMHAXL", 4, 160000, [1.0, 0.9, 0.6, 0.3], 48, "bench_conformer_large_relpos_10s")
+    if "scaled" in which:
+        scaled_case()
+    if "ctc_greedy" in which:
+        ctc_greedy_case()
     if "bench_extra" in which:
         bench_extra_case()
     if "bench_S_relpos" in which:

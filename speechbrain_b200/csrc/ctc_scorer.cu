@@ -85,15 +85,17 @@ __global__ void ctc_init_kernel(const float* __restrict__ xb, int T, int beam, f
     }
 }
 
+// The step index comes from DEVICE memory (the beam search's per-row step counters) so that one captured CUDA graph of a
+// whole search step can be replayed for every step; the ping-pong halves of the state follow the step's parity.
 struct CtcArgs {
     const float* x; const float* xb;         // [B, T, V], [B, T]
-    const float* rsum; const float* rb;      // [n_bh, T] of the prefixes being extended
-    const float* psi_prev;                   // [n_bh]
+    float* rsum_base; float* rb_base;        // [2][n_bh, T]: half (step & 1) holds the prefixes being extended
+    float* psi_base;                         // [2][n_bh]
     const int* enc_len;                      // [B]
     const int* hist_tok; const int* hist_pred;  // beam history [steps, n_bh]
-    int n_bh, step, bos, T, V, beam, blank, eos;
+    const int* step_ptr; int step_adj;       // step = step_ptr[row] + step_adj (the update runs after the counters advanced)
+    int n_bh, bos, T, V, beam, blank, eos;
     float weight; float* out; int accumulate;   // score kernel: out[n_bh, V] (+)= weight * (psi - psi_prev)
-    float* rsum_out; float* rb_out; float* psi_out;  // update kernel
 };
 
 // forward_step (ctc.py:80-249), candidates = None: thread (row, c) runs Alg.2 of Watanabe et al. over the frames.
@@ -104,15 +106,20 @@ __global__ void __launch_bounds__(CTC_THREADS) ctc_score_kernel(const CtcArgs a)
     float* s_rb = smem + a.T;
     float* s_xb = smem + 2 * a.T;
     const int row = blockIdx.y, b = row / a.beam, T = a.T, V = a.V;
+    const int step = a.step_ptr[row] + a.step_adj;
+    const size_t half = static_cast<size_t>(step & 1);
+    const float* rsum_in = a.rsum_base + half * a.n_bh * T;
+    const float* rb_in = a.rb_base + half * a.n_bh * T;
+    const float* psi_prev = a.psi_base + half * a.n_bh;
     for (int t = threadIdx.x; t < T; t += CTC_THREADS) {
-        s_rsum[t] = a.rsum[static_cast<size_t>(row) * T + t];
-        s_rb[t] = a.rb[static_cast<size_t>(row) * T + t];
+        s_rsum[t] = rsum_in[static_cast<size_t>(row) * T + t];
+        s_rb[t] = rb_in[static_cast<size_t>(row) * T + t];
         s_xb[t] = a.xb[static_cast<size_t>(b) * T + t];
     }
     __syncthreads();
     const int c = blockIdx.x * CTC_THREADS + threadIdx.x;
     if (c >= V) return;
-    const int last_char = a.step == 0 ? a.bos : a.hist_tok[static_cast<size_t>(a.step - 1) * a.n_bh + row];
+    const int last_char = step == 0 ? a.bos : a.hist_tok[static_cast<size_t>(step - 1) * a.n_bh + row];
     const float* xc = a.x + static_cast<size_t>(b) * T * V + c;
     float psi;
     if (c == a.blank && a.eos != a.blank) {
@@ -123,8 +130,8 @@ __global__ void __launch_bounds__(CTC_THREADS) ctc_score_kernel(const CtcArgs a)
         const float* phi = (c == last_char) ? s_rb : s_rsum;            // Alg.2-10
         float r_nb, r_b = CTC_NEG;
         int start;
-        if (a.step == 0) { r_nb = xc[0]; start = 1; }                   // Alg.2-6
-        else { r_nb = CTC_NEG; start = a.step; }
+        if (step == 0) { r_nb = xc[0]; start = 1; }                     // Alg.2-6
+        else { r_nb = CTC_NEG; start = step; }
         float pm = r_nb, ps = 1.0f;                                     // running logsumexp, seeded with psi_init
 #pragma unroll 4
         for (int t = start; t < T; ++t) {
@@ -139,7 +146,7 @@ __global__ void __launch_bounds__(CTC_THREADS) ctc_score_kernel(const CtcArgs a)
         }
         psi = pm + __logf(ps);
     }
-    const float sc = a.weight * (psi - a.psi_prev[row]);
+    const float sc = a.weight * (psi - psi_prev[row]);
     float* o = a.out + static_cast<size_t>(row) * V + c;
     *o = a.accumulate ? *o + sc : sc;
 }
@@ -155,10 +162,17 @@ __global__ void __launch_bounds__(128) ctc_update_kernel(const CtcArgs a) {
     float* s_nb = smem + 3 * T;
     float* s_bl = smem + 4 * T;
     const int row = blockIdx.x, b = row / a.beam;
-    const size_t h = static_cast<size_t>(a.step) * a.n_bh + row;
+    const int step = a.step_ptr[row] + a.step_adj;
+    const size_t half = static_cast<size_t>(step & 1), other = half ^ 1;
+    const float* rsum_in = a.rsum_base + half * a.n_bh * T;
+    const float* rb_in = a.rb_base + half * a.n_bh * T;
+    float* rsum_out = a.rsum_base + other * a.n_bh * T;
+    float* rb_out = a.rb_base + other * a.n_bh * T;
+    float* psi_out = a.psi_base + other * a.n_bh;
+    const size_t h = static_cast<size_t>(step) * a.n_bh + row;
     const int tok = a.hist_tok[h], prow = a.hist_pred[h];
-    const int last_char = a.step == 0 ? a.bos : a.hist_tok[static_cast<size_t>(a.step - 1) * a.n_bh + prow];
-    const float* phi = (tok == last_char) ? a.rb : a.rsum;
+    const int last_char = step == 0 ? a.bos : a.hist_tok[static_cast<size_t>(step - 1) * a.n_bh + prow];
+    const float* phi = (tok == last_char) ? rb_in : rsum_in;
     for (int t = threadIdx.x; t < T; t += blockDim.x) {
         s_phi[t] = phi[static_cast<size_t>(prow) * T + t];
         s_xn[t] = a.x[(static_cast<size_t>(b) * T + t) * V + tok];
@@ -168,8 +182,8 @@ __global__ void __launch_bounds__(128) ctc_update_kernel(const CtcArgs a) {
     if (threadIdx.x == 0) {
         float r_nb, r_b = CTC_NEG;
         int start;
-        if (a.step == 0) { r_nb = s_xn[0]; start = 1; }
-        else { r_nb = CTC_NEG; start = a.step; }
+        if (step == 0) { r_nb = s_xn[0]; start = 1; }
+        else { r_nb = CTC_NEG; start = step; }
         for (int t = 0; t < start - 1 && t < T; ++t) { s_nb[t] = CTC_NEG; s_bl[t] = CTC_NEG; }
         if (start - 1 < T) { s_nb[start - 1] = r_nb; s_bl[start - 1] = CTC_NEG; }
         float pm = r_nb, ps = 1.0f;
@@ -184,18 +198,65 @@ __global__ void __launch_bounds__(128) ctc_update_kernel(const CtcArgs a) {
             s_nb[t] = nb; s_bl[t] = bl;
         }
         float psi = pm + logf(ps);
-        if (tok == a.eos) psi = a.rsum[static_cast<size_t>(prow) * T + a.enc_len[b] - 1];
+        if (tok == a.eos) psi = rsum_in[static_cast<size_t>(prow) * T + a.enc_len[b] - 1];
         if (tok == a.blank && a.eos != a.blank) psi = CTC_NEG;
-        a.psi_out[row] = psi;
+        psi_out[row] = psi;
     }
     __syncthreads();
     for (int t = threadIdx.x; t < T; t += blockDim.x) {
-        a.rb_out[static_cast<size_t>(row) * T + t] = s_bl[t];
-        a.rsum_out[static_cast<size_t>(row) * T + t] = logaddexp_acc(s_nb[t], s_bl[t]);
+        rb_out[static_cast<size_t>(row) * T + t] = s_bl[t];
+        rsum_out[static_cast<size_t>(row) * T + t] = logaddexp_acc(s_nb[t], s_bl[t]);
     }
 }
 
 }  // namespace
+
+// --------------------------------------------------------------------------- CTC greedy (EncoderASR, decoders/ctc.py:335-378)
+// One CTA per frame: optional in-place log_softmax of the row (what the recipe's `log_softmax` module does after ctc_lin) and
+// its arg-max (first index on ties, like torch.max).
+__global__ void __launch_bounds__(256)
+rows_logsoftmax_argmax_kernel(float* __restrict__ x, int V, int do_logsoftmax, int* __restrict__ idx) {
+    __shared__ float s_val[8];
+    __shared__ int s_idx[8];
+    const int row = blockIdx.x, tid = threadIdx.x;
+    float* xr = x + static_cast<size_t>(row) * V;
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int j = tid; j < V; j += 256) {
+        const float v = xr[j];
+        if (v > best || (v == best && j < bi)) { best = v; bi = j; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if ((tid & 31) == 0) { s_val[tid >> 5] = best; s_idx[tid >> 5] = bi; }
+    __syncthreads();
+    best = s_val[0]; bi = s_idx[0];
+    for (int w = 1; w < 8; ++w)
+        if (s_val[w] > best || (s_val[w] == best && s_idx[w] < bi)) { best = s_val[w]; bi = s_idx[w]; }
+    if (idx != nullptr && tid == 0) idx[row] = bi;
+    if (!do_logsoftmax) return;
+    __syncthreads();
+    float sm = 0.0f;
+    for (int j = tid; j < V; j += 256) sm += expf(xr[j] - best);
+    sm = warp_sum(sm);
+    if ((tid & 31) == 0) s_val[tid >> 5] = sm;
+    __syncthreads();
+    float tot = 0.0f;
+    for (int w = 0; w < 8; ++w) tot += s_val[w];
+    const float lse = best + logf(tot);
+    for (int j = tid; j < V; j += 256) xr[j] -= lse;
+}
+
+int rows_logsoftmax_argmax(float* x, int rows, int V, bool do_logsoftmax, int* idx, cudaStream_t stream) {
+    if (rows == 0) return SBK_OK;
+    rows_logsoftmax_argmax_kernel<<<rows, 256, 0, stream>>>(x, V, do_logsoftmax ? 1 : 0, idx);
+    SBK_LAUNCH_CHECK();
+    return SBK_OK;
+}
 
 int ctc_prefix_reset(float* x, float* xb, const int* enc_len, int B, int T, int V, int blank, int beam, float* rsum, float* rb,
                      float* psi_prev, cudaStream_t stream) {
@@ -207,17 +268,17 @@ int ctc_prefix_reset(float* x, float* xb, const int* enc_len, int B, int T, int 
     return SBK_OK;
 }
 
-static CtcArgs make_args(const CtcStep& p) {
+static CtcArgs make_args(const CtcStep& p, int step_adj) {
     CtcArgs a;
-    a.x = p.x; a.xb = p.xb; a.rsum = p.rsum; a.rb = p.rb; a.psi_prev = p.psi_prev; a.enc_len = p.enc_len;
-    a.hist_tok = p.hist_tok; a.hist_pred = p.hist_pred; a.n_bh = p.n_bh; a.step = p.step; a.bos = p.bos; a.T = p.T; a.V = p.V;
+    a.x = p.x; a.xb = p.xb; a.rsum_base = p.rsum_base; a.rb_base = p.rb_base; a.psi_base = p.psi_base; a.enc_len = p.enc_len;
+    a.hist_tok = p.hist_tok; a.hist_pred = p.hist_pred; a.step_ptr = p.step_ptr; a.step_adj = step_adj;
+    a.n_bh = p.n_bh; a.bos = p.bos; a.T = p.T; a.V = p.V;
     a.beam = p.beam; a.blank = p.blank; a.eos = p.eos; a.weight = p.weight; a.out = p.out; a.accumulate = p.accumulate;
-    a.rsum_out = p.rsum_out; a.rb_out = p.rb_out; a.psi_out = p.psi_out;
     return a;
 }
 
 int ctc_prefix_score(const CtcStep& p, cudaStream_t stream) {
-    const CtcArgs a = make_args(p);
+    const CtcArgs a = make_args(p, 0);   // runs before the beam kernel advances the step counters
     static bool attr = false;
     if (!attr) {
         SBK_CUDA_CHECK(cudaFuncSetAttribute(ctc_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -230,7 +291,7 @@ int ctc_prefix_score(const CtcStep& p, cudaStream_t stream) {
 }
 
 int ctc_prefix_update(const CtcStep& p, cudaStream_t stream) {
-    const CtcArgs a = make_args(p);
+    const CtcArgs a = make_args(p, -1);  // runs after it
     ctc_update_kernel<<<p.n_bh, 128, 5 * p.T * 4, stream>>>(a);
     SBK_LAUNCH_CHECK();
     return SBK_OK;

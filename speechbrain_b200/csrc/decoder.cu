@@ -150,8 +150,8 @@ __global__ void __launch_bounds__(SK_WARPS * 32, ((VPL <= 4 && MT == 2) ? 2 : 1)
             __half* dst = a_sm + (warp + 8 * r) * astr;
 #pragma unroll
             for (int i = 0; i < VPL; ++i) {
-                __half2 h0 = __floats2half2_rn(v[r][i].x * rstd * gm[i].x + bt[i].x, v[r][i].y * rstd * gm[i].y + bt[i].y);
-                __half2 h1 = __floats2half2_rn(v[r][i].z * rstd * gm[i].z + bt[i].z, v[r][i].w * rstd * gm[i].w + bt[i].w);
+                __half2 h0 = floats2half2_sat(v[r][i].x * rstd * gm[i].x + bt[i].x, v[r][i].y * rstd * gm[i].y + bt[i].y);
+                __half2 h1 = floats2half2_sat(v[r][i].z * rstd * gm[i].z + bt[i].z, v[r][i].w * rstd * gm[i].w + bt[i].w);
                 uint2 u;
                 u.x = *reinterpret_cast<uint32_t*>(&h0);
                 u.y = *reinterpret_cast<uint32_t*>(&h1);
@@ -217,22 +217,22 @@ __global__ void __launch_bounds__(SK_WARPS * 32, ((VPL <= 4 && MT == 2) ? 2 : 1)
             for (int w = 0; w < SK_WARPS; ++w) v += red[w][r][j];
             if (a.bias) v += __ldg(a.bias + col);
             switch (a.epi) {
-                case SK_F16: reinterpret_cast<__half*>(a.out)[static_cast<size_t>(row) * a.ldo + col] = __float2half_rn(v); break;
+                case SK_F16: reinterpret_cast<__half*>(a.out)[static_cast<size_t>(row) * a.ldo + col] = float2half_sat(v); break;
                 case SK_F16_RELU:
-                    reinterpret_cast<__half*>(a.out)[static_cast<size_t>(row) * a.ldo + col] = __float2half_rn(fmaxf(v, 0.0f));
+                    reinterpret_cast<__half*>(a.out)[static_cast<size_t>(row) * a.ldo + col] = float2half_sat(fmaxf(v, 0.0f));
                     break;
                 case SK_F16_GELU:
-                    reinterpret_cast<__half*>(a.out)[static_cast<size_t>(row) * a.ldo + col] = __float2half_rn(gelu_erf_f(v));
+                    reinterpret_cast<__half*>(a.out)[static_cast<size_t>(row) * a.ldo + col] = float2half_sat(gelu_erf_f(v));
                     break;
                 case SK_F32: reinterpret_cast<float*>(a.out)[static_cast<size_t>(row) * a.ldo + col] = v; break;
                 case SK_RESID: reinterpret_cast<float*>(a.out)[static_cast<size_t>(row) * a.ldo + col] += v; break;
                 case SK_QKV_CACHE: {
                     if (col < a.d) {
-                        reinterpret_cast<__half*>(a.out)[static_cast<size_t>(row) * a.ldo + col] = __float2half_rn(v * a.q_scale);
+                        reinterpret_cast<__half*>(a.out)[static_cast<size_t>(row) * a.ldo + col] = float2half_sat(v * a.q_scale);
                     } else if (col < 2 * a.d) {
-                        a.kcache[(static_cast<size_t>(row) * a.S_max + step) * a.d + (col - a.d)] = __float2half_rn(v);
+                        a.kcache[(static_cast<size_t>(row) * a.S_max + step) * a.d + (col - a.d)] = float2half_sat(v);
                     } else {
-                        a.vcache[(static_cast<size_t>(row) * a.S_max + step) * a.d + (col - 2 * a.d)] = __float2half_rn(v);
+                        a.vcache[(static_cast<size_t>(row) * a.S_max + step) * a.d + (col - 2 * a.d)] = float2half_sat(v);
                     }
                     break;
                 }
@@ -421,7 +421,7 @@ __global__ void __launch_bounds__(DA_WARPS * 32, 4) dec_attention_kernel(const D
             num += part_o[w][threadIdx.x] * sc;
             den += part_l[w] * sc;
         }
-        a.out[static_cast<size_t>(r) * a.ldo + h * 64 + threadIdx.x] = __float2half_rn(num / den);
+        a.out[static_cast<size_t>(r) * a.ldo + h * 64 + threadIdx.x] = float2half_sat(num / den);
     }
 }
 
@@ -542,7 +542,7 @@ dec_cross_attention_tma_kernel(const __grid_constant__ CUtensorMap tmap_kv, cons
             num += part_o[w][threadIdx.x] * sc;
             den += part_l[w] * sc;
         }
-        a.out[static_cast<size_t>(r) * a.ldo + h * 64 + threadIdx.x] = __float2half_rn(num / den);
+        a.out[static_cast<size_t>(r) * a.ldo + h * 64 + threadIdx.x] = float2half_sat(num / den);
     }
 }
 
@@ -674,7 +674,7 @@ dec_cross_attention_persist_kernel(const __grid_constant__ CUtensorMap tmap_kv, 
                 num += part_o[w][threadIdx.x] * scl;
                 den += part_l[w] * scl;
             }
-            a.out[static_cast<size_t>(r) * a.ldo + h * 64 + threadIdx.x] = __float2half_rn(num / den);
+            a.out[static_cast<size_t>(r) * a.ldo + h * 64 + threadIdx.x] = float2half_sat(num / den);
         }
         __syncthreads();  // partials consumed before the next item overwrites them
     }
@@ -859,7 +859,7 @@ layernorm_dual_kernel(float* __restrict__ x, __half* __restrict__ x16, const flo
     for (int j = lane; j < D; j += 32) {
         const float y = (xr[j] - mean) * rstd * __ldg(gamma + j) + __ldg(beta + j);
         if (write_f32) xr[j] = y;
-        x16[static_cast<size_t>(row) * D + j] = __float2half_rn(y);
+        x16[static_cast<size_t>(row) * D + j] = float2half_sat(y);
     }
 }
 
@@ -1098,7 +1098,7 @@ __global__ void __launch_bounds__(BS_THREADS) beam_step_kernel(const BeamArgs a)
             const float v = a.lm_emb[static_cast<size_t>(s_wtok[k]) * a.lm_d + c] * a.lm_sqrt_d +
                             a.lm_pe[static_cast<size_t>(step + 1) * a.lm_d + c];
             a.lm_x_next[static_cast<size_t>(row0 + k) * a.lm_d + c] = v;
-            a.lm_x16_next[static_cast<size_t>(row0 + k) * a.lm_d + c] = __float2half_rn(v);
+            a.lm_x16_next[static_cast<size_t>(row0 + k) * a.lm_d + c] = float2half_sat(v);
         }
         if (tid < beam) a.tok_cache[static_cast<size_t>(row0 + tid) * a.S_max + step + 1] = s_wtok[tid];
     }
@@ -1127,7 +1127,7 @@ __global__ void beam_reset_kernel(int n_bh, int beam, int S_max, int bos, int* s
         for (int i = threadIdx.x; i < lm_d; i += blockDim.x) {
             const float v = lm_emb[static_cast<size_t>(bos) * lm_d + i] * lm_sqrt_d + lm_pe[i];
             lm_x[static_cast<size_t>(r) * lm_d + i] = v;
-            lm_x16[static_cast<size_t>(r) * lm_d + i] = __float2half_rn(v);
+            lm_x16[static_cast<size_t>(r) * lm_d + i] = float2half_sat(v);
         }
         if (threadIdx.x == 0) tok_cache[static_cast<size_t>(r) * S_max] = bos;
     }

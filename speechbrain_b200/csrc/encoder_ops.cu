@@ -63,7 +63,7 @@ layernorm_rows_kernel(const float* __restrict__ x, void* __restrict__ out, const
             float y3 = (v[4 * i + 3] - mean) * rstd * g.w + b.w;
             if (act_silu) { y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3); }
             if constexpr (OUT_HALF) {
-                __half2 h0 = __floats2half2_rn(y0, y1), h1 = __floats2half2_rn(y2, y3);
+                __half2 h0 = floats2half2_sat(y0, y1), h1 = floats2half2_sat(y2, y3);
                 uint2 u;
                 u.x = *reinterpret_cast<uint32_t*>(&h0);
                 u.y = *reinterpret_cast<uint32_t*>(&h1);
@@ -95,7 +95,7 @@ int layernorm_rows(const float* x, void* out, bool out_half, const float* gamma,
 __global__ void cast_f32_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, size_t n) {
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<size_t>(gridDim.x) * blockDim.x)
-        out[i] = __float2half_rn(in[i]);
+        out[i] = float2half_sat(in[i]);
 }
 int cast_f32_f16(const float* in, __half* out, size_t n, cudaStream_t stream) {
     if (n == 0) return SBK_OK;
@@ -237,7 +237,7 @@ dwconv_ln_swish_kernel(const float* __restrict__ glu, int T, int D, int K, const
                 const float2 cv = *reinterpret_cast<const float2*>(c + j);
                 const float y0 = silu_f((cv.x - mean) * rstd * g2[p].x + b2[p].x);
                 const float y1 = silu_f((cv.y - mean) * rstd * g2[p].y + b2[p].y);
-                *reinterpret_cast<__half2*>(o + j) = __floats2half2_rn(y0, y1);
+                *reinterpret_cast<__half2*>(o + j) = floats2half2_sat(y0, y1);
             }
         }
     }
@@ -299,7 +299,7 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
-    __half2 h = __floats2half2_rn(a, b);
+    __half2 h = floats2half2_sat(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
@@ -348,8 +348,8 @@ encoder_attention_kernel(const __half* __restrict__ qkv, int ld, int T, const in
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const float q = __half2float(hv[e]);
-                qu[e] = __float2half_rn((q + __ldg(pos_u + h * DH + v4 * 4 + e)) * scale);
-                qv[e] = __float2half_rn((q + __ldg(pos_v + h * DH + v4 * 4 + e)) * scale);
+                qu[e] = float2half_sat((q + __ldg(pos_u + h * DH + v4 * 4 + e)) * scale);
+                qv[e] = float2half_sat((q + __ldg(pos_v + h * DH + v4 * 4 + e)) * scale);
             }
             *reinterpret_cast<uint2*>(Qs + r * STR + v4 * 4) = *reinterpret_cast<uint2*>(qu);
             *reinterpret_cast<uint2*>(Qv + r * STR + v4 * 4) = *reinterpret_cast<uint2*>(qv);

@@ -99,7 +99,8 @@ struct AsrModel {
     int wsB = 0, wsL = 0, ws_rows = 0, ws_steps = 0;
     struct Buf {
         float *wav, *feats, *x, *glu, *enc_out, *act1_f, *cnn_f, *dx, *logits, *score, *seq_scores, *lnout;
-        int *utt_max, *enc_len, *tokens, *step, *has_ended, *ended_count, *pred, *lineage, *finished;
+        int *utt_max, *enc_len, *tokens, *step, *has_ended, *ended_count, *pred, *lineage, *finished, *hist_tok, *hist_pred;
+        float *hist_score, *hist_lp;
         float* rel_len;
         float *lx, *lh32, *lm_logits, *lm_extra;
         __half *lx16, *lq16, *latt16, *lf16, *lh16, *lkc, *lvc;
@@ -123,6 +124,11 @@ struct AsrModel {
     HostGroupKey hgroup_key{};
     cudaGraphExec_t hgroup_graph = nullptr;
     long long hgroup_nodes = 0;
+    // beam search: ONE graph of a whole search step (decoder layers + LM step + CTC scorer + beam kernel), replayed per step
+    struct BeamKey { sbk_beam_params p; int B, T, rows, S_max, fuse_ln, tc_rows; };
+    BeamKey beam_key{};
+    cudaGraphExec_t beam_graph = nullptr;
+    long long beam_nodes = 0;
     struct PipeKey { const void *wav, *rel, *enc, *pred, *score; int B, L, steps, bos, eos; };
     PipeKey pipe_key{};
     cudaGraphExec_t pipe_graph = nullptr;
@@ -462,6 +468,7 @@ int asr_clone(AsrModel* src, AsrModel** out) {
     m->pipe_graph = nullptr;
     m->group_graph = nullptr;
     m->hgroup_graph = nullptr;
+    m->beam_graph = nullptr;
     m->gwav = m->grel = nullptr; m->gwav_cap = 0;
     m->copy_stream = nullptr; m->ev_fork = nullptr;
     for (auto& e : m->ev_ready) e = nullptr;
@@ -484,6 +491,7 @@ void asr_destroy(AsrModel* m) {
     if (m->pipe_graph) cudaGraphExecDestroy(m->pipe_graph);
     if (m->group_graph) cudaGraphExecDestroy(m->group_graph);
     if (m->hgroup_graph) cudaGraphExecDestroy(m->hgroup_graph);
+    if (m->beam_graph) cudaGraphExecDestroy(m->beam_graph);
     cudaFree(m->gwav);
     if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
     if (m->ev_fork) cudaEventDestroy(m->ev_fork);
@@ -506,6 +514,7 @@ static void drop_graphs(AsrModel* m) {
     if (m->pipe_graph) { cudaGraphExecDestroy(m->pipe_graph); m->pipe_graph = nullptr; }
     if (m->group_graph) { cudaGraphExecDestroy(m->group_graph); m->group_graph = nullptr; }
     if (m->hgroup_graph) { cudaGraphExecDestroy(m->hgroup_graph); m->hgroup_graph = nullptr; }
+    if (m->beam_graph) { cudaGraphExecDestroy(m->beam_graph); m->beam_graph = nullptr; }
 }
 
 static void frames(const sbk_asr_config& c, int L, int* T0, int* T1, int* T2) {
@@ -535,6 +544,7 @@ static int ensure_workspace(AsrModel* m, int B, int L, int rows, int steps) {
     sz((size_t)Ld * rows * S * d * 2); sz((size_t)Ld * rows * S * d * 2);
     sz((size_t)rows * d * 2); sz((size_t)rows * d * 2); sz((size_t)rows * d * 2); sz((size_t)rows * F * 2);
     sz((size_t)2 * rows * S * 4); sz(B * 4 + 64); sz((size_t)2 * rows * 4); sz((size_t)rows * d * 4);
+    sz((size_t)rows * S * 4); sz((size_t)rows * S * 4); sz((size_t)rows * S * 4); sz((size_t)rows * S * 4);
     const size_t dl = m->has_lm ? c.lm_d_model : 0, Fl = m->has_lm ? c.lm_d_ffn : 0, Ll = m->has_lm ? c.lm_layers : 0;
     if (m->has_lm) {
         sz(rows * dl * 4); sz(rows * dl * 4); sz((size_t)rows * c.vocab * 4); sz((size_t)rows * c.vocab * 4);
@@ -569,6 +579,8 @@ static int ensure_workspace(AsrModel* m, int B, int L, int rows, int steps) {
     TAKE(df16, __half, (size_t)rows * F * 2);
     TAKE(lineage, int, (size_t)2 * rows * S * 4); TAKE(finished, int, B * 4 + 64); TAKE(seq_scores, float, (size_t)2 * rows * 4);
     TAKE(lnout, float, (size_t)rows * d * 4);
+    TAKE(hist_tok, int, (size_t)rows * S * 4); TAKE(hist_pred, int, (size_t)rows * S * 4);
+    TAKE(hist_score, float, (size_t)rows * S * 4); TAKE(hist_lp, float, (size_t)rows * S * 4);
     if (m->has_lm) {
         TAKE(lx, float, rows * dl * 4); TAKE(lh32, float, rows * dl * 4); TAKE(lm_logits, float, (size_t)rows * c.vocab * 4);
         TAKE(lm_extra, float, (size_t)rows * c.vocab * 4);
@@ -577,7 +589,7 @@ static int ensure_workspace(AsrModel* m, int B, int L, int rows, int steps) {
         TAKE(lkc, __half, Ll * rows * S * dl * 2); TAKE(lvc, __half, Ll * rows * S * dl * 2); TAKE(tok_cache, int, (size_t)rows * S * 4);
         if (!b.tok_cache) { set_error("workspace carve failed (LM)"); return SBK_ERR_NOMEM; }
     }
-    if (!b.df16 || !b.seq_scores || !b.lnout) { set_error("workspace carve failed"); return SBK_ERR_NOMEM; }
+    if (!b.df16 || !b.seq_scores || !b.lnout || !b.hist_lp) { set_error("workspace carve failed"); return SBK_ERR_NOMEM; }
 #undef TAKE
     m->wsB = B; m->wsL = L; m->ws_rows = rows; m->ws_steps = steps;
     return SBK_OK;
@@ -837,8 +849,8 @@ static int enqueue_lm_step(AsrModel* m, int rows, int S_max, float temperature, 
 // Beam search (decoders/seq2seq.py:1632-1723 with scorer=None): the device runs decoder step + beam_step_kernel and
 // records the per-step (token, predecessor, normalised score, log-prob) history; hypothesis bookkeeping is replayed
 // on the host from that history (speechbrain_b200/decoders/seq2seq.py).
-static int run_beam(AsrModel* m, int B, int T, const sbk_beam_params& p, int* hist_tok, int* hist_pred, float* hist_score,
-                    float* hist_lp, int* steps_done, cudaStream_t st) {
+static int run_beam(AsrModel* m, int B, int T, const sbk_beam_params& p, int* hist_tok_out, int* hist_pred_out,
+                    float* hist_score_out, float* hist_lp_out, int* steps_done, cudaStream_t st) {
     const sbk_asr_config& c = m->cfg;
     AsrModel::Buf& b = m->b;
     const int d = c.d_model, Ld = c.num_decoder_layers, M = B * T, beam = p.beam_size, rows = B * beam, S_max = m->ws_steps + 1;
@@ -856,6 +868,8 @@ static int run_beam(AsrModel* m, int B, int T, const sbk_beam_params& p, int* hi
     const bool use_lm = p.lm_weight != 0.0f;
     SBK_REQUIRE(!use_lm || m->has_lm, "beam: lm_weight != 0 but this handle has no TransformerLM weights");
     const bool use_ctc = p.ctc_weight != 0.0f;
+    // the search history lives in the workspace (fixed addresses: the step graph bakes them in) and is copied out at the end
+    int* hist_tok = b.hist_tok; int* hist_pred = b.hist_pred; float* hist_score = b.hist_score; float* hist_lp = b.hist_lp;
     CtcStep cs{};
     if (use_ctc) {  // CTCScorer.reset_mem (scorer.py:243-249) + CTCPrefixScore.__init__ (ctc.py:46-78)
         SBK_REQUIRE(m->w_ctc, "beam: ctc_weight != 0 but this handle has no ctc_lin weights");
@@ -867,6 +881,7 @@ static int run_beam(AsrModel* m, int B, int T, const sbk_beam_params& p, int* hi
         AsrModel::CtcBuf& cb = m->ctc;
         if (need > cb.cap) {
             if (cb.base) { SBK_CUDA_CHECK(cudaStreamSynchronize(st)); cudaFree(cb.base); cb.base = nullptr; cb.cap = 0; }
+            if (m->beam_graph) { cudaGraphExecDestroy(m->beam_graph); m->beam_graph = nullptr; }
             if (cudaMalloc(&cb.base, need) != cudaSuccess) { set_error("beam: CTC scorer cudaMalloc(%zu) failed", need); return SBK_ERR_NOMEM; }
             cb.cap = need;
         }
@@ -882,6 +897,7 @@ static int run_beam(AsrModel* m, int B, int T, const sbk_beam_params& p, int* hi
         RC(gemm_f16(b.enc16, d, m->w_ctc, d, e, M, c.vocab, d, st));
         RC(ctc_prefix_reset(cb.x, cb.xb, b.enc_len, B, T, c.vocab, p.blank_index, beam, cb.rsum, cb.rb, cb.psi, st));
         cs.x = cb.x; cs.xb = cb.xb; cs.enc_len = b.enc_len; cs.hist_tok = hist_tok; cs.hist_pred = hist_pred; cs.n_bh = rows;
+        cs.rsum_base = cb.rsum; cs.rb_base = cb.rb; cs.psi_base = cb.psi; cs.step_ptr = b.step;
         cs.bos = p.bos; cs.T = T; cs.V = c.vocab; cs.beam = beam; cs.blank = p.blank_index; cs.eos = p.eos;
         cs.weight = p.ctc_weight; cs.out = cb.add; cs.accumulate = use_lm ? 1 : 0;
     }
@@ -900,24 +916,44 @@ static int run_beam(AsrModel* m, int B, int T, const sbk_beam_params& p, int* hi
     a.temperature = p.temperature; a.eos_threshold = p.eos_threshold; a.minus_inf = p.minus_inf; a.min_steps = p.min_steps;
     a.eos = p.eos; a.use_eos_threshold = p.using_eos_threshold; a.length_norm = p.length_normalization;
     a.emb = m->emb; a.pe = m->dec_pe; a.d = d; a.x_next = b.dx;
+    // one whole search step; every kernel takes the step index from the device counters, so the sequence is the same
+    // for every step and can be replayed from a graph
+    auto enqueue_step = [&](cudaStream_t s_) -> int {
+        RC(enqueue_decode_layers(m, rows, beam, T, S_max, b.lineage, s_));
+        if (use_lm) RC(enqueue_lm_step(m, rows, S_max, p.lm_temperature, p.lm_weight, s_));
+        if (use_ctc) RC(ctc_prefix_score(cs, s_));  // ScorerBuilder.score (ctc after transformerlm) ...
+        RC(beam_step(a, B, s_));
+        if (use_ctc) RC(ctc_prefix_update(cs, s_));  // ... then permute_scorer_mem on the survivors
+        return SBK_OK;
+    };
+    const bool use_graph = getenv("SBK_NO_GRAPH") == nullptr;
+    if (use_graph) {
+        AsrModel::BeamKey key;
+        memset(&key, 0, sizeof(key));
+        key.p = p; key.B = B; key.T = T; key.rows = rows; key.S_max = S_max; key.fuse_ln = m->fuse_dec_ln; key.tc_rows = m->dec_tc_rows;
+        if (m->beam_graph == nullptr || memcmp(&key, &m->beam_key, sizeof(key)) != 0) {
+            if (m->beam_graph) { cudaGraphExecDestroy(m->beam_graph); m->beam_graph = nullptr; }
+            if (!m->cap_stream) SBK_CUDA_CHECK(cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
+            cudaGraph_t g;
+            SBK_CUDA_CHECK(cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal));
+            launch_count_begin_capture();
+            int rc = enqueue_step(m->cap_stream);
+            m->beam_nodes = launch_count_end_capture();
+            cudaError_t ce = cudaStreamEndCapture(m->cap_stream, &g);
+            if (rc) return rc;
+            SBK_CUDA_CHECK(ce);
+            SBK_CUDA_CHECK(cudaGraphInstantiate(&m->beam_graph, g, 0));
+            cudaGraphDestroy(g);
+            m->beam_key = key;
+        }
+    }
     const int check_every = m->poll_every > 0 ? m->poll_every : p.max_steps;
     int s = 0;
     while (s < p.max_steps) {
         const int chunk = std::min(check_every, p.max_steps - s);
         for (int i = 0; i < chunk; ++i) {
-            RC(enqueue_decode_layers(m, rows, beam, T, S_max, b.lineage, st));
-            if (use_lm) RC(enqueue_lm_step(m, rows, S_max, p.lm_temperature, p.lm_weight, st));
-            if (use_ctc) {  // ScorerBuilder.score (ctc after transformerlm), then permute_scorer_mem on the survivors
-                const int cur = (s + i) & 1;
-                const size_t rt = (size_t)rows * T;
-                cs.step = s + i;
-                cs.rsum = m->ctc.rsum + cur * rt; cs.rb = m->ctc.rb + cur * rt; cs.psi_prev = m->ctc.psi + cur * rows;
-                cs.rsum_out = m->ctc.rsum + (cur ^ 1) * rt; cs.rb_out = m->ctc.rb + (cur ^ 1) * rt;
-                cs.psi_out = m->ctc.psi + (cur ^ 1) * rows;
-                RC(ctc_prefix_score(cs, st));
-            }
-            RC(beam_step(a, B, st));
-            if (use_ctc) RC(ctc_prefix_update(cs, st));
+            if (use_graph) { SBK_CUDA_CHECK(cudaGraphLaunch(m->beam_graph, st)); launch_count_add(m->beam_nodes); }
+            else RC(enqueue_step(st));
         }
         s += chunk;
         if (s < p.max_steps && m->poll_every > 0) {  // `_check_full_beams` (:806-822), polled once per chunk
@@ -926,6 +962,11 @@ static int run_beam(AsrModel* m, int B, int T, const sbk_beam_params& p, int* hi
             if (*m->host_flag >= B) break;
         }
     }
+    const size_t hb = (size_t)s * rows * 4;
+    if (hist_tok_out) SBK_CUDA_CHECK(cudaMemcpyAsync(hist_tok_out, hist_tok, hb, cudaMemcpyDeviceToDevice, st));
+    if (hist_pred_out) SBK_CUDA_CHECK(cudaMemcpyAsync(hist_pred_out, hist_pred, hb, cudaMemcpyDeviceToDevice, st));
+    if (hist_score_out) SBK_CUDA_CHECK(cudaMemcpyAsync(hist_score_out, hist_score, hb, cudaMemcpyDeviceToDevice, st));
+    if (hist_lp_out) SBK_CUDA_CHECK(cudaMemcpyAsync(hist_lp_out, hist_lp, hb, cudaMemcpyDeviceToDevice, st));
     *steps_done = s;
     return SBK_OK;
 }
@@ -1012,7 +1053,7 @@ __global__ void lm_teacher_embed_kernel(const int* __restrict__ tokens, int L, i
     for (int i = threadIdx.x; i < d; i += blockDim.x) {
         const float v = emb[static_cast<size_t>(tok) * d + i] * sqrt_d + pe[static_cast<size_t>(s) * d + i];
         x[static_cast<size_t>(r) * d + i] = v;
-        x16[static_cast<size_t>(r) * d + i] = __float2half_rn(v);
+        x16[static_cast<size_t>(r) * d + i] = float2half_sat(v);
     }
     if (threadIdx.x == 0) step_arr[r] = s;
 }
@@ -1573,6 +1614,44 @@ int sbk_asr_transcribe_greedy_host_async(sbk_asr* mm, const float* wav_host, con
                                          int* steps_done, void* stream) {
     return transcribe_greedy_host_impl(mm, wav_host, rel_len_host, B, L, max_steps, bos, eos, pred_host, score_host,
                                        steps_done, stream, false);
+}
+
+// torch.max(dim=-1) indices of a [rows, V] fp32 matrix (ctc_greedy_decode's arg-max, decoders/ctc.py:375)
+int sbk_rows_argmax_f32(const float* x_dev, int rows, int V, int* idx_dev, void* stream) {
+    SBK_REQUIRE(x_dev && idx_dev && rows >= 0 && V >= 1, "rows_argmax: bad arguments");
+    return rows_logsoftmax_argmax(const_cast<float*>(x_dev), rows, V, false, idx_dev, static_cast<cudaStream_t>(stream));
+}
+
+// CTC head of an encoder-only recogniser (EncoderASR, inference/ASR.py:176-389): enc_dev [B, T, d] fp32 (NULL = the encoder
+// states left in the workspace by the previous encode call) -> log_probs_dev [B, T, V] fp32 = log_softmax(ctc_lin(enc)) (optional)
+// and argmax_dev [B, T] int32 (optional) -- the per-frame arg-max ctc_greedy_decode (decoders/ctc.py:335-378) starts from.
+int sbk_asr_ctc_head(sbk_asr* mm, const float* enc_dev, int B, int T, float* log_probs_dev, int* argmax_dev, void* stream) {
+    AsrModel* m = reinterpret_cast<AsrModel*>(mm);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const sbk_asr_config& c = m->cfg;
+    SBK_REQUIRE(m->w_ctc != nullptr, "ctc_head: this handle was created without ctc_lin.w.* weights");
+    SBK_REQUIRE(B >= 1 && T >= 1 && (log_probs_dev || argmax_dev), "ctc_head: bad arguments");
+    const int L = std::max(m->wsL, ((T - 1) * 4) * c.hop);
+    RC(ensure_workspace(m, std::max(B, m->wsB), L, std::max(B, m->ws_rows), std::max(1, m->ws_steps)));
+    AsrModel::Buf& b = m->b;
+    const size_t M = (size_t)B * T, V = c.vocab;
+    if (enc_dev) SBK_CUDA_CHECK(cudaMemcpyAsync(b.enc_out, enc_dev, M * c.d_model * 4, cudaMemcpyDeviceToDevice, st));
+    float* logits = log_probs_dev;
+    if (!logits) {  // arg-max only: the logits live in the (lazily grown) CTC scratch buffer
+        AsrModel::CtcBuf& cb = m->ctc;
+        const size_t need = M * V * 4 + 256;
+        if (need > cb.cap) {
+            if (cb.base) { SBK_CUDA_CHECK(cudaStreamSynchronize(st)); cudaFree(cb.base); cb.base = nullptr; cb.cap = 0; }
+            if (cudaMalloc(&cb.base, need) != cudaSuccess) { set_error("ctc_head: cudaMalloc(%zu) failed", need); return SBK_ERR_NOMEM; }
+            cb.cap = need;
+        }
+        logits = cb.base;
+    }
+    RC(cast_f32_f16(b.enc_out, b.enc16, M * c.d_model, st));
+    GemmEpilogue e;
+    e.mode = EPI_F32; e.bias = m->b_ctc; e.out = logits; e.ldo = c.vocab;
+    RC(gemm_f16(b.enc16, c.d_model, m->w_ctc, c.d_model, e, (int)M, c.vocab, c.d_model, st));
+    return rows_logsoftmax_argmax(logits, (int)M, c.vocab, log_probs_dev != nullptr, argmax_dev, st);
 }
 
 // TransformerASR.decode(tgt, encoder_out, enc_len) (TransformerASR.py:426-473): tgt_dev [n, S] int32 token ids (teacher

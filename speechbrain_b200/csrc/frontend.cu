@@ -90,7 +90,7 @@ conv1_ln_kernel(const float* __restrict__ feats, int T0, int F0, int T1, int F1,
             const float2 be = __ldg(reinterpret_cast<const float2*>(beta + gi));
             const float y0 = leaky((va[f1] - mean) * rstd * g.x + be.x);
             const float y1 = leaky((vb[f1] - mean) * rstd * g.y + be.y);
-            *reinterpret_cast<__half2*>(out_h + obase + gi) = __floats2half2_rn(y0, y1);
+            *reinterpret_cast<__half2*>(out_h + obase + gi) = floats2half2_sat(y0, y1);
             if (out_f) *reinterpret_cast<float2*>(out_f + obase + gi) = make_float2(y0, y1);
         }
 }
@@ -205,7 +205,7 @@ conv2_ln_kernel(const __half* __restrict__ act1, int T1, int F1, int T2, int F2,
             const size_t ob = (static_cast<size_t>(b) * T2 + t) * n;
             for (int i = lane; i < n; i += 32) {
                 const float y = leaky((src[(i >> 5) * 33 + (i & 31)] - mean) * rstd * __ldg(gamma + i) + __ldg(beta + i));
-                out_h[ob + i] = __float2half_rn(y);
+                out_h[ob + i] = float2half_sat(y);
                 if (out_f) out_f[ob + i] = y;
             }
         }

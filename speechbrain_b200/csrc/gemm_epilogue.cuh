@@ -69,8 +69,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const uint
             if (full) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 8) {
-                    __half2 h0 = __floats2half2_rn(v[j], v[j + 1]), h1 = __floats2half2_rn(v[j + 2], v[j + 3]);
-                    __half2 h2 = __floats2half2_rn(v[j + 4], v[j + 5]), h3 = __floats2half2_rn(v[j + 6], v[j + 7]);
+                    __half2 h0 = floats2half2_sat(v[j], v[j + 1]), h1 = floats2half2_sat(v[j + 2], v[j + 3]);
+                    __half2 h2 = floats2half2_sat(v[j + 4], v[j + 5]), h3 = floats2half2_sat(v[j + 6], v[j + 7]);
                     uint4 u;
                     u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
                     u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
@@ -79,7 +79,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const uint
             } else {
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
-                    if (col0 + j < N) o[j] = __float2half_rn(v[j]);
+                    if (col0 + j < N) o[j] = float2half_sat(v[j]);
             }
             break;
         }
@@ -126,8 +126,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const uint
                      (static_cast<size_t>(row) * e.S_max + __ldg(e.step_ptr + row)) * e.qkv_d + c;
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
-                __half2 h0 = __floats2half2_rn(v[j], v[j + 1]), h1 = __floats2half2_rn(v[j + 2], v[j + 3]);
-                __half2 h2 = __floats2half2_rn(v[j + 4], v[j + 5]), h3 = __floats2half2_rn(v[j + 6], v[j + 7]);
+                __half2 h0 = floats2half2_sat(v[j], v[j + 1]), h1 = floats2half2_sat(v[j + 2], v[j + 3]);
+                __half2 h2 = floats2half2_sat(v[j + 4], v[j + 5]), h3 = floats2half2_sat(v[j + 6], v[j + 7]);
                 uint4 u;
                 u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
                 u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
@@ -165,8 +165,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const uint
             __half* o = reinterpret_cast<__half*>(e.out) + static_cast<size_t>(row) * e.ldo + col0;
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
-                __half2 h0 = __floats2half2_rn(v[j], v[j + 1]), h1 = __floats2half2_rn(v[j + 2], v[j + 3]);
-                __half2 h2 = __floats2half2_rn(v[j + 4], v[j + 5]), h3 = __floats2half2_rn(v[j + 6], v[j + 7]);
+                __half2 h0 = floats2half2_sat(v[j], v[j + 1]), h1 = floats2half2_sat(v[j + 2], v[j + 3]);
+                __half2 h2 = floats2half2_sat(v[j + 4], v[j + 5]), h3 = floats2half2_sat(v[j + 6], v[j + 7]);
                 uint4 u;
                 u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
                 u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
@@ -284,8 +284,8 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmEpilogue& e, 
             }
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
-                __half2 h0 = __floats2half2_rn(v[j], v[j + 1]), h1 = __floats2half2_rn(v[j + 2], v[j + 3]);
-                __half2 h2 = __floats2half2_rn(v[j + 4], v[j + 5]), h3 = __floats2half2_rn(v[j + 6], v[j + 7]);
+                __half2 h0 = floats2half2_sat(v[j], v[j + 1]), h1 = floats2half2_sat(v[j + 2], v[j + 3]);
+                __half2 h2 = floats2half2_sat(v[j + 4], v[j + 5]), h3 = floats2half2_sat(v[j + 6], v[j + 7]);
                 uint4 u;
                 u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
                 u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
@@ -333,8 +333,8 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmEpilogue& e, 
                 x1 = make_float4(b0, b1, b2, b3);
             }
             if (row < M) {
-                __half2 h0 = __floats2half2_rn(x0.x, x0.y), h1 = __floats2half2_rn(x0.z, x0.w);
-                __half2 h2 = __floats2half2_rn(x1.x, x1.y), h3 = __floats2half2_rn(x1.z, x1.w);
+                __half2 h0 = floats2half2_sat(x0.x, x0.y), h1 = floats2half2_sat(x0.z, x0.w);
+                __half2 h2 = floats2half2_sat(x1.x, x1.y), h3 = floats2half2_sat(x1.z, x1.w);
                 uint4 u;
                 u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
                 u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);

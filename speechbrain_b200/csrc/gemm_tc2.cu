@@ -12,6 +12,7 @@
 // warps 2..5 epilogue.  TMEM holds two 256-column accumulator buffers, so the epilogue of tile i overlaps
 // the main loop of tile i+1.
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -88,11 +89,27 @@ __device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t desc_a, u
         : "memory");
 }
 // arrive (once) on the barrier at this offset in BOTH CTAs when all prior MMAs of this thread complete
-__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
-    const uint16_t mask = 3;
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint32_t lead_rank) {
+    const uint16_t mask = static_cast<uint16_t>(3u << lead_rank);
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(smem_u32(bar)), "h"(mask)
                  : "memory");
+}
+__device__ __forceinline__ void umma_commit_mask(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
+// 2-SM TMA load multicast to the CTAs in `mask` (same shared-memory offset in each; each destination's bytes are counted on
+// the barrier at this offset of ITS pair leader)
+__device__ __forceinline__ void tma_load_2d_2sm_mc(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                                   uint16_t mask) {
+    const uint32_t bar_leader = smem_u32(bar) & 0xFEFFFFFFu;
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_leader), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_result, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
@@ -104,10 +121,12 @@ __device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols)
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
+// Cluster size is a launch attribute: 2 (one pair) or 4 (two pairs working on the two n-neighbour tiles of the same 256
+// rows, so that both pairs pull the same A tiles from L2 at the same time -- see gemm_f16_2cta).
 template <int MODE, int ACT, int EW, int BN = G2_BN, int ST = G2_STAGES>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EW, 1)
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                const GemmEpilogue epi, int M, int N, int K) {
+                const __grid_constant__ CUtensorMap tmap_a64, const GemmEpilogue epi, int M, int N, int K, int mc) {
     using C = G2Cfg<BN, ST>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -118,7 +137,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
+    const uint32_t crank = cluster_ctarank();
+    const uint32_t rank = crank & 1u;        // rank inside the CTA pair
+    const uint32_t lead_rank = crank & ~1u;  // cluster rank of this pair's leader
     const bool leader = rank == 0;
     const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
     const int n_tiles = (N + BN - 1) / BN, m_tiles = (M + 2 * G2_BM - 1) / (2 * G2_BM);
@@ -130,7 +151,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         tma_prefetch_desc(&tmap_b);
         for (int s = 0; s < ST; ++s) {
             mbar_init(&full_bar[s], 2);   // leader's expect_tx arrive + the peer's remote arrive
-            mbar_init(&empty_bar[s], 1);  // multicast tcgen05.commit
+            mbar_init(&empty_bar[s], mc ? 2 : 1);  // multicast tcgen05.commit (A-multicast: of both pairs of the cluster)
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full_bar[i], 1);   // multicast tcgen05.commit
@@ -157,10 +178,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                     const uint32_t ph = (it / ST) & 1;
                     mbar_wait_b(&empty_bar[s], ph ^ 1, 1);
                     uint8_t* a_dst = smem + s * C::STAGE_BYTES;
-                    tma_load_2d_2sm(a_dst, &tmap_a, &full_bar[s], kb * G2_BK, m_row);
+                    if (mc) {  // this CTA fetches half of its 128 A rows and multicasts them to its twin in the other pair
+                        const int half = static_cast<int>(crank >> 1);
+                        tma_load_2d_2sm_mc(a_dst + half * (G2_A_BYTES / 2), &tmap_a64, &full_bar[s], kb * G2_BK,
+                                           m_row + half * (G2_BM / 2), static_cast<uint16_t>((1u << crank) | (1u << (crank ^ 2u))));
+                    } else {
+                        tma_load_2d_2sm(a_dst, &tmap_a, &full_bar[s], kb * G2_BK, m_row);
+                    }
                     tma_load_2d_2sm(a_dst + G2_A_BYTES, &tmap_b, &full_bar[s], kb * G2_BK, n_row);
                     if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * C::STAGE_BYTES);
-                    else mbar_arrive_remote(&full_bar[s], 0);
+                    else mbar_arrive_remote(&full_bar[s], lead_rank);
                 }
             }
         }
@@ -185,9 +212,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 #pragma unroll
                     for (int k = 0; k < G2_BK / 16; ++k)
                         umma_f16_2sm(d_addr, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-                    umma_commit_2sm(&empty_bar[s]);  // frees this stage in both CTAs
+                    if (mc) umma_commit_mask(&empty_bar[s], 0xF);  // the twin pair's producers write into this stage too
+                    else umma_commit_2sm(&empty_bar[s], lead_rank);  // frees this stage in both CTAs
                 }
-                umma_commit_2sm(&tmem_full_bar[buf]);  // accumulators ready in both CTAs
+                umma_commit_2sm(&tmem_full_bar[buf], lead_rank);  // accumulators ready in both CTAs
             }
         }
     } else {
@@ -228,7 +256,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");  // all epilogue warps are done with `buf`
             if (warp == 2 && lane == 0) {
                 if (leader) mbar_arrive(&tmem_empty_bar[buf]);
-                else mbar_arrive_remote(&tmem_empty_bar[buf], 0);
+                else mbar_arrive_remote(&tmem_empty_bar[buf], lead_rank);
             }
         }
     }
@@ -250,7 +278,7 @@ int gemm_f16_2cta(const void* A, int lda, const void* W, int ldw, const GemmEpil
     const int bn = bn128 ? 128 : G2_BN;
     rc = make_tmap_2d_f16(&tb, W, N, K, ldw, bn / 2, G2_BK);
     if (rc) return rc;
-    void (*kern)(const CUtensorMap, const CUtensorMap, const GemmEpilogue, int, int, int) = nullptr;
+    void (*kern)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmEpilogue, int, int, int, int) = nullptr;
     int smem = 0, threads = 0;
 #define G2_PICK(MODE, ACT)                                                        \
     do {                                                                          \
@@ -301,6 +329,36 @@ int gemm_f16_2cta(const void* A, int lda, const void* W, int ldw, const GemmEpil
     }
     const int n_tiles = ceil_div(N, bn), m_tiles = ceil_div(M, 2 * G2_BM);
     int pairs = std::min(num_sms / 2, n_tiles * m_tiles);
+    // SBK_GEMM_CL4=1: clusters of two pairs (needs an even tile count per row of tiles and an even pair count)
+    // SBK_GEMM_MC=1 (implies clusters of 4): the A tile is fetched once per cluster, each CTA multicasting half of its rows
+    static const bool mc_env = getenv("SBK_GEMM_MC") != nullptr;
+    static const bool cl4_env = getenv("SBK_GEMM_CL4") != nullptr || mc_env;
+    int cluster = 2, mc = 0;
+    CUtensorMap ta64 = ta;
+    if (cl4_env && n_tiles % 2 == 0 && pairs >= 2) {
+        if (mc_env) {
+            mc = 1;
+            rc = make_tmap_2d_f16(&ta64, A, M, K, lda, G2_BM / 2, G2_BK);
+            if (rc) return rc;
+        }
+        cluster = 4;
+        pairs &= ~1;
+        static int max_cl4[64] = {0};  // resident clusters of 4 the device can hold for this kernel / shared-memory size
+        int& cap = max_cl4[(epi.mode * 8 + epi.act) & 63];
+        if (cap == 0) {
+            cudaLaunchConfig_t q = {};
+            q.gridDim = dim3(num_sms / 4 * 4); q.blockDim = dim3(threads); q.dynamicSmemBytes = smem;
+            cudaLaunchAttribute qa[1];
+            qa[0].id = cudaLaunchAttributeClusterDimension;
+            qa[0].val.clusterDim.x = 4; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+            q.attrs = qa; q.numAttrs = 1;
+            int nc = 0;
+            if (cudaOccupancyMaxActiveClusters(&nc, reinterpret_cast<const void*>(kern), &q) != cudaSuccess || nc < 1) nc = 1;
+            cap = nc;
+            if (getenv("SBK_GEMM_TRACE")) fprintf(stderr, "gemm2: %d resident clusters of 4 for mode %d\n", nc, epi.mode);
+        }
+        pairs = std::min(pairs, 2 * cap);
+    }
     GemmProfile* prof = gemm_profile();
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (prof->enabled) {
@@ -308,7 +366,15 @@ int gemm_f16_2cta(const void* A, int lda, const void* W, int ldw, const GemmEpil
         cudaEventCreate(&e1);
         cudaEventRecord(e0, stream);
     }
-    kern<<<2 * pairs, threads, smem, stream>>>(ta, tb, epi, M, N, K);
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        SBK_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tb, ta64, epi, M, N, K, mc));
+    }
     if (prof->enabled) {
         cudaEventRecord(e1, stream);
         prof->ev.push_back(e0);

@@ -136,15 +136,18 @@ struct BeamStepArgs {
 };
 // CTC prefix scorer (ctc_scorer.cu)
 struct CtcStep {
-    const float* x; const float* xb; const float* rsum; const float* rb; const float* psi_prev; const int* enc_len;
+    const float* x; const float* xb; const int* enc_len;
+    float* rsum_base; float* rb_base; float* psi_base;  // [2][n_bh, T], [2][n_bh, T], [2][n_bh]: ping-pong by step parity
     const int* hist_tok; const int* hist_pred;
-    int n_bh, step, bos, T, V, beam, blank, eos;
+    const int* step_ptr;                                // device step counters [n_bh] (same value in every row)
+    int n_bh, bos, T, V, beam, blank, eos;
     float weight; float* out; int accumulate;
-    float* rsum_out; float* rb_out; float* psi_out;
 };
 int ctc_prefix_reset(float* x, float* xb, const int* enc_len, int B, int T, int V, int blank, int beam, float* rsum, float* rb,
                      float* psi_prev, cudaStream_t stream);
 int ctc_prefix_score(const CtcStep& p, cudaStream_t stream);
+// x [rows, V] fp32: optional in-place log_softmax per row, arg-max per row -> idx (may be null)
+int rows_logsoftmax_argmax(float* x, int rows, int V, bool do_logsoftmax, int* idx, cudaStream_t stream);
 int ctc_prefix_update(const CtcStep& p, cudaStream_t stream);
 int beam_reset(int n_bh, int beam, int S_max, int bos, int* step_arr, float* seq_scores, int* lineage, int* finished,
                int* n_full, const float* emb, const float* pe, int d, float* x, const BeamLm* lm, cudaStream_t stream);

@@ -210,6 +210,20 @@ class AsrEngine:
                                                 ptr(lp), ctypes.byref(done), self._sp()), "sbk_asr_greedy_from_enc")
         return pred, score, lp, done.value
 
+    def ctc_head(self, enc=None, shape=None, want_log_probs=False, want_argmax=True):
+        """log_softmax(ctc_lin(enc)) [B, T, V] and / or its per-frame arg-max [B, T] (EncoderASR + ctc_greedy_decode).
+        ``enc`` None: use the encoder states the previous encode / transcribe call left in the workspace (``shape`` = (B, T))."""
+        if enc is not None:
+            enc = enc.float().contiguous()
+            B, T, _ = enc.shape
+        else:
+            B, T = shape
+        lp = torch.empty(B, T, self.cfg["vocab"], device=self.device, dtype=torch.float32) if want_log_probs else None
+        idx = torch.empty(B, T, device=self.device, dtype=torch.int32) if want_argmax else None
+        with torch.cuda.device(self.device):
+            check(lib().sbk_asr_ctc_head(self._h, ptr(enc), B, T, ptr(lp), ptr(idx), self._sp()), "sbk_asr_ctc_head")
+        return lp, idx
+
     def decode_teacher_forced(self, tgt, enc, enc_len=None):
         """TransformerASR.decode device part: tgt [n, S] token ids, enc [n, T, d], enc_len [n] absolute -> [n, S, d] fp32."""
         enc = enc.float().contiguous()

@@ -156,3 +156,91 @@ class EncoderDecoderASR(torch.nn.Module):
         hyps, _, _, _ = greedy_outputs(pred, torch.zeros_like(pred, dtype=torch.float32), None, dec.eos_index)
         words = [self.tokenizer.decode_ids(h) for h in hyps] if self.tokenizer is not None else [" ".join(map(str, h)) for h in hyps]
         return words, hyps
+
+
+class EncoderASR(torch.nn.Module):
+    """Drop-in for speechbrain.inference.ASR.EncoderASR (inference/ASR.py:176-389) with a Conformer encoder + CTC head and
+    greedy decoding: ``encode_batch`` returns the log-posteriors [B, T, V] the reference's ``encoder`` Sequential ends in,
+    ``transcribe_batch`` runs wav -> encoder -> ctc_lin -> per-frame arg-max on the device (one fused pipeline + the CTC head
+    GEMM + ``rows_logsoftmax_argmax_kernel``) and the CTC merge / blank filter on the host.
+
+    ``modules["encoder"]``: ``LengthsCapableSequential`` of Fbank, InputNormalization, ConvolutionFrontEnd,
+    ``EncoderWrapper(TransformerASR)``, the CTC ``Linear`` and a log-softmax (``torch.nn.LogSoftmax`` /
+    ``speechbrain_b200.nnet.activations.Softmax(apply_log=True)``); ``hparams["decoding_function"]`` must be a
+    ``functools.partial`` of ``ctc_greedy_decode`` (the CTC beam searchers of the reference are not built)."""
+    HPARAMS_NEEDED = ["tokenizer", "decoding_function"]
+    MODULES_NEEDED = ["encoder"]
+
+    def __init__(self, modules=None, hparams=None, run_opts=None, freeze_params=True):
+        super().__init__()
+        import functools
+
+        from ..decoders.ctc import ctc_greedy_decode
+        from ..nnet.linear import Linear
+        modules = dict(modules or {})
+        if "encoder" not in modules:
+            raise ValueError("Need modules['encoder']")
+        self.mods = torch.nn.ModuleDict(modules)
+        self.hparams = dict(hparams) if isinstance(hparams, dict) else (dict(vars(hparams)) if hparams is not None else {})
+        for k in self.HPARAMS_NEEDED:
+            if k not in self.hparams:
+                raise ValueError(f"Need hparams['{k}']")
+        self.tokenizer = self.hparams["tokenizer"]
+        fn = self.hparams["decoding_function"]
+        if not (isinstance(fn, functools.partial) and fn.func is ctc_greedy_decode):
+            raise NotImplementedError("speechbrain_b200.EncoderASR: decoding_function must be functools.partial(ctc_greedy_decode, "
+                                      "blank_id=...) (CTC beam searchers are not built)")
+        self.decoding_function = fn
+        self.blank_id = fn.keywords.get("blank_id", -1)
+        self.device = torch.device((run_opts or {}).get("device", "cuda:0"))
+        vals = list(self.mods.values())
+        wrap = _find(vals, EncoderWrapper)
+        tr = _find(vals, TransformerASR) or (wrap.transformer if wrap is not None else None)
+        for name, m in (("fbank", _find(vals, Fbank)), ("normalize", _find(vals, InputNormalization)),
+                        ("cnn", _find(vals, ConvolutionFrontEnd)), ("transformer", tr), ("ctc_lin", _find(vals, Linear))):
+            if m is None:
+                raise ValueError(f"EncoderASR: could not find the {name} module in modules['encoder']")
+            object.__setattr__(self, name, m)
+        if self.normalize.norm_type != "global":
+            raise NotImplementedError("EncoderASR: fused pipeline needs InputNormalization(norm_type='global')")
+
+    @classmethod
+    def from_hparams(cls, source, hparams_file="hyperparams.yaml", overrides=None, savedir=None, run_opts=None, **kwargs):
+        from ..utils.hparams import load_pretrained_interface
+        return load_pretrained_interface(cls, source, hparams_file, overrides or {}, run_opts or {})
+
+    def engine(self):
+        src = {"fbank": self.fbank, "normalize": self.normalize, "CNN.": self.cnn, "ctc_lin.": self.ctc_lin}
+        return self.transformer.engine_slot(("ctc", id(self.ctc_lin))).get(self.device, ("fbank", "cnn", "encoder"), src)
+
+    def _encode(self, wavs, wav_lens):
+        eng = self.engine()
+        wavs = wavs.float().to(self.device)
+        enc = eng.encode_wav(wavs, wav_lens.to(self.device))
+        return eng, enc
+
+    @torch.no_grad()
+    def encode_batch(self, wavs, wav_lens):
+        """inference/ASR.py:297-323: -> log-posteriors [B, T, V]."""
+        eng, enc = self._encode(wavs, wav_lens)
+        lp, _ = eng.ctc_head(enc, want_log_probs=True, want_argmax=False)
+        return lp
+
+    @torch.no_grad()
+    def transcribe_batch(self, wavs, wav_lens):
+        """inference/ASR.py:325-373: -> (predicted_words, predicted_tokens)."""
+        from ..decoders.ctc import greedy_from_argmax
+        eng, enc = self._encode(wavs, wav_lens)
+        _, idx = eng.ctc_head(enc, want_log_probs=False, want_argmax=True)
+        V = eng.cfg["vocab"]
+        blank = self.blank_id + V if isinstance(self.blank_id, int) and self.blank_id < 0 else self.blank_id
+        predictions = greedy_from_argmax(idx.cpu(), wav_lens, blank)
+        if self.tokenizer is not None:
+            words = [self.tokenizer.decode_ids(t) for t in predictions]
+        else:
+            words = [" ".join(map(str, t)) for t in predictions]
+        return words, predictions
+
+    def forward(self, wavs, wav_lens):
+        """Runs the encoder (the reference's forward returns encode_batch)."""
+        return self.encode_batch(wavs, wav_lens)

@@ -276,3 +276,89 @@ def test_group_host_entry_matches_device(dev):
     # early exit: an EOS bias makes every row end at step 0..2; the reference loop breaks right after the last first-EOS
     p = torch.tensor([[5, 2, 2, 2], [2, 2, 2, 2], [7, 8, 2, 2]], dtype=torch.int32)
     assert greedy_exit_step(p, 2) == 3 and greedy_exit_step(p[:, :2], 2) == 2
+
+
+def test_encoder_asr_ctc_greedy(dev):
+    """EncoderASR (inference/ASR.py:176-389) with the CTC head + ctc_greedy_decode (decoders/ctc.py:335-378) vs the reference
+    on the 2 s golden: log-posteriors within 2e-2, per-frame arg-max identical wherever the reference's top-1/top-2 margin
+    exceeds 5e-3, and -- with the near-tie frames taken from the reference -- identical token lists (merge + blank filter)."""
+    import functools
+
+    from speechbrain_b200.decoders.ctc import ctc_greedy_decode, greedy_from_argmax
+    from speechbrain_b200.inference.ASR import EncoderASR
+    from speechbrain_b200.lobes.features import Fbank
+    from speechbrain_b200.lobes.models.convolution import ConvolutionFrontEnd
+    from speechbrain_b200.lobes.models.transformer.TransformerASR import EncoderWrapper, TransformerASR
+    from speechbrain_b200.nnet.activations import Softmax
+    from speechbrain_b200.nnet.containers import LengthsCapableSequential
+    from speechbrain_b200.nnet.linear import Linear
+    from speechbrain_b200.processing.features import InputNormalization
+    from speechbrain_b200.utils.seeded_init import seeded_asr_state
+    g = torch.load(os.path.join(GOLDEN, "conformer_large_rope.pt"))
+    gc = torch.load(os.path.join(GOLDEN, "ctc_greedy_conformer_large_rope.pt"))
+    cfg = _cfg(g)
+    sd = seeded_asr_state(cfg, 0)
+    fb = Fbank(n_fft=512, n_mels=80, win_length=32)
+    norm = InputNormalization(norm_type="global")
+    norm.glob_mean, norm.glob_std, norm.count = sd["normalize.glob_mean"], sd["normalize.glob_std"], 1
+    norm.eval()
+    cnn = ConvolutionFrontEnd(input_shape=(8, 10, 80), num_blocks=2, num_layers_per_block=1, out_channels=(64, 32),
+                              kernel_sizes=(3, 3), strides=(2, 2), residuals=(False, False))
+    cnn.load_state_dict({k[4:]: v for k, v in sd.items() if k.startswith("CNN.")})
+    tr = TransformerASR(input_size=640, tgt_vocab=5000, d_model=512, nhead=8, num_encoder_layers=12, num_decoder_layers=6,
+                        d_ffn=2048, activation=torch.nn.GELU, encoder_module="conformer", attention_type="RoPEMHA",
+                        normalize_before=True, causal=False)
+    tr.load_state_dict({k[len("Transformer."):]: v for k, v in sd.items() if k.startswith("Transformer.")}, strict=False)
+    ctc_lin = Linear(input_size=512, n_neurons=5000)
+    for name in ("plain", "merge"):
+        c = gc[name]
+        bias = sd["ctc_lin.w.bias"].clone()
+        bias[0] += c["bias_blank"]
+        bias[17] += c["bias_tok"]
+        ctc_lin.load_state_dict({"w.weight": sd["ctc_lin.w.weight"], "w.bias": bias})
+        enc = LengthsCapableSequential(compute_features=fb, normalize=norm, cnn=cnn, transformer_encoder=EncoderWrapper(tr),
+                                       ctc_lin=ctc_lin, log_softmax=Softmax(apply_log=True))
+        asr = EncoderASR(modules=dict(encoder=enc), hparams=dict(tokenizer=None, decoding_function=functools.partial(ctc_greedy_decode, blank_id=0)),
+                         run_opts={"device": str(dev)})
+        lp = asr.encode_batch(g["wav"], g["wav_lens"]).cpu()
+        assert lp.shape[:2] == g["enc_out"].shape[:2] and lp.shape[2] == 5000
+        e = (lp[:, :, :64] - c["log_probs_head"]).abs().max().item()
+        words, toks = asr.transcribe_batch(g["wav"], g["wav_lens"])
+        am = lp.argmax(-1)
+        T = lp.shape[1]
+        bad = 0
+        for b in range(lp.shape[0]):
+            n = int(torch.round(g["wav_lens"][b] * T))
+            strong = c["margin"][b, :n] >= 5e-3
+            bad += int((am[b, :n][strong] != c["argmax"][b, :n].long()[strong]).sum())
+        patched = torch.where(c["margin"] >= 5e-3, am, c["argmax"].long())
+        hy = greedy_from_argmax(patched, g["wav_lens"], 0)
+        print(f"EncoderASR[{name}] log-prob err {e:.2e}; strong-margin frames with another arg-max: {bad}; tokens {toks} ref {c['hyps']}")
+        assert e < 2e-2 and bad == 0 and hy == c["hyps"]
+        # module-by-module use of the mirror function on a CUDA tensor of log-probs
+        assert ctc_greedy_decode(lp.to(dev), g["wav_lens"], blank_id=0) == toks
+
+
+def test_fp16_range_scaled_weights(dev):
+    """fp16 operand range.  (1) The reference re-ran the 2 s golden with FFN first layers x200, attention
+    in_proj x3 and conv pw1 x4 (FFN pre-activations in the hundreds, attention logits x9): the encoder must still be within
+    1e-3 rel-L2 -- fp16 rounding is relative, the residual stream / LayerNorm / softmax statistics are fp32.  (2) With FFN
+    first layers x1e5 the FFN hidden exceeds the fp16 maximum (65504): the fp32 -> fp16 stores saturate (F2FP.SATFINITE), so
+    the output stays finite (no inf -> NaN cascade)."""
+    from oracle.make_goldens import scale_state
+    from speechbrain_b200.engine import AsrEngine
+    from speechbrain_b200.utils.seeded_init import seeded_asr_state
+    g = torch.load(os.path.join(GOLDEN, "conformer_large_rope.pt"))
+    gs = torch.load(os.path.join(GOLDEN, "conformer_large_rope_scaled.pt"))
+    cfg = _cfg(g)
+    sd = seeded_asr_state(cfg, 0)
+    cnn = g["cnn_out"].reshape(g["cnn_out"].shape[0], g["cnn_out"].shape[1], -1).to(dev)
+    eng = AsrEngine(cfg, scale_state(sd, gs["scales"]), device=dev, parts=("encoder",))
+    enc = eng.encode_from_cnn(cnn, g["wav_lens"].to(dev)).cpu()
+    r = _rel(enc, gs["enc_out"])
+    print(f"scaled weights (max |FFN pre-activation| {gs['ffn_hidden_absmax']:.0f} in the reference): encoder rel-L2 err {r:.3e}")
+    assert torch.isfinite(enc).all() and r < 1e-3
+    eng2 = AsrEngine(cfg, scale_state(sd, dict(gs["scales"], ffn_w1=1e5)), device=dev, parts=("encoder",))
+    enc2 = eng2.encode_from_cnn(cnn, g["wav_lens"].to(dev)).cpu()
+    print(f"FFN x1e5 (hidden beyond the fp16 range): finite {bool(torch.isfinite(enc2).all())}, absmax {float(enc2.abs().max()):.2f}")
+    assert torch.isfinite(enc2).all()
