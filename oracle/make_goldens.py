@@ -589,6 +589,33 @@ def scaled_case(tag="conformer_large_rope_scaled"):
     torch.save(dict(scales=SCALES, enc_out=enc, ffn_hidden_absmax=stats["ffn_hidden_absmax"]), os.path.join(OUT, f"{tag}.pt"))
 
 
+def beam66_case(tag="beam66_conformer_large_rope"):
+    """beam_size = 66, the recipe's test_beam_size (conformer_large.yaml:132), on the 2 s golden: scorer-less, temperature
+    1.15, a small EOS bias so that hypotheses finish at different steps.  All 66 hypotheses per utterance are stored."""
+    from speechbrain.decoders.seq2seq import S2STransformerBeamSearcher
+    fb, norm, mods, sd = build_reference(CFG_L, "RoPEMHA")
+    g = torch.load(os.path.join(OUT, "conformer_large_rope.pt"))
+    enc, wav_lens = g["enc_out"], g["wav_lens"]
+    T = enc.shape[1]
+    kw = dict(beam_size=66, using_eos_threshold=False, temperature=1.15, min_decode_ratio=2.5 / T)
+    eos_bias, steps = 1.5, 10
+    with torch.no_grad():
+        bias = sd["seq_lin.w.bias"].clone()
+        bias[2] += eos_bias
+        mods["seq_lin"].w.bias.copy_(bias)
+        bs = S2STransformerBeamSearcher(modules=[mods["Transformer"], mods["seq_lin"]], bos_index=1, eos_index=2,
+                                        max_decode_ratio=(steps + 0.5) / T, return_topk=True, topk=66, **kw)
+        tk_hyps, tk_len, tk_scores, tk_lp = bs(enc, wav_lens)
+        o_hyps, o_len, o_scores, o_lp = O.beam_search(enc, wav_lens, sd, dict(CFG_L, attention_type="RoPEMHA"), sd["seq_lin.w.weight"],
+                                                      bias, 1, 2, max_decode_ratio=(steps + 0.5) / T, prefix="Transformer.", topk=66,
+                                                      return_topk=True, **kw)
+    print(f"[beam66] best lens {(tk_len[:, 0] * tk_hyps.shape[2]).round().int().tolist()} max len {tk_hyps.shape[2]} scores "
+          f"{tk_scores[:, 0].tolist()} oracle equal {torch.equal(o_hyps, tk_hyps)} gap {(tk_scores[:, 0] - tk_scores[:, 1]).tolist()}")
+    assert torch.equal(o_hyps[:, 0], tk_hyps[:, 0]) and (o_scores - tk_scores).abs().max() < 1e-3
+    torch.save(dict(kwargs=kw, with_lm=False, with_ctc=False, eos_bias=eos_bias, max_decode_ratio=(steps + 0.5) / T,
+                    hyps=tk_hyps.int(), lens=tk_len, scores=tk_scores, log_probs=tk_lp), os.path.join(OUT, f"{tag}.pt"))
+
+
 BEAMS_10S = (
     ("b10_lm_ctc", dict(beam_size=10, using_eos_threshold=False, temperature=1.15, with_lm=True, with_ctc=True, eos_bias=0.0, steps=24)),
     ("b10_ctc_valid", dict(beam_size=10, using_eos_threshold=False, temperature=1.15, with_lm=False, with_ctc=True, eos_bias=0.0, steps=24)),
@@ -628,6 +655,8 @@ if __name__ == "__main__":
         bench_shape_case(CFG_L, "RoPEMHA", 4, 160000, [1.0, 0.9, 0.6, 0.3], 48, "bench_conformer_large_rope_10s", BEAMS_10S)
     if "bench_L_relpos" in which:
         bench_shape_case(CFG_L, "RelPosMHAXL", 4, 160000, [1.0, 0.9, 0.6, 0.3], 48, "bench_conformer_large_relpos_10s")
+    if "beam66" in which:
+        beam66_case()
     if "scaled" in which:
         scaled_case()
     if "ctc_greedy" in which:

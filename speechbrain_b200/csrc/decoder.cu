@@ -680,8 +680,84 @@ dec_cross_attention_persist_kernel(const __grid_constant__ CUtensorMap tmap_kv, 
     }
 }
 
+
+// Generic head_dim (<= 64, multiple of 4) variant of dec_attention_kernel: conformer_small's decoder has 4 heads of 36
+// (conformer_small.yaml).  One CTA (128 threads) per (row, head): thread-per-key scores into shared memory, block softmax,
+// then thread-per-dim p.V.  Small models only: no attempt at bandwidth efficiency.
+constexpr int DG_MAXKEYS = 2560;
+__global__ void __launch_bounds__(128) dec_attention_generic_kernel(const DecAttnArgs a) {
+    __shared__ float s_q[64];
+    __shared__ float s_p[DG_MAXKEYS];
+    __shared__ float s_red[4];
+    const int r = blockIdx.y, h = blockIdx.x, dh = a.dh, tid = threadIdx.x;
+    const int blk = r / a.rows_per_block;
+    pdl_trigger();
+    pdl_wait();
+    int n_keys;
+    if (a.n_keys_ptr) n_keys = *a.n_keys_ptr + 1;
+    else n_keys = a.enc_len ? min(a.enc_len[blk], a.n_keys_fixed) : a.n_keys_fixed;
+    const __half* kbase = a.kbase + static_cast<size_t>(blk) * a.row_stride + h * dh;
+    const __half* vbase = a.vbase + static_cast<size_t>(blk) * a.row_stride + h * dh;
+    const int* lin = nullptr;
+    if (a.lineage) lin = a.lineage + static_cast<size_t>((n_keys - 1) & 1) * gridDim.y * a.lin_stride + static_cast<size_t>(r) * a.lin_stride;
+    if (tid < dh) s_q[tid] = __half2float(a.q[static_cast<size_t>(r) * a.ldq + h * dh + tid]);
+    __syncthreads();
+    float mx = -INFINITY;
+    for (int j = tid; j < n_keys; j += 128) {
+        ptrdiff_t off = static_cast<ptrdiff_t>(j) * a.key_stride;
+        int src_row = r;
+        if (lin) { src_row = lin[j]; off += (static_cast<ptrdiff_t>(src_row) - r) * static_cast<ptrdiff_t>(a.row_stride); }
+        float dot = 0.0f;
+        for (int e = 0; e < dh; e += 4) {
+            const uint2 kv = *reinterpret_cast<const uint2*>(kbase + off + e);
+            const __half2* k2 = reinterpret_cast<const __half2*>(&kv);
+            const float2 f0 = __half22float2(k2[0]), f1 = __half22float2(k2[1]);
+            dot = fmaf(f0.x, s_q[e], dot); dot = fmaf(f0.y, s_q[e + 1], dot);
+            dot = fmaf(f1.x, s_q[e + 2], dot); dot = fmaf(f1.y, s_q[e + 3], dot);
+        }
+        if (a.tok_cache && a.tok_cache[static_cast<size_t>(src_row) * a.lin_stride + j] == a.pad_tok) dot = -INFINITY;
+        s_p[j] = dot;
+        mx = fmaxf(mx, dot);
+    }
+    mx = warp_max(mx);
+    if ((tid & 31) == 0) s_red[tid >> 5] = mx;
+    __syncthreads();
+    mx = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
+    __syncthreads();
+    float sum = 0.0f;
+    for (int j = tid; j < n_keys; j += 128) {
+        const float p = s_p[j] == -INFINITY ? 0.0f : __expf(s_p[j] - mx);
+        s_p[j] = p;
+        sum += p;
+    }
+    sum = warp_sum(sum);
+    if ((tid & 31) == 0) s_red[tid >> 5] = sum;
+    __syncthreads();
+    const float den = (s_red[0] + s_red[1]) + (s_red[2] + s_red[3]);
+    if (tid < dh) {
+        float o = 0.0f;
+        for (int j = 0; j < n_keys; ++j) {
+            ptrdiff_t off = static_cast<ptrdiff_t>(j) * a.key_stride;
+            if (lin) off += (static_cast<ptrdiff_t>(lin[j]) - r) * static_cast<ptrdiff_t>(a.row_stride);
+            o = fmaf(s_p[j], __half2float(vbase[off + tid]), o);
+        }
+        a.out[static_cast<size_t>(r) * a.ldo + h * dh + tid] = float2half_sat(o / den);
+    }
+}
+
 int dec_attention(const DecAttnArgs& a, int n_rows, int max_keys, cudaStream_t stream) {
-    SBK_REQUIRE(a.dh == 64, "dec_attention: head_dim=%d not built (64 only)", a.dh);
+    if (a.dh != 64) {
+        SBK_REQUIRE(a.dh >= 4 && a.dh <= 64 && a.dh % 4 == 0 && a.key_stride % 4 == 0 && a.row_stride % 4 == 0,
+                    "dec_attention: head_dim=%d not built (64, or a multiple of 4 below 64)", a.dh);
+        SBK_REQUIRE(max_keys <= DG_MAXKEYS, "dec_attention: %d keys exceed the generic kernel's limit %d", max_keys, DG_MAXKEYS);
+        if (n_rows == 0) return SBK_OK;
+        DecAttnArgs g = a;
+        g.n_keys_fixed = max_keys;
+        SBK_CUDA_CHECK(launch_k(dec_attention_generic_kernel, dim3(a.H, n_rows), dim3(128), 0, stream, g));
+        SBK_LAUNCH_CHECK();
+        return SBK_OK;
+    }
+
     if (n_rows == 0) return SBK_OK;
     DecAttnArgs b = a;
     b.n_keys_fixed = max_keys;
@@ -1106,6 +1182,217 @@ __global__ void __launch_bounds__(BS_THREADS) beam_step_kernel(const BeamArgs a)
     if (tid < beam) a.step_arr[row0 + tid] = step + 1;
 }
 
+
+// --------------------------------------------------------------------------- beam step for wide beams (16 < beam <= 128)
+// Same contract as beam_step_kernel; the per-thread sorted lists of that kernel (beam registers per thread) do not scale to
+// the recipes' test_beam_size = 66 (conformer_large.yaml:132), so the top-`beam` of the beam * V candidates is found by an
+// exact radix select: 4 passes of 8 bits over an order-preserving integer image of the score find the beam-th largest value,
+// one more pass collects everything above it plus the lowest-index ties, a bitonic sort orders the <= 128 survivors by
+// (score descending, candidate index ascending) -- the order the small-beam kernel produces.
+constexpr int BL_MAXB = 128;
+constexpr int BL_TIECAP = 1024;
+
+__device__ __forceinline__ uint32_t score_key(float v) {  // larger score <-> larger key; -inf is the smallest finite key
+    const uint32_t u = __float_as_uint(v);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__global__ void __launch_bounds__(BS_THREADS) beam_step_large_kernel(const BeamArgs a) {
+    __shared__ float s_red[BS_THREADS / 32];
+    __shared__ int s_redi[BS_THREADS / 32];
+    __shared__ float s_lse[BL_MAXB], s_eos[BL_MAXB], s_seq[BL_MAXB];
+    __shared__ int s_hist[256];
+    __shared__ uint32_t s_prefix;
+    __shared__ int s_remaining, s_nsel, s_ntie;
+    __shared__ float s_selv[BL_MAXB];
+    __shared__ int s_seli[BL_MAXB];
+    __shared__ int s_tie[BL_TIECAP];
+    __shared__ int s_wtok[BL_MAXB], s_wpred[BL_MAXB];
+    pdl_trigger();
+    pdl_wait();
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int beam = a.beam, V = a.V;
+    const int row0 = b * beam;
+    const int step = a.step_arr[row0];
+    const float* seq_in = a.seq_scores + static_cast<size_t>(step & 1) * a.n_bh;
+    float* seq_out = a.seq_scores + static_cast<size_t>((step + 1) & 1) * a.n_bh;
+    // ---- phase 1: per beam row log-sum-exp of logits / T and the (masked) eos log-prob (one warp per row)
+    for (int k = warp; k < beam; k += BS_THREADS / 32) {
+        const float* lg = a.logits + static_cast<size_t>(row0 + k) * V;
+        float mx = -INFINITY;
+        for (int j = lane; j < V; j += 32) mx = fmaxf(mx, lg[j] * a.inv_temp);
+        mx = warp_max(mx);
+        float sm = 0.0f, mne = -INFINITY;
+        for (int j = lane; j < V; j += 32) {
+            const float v = lg[j] * a.inv_temp;
+            sm += expf(v - mx);
+            if (j != a.eos) mne = fmaxf(mne, v);
+        }
+        sm = warp_sum(sm);
+        mne = warp_max(mne);
+        if (lane == 0) {
+            const float lse = mx + logf(sm);
+            float eos_lp = a.attn_weight * (lg[a.eos] * a.inv_temp - lse);
+            if (step < a.min_steps) eos_lp = a.minus_inf;
+            if (a.use_eos_threshold) {
+                const float max_lp = fmaxf(a.attn_weight * (mne - lse), eos_lp);
+                if (!(eos_lp > a.eos_threshold * max_lp)) eos_lp = a.minus_inf;
+            }
+            if (a.add_scores) eos_lp += a.add_scores[static_cast<size_t>(row0 + k) * V + a.eos];
+            eos_lp += a.add_const;
+            s_lse[k] = lse;
+            s_eos[k] = eos_lp;
+            s_seq[k] = seq_in[row0 + k];
+        }
+    }
+    if (tid == 0) { s_prefix = 0u; s_remaining = beam; s_nsel = 0; s_ntie = 0; }
+    __syncthreads();
+    const float inv_len = a.length_norm ? 1.0f / static_cast<float>(step + 1) : 1.0f;
+    const int n_cand = beam * V;
+    auto cand_score = [&](int cidx) -> float {
+        const int k = cidx / V, j = cidx - k * V;
+        float lp = (j == a.eos) ? s_eos[k]
+                                : a.attn_weight * (a.logits[static_cast<size_t>(row0 + k) * V + j] * a.inv_temp - s_lse[k]);
+        if (j == a.blank) lp = a.minus_inf;
+        if (a.add_scores && j != a.eos) lp += a.add_scores[static_cast<size_t>(row0 + k) * V + j];
+        if (j != a.eos) lp += a.add_const;
+        return (s_seq[k] + lp) * inv_len;
+    };
+    // ---- phase 2: radix select of the beam-th largest key
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        s_hist[tid] = 0;
+        __syncthreads();
+        const uint32_t prefix = s_prefix;
+        const uint32_t himask = pass == 0 ? 0u : (0xFFFFFFFFu << (shift + 8));
+        for (int cidx = tid; cidx < n_cand; cidx += BS_THREADS) {
+            const uint32_t key = score_key(cand_score(cidx));
+            if ((key & himask) == (prefix & himask)) atomicAdd(&s_hist[(key >> shift) & 255u], 1);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int need = s_remaining, acc = 0, bin = 255;
+            for (; bin > 0; --bin) {
+                if (acc + s_hist[bin] >= need) break;
+                acc += s_hist[bin];
+            }
+            s_prefix = prefix | (static_cast<uint32_t>(bin) << shift);
+            s_remaining = need - acc;  // how many of the candidates inside this bin are still wanted
+        }
+        __syncthreads();
+    }
+    // ---- phase 3: collect keys above the threshold, and the ties
+    const uint32_t thr = s_prefix;
+    for (int cidx = tid; cidx < n_cand; cidx += BS_THREADS) {
+        const float sc = cand_score(cidx);
+        const uint32_t key = score_key(sc);
+        if (key > thr) {
+            const int p = atomicAdd(&s_nsel, 1);
+            if (p < BL_MAXB) { s_selv[p] = sc; s_seli[p] = cidx; }
+        } else if (key == thr) {
+            const int p = atomicAdd(&s_ntie, 1);
+            if (p < BL_TIECAP) s_tie[p] = cidx;
+        }
+    }
+    __syncthreads();
+    {   // the lowest-index `remaining` ties complete the selection (ties beyond BL_TIECAP cannot occur with finite scores)
+        const int nsel = min(s_nsel, BL_MAXB), ntie = min(s_ntie, BL_TIECAP), want = min(s_remaining, beam - nsel);
+        const float tv = [&] { const uint32_t k = thr; const uint32_t u = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k; return __uint_as_float(u); }();
+        for (int r = 0; r < want; ++r) {
+            int best = 0x7fffffff, bp = -1;
+            for (int i = tid; i < ntie; i += BS_THREADS)
+                if (s_tie[i] < best) { best = s_tie[i]; bp = i; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const int ob = __shfl_xor_sync(0xffffffffu, best, o), op = __shfl_xor_sync(0xffffffffu, bp, o);
+                if (ob < best) { best = ob; bp = op; }
+            }
+            if (lane == 0) { s_redi[warp] = best; s_red[warp] = __int_as_float(bp); }
+            __syncthreads();
+            if (tid == 0) {
+                int bb = s_redi[0], pp = __float_as_int(s_red[0]);
+                for (int w = 1; w < BS_THREADS / 32; ++w)
+                    if (s_redi[w] < bb) { bb = s_redi[w]; pp = __float_as_int(s_red[w]); }
+                if (pp >= 0) { s_selv[nsel + r] = tv; s_seli[nsel + r] = bb; s_tie[pp] = 0x7fffffff; }
+                else { s_selv[nsel + r] = -INFINITY; s_seli[nsel + r] = 0x7fffffff; }
+            }
+            __syncthreads();
+        }
+        for (int i = nsel + want + tid; i < BL_MAXB; i += BS_THREADS) { s_selv[i] = -INFINITY; s_seli[i] = 0x7fffffff; }
+        __syncthreads();
+    }
+    // ---- bitonic sort of the 128 slots: score descending, candidate index ascending
+    for (int k2 = 2; k2 <= BL_MAXB; k2 <<= 1) {
+        for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+            if (tid < BL_MAXB) {
+                const int ixj = tid ^ j2;
+                if (ixj > tid) {
+                    const float v0 = s_selv[tid], v1 = s_selv[ixj];
+                    const int i0 = s_seli[tid], i1 = s_seli[ixj];
+                    const bool first_after = (v0 < v1) || (v0 == v1 && i0 > i1);  // element at tid should come after ixj
+                    const bool up = (tid & k2) == 0;
+                    if (first_after == up) { s_selv[tid] = v1; s_selv[ixj] = v0; s_seli[tid] = i1; s_seli[ixj] = i0; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // ---- winners (thread k handles new beam k)
+    if (tid < beam) {
+        const int k = tid;
+        const int cand = s_seli[k];
+        const float sc = s_selv[k];
+        int kk = 0, tok = 0;
+        if (cand != 0x7fffffff) { kk = cand / V; tok = cand - kk * V; }
+        const int row = row0 + k, prow = row0 + kk;
+        const float raw_lp = a.attn_weight * (a.logits[static_cast<size_t>(prow) * V + tok] * a.inv_temp - s_lse[kk]);
+        const size_t h = static_cast<size_t>(step) * a.n_bh + row;
+        a.hist_tok[h] = tok; a.hist_pred[h] = prow; a.hist_score[h] = sc; a.hist_lp[h] = raw_lp;
+        float ns = a.length_norm ? sc * static_cast<float>(step + 1) : sc;
+        if (tok == a.eos) ns = -INFINITY;
+        seq_out[row] = ns;
+        s_wtok[k] = tok; s_wpred[k] = prow;
+    }
+    __syncthreads();
+    // ---- phase 4: finished counters, lineage of the new beams, next decoder inputs, step counters (as beam_step_kernel)
+    if (tid == 0) {
+        int n_eos = 0;
+        for (int k = 0; k < beam; ++k) n_eos += (s_wtok[k] == a.eos) ? 1 : 0;
+        const int before = a.finished[b];
+        const int after = min(beam, before + n_eos);
+        a.finished[b] = after;
+        if (before < beam && after >= beam) atomicAdd(a.n_full, 1);
+    }
+    const int* lin_in = a.lineage + static_cast<size_t>(step & 1) * a.n_bh * a.S_max;
+    int* lin_out = a.lineage + static_cast<size_t>((step + 1) & 1) * a.n_bh * a.S_max;
+    for (int i = tid; i < beam * (step + 2); i += BS_THREADS) {
+        const int k = i / (step + 2), p = i - k * (step + 2);
+        const int row = row0 + k, prow = s_wpred[k];
+        int src;
+        if (p < step) src = lin_in[static_cast<size_t>(prow) * a.S_max + p];
+        else if (p == step) src = prow;
+        else src = row;
+        lin_out[static_cast<size_t>(row) * a.S_max + p] = src;
+    }
+    for (int i = tid; i < beam * a.d; i += BS_THREADS) {
+        const int k = i / a.d, c = i - k * a.d;
+        a.x_next[static_cast<size_t>(row0 + k) * a.d + c] =
+            a.emb[static_cast<size_t>(s_wtok[k]) * a.d + c] * a.sqrt_d + a.pe[static_cast<size_t>(step + 1) * a.d + c];
+    }
+    if (a.lm_emb) {
+        for (int i = tid; i < beam * a.lm_d; i += BS_THREADS) {
+            const int k = i / a.lm_d, c = i - k * a.lm_d;
+            const float v = a.lm_emb[static_cast<size_t>(s_wtok[k]) * a.lm_d + c] * a.lm_sqrt_d +
+                            a.lm_pe[static_cast<size_t>(step + 1) * a.lm_d + c];
+            a.lm_x_next[static_cast<size_t>(row0 + k) * a.lm_d + c] = v;
+            a.lm_x16_next[static_cast<size_t>(row0 + k) * a.lm_d + c] = float2half_sat(v);
+        }
+        if (tid < beam) a.tok_cache[static_cast<size_t>(row0 + tid) * a.S_max + step + 1] = s_wtok[tid];
+    }
+    __syncthreads();
+    if (tid < beam) a.step_arr[row0 + tid] = step + 1;
+}
+
 // step = 0 state: x = emb[bos] * sqrt(d) + pe[0]; beam 0 alive (score 0), others -inf; identity lineage.
 __global__ void beam_reset_kernel(int n_bh, int beam, int S_max, int bos, int* step_arr, float* seq_scores, int* lineage,
                                   int* finished, int* n_full, const float* __restrict__ emb, const float* __restrict__ pe,
@@ -1144,7 +1431,8 @@ int beam_reset(int n_bh, int beam, int S_max, int bos, int* step_arr, float* seq
 }
 
 int beam_step(const BeamStepArgs& p, int B, cudaStream_t stream) {
-    SBK_REQUIRE(p.beam >= 1 && p.beam <= BS_MAXB, "beam_step: beam_size=%d not in [1, %d]", p.beam, BS_MAXB);
+    SBK_REQUIRE(p.beam >= 1 && p.beam <= BL_MAXB, "beam_step: beam_size=%d not in [1, %d]", p.beam, BL_MAXB);
+    SBK_REQUIRE(p.beam <= p.V, "beam_step: beam_size=%d exceeds the vocabulary (%d)", p.beam, p.V);
     BeamArgs a;
     a.logits = p.logits; a.V = p.V; a.beam = p.beam; a.n_bh = B * p.beam; a.S_max = p.S_max;
     a.seq_scores = p.seq_scores; a.lineage = p.lineage; a.step_arr = p.step_arr; a.finished = p.finished; a.n_full = p.n_full;
@@ -1155,7 +1443,9 @@ int beam_step(const BeamStepArgs& p, int B, cudaStream_t stream) {
     a.add_scores = p.add_scores; a.attn_weight = p.attn_weight; a.blank = p.blank; a.add_const = p.add_const;
     a.lm_emb = p.lm.emb; a.lm_pe = p.lm.pe; a.lm_d = p.lm.d; a.lm_sqrt_d = p.lm.d ? sqrtf(static_cast<float>(p.lm.d)) : 0.f;
     a.lm_x_next = p.lm.x; a.lm_x16_next = p.lm.x16; a.tok_cache = p.lm.tok_cache;
-    SBK_CUDA_CHECK(launch_k(beam_step_kernel, dim3(B), dim3(BS_THREADS), 0, stream, a));
+    static const bool force_large = getenv("SBK_BEAM_RADIX") != nullptr;  // test hook: radix-select kernel for every width
+    if (p.beam > BS_MAXB || force_large) SBK_CUDA_CHECK(launch_k(beam_step_large_kernel, dim3(B), dim3(BS_THREADS), 0, stream, a));
+    else SBK_CUDA_CHECK(launch_k(beam_step_kernel, dim3(B), dim3(BS_THREADS), 0, stream, a));
     SBK_LAUNCH_CHECK();
     return SBK_OK;
 }

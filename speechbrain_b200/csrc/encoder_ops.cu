@@ -91,6 +91,103 @@ int layernorm_rows(const float* x, void* out, bool out_half, const float* gamma,
     return SBK_OK;
 }
 
+
+// Two chained LayerNorms over the same row in one pass: y = LN_a(x) (fp32, optional store) and z = LN_b(y) (fp16 GEMM operand
+// or fp32).  The Conformer layer ends with norm2 and the next layer starts with the LayerNorm of its first feed-forward
+// module (Conformer.py:498 -> :479), the last layer's norm2 is followed by the encoder's final norm (:700): fusing the pair
+// saves one launch and one 16 MB read of x per layer.  One warp per row, the row (D <= 1024) lives in registers.
+template <bool OUT_HALF>
+__global__ void __launch_bounds__(256)
+layernorm2_rows_kernel(const float* __restrict__ x, float* __restrict__ y_out, void* __restrict__ z_out,
+                       const float* __restrict__ ga, const float* __restrict__ ba, float eps_a,
+                       const float* __restrict__ gb, const float* __restrict__ bb, float eps_b, int M, int D) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const int lane = threadIdx.x & 31;
+    const float* xr = x + static_cast<size_t>(row) * D;
+    float v[LN_MAX_PER_LANE];
+    const int nv = D >> 2;
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_PER_LANE / 4; ++i) {
+        const int vi = lane + i * 32;
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (vi < nv) t = *reinterpret_cast<const float4*>(xr + vi * 4);
+        v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+        s += (t.x + t.y) + (t.z + t.w);
+    }
+    float mean = warp_sum(s) / D;
+    float q = 0.0f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_PER_LANE / 4; ++i)
+        if (lane + i * 32 < nv) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const float d = v[4 * i + j] - mean; q += d * d; }
+        }
+    float rstd = rsqrtf(warp_sum(q) / D + eps_a);
+    s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_PER_LANE / 4; ++i) {
+        const int vi = lane + i * 32;
+        if (vi < nv) {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(ga + vi * 4));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(ba + vi * 4));
+            v[4 * i] = (v[4 * i] - mean) * rstd * g.x + b.x;
+            v[4 * i + 1] = (v[4 * i + 1] - mean) * rstd * g.y + b.y;
+            v[4 * i + 2] = (v[4 * i + 2] - mean) * rstd * g.z + b.z;
+            v[4 * i + 3] = (v[4 * i + 3] - mean) * rstd * g.w + b.w;
+            if (y_out != nullptr)
+                *reinterpret_cast<float4*>(y_out + static_cast<size_t>(row) * D + vi * 4) =
+                    make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            s += (v[4 * i] + v[4 * i + 1]) + (v[4 * i + 2] + v[4 * i + 3]);
+        }
+    }
+    mean = warp_sum(s) / D;
+    q = 0.0f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_PER_LANE / 4; ++i)
+        if (lane + i * 32 < nv) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const float d = v[4 * i + j] - mean; q += d * d; }
+        }
+    rstd = rsqrtf(warp_sum(q) / D + eps_b);
+#pragma unroll
+    for (int i = 0; i < LN_MAX_PER_LANE / 4; ++i) {
+        const int vi = lane + i * 32;
+        if (vi < nv) {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(gb + vi * 4));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(bb + vi * 4));
+            const float z0 = (v[4 * i] - mean) * rstd * g.x + b.x, z1 = (v[4 * i + 1] - mean) * rstd * g.y + b.y;
+            const float z2 = (v[4 * i + 2] - mean) * rstd * g.z + b.z, z3 = (v[4 * i + 3] - mean) * rstd * g.w + b.w;
+            if constexpr (OUT_HALF) {
+                __half2 h0 = floats2half2_sat(z0, z1), h1 = floats2half2_sat(z2, z3);
+                uint2 u;
+                u.x = *reinterpret_cast<uint32_t*>(&h0);
+                u.y = *reinterpret_cast<uint32_t*>(&h1);
+                *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(z_out) + static_cast<size_t>(row) * D + vi * 4) = u;
+            } else {
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(z_out) + static_cast<size_t>(row) * D + vi * 4) =
+                    make_float4(z0, z1, z2, z3);
+            }
+        }
+    }
+}
+
+int layernorm2_rows(const float* x, float* y_out, void* z_out, bool z_half, const float* ga, const float* ba, float eps_a,
+                    const float* gb, const float* bb, float eps_b, int M, int D, cudaStream_t stream) {
+    SBK_REQUIRE(D % 4 == 0 && D <= 32 * LN_MAX_PER_LANE, "layernorm2_rows: D=%d unsupported", D);
+    if (M == 0) return SBK_OK;
+    const int rows_per_cta = 8;
+    if (z_half)
+        layernorm2_rows_kernel<true><<<ceil_div(M, rows_per_cta), rows_per_cta * 32, 0, stream>>>(x, y_out, z_out, ga, ba, eps_a,
+                                                                                                 gb, bb, eps_b, M, D);
+    else
+        layernorm2_rows_kernel<false><<<ceil_div(M, rows_per_cta), rows_per_cta * 32, 0, stream>>>(x, y_out, z_out, ga, ba, eps_a,
+                                                                                                  gb, bb, eps_b, M, D);
+    SBK_LAUNCH_CHECK();
+    return SBK_OK;
+}
+
 // fp32 -> fp16 cast (used for goldens-driven tests and the decoder memory)
 __global__ void cast_f32_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, size_t n) {
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;

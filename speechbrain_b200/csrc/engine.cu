@@ -209,8 +209,8 @@ int asr_create(const sbk_asr_config* cfg, const sbk_tensor* weights, int n_weigh
                 "asr_create: attention_type must be RoPEMHA or RelPosMHAXL");
     const int d = c.d_model, dh = d / c.nhead, F = c.d_ffn, K = c.kernel_size;
     SBK_REQUIRE(dh == 64 || dh == 36 || dh == 32, "asr_create: encoder head_dim=%d not built (64, 36, 32)", dh);
-    SBK_REQUIRE(!((c.parts & SBK_PART_DECODER) && c.num_decoder_layers > 0) || dh == 64,
-                "asr_create: the decoder kernels are built for head_dim 64 only (got %d)", dh);
+    SBK_REQUIRE(!((c.parts & SBK_PART_DECODER) && c.num_decoder_layers > 0) || (dh <= 64 && dh % 4 == 0 && d % 16 == 0),
+                "asr_create: decoder head_dim must be a multiple of 4 up to 64 and d_model a multiple of 16 (got %d, %d)", dh, d);
     SBK_REQUIRE(c.attention_type != SBK_ATT_ROPE || dh % 32 == 0, "asr_create: RoPEMHA needs head_dim %% 32 == 0");
     std::map<std::string, std::pair<const float*, int64_t>> w;
     for (int i = 0; i < n_weights; ++i) w[weights[i].name] = {weights[i].data, weights[i].numel};
@@ -616,8 +616,8 @@ static int run_encoder(AsrModel* m, const float* feats, int B, int T0, const int
     const float att_scale = 1.0f / sqrtf((float)d);  // nnet/attention.py:521,1272: 1/sqrt(embed_dim), not head_dim
     for (int l = 0; l < c.num_encoder_layers; ++l) {
         const EncLayerW& w = m->enc[l];
-        // --- ffn module 1 (Conformer.py:479)
-        RC(layernorm_rows(b.x, b.h16, true, w.ffn1_ln_g, w.ffn1_ln_b, M, d, 1e-5f, false, st));
+        // --- ffn module 1 (Conformer.py:479); its LayerNorm was fused into the previous layer's norm2 kernel
+        if (l == 0) RC(layernorm_rows(b.x, b.h16, true, w.ffn1_ln_g, w.ffn1_ln_b, M, d, 1e-5f, false, st));
         e = GemmEpilogue(); e.mode = EPI_F16; e.act = ACT_SILU; e.bias = w.ffn1_b1; e.out = b.f16; e.ldo = F;
         RC(gemm_f16(b.h16, d, w.ffn1_w1, d, e, M, F, d, st));
         e = GemmEpilogue(); e.mode = EPI_RESID; e.bias = w.ffn1_b2; e.out = b.x; e.resid = b.x; e.ldo = d; e.alpha = 0.5f;
@@ -653,9 +653,16 @@ static int run_encoder(AsrModel* m, const float* feats, int B, int T0, const int
         RC(gemm_f16(b.h16, d, w.ffn2_w1, d, e, M, F, d, st));
         e = GemmEpilogue(); e.mode = EPI_RESID; e.bias = w.ffn2_b2; e.out = b.x; e.resid = b.x; e.ldo = d; e.alpha = 0.5f;
         RC(gemm_f16(b.f16, F, w.ffn2_w2, F, e, M, d, F, st));
-        RC(layernorm_rows(b.x, b.x, false, w.norm2_g, w.norm2_b, M, d, 1e-5f, false, st));
+        if (l + 1 < c.num_encoder_layers) {  // norm2 (fp32 residual stream) + the next layer's ffn1 LayerNorm (fp16 operand)
+            const EncLayerW& nx = m->enc[l + 1];
+            RC(layernorm2_rows(b.x, b.x, b.h16, true, w.norm2_g, w.norm2_b, 1e-5f, nx.ffn1_ln_g, nx.ffn1_ln_b, 1e-5f, M, d, st));
+        } else {                             // norm2 + the encoder's final LayerNorm (Conformer.py:700)
+            RC(layernorm2_rows(b.x, nullptr, enc_out, false, w.norm2_g, w.norm2_b, 1e-5f, m->enc_norm_g, m->enc_norm_b, 1e-6f, M,
+                               d, st));
+        }
     }
-    RC(layernorm_rows(b.x, enc_out, false, m->enc_norm_g, m->enc_norm_b, M, d, 1e-6f, false, st));  // Conformer.py:700
+    if (c.num_encoder_layers == 0)
+        RC(layernorm_rows(b.x, enc_out, false, m->enc_norm_g, m->enc_norm_b, M, d, 1e-6f, false, st));
     return SBK_OK;
 }
 
@@ -671,7 +678,7 @@ __global__ void abs_len_kernel(const float* rel, int B, int T, int* out) {
 static int dec_ln(AsrModel* m, SkinnyArgs& a, const float* g, const float* bta, int rows, cudaStream_t st) {
     AsrModel::Buf& b = m->b;
     const int d = m->cfg.d_model;
-    if (m->fuse_dec_ln) {
+    if (m->fuse_dec_ln && (d == 256 || d == 512 || d == 768 || d == 1024)) {  // widths the LN-fused projection is built for
         a.X = b.dx; a.ln_g = g; a.ln_b = bta; a.ln_eps = 1e-6f;
         return SBK_OK;
     }
@@ -732,7 +739,8 @@ static int enqueue_decode_layers_tc(AsrModel* m, int rows, int rows_per_utt, int
 
 static int enqueue_decode_layers(AsrModel* m, int rows, int rows_per_utt, int T, int S_max, const int* lineage,
                                  cudaStream_t st, bool with_head = true) {
-    if (rows >= m->dec_tc_rows) return enqueue_decode_layers_tc(m, rows, rows_per_utt, T, S_max, lineage, st, with_head);
+    if (rows >= m->dec_tc_rows && m->cfg.d_model % 32 == 0)  // (the QKV -> cache scatter epilogue works on 32-column chunks)
+        return enqueue_decode_layers_tc(m, rows, rows_per_utt, T, S_max, lineage, st, with_head);
     const sbk_asr_config& c = m->cfg;
     AsrModel::Buf& b = m->b;
     const int d = c.d_model, F = c.d_ffn, H = c.nhead, dh = d / H, Ld = c.num_decoder_layers;
@@ -803,7 +811,48 @@ static int enqueue_decode_step(AsrModel* m, int rows, int rows_per_utt, int T, i
 // One TransformerLM step over `rows` hypotheses (post-norm encoder layers with a lineage-indexed KV cache), ending in
 // b.lm_extra[rows, V] = weight * log_softmax(lm_logits / temperature): TransformerLMScorer.score (scorer.py:510-543)
 // scaled by ScorerBuilder's weight.  b.lx / b.lx16 hold emb[token] * sqrt(d) + pe[step] (beam_reset / beam_step).
+// The same step with the projections on the tcgen05 GEMM (128 x 32/64 tiles): used when many hypotheses are live (wide beams,
+// B * beam >= dec_tc_rows), where the weight-streaming kernel's cost grows with every 32 rows.
+static int enqueue_lm_step_tc(AsrModel* m, int rows, int S_max, float temperature, float weight, cudaStream_t st) {
+    const sbk_asr_config& c = m->cfg;
+    AsrModel::Buf& b = m->b;
+    const int dl = c.lm_d_model, Fl = c.lm_d_ffn, H = c.lm_nhead;
+    for (int l = 0; l < c.lm_layers; ++l) {
+        const LmLayerW& w = m->lm[l];
+        __half* kc = b.lkc + (size_t)l * rows * S_max * dl;
+        __half* vc = b.lvc + (size_t)l * rows * S_max * dl;
+        GemmEpilogue e;
+        e.mode = EPI_QKV_CACHE; e.bias = w.b_in; e.out = b.lq16; e.ldo = dl; e.kcache = kc; e.vcache = vc;
+        e.step_ptr = b.step; e.S_max = S_max; e.qkv_d = dl;
+        RC(gemm_f16_small(b.lx16, dl, w.w_in, dl, e, rows, 3 * dl, dl, st));
+        DecAttnArgs t{};
+        t.q = b.lq16; t.ldq = dl; t.kbase = kc; t.vbase = vc; t.row_stride = (size_t)S_max * dl; t.key_stride = dl;
+        t.rows_per_block = 1; t.n_keys_ptr = b.step; t.H = H; t.dh = 64; t.out = b.latt16; t.ldo = dl;
+        t.lineage = b.lineage; t.lin_stride = S_max; t.tok_cache = b.tok_cache; t.pad_tok = 0;
+        RC(dec_attention(t, rows, S_max, st));
+        e = GemmEpilogue(); e.mode = EPI_RESID; e.bias = w.b_out; e.out = b.lx; e.resid = b.lx; e.ldo = dl;
+        RC(gemm_f16_small(b.latt16, dl, w.w_out, dl, e, rows, dl, dl, st));
+        RC(layernorm_dual(b.lx, b.lx16, w.n1g, w.n1b, rows, dl, 1e-6f, true, st));
+        e = GemmEpilogue(); e.mode = EPI_F16; e.act = c.lm_activation == SBK_ACT_GELU ? ACT_GELU : ACT_RELU;
+        e.bias = w.b1; e.out = b.lf16; e.ldo = Fl;
+        RC(gemm_f16_small(b.lx16, dl, w.w1, dl, e, rows, Fl, dl, st));
+        e = GemmEpilogue(); e.mode = EPI_RESID; e.bias = w.b2; e.out = b.lx; e.resid = b.lx; e.ldo = dl;
+        RC(gemm_f16_small(b.lf16, Fl, w.w2, Fl, e, rows, dl, Fl, st));
+        RC(layernorm_dual(b.lx, b.lx16, w.n2g, w.n2b, rows, dl, 1e-6f, true, st));
+    }
+    RC(layernorm_dual(b.lx, b.lx16, m->lm_norm_g, m->lm_norm_b, rows, dl, 1e-6f, false, st));  // encoder.norm
+    GemmEpilogue e;
+    e.mode = EPI_F32; e.bias = m->lm_bp0; e.out = b.lh32; e.ldo = dl;
+    RC(gemm_f16_small(b.lx16, dl, m->lm_wp0, dl, e, rows, dl, dl, st));
+    RC(layernorm_dual(b.lh32, b.lh16, m->lm_lnp_g, m->lm_lnp_b, rows, dl, 1e-6f, false, st));
+    e = GemmEpilogue(); e.mode = EPI_F32; e.bias = m->lm_bp2; e.out = b.lm_logits; e.ldo = c.vocab;
+    RC(gemm_f16_small(b.lh16, dl, m->lm_wp2, dl, e, rows, c.vocab, dl, st));
+    RC(weighted_log_softmax(b.lm_logits, b.lm_extra, rows, c.vocab, temperature, weight, st));
+    return SBK_OK;
+}
+
 static int enqueue_lm_step(AsrModel* m, int rows, int S_max, float temperature, float weight, cudaStream_t st) {
+    if (rows >= m->dec_tc_rows) return enqueue_lm_step_tc(m, rows, S_max, temperature, weight, st);
     const sbk_asr_config& c = m->cfg;
     AsrModel::Buf& b = m->b;
     const int dl = c.lm_d_model, Fl = c.lm_d_ffn, H = c.lm_nhead;

@@ -10,6 +10,8 @@
 // conv1 (C_in = 1) is HBM/latency bound: one CTA per output frame, fused LN + LeakyReLU.
 // conv2 (C1 -> C2, K = 9*C1 = 576) is an implicit GEMM on mma.sync.m16n8k16 (fp16 in, fp32 accumulate);
 // the weight matrix and a 9-frame input patch live in shared memory; LN + LeakyReLU fused.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -212,6 +214,173 @@ conv2_ln_kernel(const __half* __restrict__ act1, int T1, int F1, int T2, int F2,
     }
 }
 
+
+// --------------------------------------------------------------------------- conv1 + conv2 fused
+// The two-kernel version wrote conv1's output (B x T1 x F1 x 64 fp16 = 82 MB per 32 x 10 s batch) to global memory and read
+// it back: conv2 alone took 141 us on 82 MB of DRAM reads at 15 % occupancy (ncu, profiles/r2b_enc_summary.csv), conv1 92 us.
+// Here one CTA produces C2_FRAMES output frames from the input features directly: its 9 warps each compute one conv1 frame
+// (3x3 conv, LayerNorm over (F1, 64), LeakyReLU) with the frame held in registers, and write it -- fp16, reflect columns
+// included -- straight into the shared-memory patch the implicit-GEMM conv2 reads.  Global traffic per batch: the 10 MB of
+// features (re-read ~2.3x through L2) + the 10 MB output instead of 2 x 82 MB.  Same arithmetic as the two kernels
+// (conv1 fp32 -> LN -> fp16; conv2 fp16 operands, fp32 accumulate), so the results are bit-identical to them.
+constexpr int CF_WARPS = 2 * C2_FRAMES + 1;  // one per conv1 frame of the patch
+
+template <int MAXF>
+__global__ void __launch_bounds__(CF_WARPS * 32, 2)
+cnn_fused_kernel(const float* __restrict__ feats, int T0, int F0, int T1, int F1, int T2, int F2, const float* __restrict__ w1,
+                 const float* __restrict__ b1, const float* __restrict__ g1, const float* __restrict__ be1,
+                 const __half* __restrict__ w2p, const float* __restrict__ b2, const float* __restrict__ g2,
+                 const float* __restrict__ be2, __half* __restrict__ out_h, float* __restrict__ out_f) {
+    extern __shared__ __align__(16) uint8_t c2_smem[];
+    constexpr int C1 = C2_CIN;
+    const int FPAD = F1 + 2, FP0 = F0 + 2;
+    constexpr int n_trows = CF_WARPS;
+    __half* patch = reinterpret_cast<__half*>(c2_smem);                 // [n_trows][FPAD][C2_CELL]
+    __half* wsm = patch + n_trows * FPAD * C2_CELL;                     // [32][C2_WROW]
+    float* cbuf = reinterpret_cast<float*>(wsm + C2_COUT * C2_WROW);    // [C2_FRAMES * F2][33]
+    float* in_all = cbuf + C2_FRAMES * F2 * 33;                         // [CF_WARPS][3][F0 + 2]
+    const int b = blockIdx.y, t0 = blockIdx.x * C2_FRAMES;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // conv2 weights -> shared memory (independent of everything else: issued first)
+    for (int i = threadIdx.x; i < C2_COUT * (9 * C2_CIN / 8); i += blockDim.x) {
+        const int o = i / (9 * C2_CIN / 8), v8 = i - o * (9 * C2_CIN / 8);
+        *reinterpret_cast<uint4*>(wsm + o * C2_WROW + v8 * 8) =
+            *reinterpret_cast<const uint4*>(w2p + static_cast<size_t>(o) * 9 * C2_CIN + v8 * 8);
+    }
+    // ---- stage 1: warp `warp` computes conv1 frame t1 = reflect(2 t0 + warp - 1) into patch row `warp`
+    {
+        int t1 = reflect_idx(2 * t0 + warp - 1, T1);
+        t1 = min(max(t1, 0), T1 - 1);  // tail tiles: keep loads in range (results discarded)
+        float* in = in_all + warp * 3 * FP0;
+        for (int i = lane; i < 3 * FP0; i += 32) {
+            const int kt = i / FP0, fp = i - kt * FP0;
+            const int t = reflect_idx(2 * t1 + kt - 1, T0);
+            const int f = reflect_idx(fp - 1, F0);
+            in[i] = __ldg(feats + (static_cast<size_t>(b) * T0 + t) * F0 + f);
+        }
+        const int c0 = 2 * lane;
+        float wa[9], wb[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) { wa[i] = __ldg(w1 + c0 * 9 + i); wb[i] = __ldg(w1 + (c0 + 1) * 9 + i); }
+        const float ba = __ldg(b1 + c0), bb = __ldg(b1 + c0 + 1);
+        __syncwarp();
+        float va[MAXF], vb[MAXF];
+        float s = 0.0f;
+#pragma unroll
+        for (int f1 = 0; f1 < MAXF; ++f1) {
+            va[f1] = 0.0f; vb[f1] = 0.0f;
+            if (f1 < F1) {
+                float a = ba, bq = bb;
+#pragma unroll
+                for (int kf = 0; kf < 3; ++kf)
+#pragma unroll
+                    for (int kt = 0; kt < 3; ++kt) {
+                        const float x = in[kt * FP0 + 2 * f1 + kf];
+                        a = fmaf(wa[kf * 3 + kt], x, a);
+                        bq = fmaf(wb[kf * 3 + kt], x, bq);
+                    }
+                va[f1] = a; vb[f1] = bq;
+                s += a + bq;
+            }
+        }
+        const float n = static_cast<float>(F1 * C1);
+        const float mean = warp_sum(s) / n;
+        float q = 0.0f;
+#pragma unroll
+        for (int f1 = 0; f1 < MAXF; ++f1)
+            if (f1 < F1) {
+                const float da = va[f1] - mean, db = vb[f1] - mean;
+                q += da * da + db * db;
+            }
+        const float rstd = rsqrtf(warp_sum(q) / n + 1e-5f);
+        __half* prow = patch + static_cast<size_t>(warp) * FPAD * C2_CELL;
+#pragma unroll
+        for (int f1 = 0; f1 < MAXF; ++f1)
+            if (f1 < F1) {
+                const int gi = f1 * C1 + c0;
+                const float2 g = __ldg(reinterpret_cast<const float2*>(g1 + gi));
+                const float2 be = __ldg(reinterpret_cast<const float2*>(be1 + gi));
+                const __half2 y = floats2half2_sat(leaky((va[f1] - mean) * rstd * g.x + be.x),
+                                                   leaky((vb[f1] - mean) * rstd * g.y + be.y));
+                *reinterpret_cast<__half2*>(prow + (f1 + 1) * C2_CELL + c0) = y;
+                // reflect padding of the feature axis: column -1 mirrors f1 = 1, column F1 mirrors f1 = F1 - 2
+                if (f1 == 1) *reinterpret_cast<__half2*>(prow + c0) = y;
+                if (f1 == F1 - 2) *reinterpret_cast<__half2*>(prow + (F1 + 1) * C2_CELL + c0) = y;
+            }
+    }
+    __syncthreads();
+
+    // ---- stage 2: conv2 as an implicit GEMM over the patch (identical to conv2_ln_kernel from here on)
+    const int rows = C2_FRAMES * F2;
+    const int g = lane >> 2, c = lane & 3;
+    const int r0 = warp * 16 + g, r1 = r0 + 8;
+    if (warp * 16 < rows) {
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+        const int rr0 = min(r0, rows - 1), rr1 = min(r1, rows - 1);
+        const int fr0 = rr0 / F2, f20 = rr0 - fr0 * F2;
+        const int fr1 = rr1 / F2, f21 = rr1 - fr1 * F2;
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap) {
+            const int kf = tap / 3, kt = tap - kf * 3;
+            const __half* a0p = patch + ((2 * fr0 + kt) * FPAD + 2 * f20 + kf) * C2_CELL + 2 * c;
+            const __half* a1p = patch + ((2 * fr1 + kt) * FPAD + 2 * f21 + kf) * C2_CELL + 2 * c;
+#pragma unroll
+            for (int ks = 0; ks < C2_CIN / 16; ++ks) {
+                uint32_t a[4];
+                a[0] = *reinterpret_cast<const uint32_t*>(a0p + ks * 16);
+                a[1] = *reinterpret_cast<const uint32_t*>(a1p + ks * 16);
+                a[2] = *reinterpret_cast<const uint32_t*>(a0p + ks * 16 + 8);
+                a[3] = *reinterpret_cast<const uint32_t*>(a1p + ks * 16 + 8);
+                const int kk = tap * C2_CIN + ks * 16 + 2 * c;
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    uint32_t bb[2];
+                    const __half* wp = wsm + (nt * 8 + g) * C2_WROW + kk;
+                    bb[0] = *reinterpret_cast<const uint32_t*>(wp);
+                    bb[1] = *reinterpret_cast<const uint32_t*>(wp + 8);
+                    mma_16816(acc[nt], a, bb);
+                }
+            }
+        }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            const int col = nt * 8 + 2 * c;
+            const float bz0 = __ldg(b2 + col), bz1 = __ldg(b2 + col + 1);
+            if (r0 < rows) { cbuf[r0 * 33 + col] = acc[nt][0] + bz0; cbuf[r0 * 33 + col + 1] = acc[nt][1] + bz1; }
+            if (r1 < rows) { cbuf[r1 * 33 + col] = acc[nt][2] + bz0; cbuf[r1 * 33 + col + 1] = acc[nt][3] + bz1; }
+        }
+    }
+    __syncthreads();
+    // LayerNorm over (F2, 32) per frame + LeakyReLU; one warp per frame
+    if (warp < C2_FRAMES) {
+        const int t = t0 + warp;
+        if (t < T2) {
+            const int n = F2 * C2_COUT;
+            const float* src = cbuf + warp * F2 * 33;
+            float s = 0.0f;
+            for (int i = lane; i < n; i += 32) s += src[(i >> 5) * 33 + (i & 31)];
+            const float mean = warp_sum(s) / n;
+            float q = 0.0f;
+            for (int i = lane; i < n; i += 32) {
+                const float d = src[(i >> 5) * 33 + (i & 31)] - mean;
+                q += d * d;
+            }
+            const float rstd = rsqrtf(warp_sum(q) / n + 1e-5f);
+            const size_t ob = (static_cast<size_t>(b) * T2 + t) * n;
+            for (int i = lane; i < n; i += 32) {
+                const float y = leaky((src[(i >> 5) * 33 + (i & 31)] - mean) * rstd * __ldg(g2 + i) + __ldg(be2 + i));
+                out_h[ob + i] = float2half_sat(y);
+                if (out_f) out_f[ob + i] = y;
+            }
+        }
+    }
+}
+
 int cnn_frontend_forward(const float* feats, int B, int T0, int F0, const float* w1, const float* b1, const float* g1,
                          const float* be1, int C1, const __half* w2p, const float* b2, const float* g2,
                          const float* be2, int C2, __half* act1_h, float* act1_f, __half* out_h, float* out_f,
@@ -221,6 +390,18 @@ int cnn_frontend_forward(const float* feats, int B, int T0, int F0, const float*
     const int T1 = (T0 - 1) / 2 + 1, F1 = (F0 - 1) / 2 + 1;
     const int T2 = (T1 - 1) / 2 + 1, F2 = (F1 - 1) / 2 + 1;
     SBK_REQUIRE(F1 <= 64 && F2 * C2_FRAMES <= 96, "cnn_frontend: feature dim too large (F0=%d)", F0);
+    // default: the fused kernel (conv1 output never leaves the SM); SBK_CNN_UNFUSED=1 or a caller that wants conv1's output
+    // runs the two-kernel version
+    static const bool unfused = getenv("SBK_CNN_UNFUSED") != nullptr;
+    if (!unfused && act1_f == nullptr && F1 <= 40 && F1 >= 3 && C2_FRAMES * F2 <= 16 * CF_WARPS) {
+        const size_t smem = static_cast<size_t>(CF_WARPS) * (F1 + 2) * C2_CELL * 2 + C2_COUT * C2_WROW * 2 +
+                            static_cast<size_t>(C2_FRAMES) * F2 * 33 * 4 + static_cast<size_t>(CF_WARPS) * 3 * (F0 + 2) * 4;
+        SBK_CUDA_CHECK(cudaFuncSetAttribute(cnn_fused_kernel<40>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cnn_fused_kernel<40><<<dim3(ceil_div(T2, C2_FRAMES), B), CF_WARPS * 32, smem, stream>>>(
+            feats, T0, F0, T1, F1, T2, F2, w1, b1, g1, be1, w2p, b2, g2, be2, out_h, out_f);
+        SBK_LAUNCH_CHECK();
+        return SBK_OK;
+    }
     {
         const size_t smem = static_cast<size_t>(C1_WARPS) * 3 * (F0 + 2) * sizeof(float);
         const dim3 grid(ceil_div(T1, C1_WARPS), B);

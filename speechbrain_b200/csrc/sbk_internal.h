@@ -78,6 +78,9 @@ int cnn_frontend_forward(const float* feats, int B, int T0, int F0, const float*
 // ---- encoder_ops.cu
 int layernorm_rows(const float* x, void* out, bool out_half, const float* gamma, const float* beta, int M, int D,
                    float eps, bool act_silu, cudaStream_t stream);
+// y = LN_a(x) (fp32, stored when y_out != null), z = LN_b(y) -> z_out (fp16 or fp32): two chained LayerNorms in one pass
+int layernorm2_rows(const float* x, float* y_out, void* z_out, bool z_half, const float* ga, const float* ba, float eps_a,
+                    const float* gb, const float* bb, float eps_b, int M, int D, cudaStream_t stream);
 int cast_f32_f16(const float* in, __half* out, size_t n, cudaStream_t stream);
 int dwconv_ln_swish(const float* glu, int B, int T, int D, int K, const float* wdw, const float* bdw,
                     const float* gamma, const float* beta, float eps, __half* out, cudaStream_t stream);

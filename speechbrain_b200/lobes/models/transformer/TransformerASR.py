@@ -57,6 +57,8 @@ class TransformerASR(torch.nn.Module):
             unsupported.append("conformer_activation other than Swish")
         if d_model % nhead or d_model // nhead not in (64, 36, 32):
             unsupported.append(f"head_dim={d_model // max(nhead, 1)} (64, 36 or 32)")
+        if d_model % 16:
+            unsupported.append("d_model not a multiple of 16")
         if unsupported:
             raise NotImplementedError("speechbrain_b200.TransformerASR: not built: " + ", ".join(unsupported))
         act_name = getattr(activation, "__name__", str(activation))

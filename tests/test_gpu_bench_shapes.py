@@ -141,11 +141,23 @@ BEAM_CASES = [("bench_conformer_large_rope_10s", "beam_b10_lm_ctc"), ("bench_con
 def test_bench_shape_beam10(dev, file, case):
     """BASELINE config 4 family: beam = 10 on T = 251 memories: [TransformerLM 0.6, CTC 0.4] (test search), [CTC] (valid
     search) for 24 steps, and scorer-less searches whose hypotheses finish gradually (up to 48 steps)."""
+    g = torch.load(os.path.join(GOLDEN, "bench_conformer_large_rope_10s.pt"))
+    gb = torch.load(os.path.join(GOLDEN, file + ".pt"))[case]
+    _check_beam(dev, g, gb, case)
+
+
+def test_beam66_recipe_width(dev):
+    """beam_size = 66 (the recipe's test_beam_size, conformer_large.yaml:132) through the radix-select beam kernel, vs the
+    reference on the 2 s golden."""
+    g = torch.load(os.path.join(GOLDEN, "conformer_large_rope.pt"))
+    gb = torch.load(os.path.join(GOLDEN, "beam66_conformer_large_rope.pt"))
+    _check_beam(dev, g, gb, "beam66")
+
+
+def _check_beam(dev, g, gb, case):
     import bench
     from oracle import asr_oracle as O
     from speechbrain_b200.utils.seeded_init import seeded_asr_state, seeded_state_dict
-    g = torch.load(os.path.join(GOLDEN, "bench_conformer_large_rope_10s.pt"))
-    gb = torch.load(os.path.join(GOLDEN, file + ".pt"))[case]
     cfg = _cfg(g)
     sd = seeded_asr_state(cfg, 0)
     sd["seq_lin.w.bias"] = sd["seq_lin.w.bias"].clone()
@@ -156,6 +168,14 @@ def test_bench_shape_beam10(dev, file, case):
     bs.return_topk, bs.topk = True, gb["kwargs"]["beam_size"]
     enc, lens = g["enc_out"].to(dev), g["wav_lens"].to(dev)
     hyps, hlens, scores, lp = bs(enc, lens)
+    if gb["with_lm"] or case.endswith("eos16"):
+        # the same search with every projection (decoder AND TransformerLM step) on the tcgen05 GEMM instead of the
+        # weight-streaming kernel (what wide beams / many utterances use): same hypotheses, scores within 2e-3
+        bs._get_engine(dev).set_decoder_tc_min_rows(1)
+        h2, l2, s2, _ = bs(enc, lens)
+        bs._get_engine(dev).set_decoder_tc_min_rows(64)
+        print(f"beam[{case}] tcgen05 projections: best scores {s2[:, 0].tolist()}")
+        assert (s2[:, 0].cpu() - scores[:, 0].cpu()).abs().max() < 2e-3
     hyps, hlens, scores = hyps.cpu(), hlens.cpu(), scores.cpu()
     B, L = hyps.shape[0], hyps.shape[2]
     ref_h, ref_len, ref_s = gb["hyps"].long(), gb["lens"], gb["scores"]
@@ -167,8 +187,13 @@ def test_bench_shape_beam10(dev, file, case):
         assert abs(float(scores[b, 0]) - float(ref_s[b, 0])) < tol, f"best score {float(scores[b, 0])} vs reference {float(ref_s[b, 0])}"
         if ours != ref:
             diverged.append((b, ours))
+    # the n-best list as a whole: sorted scores of all `beam` hypotheses track the reference's
+    k = min(scores.shape[1], ref_s.shape[1])
+    nbest_err = (scores[:, :k] - ref_s[:, :k]).abs().max().item()
     print(f"beam[{case}] best scores {scores[:, 0].tolist()} ref {ref_s[:, 0].tolist()}; identical best hypothesis for "
-          f"{B - len(diverged)}/{B} utterances (reference top-1/top-2 gaps {(ref_s[:, 0] - ref_s[:, 1]).tolist()})")
+          f"{B - len(diverged)}/{B} utterances (reference top-1/top-2 gaps {(ref_s[:, 0] - ref_s[:, 1]).tolist()}); "
+          f"max |n-best score - reference| over all {k} ranks {nbest_err:.2e}")
+    assert nbest_err < tol
     if diverged:  # judge the near-tied alternative with the CPU oracle walked along OUR tokens
         lm = ctc = None
         if gb["with_lm"]:
@@ -180,12 +205,11 @@ def test_bench_shape_beam10(dev, file, case):
         if gb["with_ctc"]:
             ctc = dict(w=sd["ctc_lin.w.weight"], b=sd["ctc_lin.w.bias"], weight=0.4, blank_index=0)
         idx = [b for b, _ in diverged]
-        kw = {k: v for k, v in gb["kwargs"].items() if k != "beam_size"}
+        kw = {k_: v for k_, v in gb["kwargs"].items() if k_ != "beam_size"}
         ocfg = dict(g["cfg"])
         with torch.no_grad():
-            o = O.beam_search(g["enc_out"][idx], g["wav_lens"][idx] if len(idx) == B else _sub_lens(g, idx), sd, ocfg,
-                              sd["seq_lin.w.weight"], sd["seq_lin.w.bias"], 1, 2, beam_size=1, prefix="Transformer.", lm=lm, ctc=ctc,
-                              forced=[t for _, t in diverged], **kw)
+            o = O.beam_search(g["enc_out"][idx], g["wav_lens"][idx], sd, ocfg, sd["seq_lin.w.weight"], sd["seq_lin.w.bias"], 1, 2,
+                              beam_size=1, prefix="Transformer.", lm=lm, ctc=ctc, forced=[t for _, t in diverged], **kw)
         for (b, toks), osc in zip(diverged, o.tolist()):
             print(f"   utterance {b}: our hypothesis ({len(toks)} tokens) scores {float(scores[b, 0]):.5f}, the oracle gives it "
                   f"{osc:.5f}; reference best {float(ref_s[b, 0]):.5f}")
@@ -362,3 +386,31 @@ def test_fp16_range_scaled_weights(dev):
     enc2 = eng2.encode_from_cnn(cnn, g["wav_lens"].to(dev)).cpu()
     print(f"FFN x1e5 (hidden beyond the fp16 range): finite {bool(torch.isfinite(enc2).all())}, absmax {float(enc2.abs().max()):.2f}")
     assert torch.isfinite(enc2).all()
+
+
+def test_conformer_small_decoder_greedy(dev):
+    """conformer_small.yaml end to end (d_model 144, 4 heads of 36, 4 decoder layers): the decoder runs on the generic
+    head-dim decode attention and the unfused-LayerNorm projections; greedy tokens / log-probs vs the reference golden."""
+    g = torch.load(os.path.join(GOLDEN, "conformer_small_relpos.pt"))
+    cfg = _cfg(g)
+    eng, sd = _engine(cfg, dev)
+    n_steps = g["greedy_logits"].shape[1]
+    ref_lp = torch.log_softmax(g["greedy_logits"], -1)
+    top2 = g["greedy_logits"].topk(2, -1).values
+    margin = top2[..., 0] - top2[..., 1]
+    ref_tok = g["greedy_logits"].argmax(-1)
+    pred, score, lp, done = eng.greedy_from_enc(g["enc_out"].to(dev), g["wav_lens"].to(dev), n_steps, 1, 2, want_log_probs=True)
+    pred, lp = pred.cpu(), lp.cpu()
+    worst, compared = 0.0, 0
+    for b in range(pred.shape[0]):
+        for s in range(n_steps):
+            if pred[b, s] != ref_tok[b, s]:
+                assert margin[b, s] < 5e-3, f"token mismatch at b={b} s={s} with margin {margin[b, s]}"
+                break
+            worst = max(worst, (lp[b, s] - ref_lp[b, s]).abs().max().item())
+            compared += 1
+    print(f"[conformer_small] greedy tokens {pred.tolist()} ref {g['hyps']}; {compared} steps compared, max log-prob err {worst:.2e}")
+    assert worst < 2e-2 and compared >= n_steps
+    # and the whole path from the waveform
+    p2, _, enc, _ = eng.transcribe_greedy_dev(g["wav"].to(dev), g["wav_lens"].to(dev), n_steps, 1, 2, want_enc=True)
+    assert _rel(enc.cpu(), g["enc_out"]) < 1.5e-3
