@@ -545,11 +545,11 @@ def run_greedy32(args):
         dist.destroy_process_group()
 
 
-def build_product_asr(cfg, sd, dev, decoder="greedy", beam=10, lm=False, ctc=False):
+def build_product_asr(cfg, sd, dev, decoder="greedy", beam=10, lm=False, ctc=False, coverage=None):
     """speechbrain_b200 module mirrors wired like the recipe, loaded with the seeded state through load_state_dict."""
     import torch
 
-    from speechbrain_b200.decoders.scorer import CTCScorer, ScorerBuilder, TransformerLMScorer
+    from speechbrain_b200.decoders.scorer import CoverageScorer, CTCScorer, ScorerBuilder, TransformerLMScorer
     from speechbrain_b200.decoders.seq2seq import S2STransformerBeamSearcher, S2STransformerGreedySearcher
     from speechbrain_b200.inference.ASR import EncoderDecoderASR
     from speechbrain_b200.lobes.features import Fbank
@@ -591,6 +591,9 @@ def build_product_asr(cfg, sd, dev, decoder="greedy", beam=10, lm=False, ctc=Fal
             ctc_lin.load_state_dict({"w.weight": sd["ctc_lin.w.weight"], "w.bias": sd["ctc_lin.w.bias"]})
             full.append(CTCScorer(eos_index=EOS, blank_index=0, ctc_fc=ctc_lin))
             weights["ctc"] = 0.4
+        if coverage is not None:  # (weight, threshold)
+            full.append(CoverageScorer(cfg["vocab"], threshold=coverage[1]))
+            weights["coverage"] = coverage[0]
         scorer = ScorerBuilder(full_scorers=full, weights=weights) if full else None
         dec = S2STransformerBeamSearcher(modules=[tr, lin], bos_index=BOS, eos_index=EOS, min_decode_ratio=0.0,
                                          max_decode_ratio=(DECODE_STEPS + 0.5) / 251.0, beam_size=beam, temperature=1.15,

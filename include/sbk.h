@@ -61,6 +61,9 @@ typedef struct {
     int blank_index;
     /* LengthScorer (decoders/scorer.py:956-1072): this constant is added to every token's log-prob at every step */
     float length_weight;
+    /* CoverageScorer (decoders/scorer.py:788-955) on the last decoder layer's head-averaged cross-attention:
+       score = -(sum_t max(coverage_t, threshold) - T * threshold) / time_step, weighted; 0 weight = off */
+    float coverage_weight, coverage_threshold;
 } sbk_beam_params;
 
 const char* sbk_last_error(void); /* thread-local message of the last failing call */

@@ -421,7 +421,7 @@ def full_pipeline_features(wav, wav_lens, sd, cfg):
 def beam_search(enc_states, wav_len, sd, cfg, seq_lin_w, seq_lin_b, bos_index=1, eos_index=2, beam_size=4,
                 min_decode_ratio=0.0, max_decode_ratio=1.0, temperature=1.0, using_eos_threshold=True,
                 eos_threshold=1.5, length_normalization=True, minus_inf=-1e20, topk=1, prefix="", return_history=False,
-                lm=None, ctc=None, return_topk=False, length_weight=0.0, forced=None):
+                lm=None, ctc=None, return_topk=False, length_weight=0.0, forced=None, coverage=None):
     """S2STransformerBeamSearcher.forward, using_max_attn_shift=False; scorer=None, or a ScorerBuilder with full scorers
     TransformerLMScorer (``lm`` = dict(sd, cfg, weight, temperature, prefix)) and/or CTCScorer (``ctc`` = dict(w, b, weight,
     blank_index)), in the recipe's order [transformerlm, ctc] (scorer.py:1221-1268; conformer_large.yaml:209-223).
@@ -477,7 +477,7 @@ def beam_search(enc_states, wav_len, sd, cfg, seq_lin_w, seq_lin_b, bos_index=1,
         if forced is None and [len(f) for f in finished] == [beam_size] * B:
             break
         memory = inp.unsqueeze(1) if memory is None else torch.cat([memory, inp.unsqueeze(1)], dim=-1)
-        pred, _ = decode(memory, enc, enc_l, sd, cfg, prefix)
+        pred, attn = decode(memory, enc, enc_l, sd, cfg, prefix)
         log_probs = F.log_softmax(F.linear(pred, seq_lin_w, seq_lin_b) / temperature, dim=-1)[:, -1, :]
         if ctc is not None:
             log_probs = attn_weight * log_probs  # _attn_weight_step (:916-921)
@@ -495,6 +495,10 @@ def beam_search(enc_states, wav_len, sd, cfg, seq_lin_w, seq_lin_b, bos_index=1,
             log_probs[:, ctc["blank_index"]] = ctc_state["minus_inf"]
             ctc_score, ctc_mem = ctc_prefix_step(ctc_state, inp, ctc_mem, beam_size)
             log_probs = log_probs + ctc["weight"] * ctc_score
+        if coverage is not None:  # CoverageScorer.score (scorer.py:880-922): attn (n_bh, s, T) of the last decoder layer
+            cov = attn.sum(dim=1)
+            penalty = torch.max(cov, cov.clone().fill_(coverage["threshold"])).sum(-1) - cov.size(-1) * coverage["threshold"]
+            log_probs = log_probs + coverage["weight"] * (-penalty / (step + 1)).unsqueeze(1)
         if length_weight != 0.0:  # LengthScorer.score (scorer.py:1043-1071): ones * weight on every token
             log_probs = log_probs + length_weight
         sc = seq_scores.unsqueeze(1) + log_probs

@@ -549,7 +549,8 @@ def ctc_greedy_case(tag="ctc_greedy_conformer_large_rope"):
     torch.save(out, os.path.join(OUT, f"{tag}.pt"))
 
 
-SCALES = {"ffn_w1": 200.0, "qkv": 3.0, "pw1": 4.0}
+SCALES = {"ffn": {"ffn_w1": 200.0, "qkv": 1.0, "pw1": 1.0},      # FFN pre-activations in the hundreds
+          "attn": {"ffn_w1": 1.0, "qkv": 3.0, "pw1": 4.0}}        # attention logits x9 (peaky softmax), GLU inputs x4
 
 
 def scale_state(sd, scales):
@@ -566,27 +567,31 @@ def scale_state(sd, scales):
 
 
 def scaled_case(tag="conformer_large_rope_scaled"):
-    """fp16 range: the 2 s RoPE golden re-run by the reference with FFN-hidden / attention-logit / GLU
-    pre-activations pushed far above what random init gives (max |FFN hidden| in the thousands, attention logits x9)."""
-    fb, norm, mods, sd = build_reference(CFG_L, "RoPEMHA")
+    """fp16 range: the 2 s RoPE golden re-run by the reference with (a) FFN pre-activations pushed into the
+    hundreds, (b) attention logits x9 and GLU inputs x4 -- far above what random init gives."""
     g = torch.load(os.path.join(OUT, "conformer_large_rope.pt"))
-    sds = scale_state(sd, SCALES)
-    mods.load_state_dict({k: v for k, v in sds.items() if not k.startswith("normalize.")})
-    stats = {"ffn_hidden_absmax": 0.0, "qkv_absmax": 0.0}
+    out = {}
+    for name, sc in SCALES.items():
+        fb, norm, mods, sd = build_reference(CFG_L, "RoPEMHA")
+        sds = scale_state(sd, sc)
+        mods.load_state_dict({k: v for k, v in sds.items() if not k.startswith("normalize.")})
+        stats = {"ffn_hidden_absmax": 0.0}
 
-    def hook_ffn(m, i, o):
-        stats["ffn_hidden_absmax"] = max(stats["ffn_hidden_absmax"], float(o.abs().max()))
-    for layer in mods["Transformer"].encoder.layers:
-        layer.ffn_module1[1].ffn[0].register_forward_hook(hook_ffn)
-        layer.ffn_module2[1].ffn[0].register_forward_hook(hook_ffn)
-    with torch.no_grad():
-        enc = mods["Transformer"].encode(g["cnn_out"], g["wav_lens"])
-        oenc = O.encode(g["cnn_out"].reshape(g["cnn_out"].shape[0], g["cnn_out"].shape[1], -1), g["wav_lens"], sds,
-                        dict(CFG_L, attention_type="RoPEMHA"), "Transformer.")
-    print(f"[scaled] enc finite {bool(torch.isfinite(enc).all())} oracle rel {rel(oenc, enc):.2e} max |FFN pre-activation| "
-          f"{stats['ffn_hidden_absmax']:.1f} enc absmax {float(enc.abs().max()):.2f}")
-    assert rel(oenc, enc) < 1e-5
-    torch.save(dict(scales=SCALES, enc_out=enc, ffn_hidden_absmax=stats["ffn_hidden_absmax"]), os.path.join(OUT, f"{tag}.pt"))
+        def hook_ffn(m, i, o):
+            stats["ffn_hidden_absmax"] = max(stats["ffn_hidden_absmax"], float(o.abs().max()))
+        for layer in mods["Transformer"].encoder.layers:
+            layer.ffn_module1[1].ffn[0].register_forward_hook(hook_ffn)
+            layer.ffn_module2[1].ffn[0].register_forward_hook(hook_ffn)
+        with torch.no_grad():
+            enc = mods["Transformer"].encode(g["cnn_out"], g["wav_lens"])
+            oenc = O.encode(g["cnn_out"].reshape(g["cnn_out"].shape[0], g["cnn_out"].shape[1], -1), g["wav_lens"], sds,
+                            dict(CFG_L, attention_type="RoPEMHA"), "Transformer.")
+        print(f"[scaled {name}] enc finite {bool(torch.isfinite(enc).all())} oracle rel {rel(oenc, enc):.2e} max |FFN pre-activation| "
+              f"{stats['ffn_hidden_absmax']:.1f} enc absmax {float(enc.abs().max()):.2f}")
+        assert rel(oenc, enc) < 1e-5
+        out[name] = dict(scales=sc, enc_out=enc, ffn_hidden_absmax=stats["ffn_hidden_absmax"])
+    torch.save(out, os.path.join(OUT, f"{tag}.pt"))
+
 
 
 def beam66_case(tag="beam66_conformer_large_rope"):
@@ -614,6 +619,40 @@ def beam66_case(tag="beam66_conformer_large_rope"):
     assert torch.equal(o_hyps[:, 0], tk_hyps[:, 0]) and (o_scores - tk_scores).abs().max() < 1e-3
     torch.save(dict(kwargs=kw, with_lm=False, with_ctc=False, eos_bias=eos_bias, max_decode_ratio=(steps + 0.5) / T,
                     hyps=tk_hyps.int(), lens=tk_len, scores=tk_scores, log_probs=tk_lp), os.path.join(OUT, f"{tag}.pt"))
+
+
+def beam_cov_case(tag="beam_cov_conformer_large_rope"):
+    """ScorerBuilder(full_scorers=[CoverageScorer]) (scorer.py:788-955): coverage penalty on the last decoder layer's
+    head-averaged cross-attention, weight chosen large enough to change the result of the scorer-less search."""
+    from speechbrain.decoders.scorer import CoverageScorer, ScorerBuilder
+    from speechbrain.decoders.seq2seq import S2STransformerBeamSearcher
+    fb, norm, mods, sd = build_reference(CFG_L, "RoPEMHA")
+    g = torch.load(os.path.join(OUT, "conformer_large_rope.pt"))
+    enc, wav_lens = g["enc_out"], g["wav_lens"]
+    T = enc.shape[1]
+    kwargs = dict(beam_size=5, using_eos_threshold=False, temperature=1.15, min_decode_ratio=2.5 / T)
+    eos_bias, w_cov, thr, steps = 1.5, 40.0, 0.05, 10
+    with torch.no_grad():
+        bias = sd["seq_lin.w.bias"].clone()
+        bias[2] += eos_bias
+        mods["seq_lin"].w.bias.copy_(bias)
+        res = {}
+        for name, scorer in (("off", None), ("on", ScorerBuilder(full_scorers=[CoverageScorer(5000, threshold=thr)],
+                                                                 weights={"coverage": w_cov}))):
+            bs = S2STransformerBeamSearcher(modules=[mods["Transformer"], mods["seq_lin"]], bos_index=1, eos_index=2,
+                                            max_decode_ratio=(steps + 0.5) / T, scorer=scorer, return_topk=True, topk=5, **kwargs)
+            res[name] = bs(enc, wav_lens)
+        o = O.beam_search(enc, wav_lens, sd, dict(CFG_L, attention_type="RoPEMHA"), sd["seq_lin.w.weight"], bias, 1, 2,
+                          max_decode_ratio=(steps + 0.5) / T, prefix="Transformer.", topk=5, return_topk=True,
+                          coverage=dict(weight=w_cov, threshold=thr), **kwargs)
+    hyps, lens, scores, lp = res["on"]
+    print(f"[beam cov] without {res['off'][0][:, 0].tolist()} {res['off'][2][:, 0].tolist()} with {hyps[:, 0].tolist()} scores "
+          f"{scores[:, 0].tolist()} | oracle equal: {torch.equal(o[0], hyps)} score err {(o[2] - scores).abs().max():.2e}")
+    assert torch.equal(o[0][:, 0], hyps[:, 0]) and (o[2] - scores).abs().max() < 1e-3
+    assert not torch.equal(res["off"][2], scores)
+    torch.save(dict(kwargs=kwargs, with_lm=False, with_ctc=False, eos_bias=eos_bias, coverage_weight=w_cov, coverage_threshold=thr,
+                    max_decode_ratio=(steps + 0.5) / T, hyps=hyps.int(), lens=lens, scores=scores, log_probs=lp,
+                    scores_without=res["off"][2]), os.path.join(OUT, f"{tag}.pt"))
 
 
 BEAMS_10S = (
@@ -655,6 +694,8 @@ if __name__ == "__main__":
         bench_shape_case(CFG_L, "RoPEMHA", 4, 160000, [1.0, 0.9, 0.6, 0.3], 48, "bench_conformer_large_rope_10s", BEAMS_10S)
     if "bench_L_relpos" in which:
         bench_shape_case(CFG_L, "RelPosMHAXL", 4, 160000, [1.0, 0.9, 0.6, 0.3], 48, "bench_conformer_large_relpos_10s")
+    if "beam_cov" in which:
+        beam_cov_case()
     if "beam66" in which:
         beam66_case()
     if "scaled" in which:

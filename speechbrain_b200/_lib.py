@@ -32,7 +32,8 @@ class sbk_beam_params(ctypes.Structure):
                 ("using_eos_threshold", ctypes.c_int), ("eos_threshold", ctypes.c_float),
                 ("length_normalization", ctypes.c_int), ("minus_inf", ctypes.c_float),
                 ("lm_weight", ctypes.c_float), ("lm_temperature", ctypes.c_float),
-                ("ctc_weight", ctypes.c_float), ("blank_index", ctypes.c_int), ("length_weight", ctypes.c_float)]
+                ("ctc_weight", ctypes.c_float), ("blank_index", ctypes.c_int), ("length_weight", ctypes.c_float),
+                ("coverage_weight", ctypes.c_float), ("coverage_threshold", ctypes.c_float)]
 
 
 SBK_ATT_ROPE, SBK_ATT_RELPOS = 0, 1

@@ -1011,6 +1011,7 @@ struct BeamArgs {
     // optional shallow-fusion scorer (TransformerLMScorer): pre-weighted scores added to the (masked) log-probs,
     // and the LM's own next input (embedding + PE in fp32 and fp16) and token cache (pad-mask on id 0)
     const float* add_scores;
+    const float* add_row;   // [n_bh] per-hypothesis score added to every token (CoverageScorer), or null
     float attn_weight; int blank; float add_const;
     const float* lm_emb; const float* lm_pe; int lm_d; float lm_sqrt_d; float* lm_x_next; __half* lm_x16_next; int* tok_cache;
 };
@@ -1064,6 +1065,7 @@ __global__ void __launch_bounds__(BS_THREADS) beam_step_kernel(const BeamArgs a)
             }
             if (a.add_scores) eos_lp += a.add_scores[static_cast<size_t>(row0 + k) * V + a.eos];  // ScorerBuilder.score
             eos_lp += a.add_const;
+            if (a.add_row) eos_lp += a.add_row[row0 + k];
             s_lse[k] = lse;
             s_eos[k] = eos_lp;
         }
@@ -1083,6 +1085,7 @@ __global__ void __launch_bounds__(BS_THREADS) beam_step_kernel(const BeamArgs a)
         if (j == a.blank) lp = a.minus_inf;
         if (a.add_scores && j != a.eos) lp += a.add_scores[static_cast<size_t>(row0 + k) * V + j];
         if (j != a.eos) lp += a.add_const;
+        if (a.add_row && j != a.eos) lp += a.add_row[row0 + k];
         const float sc = (seq_in[row0 + k] + lp) * inv_len;
         if (sc > bv[BS_MAXB - 1] && sc > -INFINITY) {  // insert (list sorted descending; only the first `beam` matter)
             float v = sc;
@@ -1183,6 +1186,116 @@ __global__ void __launch_bounds__(BS_THREADS) beam_step_kernel(const BeamArgs a)
 }
 
 
+
+// --------------------------------------------------------------------------- CoverageScorer (decoders/scorer.py:788-955)
+// For the Transformer decoder `attn` is the LAST decoder layer's head-averaged cross-attention distribution of every
+// prefix position (Transformer.py:915-963 multihead_attns[-1]); coverage = its sum over the positions, the score
+// -(sum_t max(coverage_t, threshold) - T * threshold) / time_step is the same for every token of a hypothesis.
+// One CTA per hypothesis row: recompute this step's last-layer attention from the query the layer loop left in q
+// (pre-scaled) and the layer's cached keys, add it to the coverage inherited from the row's predecessor (ping-pong by
+// step parity, like the CTC state), write the row's score.
+struct CoverageArgs {
+    const __half* q; int ldq;             // last layer's cross-attention queries [rows, d]
+    const __half* kbase; size_t utt_stride; int key_stride;  // keys of the last layer: kbase + utt * utt_stride + t * key_stride + h * 64
+    const int* enc_len; int rows_per_utt; int T; int H;
+    float* cov_base;                      // [2][rows][T]
+    const int* hist_pred; const int* step_ptr; int n_bh;
+    float threshold, weight; float* out;  // out[row] = weight * score
+};
+
+__global__ void __launch_bounds__(256) coverage_score_kernel(const CoverageArgs a) {
+    extern __shared__ float cv_smem[];  // [T] probabilities of the current head, [T] head average
+    float* s_p = cv_smem;
+    float* s_avg = cv_smem + a.T;
+    __shared__ float s_q[64];
+    __shared__ float s_red[8];
+    pdl_trigger();
+    pdl_wait();
+    const int r = blockIdx.x, tid = threadIdx.x, T = a.T;
+    const int utt = r / a.rows_per_utt;
+    const int n_keys = min(a.enc_len[utt], T);
+    const int step = a.step_ptr[r];
+    for (int t = tid; t < T; t += 256) s_avg[t] = 0.0f;
+    for (int h = 0; h < a.H; ++h) {
+        __syncthreads();
+        if (tid < 64) s_q[tid] = __half2float(a.q[static_cast<size_t>(r) * a.ldq + h * 64 + tid]);
+        __syncthreads();
+        float mx = -INFINITY;
+        for (int t = tid; t < n_keys; t += 256) {
+            const __half* kp = a.kbase + static_cast<size_t>(utt) * a.utt_stride + static_cast<size_t>(t) * a.key_stride + h * 64;
+            float dot = 0.0f;
+#pragma unroll
+            for (int e = 0; e < 64; e += 8) {
+                const uint4 kv = *reinterpret_cast<const uint4*>(kp + e);
+                const __half2* k2 = reinterpret_cast<const __half2*>(&kv);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float2 f = __half22float2(k2[u]);
+                    dot = fmaf(f.x, s_q[e + 2 * u], dot);
+                    dot = fmaf(f.y, s_q[e + 2 * u + 1], dot);
+                }
+            }
+            s_p[t] = dot;
+            mx = fmaxf(mx, dot);
+        }
+        mx = warp_max(mx);
+        if ((tid & 31) == 0) s_red[tid >> 5] = mx;
+        __syncthreads();
+        mx = s_red[0];
+        for (int w = 1; w < 8; ++w) mx = fmaxf(mx, s_red[w]);
+        __syncthreads();
+        float sm = 0.0f;
+        for (int t = tid; t < n_keys; t += 256) {
+            const float p = __expf(s_p[t] - mx);
+            s_p[t] = p;
+            sm += p;
+        }
+        sm = warp_sum(sm);
+        if ((tid & 31) == 0) s_red[tid >> 5] = sm;
+        __syncthreads();
+        float tot = 0.0f;
+        for (int w = 0; w < 8; ++w) tot += s_red[w];
+        const float inv = 1.0f / (tot * static_cast<float>(a.H));
+        for (int t = tid; t < n_keys; t += 256) s_avg[t] += s_p[t] * inv;
+    }
+    __syncthreads();
+    // coverage of the prefix = coverage of the predecessor's prefix + this position's attention
+    const float* cov_in = a.cov_base + static_cast<size_t>(step & 1) * a.n_bh * T;
+    float* cov_out = a.cov_base + static_cast<size_t>((step + 1) & 1) * a.n_bh * T;
+    const int prow = step == 0 ? r : a.hist_pred[static_cast<size_t>(step - 1) * a.n_bh + r];
+    float pen = 0.0f;
+    for (int t = tid; t < T; t += 256) {
+        const float c = (step == 0 ? 0.0f : cov_in[static_cast<size_t>(prow) * T + t]) + s_avg[t];
+        cov_out[static_cast<size_t>(r) * T + t] = c;
+        pen += fmaxf(c, a.threshold);
+    }
+    pen = warp_sum(pen);
+    if ((tid & 31) == 0) s_red[tid >> 5] = pen;
+    __syncthreads();
+    if (tid == 0) {
+        float p = 0.0f;
+        for (int w = 0; w < 8; ++w) p += s_red[w];
+        p -= static_cast<float>(T) * a.threshold;
+        a.out[r] = a.weight * (-p / static_cast<float>(step + 1));
+    }
+}
+
+int coverage_score(const CoverageStep& p, cudaStream_t stream) {
+    SBK_REQUIRE(p.T >= 1 && p.T * 8 <= 96 * 1024, "coverage scorer: T=%d out of range", p.T);
+    CoverageArgs a;
+    a.q = p.q; a.ldq = p.ldq; a.kbase = p.kbase; a.utt_stride = p.utt_stride; a.key_stride = p.key_stride; a.enc_len = p.enc_len;
+    a.rows_per_utt = p.rows_per_utt; a.T = p.T; a.H = p.H; a.cov_base = p.cov_base; a.hist_pred = p.hist_pred;
+    a.step_ptr = p.step_ptr; a.n_bh = p.n_bh; a.threshold = p.threshold; a.weight = p.weight; a.out = p.out;
+    static bool attr = false;
+    if (!attr) {
+        SBK_CUDA_CHECK(cudaFuncSetAttribute(coverage_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        attr = true;
+    }
+    SBK_CUDA_CHECK(launch_k(coverage_score_kernel, dim3(p.n_bh), dim3(256), static_cast<size_t>(p.T) * 8, stream, a));
+    SBK_LAUNCH_CHECK();
+    return SBK_OK;
+}
+
 // --------------------------------------------------------------------------- beam step for wide beams (16 < beam <= 128)
 // Same contract as beam_step_kernel; the per-thread sorted lists of that kernel (beam registers per thread) do not scale to
 // the recipes' test_beam_size = 66 (conformer_large.yaml:132), so the top-`beam` of the beam * V candidates is found by an
@@ -1240,6 +1353,7 @@ __global__ void __launch_bounds__(BS_THREADS) beam_step_large_kernel(const BeamA
             }
             if (a.add_scores) eos_lp += a.add_scores[static_cast<size_t>(row0 + k) * V + a.eos];
             eos_lp += a.add_const;
+            if (a.add_row) eos_lp += a.add_row[row0 + k];
             s_lse[k] = lse;
             s_eos[k] = eos_lp;
             s_seq[k] = seq_in[row0 + k];
@@ -1256,6 +1370,7 @@ __global__ void __launch_bounds__(BS_THREADS) beam_step_large_kernel(const BeamA
         if (j == a.blank) lp = a.minus_inf;
         if (a.add_scores && j != a.eos) lp += a.add_scores[static_cast<size_t>(row0 + k) * V + j];
         if (j != a.eos) lp += a.add_const;
+        if (a.add_row && j != a.eos) lp += a.add_row[row0 + k];
         return (s_seq[k] + lp) * inv_len;
     };
     // ---- phase 2: radix select of the beam-th largest key
@@ -1440,7 +1555,7 @@ int beam_step(const BeamStepArgs& p, int B, cudaStream_t stream) {
     a.inv_temp = 1.0f / p.temperature; a.eos_threshold = p.eos_threshold; a.minus_inf = p.minus_inf;
     a.min_steps = p.min_steps; a.eos = p.eos; a.use_eos_threshold = p.use_eos_threshold; a.length_norm = p.length_norm;
     a.emb = p.emb; a.pe = p.pe; a.d = p.d; a.sqrt_d = sqrtf(static_cast<float>(p.d)); a.x_next = p.x_next;
-    a.add_scores = p.add_scores; a.attn_weight = p.attn_weight; a.blank = p.blank; a.add_const = p.add_const;
+    a.add_scores = p.add_scores; a.add_row = p.add_row; a.attn_weight = p.attn_weight; a.blank = p.blank; a.add_const = p.add_const;
     a.lm_emb = p.lm.emb; a.lm_pe = p.lm.pe; a.lm_d = p.lm.d; a.lm_sqrt_d = p.lm.d ? sqrtf(static_cast<float>(p.lm.d)) : 0.f;
     a.lm_x_next = p.lm.x; a.lm_x16_next = p.lm.x16; a.tok_cache = p.lm.tok_cache;
     static const bool force_large = getenv("SBK_BEAM_RADIX") != nullptr;  // test hook: radix-select kernel for every width

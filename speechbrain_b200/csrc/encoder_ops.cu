@@ -203,7 +203,10 @@ int cast_f32_f16(const float* in, __half* out, size_t n, cudaStream_t stream) {
 }
 
 // --------------------------------------------------------------------------- depthwise conv + LN + Swish
-// glu [B*T, D] fp32 (GLU output) -> out [B*T, D] fp16 = Swish(LN(dwconv(glu) + bias)).
+// glu [B*T, D] fp32 (GLU output) -> out [B*T, D] fp16 = Swish(LN(dwconv(glu) + bias)).  The tap weights arrive TAP-MAJOR
+// ([K, D], repacked from the reference's (D, 1, K) at load time): thread = channel, so the 31 weight loads of a thread are
+// coalesced across the warp (the channel-major layout made every load touch 32 cache lines -- ncu: lg_throttle the top
+// stall of the kernel).
 // Zero padding at utterance edges only: padded frames inside T are real inputs (Conformer.py:318-325
 // runs the conv before masking). One CTA per (utterance, tile of DW_TT frames); the (DW_TT + K - 1) x D
 // input slab is staged in shared memory once.
@@ -212,7 +215,7 @@ constexpr int DW_TT = 16;
 // KT > 0: compile-time kernel size (taps held in registers); KT == 0: runtime K.  MAXC: channels per thread (D <= 256 * MAXC)
 template <int KT, int MAXC>
 __global__ void __launch_bounds__(256, 2)
-dwconv_ln_swish_kernel(const float* __restrict__ glu, int T, int D, int K, const float* __restrict__ wdw /*[D,K]*/,
+dwconv_ln_swish_kernel(const float* __restrict__ glu, int T, int D, int K, const float* __restrict__ wdw /*[K,D] tap-major*/,
                        const float* __restrict__ bdw, const float* __restrict__ gamma, const float* __restrict__ beta,
                        float eps, __half* __restrict__ out) {
     extern __shared__ __align__(128) float dw_smem[];
@@ -257,7 +260,7 @@ dwconv_ln_swish_kernel(const float* __restrict__ glu, int T, int D, int K, const
             breg[cc] = __ldg(bdw + ch);
             if constexpr (KT > 0) {
 #pragma unroll
-                for (int k = 0; k < KT; ++k) wreg[cc][k] = __ldg(wdw + static_cast<size_t>(ch) * K + k);
+                for (int k = 0; k < KT; ++k) wreg[cc][k] = __ldg(wdw + static_cast<size_t>(k) * D + ch);  // coalesced over channels
             }
         }
     }
@@ -271,7 +274,7 @@ dwconv_ln_swish_kernel(const float* __restrict__ glu, int T, int D, int K, const
             const float bz = breg[cc];
 #pragma unroll
             for (int i = 0; i < DW_TT; ++i) acc[cc][i] = bz;
-            const float* w = wdw + static_cast<size_t>(ch) * K;
+            const float* w = wdw + ch;  // tap k at w[k * D]
             if constexpr (KT > 0) {
 #pragma unroll
                 for (int r = 0; r < DW_TT + KT - 1; ++r) {
@@ -286,7 +289,7 @@ dwconv_ln_swish_kernel(const float* __restrict__ glu, int T, int D, int K, const
 #pragma unroll
                     for (int i = 0; i < DW_TT; ++i) {
                         const int k = r - i;
-                        if (k >= 0 && k < K) acc[cc][i] = fmaf(xv, __ldg(w + k), acc[cc][i]);
+                        if (k >= 0 && k < K) acc[cc][i] = fmaf(xv, __ldg(w + static_cast<size_t>(k) * D), acc[cc][i]);
                     }
                 }
             }

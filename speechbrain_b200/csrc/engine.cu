@@ -95,6 +95,7 @@ struct AsrModel {
     // CTC prefix scorer state (allocated on the first beam search that uses it): x [B, T, V] masked log-posteriors,
     // xb [B, T], rsum/rb [2][rows, T] and psi [2][rows] ping-pong by step parity, add [rows, V] when there is no LM buffer
     struct CtcBuf { float* base = nullptr; size_t cap = 0; float *x, *xb, *rsum, *rb, *psi, *add; } ctc;
+    struct CovBuf { float* base = nullptr; size_t cap = 0; } cov;  // CoverageScorer: [2][rows][T] coverage + [rows] scores
     // shapes the workspace is carved for
     int wsB = 0, wsL = 0, ws_rows = 0, ws_steps = 0;
     struct Buf {
@@ -298,7 +299,15 @@ int asr_create(const sbk_asr_config* cfg, const sbk_tensor* weights, int n_weigh
             e.wpw1 = p.f16_raw(wi.data(), wi.size());
             e.bpw1 = p.f32_raw(bi.data(), bi.size());
         }
-        e.wdw = p.f32(q + "convolution_module.conv.weight", (int64_t)d * K); e.bdw = p.f32(q + "convolution_module.conv.bias", d);
+        {   // depthwise taps (d, 1, K) -> tap-major [K, d] so that a warp's channels read one cache line per tap
+            const float* src = find(w, q + "convolution_module.conv.weight", (int64_t)d * K);
+            if (!src) { p.ok = false; break; }
+            std::vector<float> wt((size_t)K * d);
+            for (int ch = 0; ch < d; ++ch)
+                for (int k = 0; k < K; ++k) wt[(size_t)k * d + ch] = src[(size_t)ch * K + k];
+            e.wdw = p.f32_raw(wt.data(), wt.size());
+        }
+        e.bdw = p.f32(q + "convolution_module.conv.bias", d);
         e.aconv_ln_g = p.f32(q + "convolution_module.after_conv.0.weight", d); e.aconv_ln_b = p.f32(q + "convolution_module.after_conv.0.bias", d);
         e.wpw2 = p.f16(q + "convolution_module.after_conv.2.weight", (int64_t)d * d); e.bpw2 = p.f32(q + "convolution_module.after_conv.2.bias", d);
         e.ffn2_ln_g = p.f32(q + "ffn_module2.0.weight", d); e.ffn2_ln_b = p.f32(q + "ffn_module2.0.bias", d);
@@ -464,6 +473,7 @@ int asr_clone(AsrModel* src, AsrModel** out) {
     m->wsB = m->wsL = m->ws_rows = m->ws_steps = 0;
     m->b = AsrModel::Buf();
     m->ctc = AsrModel::CtcBuf();
+    m->cov = AsrModel::CovBuf();
     m->step_graph = nullptr;
     m->pipe_graph = nullptr;
     m->group_graph = nullptr;
@@ -503,6 +513,7 @@ void asr_destroy(AsrModel* m) {
     }
     cudaFree(m->ws.base);
     cudaFree(m->ctc.base);
+    cudaFree(m->cov.base);
     if (m->host_flag) cudaFreeHost(m->host_flag);
     if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
     delete m;
@@ -950,6 +961,22 @@ static int run_beam(AsrModel* m, int B, int T, const sbk_beam_params& p, int* hi
         cs.bos = p.bos; cs.T = T; cs.V = c.vocab; cs.beam = beam; cs.blank = p.blank_index; cs.eos = p.eos;
         cs.weight = p.ctc_weight; cs.out = cb.add; cs.accumulate = use_lm ? 1 : 0;
     }
+    const bool use_cov = p.coverage_weight != 0.0f;
+    CoverageStep cv{};
+    if (use_cov) {  // CoverageScorer (scorer.py:788-955) on the last decoder layer's head-averaged cross-attention
+        SBK_REQUIRE(d / c.nhead == 64, "beam: the coverage scorer is built for head_dim 64");
+        const size_t need = ((size_t)2 * rows * T + rows) * 4 + 256;
+        if (need > m->cov.cap) {
+            if (m->cov.base) { SBK_CUDA_CHECK(cudaStreamSynchronize(st)); cudaFree(m->cov.base); m->cov.base = nullptr; m->cov.cap = 0; }
+            if (m->beam_graph) { cudaGraphExecDestroy(m->beam_graph); m->beam_graph = nullptr; }
+            if (cudaMalloc(&m->cov.base, need) != cudaSuccess) { set_error("beam: coverage scorer cudaMalloc(%zu) failed", need); return SBK_ERR_NOMEM; }
+            m->cov.cap = need;
+        }
+        cv.q = b.dq16; cv.ldq = d; cv.kbase = b.ckv16 + (size_t)(Ld - 1) * M * 2 * d; cv.utt_stride = (size_t)T * 2 * d;
+        cv.key_stride = 2 * d; cv.enc_len = b.enc_len; cv.rows_per_utt = beam; cv.T = T; cv.H = c.nhead;
+        cv.cov_base = m->cov.base; cv.hist_pred = hist_pred; cv.step_ptr = b.step; cv.n_bh = rows;
+        cv.threshold = p.coverage_threshold; cv.weight = p.coverage_weight; cv.out = m->cov.base + (size_t)2 * rows * T;
+    }
     BeamLm lm;
     if (use_lm) { lm.emb = m->lm_emb; lm.pe = m->lm_pe; lm.d = c.lm_d_model; lm.x = b.lx; lm.x16 = b.lx16; lm.tok_cache = b.tok_cache; }
     RC(beam_reset(rows, beam, S_max, p.bos, b.step, b.seq_scores, b.lineage, b.finished, b.ended_count, m->emb, m->dec_pe, d,
@@ -959,6 +986,7 @@ static int run_beam(AsrModel* m, int B, int T, const sbk_beam_params& p, int* hi
     a.lm = lm;
     if (use_ctc) { a.attn_weight = 1.0f - p.ctc_weight; a.blank = p.blank_index; }
     a.add_const = p.length_weight;
+    a.add_row = use_cov ? cv.out : nullptr;
     a.logits = b.logits; a.V = c.vocab; a.beam = beam; a.S_max = S_max; a.seq_scores = b.seq_scores; a.lineage = b.lineage;
     a.step_arr = b.step; a.finished = b.finished; a.n_full = b.ended_count;
     a.hist_tok = hist_tok; a.hist_pred = hist_pred; a.hist_score = hist_score; a.hist_lp = hist_lp;
@@ -969,6 +997,7 @@ static int run_beam(AsrModel* m, int B, int T, const sbk_beam_params& p, int* hi
     // for every step and can be replayed from a graph
     auto enqueue_step = [&](cudaStream_t s_) -> int {
         RC(enqueue_decode_layers(m, rows, beam, T, S_max, b.lineage, s_));
+        if (use_cov) RC(coverage_score(cv, s_));  // reads the last layer's cross-attention query left in b.dq16
         if (use_lm) RC(enqueue_lm_step(m, rows, S_max, p.lm_temperature, p.lm_weight, s_));
         if (use_ctc) RC(ctc_prefix_score(cs, s_));  // ScorerBuilder.score (ctc after transformerlm) ...
         RC(beam_step(a, B, s_));

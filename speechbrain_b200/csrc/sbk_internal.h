@@ -136,7 +136,15 @@ struct BeamStepArgs {
     float attn_weight = 1.0f;  // 1 - ctc_weight (seq2seq.py:803-804, _attn_weight_step)
     int blank = -1;            // CTC blank index, blocked in the log-probs (scorer.py:1248-1250); -1 = no CTC scorer
     float add_const = 0.0f;    // LengthScorer: weight * 1 added to every token (scorer.py:1043-1071)
+    const float* add_row = nullptr;  // CoverageScorer: [n_bh] weighted score added to every token of a hypothesis
 };
+// CoverageScorer (decoders/scorer.py:788-955) on the last decoder layer's head-averaged cross-attention
+struct CoverageStep {
+    const __half* q; int ldq; const __half* kbase; size_t utt_stride; int key_stride; const int* enc_len;
+    int rows_per_utt, T, H; float* cov_base; const int* hist_pred; const int* step_ptr; int n_bh;
+    float threshold, weight; float* out;
+};
+int coverage_score(const CoverageStep& p, cudaStream_t stream);
 // CTC prefix scorer (ctc_scorer.cu)
 struct CtcStep {
     const float* x; const float* xb; const int* enc_len;

@@ -1,8 +1,8 @@
 """Scorer interfaces of the beam search -- mirrors of speechbrain.decoders.scorer for what is built on the B200 path:
 ``TransformerLMScorer`` (scorer.py:455-560) and ``CTCScorer`` (scorer.py:81-249, CTCPrefixScore decoders/ctc.py:46-295)
 as *full* scorers of a ``ScorerBuilder`` (scorer.py:1075-1341), i.e. the recipe's ``scorer_test_search`` /
-``scorer_valid_search`` (conformer_large.yaml:209-228).  Coverage / length / KenLM / RNNLM scorers and partial scorers
-raise.  The scoring itself runs inside the engine's beam search (csrc/engine.cu run_beam, csrc/ctc_scorer.cu).
+``scorer_valid_search`` (conformer_large.yaml:209-228), plus ``CoverageScorer`` (:788-955) and ``LengthScorer`` (:956-1072).
+KenLM / RNNLM scorers and partial scorers raise.  The scoring itself runs inside the engine's beam search (csrc/engine.cu run_beam, csrc/ctc_scorer.cu).
 
 ``TransformerLMRescorer`` (scorer.py:1642-1882) + ``RescorerBuilder`` (scorer.py:2068-2189): n-best rescoring of text
 hypotheses; tokenisation and the re-ranking stay on the host like in the reference, the LM forward runs teacher-forced on
@@ -33,7 +33,15 @@ class LengthScorer:
         self.vocab_size = vocab_size
 
 
-_NAMES = {TransformerLMScorer: "transformerlm", CTCScorer: "ctc", LengthScorer: "length"}
+class CoverageScorer:
+    """Coverage penalty (scorer.py:788-955): cumulative last-layer cross-attention above ``threshold`` per frame is penalised."""
+
+    def __init__(self, vocab_size, threshold=0.5):
+        self.vocab_size = vocab_size
+        self.threshold = threshold
+
+
+_NAMES = {TransformerLMScorer: "transformerlm", CTCScorer: "ctc", LengthScorer: "length", CoverageScorer: "coverage"}
 _ALL = ("ctc", "rnnlm", "transformerlm", "kenlm", "coverage", "length")
 
 
@@ -46,7 +54,7 @@ class ScorerBuilder:
         for impl in full_scorers:
             if type(impl) not in _NAMES:
                 raise NotImplementedError(f"speechbrain_b200.ScorerBuilder: {type(impl).__name__} is not built "
-                                          "(TransformerLMScorer, CTCScorer and LengthScorer are)")
+                                          "(TransformerLMScorer, CTCScorer, CoverageScorer and LengthScorer are)")
             names.append(_NAMES[type(impl)])
         if len(set(names)) != len(names):
             raise ValueError("ScorerBuilder: duplicate scorers")

@@ -68,6 +68,7 @@ class S2STransformerBeamSearcher(torch.nn.Module):
         if bos_index is None or eos_index is None or beam_size is None:
             raise TypeError("bos_index, eos_index and beam_size are required")
         self.lm_scorer, self.lm_weight, self.ctc_scorer, self.ctc_weight, self.length_weight = None, 0.0, None, 0.0, 0.0
+        self.coverage_weight, self.coverage_threshold = 0.0, 0.5
         if scorer is not None:
             from .scorer import ScorerBuilder
             if not isinstance(scorer, ScorerBuilder):
@@ -76,6 +77,9 @@ class S2STransformerBeamSearcher(torch.nn.Module):
                 raise ValueError("Length normalization is not compatible with length rewarding.")
             if "length" in scorer.full_scorers:
                 self.length_weight = scorer.weights["length"]
+            if "coverage" in scorer.full_scorers:
+                self.coverage_weight = scorer.weights["coverage"]
+                self.coverage_threshold = scorer.full_scorers["coverage"].threshold
             self.lm_scorer = scorer.full_scorers.get("transformerlm")
             self.lm_weight = scorer.weights["transformerlm"] if self.lm_scorer is not None else 0.0
             self.ctc_scorer = scorer.full_scorers.get("ctc")
@@ -128,7 +132,7 @@ class S2STransformerBeamSearcher(torch.nn.Module):
             self.using_eos_threshold, self.eos_threshold, self.length_normalization, self.minus_inf,
             lm_weight=self.lm_weight, lm_temperature=self.lm_scorer.temperature if self.lm_scorer is not None else 1.0,
             ctc_weight=self.ctc_weight, blank_index=self.ctc_scorer.blank_index if self.ctc_scorer is not None else -1,
-            length_weight=self.length_weight)
+            length_weight=self.length_weight, coverage_weight=self.coverage_weight, coverage_threshold=self.coverage_threshold)
         out = replay_beam_history(hist, B, self.beam_size, self.eos_index, self.topk)
         topk_hyps, topk_lengths, topk_scores, topk_log_probs = (t.to(enc_states.device) for t in out)
         if self.return_topk:

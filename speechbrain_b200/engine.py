@@ -239,7 +239,8 @@ class AsrEngine:
 
     def beam_from_enc(self, enc, wav_lens, beam_size, max_steps, min_steps, bos, eos, temperature=1.0,
                       using_eos_threshold=True, eos_threshold=1.5, length_normalization=True, minus_inf=-1e20,
-                      lm_weight=0.0, lm_temperature=1.0, ctc_weight=0.0, blank_index=-1, length_weight=0.0):
+                      lm_weight=0.0, lm_temperature=1.0, ctc_weight=0.0, blank_index=-1, length_weight=0.0,
+                      coverage_weight=0.0, coverage_threshold=0.5):
         """Device part of the beam search: returns the per-step history (tok, pred, score, lp) [steps, B*beam] on CPU."""
         enc = enc.float().contiguous()
         B, T, _ = enc.shape
@@ -252,7 +253,7 @@ class AsrEngine:
         wl = wav_lens.float().contiguous().to(enc.device) if wav_lens is not None else None
         prm = _lib.sbk_beam_params(beam_size, max_steps, min_steps, bos, eos, temperature, int(bool(using_eos_threshold)),
                                    eos_threshold, int(bool(length_normalization)), minus_inf, lm_weight, lm_temperature, ctc_weight,
-                                   int(blank_index), length_weight)
+                                   int(blank_index), length_weight, coverage_weight, coverage_threshold)
         done = ctypes.c_int()
         with torch.cuda.device(self.device):
             check(lib().sbk_asr_beam_from_enc(self._h, ptr(enc), ptr(wl), B, T, ctypes.byref(prm), ptr(tok), ptr(pred),
