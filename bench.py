@@ -296,7 +296,7 @@ def main():
     ap.add_argument("--ref-budget-s", type=float, default=170.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the informational eager-PyTorch-on-GPU reference leg")
-    ap.add_argument("--lanes", type=int, default=4, help="groups in flight per GPU (engine clones on their own streams)")
+    ap.add_argument("--lanes", type=int, default=3, help="groups in flight per GPU (engine clones on their own streams)")
     ap.add_argument("--group", type=int, default=16, help="max batches whose decode is coalesced into one greedy loop")
     ap.add_argument("--decode-steps", type=int, default=48, help="diagnostic: override the pinned 48 decode steps")
     ap.add_argument("--fuse-dec-ln", type=int, default=1)

@@ -100,6 +100,11 @@ int sbk_asr_create(const sbk_asr_config* cfg, const sbk_tensor* weights, int n_w
 void sbk_asr_destroy(sbk_asr* m);
 /* A clone shares the repacked weights and owns its own workspace: one clone ("lane") per batch in flight. */
 int sbk_asr_clone(sbk_asr* src, sbk_asr** out);
+/* DynChunkTrainConfig(chunk_size, left_context_size) for the following encode calls (TransformerASR.encode(...,
+ * dynchunktrain_config=...), TransformerASR.py:46-105,475-544; Conformer.py:190-313): chunked attention (a frame sees its own
+ * chunk and `left_context_chunks` chunks before it; < 0 = the whole past) and the Dynamic Chunk Convolution.  chunk_size 0
+ * (default) = full-context. */
+int sbk_asr_set_dynchunk(sbk_asr* m, int chunk_size, int left_context_chunks);
 /* Greedy early-exit (`has_ended.all()`, decoders/seq2seq.py:256) is polled every n steps with a stream sync;
  * 0 = never poll: run exactly max_steps and never block the host (fully asynchronous enqueue). Default 8. */
 int sbk_asr_set_poll_interval(sbk_asr* m, int every_n_steps);

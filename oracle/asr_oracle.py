@@ -183,7 +183,20 @@ def _mm(x, w, b=None, q=None):
     return F.linear(x, w, b)
 
 
-def rope_mha(x, sd, p, nhead, key_padding_mask, q=None):
+def chunk_mask(T, chunk_size, left_context_chunks=None):
+    """TransformerASR.py:46-105 make_transformer_src_mask with a DynChunkTrainConfig: (T, T) bool, True = masked.
+    Frame i (chunk c = i // chunk_size) sees keys j < (c + 1) * chunk_size and, with a finite left context of n chunks,
+    j >= (c - n) * chunk_size."""
+    i = torch.arange(T)
+    hi = (i // chunk_size + 1) * chunk_size
+    m = i[None, :] >= hi[:, None]
+    if left_context_chunks is not None:
+        lo = hi - chunk_size * (left_context_chunks + 1)
+        m = m | (i[None, :] < lo[:, None])
+    return m
+
+
+def rope_mha(x, sd, p, nhead, key_padding_mask, q=None, attn_mask=None):
     """nnet/attention.py:1284-1399 RoPEMHA.forward (self-attention branch) with
     masks_union :1402-1440 and SDPA(scale=1/sqrt(embed_dim) :1272)."""
     B, T, d = x.shape
@@ -195,12 +208,14 @@ def rope_mha(x, sd, p, nhead, key_padding_mask, q=None):
     s = torch.einsum("bihd,bjhd->bhij", qh, kh) * scale
     if key_padding_mask is not None:
         s = s.masked_fill(key_padding_mask.view(B, 1, 1, T), float("-inf"))
+    if attn_mask is not None:  # masks_union :1402-1440 (chunked attention, True = masked)
+        s = s.masked_fill(attn_mask.view(1, 1, T, T), float("-inf"))
     a = torch.softmax(s, dim=-1)
     o = torch.einsum("bhij,bjhd->bihd", a, vh).reshape(B, T, d)
     return _mm(o, sd[p + "out_proj.weight"], sd[p + "out_proj.bias"], q)
 
 
-def relpos_mha(x, pos_embs, sd, p, nhead, key_padding_mask, q=None):
+def relpos_mha(x, pos_embs, sd, p, nhead, key_padding_mask, q=None, attn_mask=None):
     """nnet/attention.py:555-742 RelPosMHAXL.forward + rel_shift :537-553.
 
     Quirks kept: scale 1/sqrt(embed_dim); pos_bias_{u,v} stored (d_h, H) but
@@ -220,9 +235,13 @@ def relpos_mha(x, pos_embs, sd, p, nhead, key_padding_mask, q=None):
     b_, h_, ql, pl = bd.shape
     bd = F.pad(bd, (1, 0)).view(b_, h_, -1, ql)[:, :, 1:].reshape(b_, h_, ql, pl)[..., : pl // 2 + 1]
     s = ac + bd
+    if attn_mask is not None:  # attention.py:694-702 (bool mask: masked_fill -inf before the softmax, 0 after)
+        s = s.masked_fill(attn_mask.view(1, 1, T, T), float("-inf"))
     if key_padding_mask is not None:
         s = s.masked_fill(key_padding_mask.view(B, 1, 1, T), float("-inf"))
     a = torch.softmax(s, dim=-1)
+    if attn_mask is not None:
+        a = a.masked_fill(attn_mask.view(1, 1, T, T), 0.0)
     if key_padding_mask is not None:
         a = a.masked_fill(key_padding_mask.view(B, 1, 1, T), 0.0)
     o = torch.matmul(a, vh.transpose(1, 2)).transpose(1, 2).reshape(B, T, d)
@@ -241,8 +260,9 @@ def conformer_ffn(x, sd, p, q=None):
     return _mm(h, sd[p + "1.ffn.3.weight"], sd[p + "1.ffn.3.bias"], q)
 
 
-def conv_module(x, sd, p, conv_mask, q=None):
-    """Conformer.py:314-330 ConvolutionModule.forward (non-chunked branch)."""
+def conv_module(x, sd, p, conv_mask, q=None, chunk_size=None):
+    """Conformer.py:314-330 ConvolutionModule.forward (non-chunked branch) and :190-313 (Dynamic Chunk Convolution: a normal
+    'same' convolution in which, for every output frame, the inputs beyond the end of its own chunk are zero)."""
     d = x.shape[-1]
     h = _ln(x, sd, p + "layer_norm.", 1e-5)
     w = sd[p + "bottleneck.0.weight"]
@@ -250,7 +270,20 @@ def conv_module(x, sd, p, conv_mask, q=None):
     h = F.glu(h, dim=-1)
     wdw = sd[p + "conv.weight"]
     K = wdw.shape[-1]
-    h = F.conv1d(h.transpose(1, 2), wdw, sd[p + "conv.bias"], padding=(K - 1) // 2, groups=d).transpose(1, 2)
+    if chunk_size is None:
+        h = F.conv1d(h.transpose(1, 2), wdw, sd[p + "conv.bias"], padding=(K - 1) // 2, groups=d).transpose(1, 2)
+    else:  # explicit sum over taps with the future-of-the-chunk mask (restates the unfold / pad construction of the reference)
+        B_, T_, _ = h.shape
+        pad = (K - 1) // 2
+        hp = F.pad(h, (0, 0, pad, pad))
+        t = torch.arange(T_)
+        chunk_end = (t // chunk_size + 1) * chunk_size
+        out = sd[p + "conv.bias"].view(1, 1, d).expand(B_, T_, d).clone()
+        for k in range(K):
+            src_t = t + k - pad
+            ok = (src_t < chunk_end).view(1, T_, 1)
+            out = out + torch.where(ok, hp[:, k:k + T_, :], torch.zeros(())) * wdw[:, 0, k].view(1, 1, d)
+        h = out
     h = F.silu(_ln(h, sd, p + "after_conv.0.", 1e-5))
     h = _mm(h, sd[p + "after_conv.2.weight"], sd[p + "after_conv.2.bias"], q)
     if conv_mask is not None:
@@ -258,24 +291,24 @@ def conv_module(x, sd, p, conv_mask, q=None):
     return h
 
 
-def conformer_layer(x, sd, p, nhead, attention_type, key_padding_mask, pos_embs, q=None):
+def conformer_layer(x, sd, p, nhead, attention_type, key_padding_mask, pos_embs, q=None, attn_mask=None, chunk_size=None):
     """Conformer.py:451-499 ConformerEncoderLayer.forward."""
     conv_mask = key_padding_mask.unsqueeze(-1) if key_padding_mask is not None else None
     x = x + 0.5 * conformer_ffn(x, sd, p + "ffn_module1.", q)
     skip = x
     h = _ln(x, sd, p + "norm1.norm.", 1e-5)
     if attention_type == "RoPEMHA":
-        h = rope_mha(h, sd, p + "mha_layer.", nhead, key_padding_mask, q)
+        h = rope_mha(h, sd, p + "mha_layer.", nhead, key_padding_mask, q, attn_mask)
     elif attention_type == "RelPosMHAXL":
-        h = relpos_mha(h, pos_embs, sd, p + "mha_layer.", nhead, key_padding_mask, q)
+        h = relpos_mha(h, pos_embs, sd, p + "mha_layer.", nhead, key_padding_mask, q, attn_mask)
     else:
         raise ValueError(attention_type)
     x = h + skip
-    x = x + conv_module(x, sd, p + "convolution_module.", conv_mask, q)
+    x = x + conv_module(x, sd, p + "convolution_module.", conv_mask, q, chunk_size)
     return _ln(x + 0.5 * conformer_ffn(x, sd, p + "ffn_module2.", q), sd, p + "norm2.norm.", 1e-5)
 
 
-def encode(src, wav_len, sd, cfg, prefix="", q=None, return_layers=False):
+def encode(src, wav_len, sd, cfg, prefix="", q=None, return_layers=False, dynchunk=None):
     """TransformerASR.py:475-544 TransformerASR.encode (+ :106-164 masks,
     Conformer.py:705-778 ConformerEncoder.forward incl. final LayerNorm(eps=1e-6))."""
     if src.dim() == 4:
@@ -291,10 +324,14 @@ def encode(src, wav_len, sd, cfg, prefix="", q=None, return_layers=False):
     x = _mm(src, sd[prefix + "custom_src_module.layers.0.w.weight"],
             sd[prefix + "custom_src_module.layers.0.w.bias"], q)
     pos = relpos_table(T, x.shape[-1]) if cfg["attention_type"] == "RelPosMHAXL" else None
+    amask = csz = None
+    if dynchunk is not None:  # (chunk_size, left_context_chunks or None): encode(..., dynchunktrain_config=...) masked mode
+        csz = dynchunk[0]
+        amask = chunk_mask(T, csz, dynchunk[1])
     layers = []
     for i in range(cfg["num_encoder_layers"]):
         x = conformer_layer(x, sd, f"{prefix}encoder.layers.{i}.", cfg["nhead"],
-                            cfg["attention_type"], kpm, pos, q)
+                            cfg["attention_type"], kpm, pos, q, amask, csz)
         layers.append(x)
     x = _ln(x, sd, prefix + "encoder.norm.norm.", 1e-6)
     return (x, layers) if return_layers else x

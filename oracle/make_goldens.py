@@ -655,6 +655,27 @@ def beam_cov_case(tag="beam_cov_conformer_large_rope"):
                     scores_without=res["off"][2]), os.path.join(OUT, f"{tag}.pt"))
 
 
+def dynchunk_case(tag="dynchunk_conformer_large"):
+    """TransformerASR.encode(src, wav_len, dynchunktrain_config=DynChunkTrainConfig(chunk_size, left_context_size)) -- the
+    masked ("streaming-equivalent") evaluation mode (TransformerASR.py:46-105,475-544; Conformer.py:190-313 Dynamic Chunk
+    Convolution): chunked attention masks + future-masked convolution.  RoPE with a finite left context and RelPos with an
+    infinite one, ragged batch, chunk sizes that do not divide T = 51."""
+    from speechbrain.utils.dynamic_chunk_training import DynChunkTrainConfig
+    out = {}
+    for att, cs, lc in (("RoPEMHA", 8, 2), ("RelPosMHAXL", 16, None), ("RoPEMHA", 5, 3), ("RelPosMHAXL", 4, 4)):
+        fb, norm, mods, sd = build_reference(CFG_L, att)
+        g = torch.load(os.path.join(OUT, "conformer_large_rope.pt" if att == "RoPEMHA" else "conformer_large_relpos.pt"))
+        with torch.no_grad():
+            enc = mods["Transformer"].encode(g["cnn_out"], g["wav_lens"], dynchunktrain_config=DynChunkTrainConfig(cs, lc))
+            src = g["cnn_out"].reshape(g["cnn_out"].shape[0], g["cnn_out"].shape[1], -1)
+            oenc = O.encode(src, g["wav_lens"], sd, dict(CFG_L, attention_type=att), "Transformer.", dynchunk=(cs, lc))
+        print(f"[dynchunk {att} chunk {cs} left {lc}] oracle rel {rel(oenc, enc):.2e}; differs from full-context by "
+              f"{rel(enc, g['enc_out']):.2e}")
+        assert rel(oenc, enc) < 1e-5 and rel(enc, g["enc_out"]) > 1e-2
+        out[f"{att}_{cs}_{lc}"] = dict(attention_type=att, chunk_size=cs, left_context_size=lc, enc_out=enc)
+    torch.save(out, os.path.join(OUT, f"{tag}.pt"))
+
+
 BEAMS_10S = (
     ("b10_lm_ctc", dict(beam_size=10, using_eos_threshold=False, temperature=1.15, with_lm=True, with_ctc=True, eos_bias=0.0, steps=24)),
     ("b10_ctc_valid", dict(beam_size=10, using_eos_threshold=False, temperature=1.15, with_lm=False, with_ctc=True, eos_bias=0.0, steps=24)),
@@ -694,6 +715,8 @@ if __name__ == "__main__":
         bench_shape_case(CFG_L, "RoPEMHA", 4, 160000, [1.0, 0.9, 0.6, 0.3], 48, "bench_conformer_large_rope_10s", BEAMS_10S)
     if "bench_L_relpos" in which:
         bench_shape_case(CFG_L, "RelPosMHAXL", 4, 160000, [1.0, 0.9, 0.6, 0.3], 48, "bench_conformer_large_relpos_10s")
+    if "dynchunk" in which:
+        dynchunk_case()
     if "beam_cov" in which:
         beam_cov_case()
     if "beam66" in which:

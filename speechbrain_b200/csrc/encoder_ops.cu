@@ -213,11 +213,13 @@ int cast_f32_f16(const float* in, __half* out, size_t n, cudaStream_t stream) {
 constexpr int DW_TT = 16;
 
 // KT > 0: compile-time kernel size (taps held in registers); KT == 0: runtime K.  MAXC: channels per thread (D <= 256 * MAXC)
-template <int KT, int MAXC>
+// CHUNKED: Dynamic Chunk Convolution (Conformer.py:190-313): for every output frame the inputs beyond the end of its own
+// chunk of `chunk` frames count as zero (the past, other chunks included, is visible as usual).
+template <int KT, int MAXC, bool CHUNKED = false>
 __global__ void __launch_bounds__(256, 2)
 dwconv_ln_swish_kernel(const float* __restrict__ glu, int T, int D, int K, const float* __restrict__ wdw /*[K,D] tap-major*/,
                        const float* __restrict__ bdw, const float* __restrict__ gamma, const float* __restrict__ beta,
-                       float eps, __half* __restrict__ out) {
+                       float eps, __half* __restrict__ out, int chunk) {
     extern __shared__ __align__(128) float dw_smem[];
     __shared__ uint64_t bar;
     const int halo = (K - 1) / 2;
@@ -276,12 +278,20 @@ dwconv_ln_swish_kernel(const float* __restrict__ glu, int T, int D, int K, const
             for (int i = 0; i < DW_TT; ++i) acc[cc][i] = bz;
             const float* w = wdw + ch;  // tap k at w[k * D]
             if constexpr (KT > 0) {
+                int lim[CHUNKED ? DW_TT : 1];  // slab row of the first frame past output i's chunk
+                if constexpr (CHUNKED) {
+#pragma unroll
+                    for (int i = 0; i < DW_TT; ++i) lim[i] = ((t0 + i) / chunk + 1) * chunk - t0 + halo;
+                }
 #pragma unroll
                 for (int r = 0; r < DW_TT + KT - 1; ++r) {
                     const float xv = slab[r * D + ch];
 #pragma unroll
                     for (int i = 0; i < DW_TT; ++i)
-                        if (r - i >= 0 && r - i < KT) acc[cc][i] = fmaf(xv, wreg[cc][r - i], acc[cc][i]);
+                        if (r - i >= 0 && r - i < KT) {
+                            if constexpr (CHUNKED) acc[cc][i] = fmaf(r < lim[i] ? xv : 0.0f, wreg[cc][r - i], acc[cc][i]);
+                            else acc[cc][i] = fmaf(xv, wreg[cc][r - i], acc[cc][i]);
+                        }
                 }
             } else {
                 for (int r = 0; r < rows_in; ++r) {
@@ -289,7 +299,8 @@ dwconv_ln_swish_kernel(const float* __restrict__ glu, int T, int D, int K, const
 #pragma unroll
                     for (int i = 0; i < DW_TT; ++i) {
                         const int k = r - i;
-                        if (k >= 0 && k < K) acc[cc][i] = fmaf(xv, __ldg(w + static_cast<size_t>(k) * D), acc[cc][i]);
+                        if (k >= 0 && k < K && (!CHUNKED || r < ((t0 + i) / chunk + 1) * chunk - t0 + halo))
+                            acc[cc][i] = fmaf(xv, __ldg(w + static_cast<size_t>(k) * D), acc[cc][i]);
                     }
                 }
             }
@@ -344,15 +355,21 @@ dwconv_ln_swish_kernel(const float* __restrict__ glu, int T, int D, int K, const
 }
 
 int dwconv_ln_swish(const float* glu, int B, int T, int D, int K, const float* wdw, const float* bdw,
-                    const float* gamma, const float* beta, float eps, __half* out, cudaStream_t stream) {
+                    const float* gamma, const float* beta, float eps, __half* out, cudaStream_t stream, int chunk) {
     SBK_REQUIRE(D % 4 == 0 && D <= 1024 && (K & 1) == 1, "dwconv_ln_swish: D %% 4, D <= 1024 and odd K required (D=%d K=%d)", D, K);
     SBK_REQUIRE((reinterpret_cast<uintptr_t>(glu) & 15) == 0, "dwconv_ln_swish: input must be 16-byte aligned");
     const size_t smem = static_cast<size_t>(DW_TT + K - 1) * D * sizeof(float);
     SBK_REQUIRE(smem <= 200 * 1024, "dwconv_ln_swish: tile too large for shared memory (D=%d K=%d)", D, K);
     auto kern = dwconv_ln_swish_kernel<0, 4>;
-    if (K == 31) kern = D <= 256 ? dwconv_ln_swish_kernel<31, 1> : D <= 512 ? dwconv_ln_swish_kernel<31, 2> : dwconv_ln_swish_kernel<31, 4>;
+    if (chunk > 0) {
+        kern = dwconv_ln_swish_kernel<0, 4, true>;
+        if (K == 31) kern = D <= 256 ? dwconv_ln_swish_kernel<31, 1, true> : D <= 512 ? dwconv_ln_swish_kernel<31, 2, true>
+                                                                                        : dwconv_ln_swish_kernel<31, 4, true>;
+    } else if (K == 31) {
+        kern = D <= 256 ? dwconv_ln_swish_kernel<31, 1> : D <= 512 ? dwconv_ln_swish_kernel<31, 2> : dwconv_ln_swish_kernel<31, 4>;
+    }
     SBK_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<dim3(ceil_div(T, DW_TT), B), 256, smem, stream>>>(glu, T, D, K, wdw, bdw, gamma, beta, eps, out);
+    kern<<<dim3(ceil_div(T, DW_TT), B), 256, smem, stream>>>(glu, T, D, K, wdw, bdw, gamma, beta, eps, out, chunk);
     SBK_LAUNCH_CHECK();
     return SBK_OK;
 }
@@ -407,7 +424,8 @@ template <int DH, int DHP, bool RELPOS>  // DHP = DH rounded up to a multiple of
 __global__ void __launch_bounds__(128)
 encoder_attention_kernel(const __half* __restrict__ qkv, int ld, int T, const int* __restrict__ lens,
                          const float* __restrict__ pos_u, const float* __restrict__ pos_v,
-                         const __half* __restrict__ P, int ldp, float scale, __half* __restrict__ out, int ldo) {
+                         const __half* __restrict__ P, int ldp, float scale, __half* __restrict__ out, int ldo,
+                         int chunk, int left_chunks) {
     constexpr int STR = DHP + 8;  // padded row stride (halfs): conflict-free fragment loads
     constexpr int KS = DHP / 16;
     constexpr int GW = 80;        // relpos band width (16 + 64 - 1 rounded to 8)
@@ -494,7 +512,22 @@ encoder_attention_kernel(const __half* __restrict__ qkv, int ld, int T, const in
     for (int i = 0; i < DHP / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.0f;
     float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.0f, 0.0f};
     const float LOG2E = 1.4426950408889634f;
-    const int n_blk = (len + ATT_BK - 1) / ATT_BK;
+    // Dynamic-chunk (streaming-equivalent) attention, TransformerASR.py:46-105: query i of chunk c = i / chunk sees keys
+    // [max(0, (c - left_chunks) * chunk), min(len, (c + 1) * chunk)); left_chunks < 0 = unlimited past.  chunk == 0: off.
+    int blk_begin = 0, n_blk = (len + ATT_BK - 1) / ATT_BK;
+    int klo[2] = {0, 0}, khi[2] = {len, len};  // key window of this thread's two query rows (g and g + 8 of the warp's 16)
+    if (chunk > 0) {
+        const int i_last = min(i0 + ATT_BQ, T) - 1;
+        const int hi_last = min(len, (i_last / chunk + 1) * chunk);
+        n_blk = (hi_last + ATT_BK - 1) / ATT_BK;
+        if (left_chunks >= 0) blk_begin = max(0, (i0 / chunk - left_chunks) * chunk) / ATT_BK;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int i = min(i0 + warp * 16 + g + 8 * r, T - 1);
+            khi[r] = min(len, (i / chunk + 1) * chunk);
+            klo[r] = left_chunks >= 0 ? max(0, (i / chunk - left_chunks) * chunk) : 0;
+        }
+    }
 
     auto stage_async = [&](int jb, __half* kd, __half* vd) {  // 16-byte cp.async, rows >= T zero-filled
         const int j0 = jb * ATT_BK;
@@ -512,19 +545,19 @@ encoder_attention_kernel(const __half* __restrict__ qkv, int ld, int T, const in
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     if constexpr (ASYNC) {
-        if (n_blk > 0) stage_async(0, Ks, Vs);
+        if (n_blk > blk_begin) stage_async(blk_begin, Ks, Vs);
     }
 
-    for (int jb = 0; jb < n_blk; ++jb) {
+    for (int jb = blk_begin; jb < n_blk; ++jb) {
         const int j0 = jb * ATT_BK;
         const __half* Kc = Ks;
         const __half* Vc = Vs;
         if constexpr (ASYNC) {
-            if (jb & 1) { Kc = KV1; Vc = KV1 + ATT_BK * STR; }
+            if ((jb - blk_begin) & 1) { Kc = KV1; Vc = KV1 + ATT_BK * STR; }
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncthreads();  // block jb has landed for everyone; block jb-1 (the other buffer) is fully consumed
             if (jb + 1 < n_blk) {
-                if (jb & 1) stage_async(jb + 1, Ks, Vs);
+                if ((jb - blk_begin) & 1) stage_async(jb + 1, Ks, Vs);
                 else stage_async(jb + 1, KV1, KV1 + ATT_BK * STR);
             }
         } else {
@@ -596,7 +629,15 @@ encoder_attention_kernel(const __half* __restrict__ qkv, int ld, int T, const in
         }
         // ---- key padding mask + online softmax (rows g and g+8 of this warp's 16)
         float mx[2] = {-INFINITY, -INFINITY};
-        if (j0 + ATT_BK > len) {  // only the last key block holds masked keys
+        if (chunk > 0) {  // chunked attention: every block can hold keys outside a row's window
+#pragma unroll
+            for (int nt = 0; nt < ATT_BK / 8; ++nt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int j = j0 + nt * 8 + 2 * c + (e & 1);
+                    if (j < klo[e >> 1] || j >= khi[e >> 1]) s[nt][e] = -INFINITY;
+                }
+        } else if (j0 + ATT_BK > len) {  // only the last key block holds masked keys
 #pragma unroll
             for (int nt = 0; nt < ATT_BK / 8; ++nt)
 #pragma unroll
@@ -613,14 +654,15 @@ encoder_attention_kernel(const __half* __restrict__ qkv, int ld, int T, const in
             mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
             mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
             const float m_new = fmaxf(m_run[r], mx[r]);
-            alpha[r] = ex2_ftz((m_run[r] - m_new) * LOG2E);
+            // (a row can meet a fully masked block before its first visible key when chunk windows differ inside the tile)
+            alpha[r] = m_new == -INFINITY ? 1.0f : ex2_ftz((m_run[r] - m_new) * LOG2E);
             m_run[r] = m_new;
         }
         float rs[2] = {0.0f, 0.0f};
         uint32_t pa[ATT_BK / 16][4];
 #pragma unroll
         for (int nt = 0; nt < ATT_BK / 8; ++nt) {
-            const float ms0 = m_run[0] * LOG2E, ms1 = m_run[1] * LOG2E;
+            const float ms0 = m_run[0] == -INFINITY ? 0.0f : m_run[0] * LOG2E, ms1 = m_run[1] == -INFINITY ? 0.0f : m_run[1] * LOG2E;
             const float p0 = ex2_ftz(fmaf(s[nt][0], LOG2E, -ms0)), p1 = ex2_ftz(fmaf(s[nt][1], LOG2E, -ms0));
             const float p2 = ex2_ftz(fmaf(s[nt][2], LOG2E, -ms1)), p3 = ex2_ftz(fmaf(s[nt][3], LOG2E, -ms1));
             rs[0] += p0 + p1;
@@ -658,7 +700,8 @@ encoder_attention_kernel(const __half* __restrict__ qkv, int ld, int T, const in
     }
     // ---- normalise and store
     const int r0 = i0 + warp * 16 + g, r1 = r0 + 8;
-    const float inv0 = 1.0f / l_run[0], inv1 = 1.0f / l_run[1];
+    // (l == 0: a padded query row whose whole window is padding -- only possible with chunked attention; emit zeros)
+    const float inv0 = l_run[0] > 0.0f ? 1.0f / l_run[0] : 0.0f, inv1 = l_run[1] > 0.0f ? 1.0f / l_run[1] : 0.0f;
     __half* ob = out + static_cast<size_t>(b) * T * ldo + h * DH;
 #pragma unroll
     for (int nt = 0; nt < DHP / 8; ++nt) {
@@ -672,14 +715,14 @@ encoder_attention_kernel(const __half* __restrict__ qkv, int ld, int T, const in
 template <int DH, int DHP>
 static int launch_encoder_attention(const __half* qkv, int ld, int B, int T, int H, const int* lens, bool relpos,
                                     const float* pos_u, const float* pos_v, const __half* P, int ldp, float scale,
-                                    __half* out, int ldo, cudaStream_t stream) {
+                                    __half* out, int ldo, int chunk, int left_chunks, cudaStream_t stream) {
     constexpr int STR = DHP + 8;
     dim3 grid(ceil_div(T, ATT_BQ), H, B);
     if (!relpos) {
         const size_t smem = 4ull * ATT_BQ * STR * 2 + 2ull * ATT_BK * STR * 2;  // + second K/V buffer pair
         auto kern = encoder_attention_kernel<DH, DHP, false>;
         SBK_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, 128, smem, stream>>>(qkv, ld, T, lens, nullptr, nullptr, nullptr, 0, scale, out, ldo);
+        kern<<<grid, 128, smem, stream>>>(qkv, ld, T, lens, nullptr, nullptr, nullptr, 0, scale, out, ldo, chunk, left_chunks);
     } else {
         SBK_REQUIRE(ldp % 4 == 0, "encoder_attention: bad ldp");
         const size_t smem = 4ull * ATT_BQ * STR * 2 + static_cast<size_t>(T) * STR * 2 + 4ull * 16 * 81 * 4 +
@@ -687,7 +730,7 @@ static int launch_encoder_attention(const __half* qkv, int ld, int B, int T, int
         SBK_REQUIRE(smem <= 220 * 1024, "encoder_attention(RelPos): T=%d too long for the shared-memory table", T);
         auto kern = encoder_attention_kernel<DH, DHP, true>;
         SBK_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, 128, smem, stream>>>(qkv, ld, T, lens, pos_u, pos_v, P, ldp, scale, out, ldo);
+        kern<<<grid, 128, smem, stream>>>(qkv, ld, T, lens, pos_u, pos_v, P, ldp, scale, out, ldo, chunk, left_chunks);
     }
     SBK_LAUNCH_CHECK();
     return SBK_OK;
@@ -696,16 +739,17 @@ static int launch_encoder_attention(const __half* qkv, int ld, int B, int T, int
 // qkv [B*T, ld] fp16 with per-head [q | k | v] blocks of head_dim; out [B*T, ldo] fp16.
 int encoder_attention(const __half* qkv, int ld, int B, int T, int H, int head_dim, const int* lens, bool relpos,
                       const float* pos_u, const float* pos_v, const __half* P, int ldp, float scale, __half* out,
-                      int ldo, cudaStream_t stream) {
+                      int ldo, cudaStream_t stream, int chunk, int left_chunks) {
+    SBK_REQUIRE(chunk >= 0, "encoder_attention: chunk size must be >= 0");
     SBK_REQUIRE(ld % 4 == 0 && ldo % 2 == 0, "encoder_attention: bad leading dims");
     if (head_dim % 8 == 0)  // cp.async 16-byte K/V staging
         SBK_REQUIRE(ld % 8 == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0, "encoder_attention: qkv must be 16-byte aligned");
     if (head_dim == 64)
-        return launch_encoder_attention<64, 64>(qkv, ld, B, T, H, lens, relpos, pos_u, pos_v, P, ldp, scale, out, ldo, stream);
+        return launch_encoder_attention<64, 64>(qkv, ld, B, T, H, lens, relpos, pos_u, pos_v, P, ldp, scale, out, ldo, chunk, left_chunks, stream);
     if (head_dim == 36)  // conformer_small: 144 / 4 heads, zero-padded to 48 for the k16 steps
-        return launch_encoder_attention<36, 48>(qkv, ld, B, T, H, lens, relpos, pos_u, pos_v, P, ldp, scale, out, ldo, stream);
+        return launch_encoder_attention<36, 48>(qkv, ld, B, T, H, lens, relpos, pos_u, pos_v, P, ldp, scale, out, ldo, chunk, left_chunks, stream);
     if (head_dim == 32)
-        return launch_encoder_attention<32, 32>(qkv, ld, B, T, H, lens, relpos, pos_u, pos_v, P, ldp, scale, out, ldo, stream);
+        return launch_encoder_attention<32, 32>(qkv, ld, B, T, H, lens, relpos, pos_u, pos_v, P, ldp, scale, out, ldo, chunk, left_chunks, stream);
     set_error("encoder_attention: head_dim=%d not built (64, 36, 32)", head_dim);
     return SBK_ERR_UNSUPPORTED;
 }

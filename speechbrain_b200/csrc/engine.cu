@@ -136,6 +136,7 @@ struct AsrModel {
     long long pipe_nodes = 0;
     int* weight_refs = nullptr;  // weights (arena + fbank plan) are shared between a handle and its clones (lanes)
     int dec_tc_rows = getenv("SBK_DEC_TC_ROWS") ? atoi(getenv("SBK_DEC_TC_ROWS")) : 64;  // >= this many live hypotheses: tcgen05 decode GEMMs
+    int dyn_chunk = 0, dyn_left = -1;  // DynChunkTrainConfig of the next encode calls (chunk frames, left-context chunks; 0 = off)
     int fuse_dec_ln = 1;         // 1: LayerNorm inside the projection kernel (latency); 0: separate LN kernel (throughput)
     int poll_every = 8;          // greedy early-exit poll interval in steps; 0 = never sync, run exactly max_steps
     bool has_fbank = false, has_cnn = false, has_enc = false, has_dec = false;
@@ -647,14 +648,14 @@ static int run_encoder(AsrModel* m, const float* feats, int B, int T0, const int
             RC(gemm_f16(m->relpos_pe, d, w.wpos, d, e, T, d, d, st));
         }
         RC(encoder_attention(b.qkv16, 3 * d, B, T, H, dh, enc_len, c.attention_type == SBK_ATT_RELPOS, w.pos_u, w.pos_v,
-                             b.P16, d, att_scale, b.att16, d, st));
+                             b.P16, d, att_scale, b.att16, d, st, m->dyn_chunk, m->dyn_left));
         e = GemmEpilogue(); e.mode = EPI_RESID; e.bias = w.bo; e.out = b.x; e.resid = b.x; e.ldo = d; e.alpha = 1.0f;
         RC(gemm_f16(b.att16, d, w.wo, d, e, M, d, d, st));
         // --- convolution module (Conformer.py:314-330, 494)
         RC(layernorm_rows(b.x, b.h16, true, w.conv_ln_g, w.conv_ln_b, M, d, 1e-5f, false, st));
         e = GemmEpilogue(); e.mode = EPI_GLU; e.bias = w.bpw1; e.out = b.glu; e.ldo = d;
         RC(gemm_f16(b.h16, d, w.wpw1, d, e, M, 2 * d, d, st));
-        RC(dwconv_ln_swish(b.glu, B, T, d, c.kernel_size, w.wdw, w.bdw, w.aconv_ln_g, w.aconv_ln_b, 1e-5f, b.h16, st));
+        RC(dwconv_ln_swish(b.glu, B, T, d, c.kernel_size, w.wdw, w.bdw, w.aconv_ln_g, w.aconv_ln_b, 1e-5f, b.h16, st, m->dyn_chunk));
         e = GemmEpilogue(); e.mode = EPI_RESID; e.bias = w.bpw2; e.out = b.x; e.resid = b.x; e.ldo = d; e.alpha = 1.0f;
         e.row_lens = enc_len; e.T = T;
         RC(gemm_f16(b.h16, d, w.wpw2, d, e, M, d, d, st));
@@ -1290,6 +1291,15 @@ int sbk_asr_set_decoder_tc_min_rows(sbk_asr* m, int rows) {
     AsrModel* mm = reinterpret_cast<AsrModel*>(m);
     if (mm->dec_tc_rows != rows) drop_graphs(mm);
     mm->dec_tc_rows = rows;
+    return SBK_OK;
+}
+int sbk_asr_set_dynchunk(sbk_asr* m, int chunk_size, int left_context_chunks) {
+    AsrModel* mm = reinterpret_cast<AsrModel*>(m);
+    SBK_REQUIRE(chunk_size >= 0, "set_dynchunk: chunk_size must be >= 0 (0 = full-context attention)");
+    const int left = left_context_chunks < 0 ? -1 : left_context_chunks;
+    if (mm->dyn_chunk != chunk_size || mm->dyn_left != left) drop_graphs(mm);  // cached graphs bake the kernel arguments in
+    mm->dyn_chunk = chunk_size;
+    mm->dyn_left = left;
     return SBK_OK;
 }
 int sbk_asr_set_poll_interval(sbk_asr* m, int every_n_steps) {

@@ -82,11 +82,12 @@ int layernorm_rows(const float* x, void* out, bool out_half, const float* gamma,
 int layernorm2_rows(const float* x, float* y_out, void* z_out, bool z_half, const float* ga, const float* ba, float eps_a,
                     const float* gb, const float* bb, float eps_b, int M, int D, cudaStream_t stream);
 int cast_f32_f16(const float* in, __half* out, size_t n, cudaStream_t stream);
+// chunk > 0: Dynamic Chunk Convolution (inputs past the end of the output frame's chunk are zero)
 int dwconv_ln_swish(const float* glu, int B, int T, int D, int K, const float* wdw, const float* bdw,
-                    const float* gamma, const float* beta, float eps, __half* out, cudaStream_t stream);
+                    const float* gamma, const float* beta, float eps, __half* out, cudaStream_t stream, int chunk = 0);
 int encoder_attention(const __half* qkv, int ld, int B, int T, int H, int head_dim, const int* lens, bool relpos,
                       const float* pos_u, const float* pos_v, const __half* P, int ldp, float scale, __half* out,
-                      int ldo, cudaStream_t stream);
+                      int ldo, cudaStream_t stream, int chunk = 0, int left_chunks = -1);
 
 // ---- decoder.cu
 enum SkinnyEpi { SK_F16 = 0, SK_F16_GELU = 1, SK_F32 = 2, SK_RESID = 3, SK_QKV_CACHE = 4, SK_F16_RELU = 5 };

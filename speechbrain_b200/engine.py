@@ -133,6 +133,11 @@ class AsrEngine:
             check(lib().sbk_asr_clone(self._h, ctypes.byref(other._h)), "sbk_asr_clone")
         return other
 
+    def set_dynchunk(self, chunk_size=0, left_context_chunks=None):
+        """DynChunkTrainConfig of the following encode calls (0 = full-context; left None = the whole past)."""
+        check(lib().sbk_asr_set_dynchunk(self._h, int(chunk_size), -1 if left_context_chunks is None else int(left_context_chunks)),
+              "sbk_asr_set_dynchunk")
+
     def set_poll_interval(self, every_n_steps):
         check(lib().sbk_asr_set_poll_interval(self._h, int(every_n_steps)), "sbk_asr_set_poll_interval")
 

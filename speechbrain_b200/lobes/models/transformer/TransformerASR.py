@@ -120,9 +120,10 @@ class TransformerASR(torch.nn.Module):
 
     @torch.no_grad()
     def encode(self, src, wav_len=None, pad_idx=0, dynchunktrain_config=None):
-        """src [B, T, F] or [B, T, F', C] -> encoder_out [B, T, d_model] (TransformerASR.py:475-544)."""
-        if dynchunktrain_config is not None:
-            raise NotImplementedError("speechbrain_b200.TransformerASR: dynamic chunk training/streaming is not built")
+        """src [B, T, F] or [B, T, F', C] -> encoder_out [B, T, d_model] (TransformerASR.py:475-544).
+
+        ``dynchunktrain_config`` (a ``DynChunkTrainConfig``): chunked attention + Dynamic Chunk Convolution, i.e. the masked
+        evaluation mode whose outputs equal chunk-by-chunk streaming (TransformerASR.py:46-105, Conformer.py:190-313)."""
         require_cuda(src, "TransformerASR.encode")
         if src.dim() == 4:
             bz, t, ch1, ch2 = src.shape
@@ -130,7 +131,16 @@ class TransformerASR(torch.nn.Module):
         if wav_len is not None and float(wav_len.max()) < 1.0 - 1e-6:
             # the reference builds its mask with width max(abs_len) and then fails to broadcast (dataio.py:836)
             raise ValueError("wav_len: the longest utterance must have relative length 1.0")
-        return self._get_engine(src.device).encode_from_cnn(src, wav_len)
+        eng = self._get_engine(src.device)
+        if dynchunktrain_config is None:
+            return eng.encode_from_cnn(src, wav_len)
+        if dynchunktrain_config.chunk_size <= 0:
+            raise ValueError("DynChunkTrainConfig.chunk_size must be > 0")
+        eng.set_dynchunk(dynchunktrain_config.chunk_size, dynchunktrain_config.left_context_size)
+        try:
+            return eng.encode_from_cnn(src, wav_len)
+        finally:
+            eng.set_dynchunk(0)
 
     def _decoder_engine(self, device):
         """Engine for ``decode``: a searcher's slot when one is wired to this model (its engine already holds the decoder),

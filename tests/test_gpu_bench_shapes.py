@@ -391,13 +391,15 @@ def test_fp16_range_scaled_weights(dev):
     cfg = _cfg(g)
     sd = seeded_asr_state(cfg, 0)
     cnn = g["cnn_out"].reshape(g["cnn_out"].shape[0], g["cnn_out"].shape[1], -1).to(dev)
+    results = []
     for name, bar in (("ffn", 1e-3), ("attn", 3e-3)):
         eng = AsrEngine(cfg, scale_state(sd, gs[name]["scales"]), device=dev, parts=("encoder",))
         enc = eng.encode_from_cnn(cnn, g["wav_lens"].to(dev)).cpu()
         r = _rel(enc, gs[name]["enc_out"])
         print(f"scaled weights [{name}] {gs[name]['scales']} (max |FFN pre-activation| {gs[name]['ffn_hidden_absmax']:.0f} in the "
               f"reference): encoder rel-L2 err {r:.3e} (bar {bar:g})")
-        assert torch.isfinite(enc).all() and r < bar
+        results.append((name, bool(torch.isfinite(enc).all()), r, bar))
+    assert all(fin and r < bar for _, fin, r, bar in results), results
     eng2 = AsrEngine(cfg, scale_state(sd, dict(gs["ffn"]["scales"], ffn_w1=1e5)), device=dev, parts=("encoder",))
     enc2 = eng2.encode_from_cnn(cnn, g["wav_lens"].to(dev)).cpu()
     print(f"FFN x1e5 (hidden beyond the fp16 range): finite {bool(torch.isfinite(enc2).all())}, absmax {float(enc2.abs().max()):.2f}")
@@ -430,3 +432,27 @@ def test_conformer_small_decoder_greedy(dev):
     # and the whole path from the waveform
     p2, _, enc, _ = eng.transcribe_greedy_dev(g["wav"].to(dev), g["wav_lens"].to(dev), n_steps, 1, 2, want_enc=True)
     assert _rel(enc.cpu(), g["enc_out"]) < 1.5e-3
+
+
+def test_dynamic_chunk_encode(dev):
+    """TransformerASR.encode(src, wav_len, dynchunktrain_config=DynChunkTrainConfig(chunk, left)) -- chunked attention masks +
+    Dynamic Chunk Convolution (the streaming-equivalent masked mode) -- vs the reference: RoPE and RelPos, finite and
+    infinite left context, chunk sizes that do not divide T, ragged batch."""
+    import bench
+    from speechbrain_b200.utils.dynamic_chunk_training import DynChunkTrainConfig
+    from speechbrain_b200.utils.seeded_init import seeded_asr_state
+    gd = torch.load(os.path.join(GOLDEN, "dynchunk_conformer_large.pt"))
+    asrs = {}
+    for key, c in gd.items():
+        att = c["attention_type"]
+        g = torch.load(os.path.join(GOLDEN, "conformer_large_rope.pt" if att == "RoPEMHA" else "conformer_large_relpos.pt"))
+        if att not in asrs:
+            cfg = _cfg(g)
+            asrs[att] = bench.build_product_asr(cfg, seeded_asr_state(cfg, 0), dev).transformer
+        tr = asrs[att]
+        src = g["cnn_out"].to(dev)
+        enc = tr.encode(src, g["wav_lens"].to(dev), dynchunktrain_config=DynChunkTrainConfig(c["chunk_size"], c["left_context_size"])).cpu()
+        r = _rel(enc, c["enc_out"])
+        full = tr.encode(src, g["wav_lens"].to(dev)).cpu()  # the engine is back in full-context mode afterwards
+        print(f"[dynchunk {key}] encoder rel-L2 err {r:.3e}; full-context afterwards rel {_rel(full, g['enc_out']):.3e}")
+        assert r < 1e-3 and _rel(full, g["enc_out"]) < 1e-3
