@@ -178,7 +178,7 @@ def build_reference_asr(cfg, sd, device="cpu", beam=None, lm_sd=None):
     return run
 
 
-def best_thread_count(run, seconds):
+def best_thread_count(run, seconds, encode_only=False):
     """The reference's decode loop is thousands of small ops per step: more threads than it can use make it slower (measured
     on the 128-core GPU box in round 1: 16 threads 60x faster than 128).  Give it the count that is fastest on a quick probe
     (4 utterances, encode + 4 greedy steps) among {8, 16, 32, 64, all}."""
@@ -188,9 +188,9 @@ def best_thread_count(run, seconds):
     best, best_t = n_all, None
     for n in sorted({min(n_all, c) for c in (8, 16, 32, 64, n_all)}):
         torch.set_num_threads(n)
-        run(wav, lens, 2)
+        run(wav, lens, 2, encode_only)
         t0 = time.perf_counter()
-        run(wav, lens, 4)
+        run(wav, lens, 4, encode_only)
         dt = time.perf_counter() - t0
         if best_t is None or dt < best_t:
             best, best_t = n, dt
@@ -202,8 +202,8 @@ def time_reference(cfg, sd, B, seconds, steps, device, n_steps, warmup, budget_s
     """`n_steps` timed passes of the reference over one B x `seconds` batch (stops early when `budget_s` is spent)."""
     import torch
     run = build_reference_asr(cfg, sd, device, beam=beam)
-    if tune_threads and device == "cpu" and not encode_only:
-        best_thread_count(run, seconds)
+    if tune_threads and device == "cpu":
+        best_thread_count(run, seconds, encode_only)
     wav, lens = synth_batch(B, seconds, 1234)
     times = []
     t_start = time.perf_counter()

@@ -142,6 +142,40 @@ class TransformerASR(torch.nn.Module):
         finally:
             eng.set_dynchunk(0)
 
+    # ------------------------------------------------------------------ streaming (TransformerASR.py:546-670)
+    def make_streaming_context(self, dynchunktrain_config):
+        """Streaming context for ``encode_streaming`` (TransformerASR.py:645-670)."""
+        if dynchunktrain_config is None or dynchunktrain_config.chunk_size <= 0:
+            raise ValueError("make_streaming_context needs a DynChunkTrainConfig with chunk_size > 0")
+        return TransformerASRStreamingContext(dynchunktrain_config)
+
+    @torch.no_grad()
+    def encode_streaming(self, src, context):
+        """Encoder output for one more chunk of ``src`` [B, chunk_size, F] (TransformerASR.py:546-643).
+
+        The reference carries per-layer left-context caches; its outputs equal the masked full-sequence run
+        (``encode(..., dynchunktrain_config)``, tests/unittests/test_conformer.py).  This implementation keeps the chunk
+        *inputs* seen so far in the context and re-runs that masked encode over the window the new chunk can depend on
+        (12 layers x (left context + convolution halo); everything, for an infinite left context), returning the rows of the
+        new chunk: the same values, at the cost of recomputing the window instead of reusing per-layer caches."""
+        require_cuda(src, "TransformerASR.encode_streaming")
+        cfg = context.dynchunktrain_config
+        if src.dim() == 4:
+            src = src.reshape(src.shape[0], src.shape[1], -1)
+        if context.history is not None and context.history.shape[1] % cfg.chunk_size != 0:
+            raise ValueError("encode_streaming: only the last chunk of a stream may be shorter than chunk_size")
+        hist = src if context.history is None else torch.cat([context.history, src], dim=1)
+        out = self.encode(hist, None, dynchunktrain_config=cfg)[:, -src.shape[1]:].contiguous()
+        if not cfg.is_infinite_left_context():  # trim to the receptive field of the next chunk, on a chunk boundary
+            halo = (self.kernel_size - 1) // 2
+            per_layer = max(cfg.left_context_size * cfg.chunk_size + cfg.chunk_size - 1, halo)
+            keep = self.num_encoder_layers * per_layer + cfg.chunk_size
+            keep = -(-keep // cfg.chunk_size) * cfg.chunk_size
+            if hist.shape[1] > keep and hist.shape[1] % cfg.chunk_size == 0:
+                hist = hist[:, -keep:]
+        context.history = hist
+        return out
+
     def _decoder_engine(self, device):
         """Engine for ``decode``: a searcher's slot when one is wired to this model (its engine already holds the decoder),
         else a decoder-only engine without the output head."""
@@ -175,6 +209,14 @@ class TransformerASR(torch.nn.Module):
         return enc, dec
 
 
+class TransformerASRStreamingContext:
+    """Mutable streaming state (TransformerASR.py:26-43): the DynChunkTrainConfig and the chunk inputs seen so far."""
+
+    def __init__(self, dynchunktrain_config):
+        self.dynchunktrain_config = dynchunktrain_config
+        self.history = None
+
+
 class EncoderWrapper(torch.nn.Module):
     """TransformerASR.py:678-714: calls ``transformer.encode`` so the model can sit at the end of a Sequential."""
 
@@ -184,3 +226,10 @@ class EncoderWrapper(torch.nn.Module):
 
     def forward(self, x, wav_lens=None, pad_idx=0, **kwargs):
         return self.transformer.encode(x, wav_lens, pad_idx, **kwargs)
+
+    def forward_streaming(self, x, context):
+        """TransformerASR.py:716-737: one chunk through ``encode_streaming``."""
+        return self.transformer.encode_streaming(x, context)
+
+    def make_streaming_context(self, *args, **kwargs):
+        return self.transformer.make_streaming_context(*args, **kwargs)

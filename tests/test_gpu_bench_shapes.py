@@ -459,3 +459,29 @@ def test_dynamic_chunk_encode(dev):
         full = tr.encode(src, g["wav_lens"].to(dev)).cpu()  # the engine is back in full-context mode afterwards
         print(f"[dynchunk {key}] encoder rel-L2 err {r:.3e}; full-context afterwards rel {_rel(full, g['enc_out']):.3e}")
         assert r < 1e-3 and _rel(full, g["enc_out"]) < 1e-3
+
+
+def test_encode_streaming_equals_masked(dev):
+    """encode_streaming(chunk, context) chunk by chunk == encode(full, dynchunktrain_config) (the reference's own streaming
+    test, tests/unittests/test_conformer.py, asserts exactly this equivalence): finite left context with history trimming
+    (a 3-layer model so that the stream is longer than the retained window) and infinite left context, a short last chunk."""
+    import bench
+    from speechbrain_b200.utils.dynamic_chunk_training import DynChunkTrainConfig
+    from speechbrain_b200.utils.seeded_init import CONFORMER_LARGE, seeded_asr_state
+    for att, cs, lc, n_layers in (("RoPEMHA", 8, 1, 3), ("RelPosMHAXL", 6, None, 2)):
+        cfg = dict(CONFORMER_LARGE, attention_type=att, num_encoder_layers=n_layers, num_decoder_layers=1)
+        tr = bench.build_product_asr(cfg, seeded_asr_state(cfg, 0), dev).transformer
+        gen = torch.Generator().manual_seed(5)
+        T = 20 * cs + 3
+        src = torch.randn(2, T, 640, generator=gen).to(dev)
+        dc = DynChunkTrainConfig(cs, lc)
+        full = tr.encode(src, None, dynchunktrain_config=dc)
+        ctx = tr.make_streaming_context(dc)
+        outs = [tr.encode_streaming(src[:, t:t + cs].contiguous(), ctx) for t in range(0, T, cs)]
+        stream = torch.cat(outs, dim=1)
+        r = _rel(stream.cpu(), full.cpu())
+        print(f"[streaming {att} chunk {cs} left {lc}] {len(outs)} chunks, retained history {ctx.history.shape[1]} of {T} frames, "
+              f"rel diff vs masked {r:.2e}")
+        assert stream.shape == full.shape and r < 3e-4  # same maths; the online-softmax key-block partition differs with the window
+        if lc is not None:
+            assert ctx.history.shape[1] < T
