@@ -370,11 +370,16 @@ def run_greedy32(args):
     wavs_host = [[wav_host.clone().pin_memory() for _ in range(G)] for _ in range(NL)]
     lens_host_l = [[lens_host.clone().pin_memory() for _ in range(G)] for _ in range(NL)]
     preds_host = [[torch.empty(BATCH, DECODE_STEPS, dtype=torch.int32).pin_memory() for _ in range(G)] for _ in range(NL)]
-    gathered = [None] * NL
+    gathered = {}
 
     def gather(ln, g):
         if world > 1:  # the path's only collective: every rank ends up with all ranks' hypotheses of this group
-            gathered[ln] = gather_hypotheses(pred_all[ln][: g * BATCH], world * g * BATCH, world)
+            key = (ln, g)
+            if key not in gathered:
+                gathered[key] = torch.empty(world * g * BATCH, DECODE_STEPS, dtype=torch.int32, device=dev)
+            # max_len = the decode limit: a static width, so the helper needs no width-agreeing all-reduce (whose .item() would
+            # block the host until this lane's group has finished and serialise the lanes)
+            gather_hypotheses(pred_all[ln][: g * BATCH], world * g * BATCH, world, max_len=DECODE_STEPS, out=gathered[key])
 
     def step_dev(i):
         ln, g = i % NL, sizes[i]
@@ -663,7 +668,7 @@ def run_other(args):
                 hyp_buf.fill_(-1)
                 for b, h in enumerate(hyps):
                     hyp_buf[b, : len(h)] = torch.tensor(h, dtype=torch.int32)
-                gather_hypotheses(hyp_buf, world * B, world)
+                gather_hypotheses(hyp_buf, world * B, world, max_len=DECODE_STEPS)
         d2h = B * wl["beam"] * DECODE_STEPS * 16
 
     def barrier():
