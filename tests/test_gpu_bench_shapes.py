@@ -485,3 +485,66 @@ def test_encode_streaming_equals_masked(dev):
         assert stream.shape == full.shape and r < 3e-4  # same maths; the online-softmax key-block partition differs with the window
         if lc is not None:
             assert ctx.history.shape[1] < T
+
+
+@pytest.mark.parametrize("B,L,lens,att", [(1, 16000, [1.0], "RoPEMHA"), (3, 12345, [1.0, 0.5, 0.21], "RelPosMHAXL"),
+                                          (2, 1999, [1.0, 0.6], "RoPEMHA"), (5, 48000, [0.37, 1.0, 0.99, 0.5, 0.8], "RoPEMHA")])
+def test_edge_shapes_vs_oracle(dev, B, L, lens, att):
+    """Edge shapes through the fused wav -> ids pipeline vs the CPU oracle (pinned to the reference by the golden generator):
+    a single utterance, sample counts that are not multiples of 4 (no TMA staging) or of the hop, very short audio (T = 4 encoder
+    frames), batch sizes that are not powers of two, utterances padded to a fifth of the batch length."""
+    from oracle import asr_oracle as O
+    from speechbrain_b200.engine import AsrEngine
+    from speechbrain_b200.utils.seeded_init import CONFORMER_LARGE, seeded_asr_state
+    cfg = dict(CONFORMER_LARGE, attention_type=att, num_encoder_layers=3, num_decoder_layers=2)
+    sd = seeded_asr_state(cfg, 0)
+    eng = AsrEngine(cfg, sd, device=dev)
+    gen = torch.Generator().manual_seed(B * 1000 + L)
+    wav = torch.randn(B, L, generator=gen)
+    wl = torch.tensor(lens)
+    for b in range(B):
+        wav[b, int(round(lens[b] * L)):] = 0
+    steps = 3
+    pred, score, enc, done = eng.transcribe_greedy_dev(wav.to(dev), wl.to(dev), steps, 1, 2, want_enc=True)
+    torch.cuda.synchronize()
+    ocfg = dict(cfg, win_length=32)
+    with torch.no_grad():
+        feats = O.full_pipeline_features(wav, wl, sd, ocfg)
+        ref = O.encode(feats, wl, sd, cfg, "Transformer.")
+        T = ref.shape[1]
+        out = O.greedy_search(ref, wl, sd, cfg, sd["seq_lin.w.weight"], sd["seq_lin.w.bias"], 1, 2, 0.0, (steps + 0.5) / T,
+                              "Transformer.", return_logits=True)
+    r = _rel(enc.cpu(), ref)
+    logits = out[4]
+    n = logits.shape[1]
+    top2 = logits.topk(2, -1).values
+    ok = True
+    for b in range(B):
+        for s in range(min(n, done)):
+            if int(pred[b, s]) != int(logits[b, s].argmax()):
+                ok = ok and float(top2[b, s, 0] - top2[b, s, 1]) < 5e-3
+                break
+    print(f"edge B={B} L={L} lens={lens} {att}: T={T} encoder rel-L2 {r:.3e}, steps {done}/{n}, tokens ok {ok}")
+    assert enc.shape == ref.shape and torch.isfinite(enc).all() and r < 1e-3 and ok
+
+
+def test_long_utterance_vs_oracle(dev):
+    """Maximum-size direction: 2 x 40 s (T = 1001 encoder frames = 16 key blocks, 8 x the bench length), ragged, 2 Conformer
+    layers, RoPE: encoder vs the CPU oracle."""
+    from oracle import asr_oracle as O
+    from speechbrain_b200.engine import AsrEngine
+    from speechbrain_b200.utils.seeded_init import CONFORMER_LARGE, seeded_asr_state
+    cfg = dict(CONFORMER_LARGE, num_encoder_layers=2, num_decoder_layers=1)
+    sd = seeded_asr_state(cfg, 0)
+    eng = AsrEngine(cfg, sd, device=dev, parts=("fbank", "cnn", "encoder"))
+    gen = torch.Generator().manual_seed(40)
+    L = 640000
+    wav = torch.randn(2, L, generator=gen)
+    wl = torch.tensor([1.0, 0.73])
+    wav[1, int(0.73 * L):] = 0
+    enc = eng.encode_wav(wav.to(dev), wl.to(dev)).cpu()
+    with torch.no_grad():
+        ref = O.encode(O.full_pipeline_features(wav, wl, sd, dict(cfg, win_length=32)), wl, sd, cfg, "Transformer.")
+    r = _rel(enc, ref)
+    print(f"long utterance: T={ref.shape[1]} encoder rel-L2 {r:.3e}")
+    assert enc.shape == ref.shape and r < 1e-3
