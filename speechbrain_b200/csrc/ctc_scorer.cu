@@ -4,12 +4,17 @@
 // CTCScorer (decoders/scorer.py:183-249) as a *full* scorer of ScorerBuilder.score (:1221-1268), ctc_window_size = 0.
 //
 // The reference materialises the forward variables r (T, 2, n_bh, V) for EVERY candidate token at every step (1.3 GB
-// at B=32, beam 4) and then gathers the `beam` survivors (permute_mem).  Here the prefix probability psi of all
-// n_bh x V candidates is computed with the recurrence held in registers (one thread per (hypothesis, token), frames
-// streamed from the masked CTC log-posteriors x[B, T, V] -- coalesced over the token axis), nothing of r is stored; after
-// the beam kernel has picked the survivors, `ctc_update` re-runs the recurrence for just those n_bh (parent, token)
-// pairs and writes their forward variables (T x 2 per hypothesis) for the next step.  HBM-bound: x is read once per
-// hypothesis row per step (L2-resident across the beams of an utterance).
+// at B=32, beam 4) and then gathers the `beam` survivors (permute_mem).  The score it returns, though, only needs
+//   psi(h, c) = logsumexp_t( phi_h[t-1] + x[t, c] )        phi_h = the PARENT's forward variables (Alg.2-10/13),
+// i.e. a log-semiring product [n_bh, T] x [T, V] per utterance.  Here it is evaluated in the linear domain: the
+// posteriors are exponentiated once per utterance (xlin = exp(x), next to x), each hypothesis' phi is shifted by its
+// own maximum and exponentiated once per step into shared memory, and thread (utterance, token) accumulates
+// sum_t A_h[t] * xlin[t, c] for all the `beam` hypotheses of its utterance at once -- no transcendental in the inner
+// loop, xlin read once per utterance per step (coalesced over the token axis) instead of once per hypothesis.  A sum
+// that underflows (every term more than ~e^-69 below the row maximum) is redone for that one (hypothesis, token) in
+// the log domain, so the result never depends on the fp32 exponent range.  Nothing of r is stored; after the beam
+// kernel has picked the survivors, `ctc_update` runs the recurrence for just those n_bh (parent, token) pairs and
+// writes their forward variables (T x 2 per hypothesis) for the next step.
 //
 // State per hypothesis row (ping-pong by step parity):  rsum[t] = logsumexp(r_nb[t], r_b[t]),  rb[t] = r_b[t],
 // psi_prev = psi of the prefix itself.
@@ -22,26 +27,23 @@ namespace {
 
 constexpr float CTC_NEG = -1e20f;  // CTCPrefixScore.minus_inf (ctc.py:54)
 
-// log(exp(a) + exp(b)), accurate version (state update) and fast version (full-vocabulary scoring)
+// log(exp(a) + exp(b))
 __device__ __forceinline__ float logaddexp_acc(float a, float b) {
     const float m = fmaxf(a, b);
     return m + log1pf(expf(-fabsf(a - b)));
-}
-__device__ __forceinline__ float logaddexp_fast(float a, float b) {
-    const float m = fmaxf(a, b);
-    return m + __logf(1.0f + __expf(-fabsf(a - b)));
 }
 
 // In place: x[b, t, :] = log_softmax(x[b, t, :]); frames t >= enc_len[b]: minus_inf everywhere, 0 at index 0
 // (ctc.py:59-62 hard-codes channel 0 there); xb[b, t] = x[b, t, blank].
 __global__ void __launch_bounds__(256)
-ctc_logsoftmax_mask_kernel(float* __restrict__ x, float* __restrict__ xb, const int* __restrict__ enc_len, int T, int V,
-                           int blank) {
+ctc_logsoftmax_mask_kernel(float* __restrict__ x, float* __restrict__ xlin, float* __restrict__ xb,
+                           const int* __restrict__ enc_len, int T, int V, int blank) {
     __shared__ float s_red[8];
     const int row = blockIdx.x, b = row / T, t = row - b * T, tid = threadIdx.x;
     float* xr = x + static_cast<size_t>(row) * V;
+    float* xl = xlin + static_cast<size_t>(row) * V;
     if (t >= enc_len[b]) {
-        for (int j = tid; j < V; j += 256) xr[j] = (j == 0) ? 0.0f : CTC_NEG;
+        for (int j = tid; j < V; j += 256) { xr[j] = (j == 0) ? 0.0f : CTC_NEG; xl[j] = (j == 0) ? 1.0f : 0.0f; }
         if (tid == 0) xb[row] = (blank == 0) ? 0.0f : CTC_NEG;
         return;
     }
@@ -64,6 +66,7 @@ ctc_logsoftmax_mask_kernel(float* __restrict__ x, float* __restrict__ xb, const 
     for (int j = tid; j < V; j += 256) {
         const float v = xr[j] - lse;
         xr[j] = v;
+        xl[j] = expf(v);
         if (j == blank) xb[row] = v;
     }
 }
@@ -89,6 +92,7 @@ __global__ void ctc_init_kernel(const float* __restrict__ xb, int T, int beam, f
 // whole search step can be replayed for every step; the ping-pong halves of the state follow the step's parity.
 struct CtcArgs {
     const float* x; const float* xb;         // [B, T, V], [B, T]
+    const float* xlin;                       // exp(x)
     float* rsum_base; float* rb_base;        // [2][n_bh, T]: half (step & 1) holds the prefixes being extended
     float* psi_base;                         // [2][n_bh]
     const int* enc_len;                      // [B]
@@ -98,57 +102,92 @@ struct CtcArgs {
     float weight; float* out; int accumulate;   // score kernel: out[n_bh, V] (+)= weight * (psi - psi_prev)
 };
 
-// forward_step (ctc.py:80-249), candidates = None: thread (row, c) runs Alg.2 of Watanabe et al. over the frames.
+// forward_step (ctc.py:80-249), candidates = None, for the R hypotheses blockIdx.y * R .. + R of one utterance (R divides
+// the beam width) and 128 tokens.  Shared memory: A[2][R][Tp] -- variant 0 from rsum (Alg.2-10, c != last token), variant 1
+// from r_b (c == last token); A[.][h][t] = exp(phi_h[t-1] - M_h) for t >= max(step, 1), and at step 0 the seed
+// psi_init = x[0, c] (Alg.2-6) is the extra term A[.][h][0] = exp(-M_h) of the same sum.
 constexpr int CTC_THREADS = 128;
+template <int R>
 __global__ void __launch_bounds__(CTC_THREADS) ctc_score_kernel(const CtcArgs a) {
-    extern __shared__ float smem[];
-    float* s_rsum = smem;
-    float* s_rb = smem + a.T;
-    float* s_xb = smem + 2 * a.T;
-    const int row = blockIdx.y, b = row / a.beam, T = a.T, V = a.V;
-    const int step = a.step_ptr[row] + a.step_adj;
+    extern __shared__ __align__(16) float smem[];
+    __shared__ float s_M[2][R];
+    __shared__ int s_last[R];
+    const int T = a.T, V = a.V, Tp = (T + 3) & ~3;
+    const int row0 = blockIdx.y * R, b = row0 / a.beam;
+    const int step = a.step_ptr[row0] + a.step_adj;
     const size_t half = static_cast<size_t>(step & 1);
     const float* rsum_in = a.rsum_base + half * a.n_bh * T;
     const float* rb_in = a.rb_base + half * a.n_bh * T;
     const float* psi_prev = a.psi_base + half * a.n_bh;
-    for (int t = threadIdx.x; t < T; t += CTC_THREADS) {
-        s_rsum[t] = rsum_in[static_cast<size_t>(row) * T + t];
-        s_rb[t] = rb_in[static_cast<size_t>(row) * T + t];
-        s_xb[t] = a.xb[static_cast<size_t>(b) * T + t];
+    const int t_lo = step == 0 ? 0 : step;   // first term of the sum
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // per (variant, hypothesis): maximum of the exponents, one warp each
+    for (int i = warp; i < 2 * R; i += CTC_THREADS / 32) {
+        const int var = i / R, h = i - var * R;
+        const float* phi = (var ? rb_in : rsum_in) + static_cast<size_t>(row0 + h) * T;
+        float mx = step == 0 ? 0.0f : -INFINITY;
+        for (int t = max(t_lo, 1) + lane; t < T; t += 32) mx = fmaxf(mx, phi[t - 1]);
+        mx = warp_max(mx);
+        if (lane == 0) s_M[var][h] = mx;
+    }
+    if (threadIdx.x < R)
+        s_last[threadIdx.x] = step == 0 ? a.bos : a.hist_tok[static_cast<size_t>(step - 1) * a.n_bh + row0 + threadIdx.x];
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * R * Tp; i += CTC_THREADS) {
+        const int vh = i / Tp, t = i - vh * Tp, var = vh / R, h = vh - var * R;
+        float v = 0.0f;
+        if (t < T && t >= t_lo) {
+            const float M = s_M[var][h];
+            v = t == 0 ? __expf(-M) : __expf((var ? rb_in : rsum_in)[static_cast<size_t>(row0 + h) * T + t - 1] - M);
+        }
+        smem[i] = v;
     }
     __syncthreads();
     const int c = blockIdx.x * CTC_THREADS + threadIdx.x;
     if (c >= V) return;
-    const int last_char = step == 0 ? a.bos : a.hist_tok[static_cast<size_t>(step - 1) * a.n_bh + row];
-    const float* xc = a.x + static_cast<size_t>(b) * T * V + c;
-    float psi;
-    if (c == a.blank && a.eos != a.blank) {
-        psi = CTC_NEG;
-    } else if (c == a.eos) {
-        psi = s_rsum[a.enc_len[b] - 1];                                 // Alg.2-3
-    } else {
-        const float* phi = (c == last_char) ? s_rb : s_rsum;            // Alg.2-10
-        float r_nb, r_b = CTC_NEG;
-        int start;
-        if (step == 0) { r_nb = xc[0]; start = 1; }                     // Alg.2-6
-        else { r_nb = CTC_NEG; start = step; }
-        float pm = r_nb, ps = 1.0f;                                     // running logsumexp, seeded with psi_init
-#pragma unroll 4
-        for (int t = start; t < T; ++t) {
-            const float ph = phi[t - 1];
-            const float xn = xc[static_cast<size_t>(t) * V];
-            const float nb = logaddexp_fast(r_nb, ph) + xn;             // Alg.2-11
-            const float bl = logaddexp_fast(r_nb, r_b) + s_xb[t];       // Alg.2-12
-            const float term = ph + xn;                                 // Alg.2-13
-            if (term > pm) { ps = ps * __expf(pm - term) + 1.0f; pm = term; }
-            else ps += __expf(term - pm);
-            r_nb = nb; r_b = bl;
+    int base[R];
+    float acc[R];
+#pragma unroll
+    for (int h = 0; h < R; ++h) { base[h] = ((c == s_last[h]) ? R * Tp : 0) + h * Tp; acc[h] = 0.0f; }
+    const float* xc = a.xlin + static_cast<size_t>(b) * T * V + c;
+    for (int t = t_lo & ~3; t < T; t += 4) {
+        float xv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) xv[u] = (t + u < T) ? xc[static_cast<size_t>(t + u) * V] : 0.0f;
+#pragma unroll
+        for (int h = 0; h < R; ++h) {
+            const float4 av = *reinterpret_cast<const float4*>(smem + base[h] + t);
+            acc[h] = fmaf(av.x, xv[0], acc[h]); acc[h] = fmaf(av.y, xv[1], acc[h]);
+            acc[h] = fmaf(av.z, xv[2], acc[h]); acc[h] = fmaf(av.w, xv[3], acc[h]);
         }
-        psi = pm + __logf(ps);
     }
-    const float sc = a.weight * (psi - psi_prev[row]);
-    float* o = a.out + static_cast<size_t>(row) * V + c;
-    *o = a.accumulate ? *o + sc : sc;
+#pragma unroll
+    for (int h = 0; h < R; ++h) {
+        const int row = row0 + h;
+        float psi;
+        if (c == a.blank && a.eos != a.blank) {
+            psi = CTC_NEG;
+        } else if (c == a.eos) {
+            psi = rsum_in[static_cast<size_t>(row) * T + a.enc_len[b] - 1];   // Alg.2-3
+        } else if (acc[h] > 1e-30f) {
+            psi = s_M[c == s_last[h] ? 1 : 0][h] + __logf(acc[h]);
+        } else {   // out of the linear range: the same sum in the log domain (rare; keeps the result range-independent)
+            const float* phi = ((c == s_last[h]) ? rb_in : rsum_in) + static_cast<size_t>(row) * T;
+            const float* xg = a.x + static_cast<size_t>(b) * T * V + c;
+            float pm, ps = 1.0f;
+            int start;
+            if (step == 0) { pm = xg[0]; start = 1; } else { pm = CTC_NEG; start = step; }
+            for (int t = start; t < T; ++t) {
+                const float term = phi[t - 1] + xg[static_cast<size_t>(t) * V];
+                if (term > pm) { ps = ps * __expf(pm - term) + 1.0f; pm = term; }
+                else ps += __expf(term - pm);
+            }
+            psi = pm + __logf(ps);
+        }
+        const float sc = a.weight * (psi - psi_prev[row]);
+        float* o = a.out + static_cast<size_t>(row) * V + c;
+        *o = a.accumulate ? *o + sc : sc;
+    }
 }
 
 // permute_mem (ctc.py:251-295) without the (T, 2, n_bh, V) tensor: re-run the recurrence for the chosen (parent, token)
@@ -162,7 +201,8 @@ __global__ void __launch_bounds__(128) ctc_update_kernel(const CtcArgs a) {
     float* s_nb = smem + 3 * T;
     float* s_bl = smem + 4 * T;
     const int row = blockIdx.x, b = row / a.beam;
-    const int step = a.step_ptr[row] + a.step_adj;
+    const int step = a.step_ptr[row] + a.step_adj;   // the step whose survivors are being updated
+    if (step < 0) return;                            // enqueued at the head of every search step: nothing to do before the first
     const size_t half = static_cast<size_t>(step & 1), other = half ^ 1;
     const float* rsum_in = a.rsum_base + half * a.n_bh * T;
     const float* rb_in = a.rb_base + half * a.n_bh * T;
@@ -258,10 +298,10 @@ int rows_logsoftmax_argmax(float* x, int rows, int V, bool do_logsoftmax, int* i
     return SBK_OK;
 }
 
-int ctc_prefix_reset(float* x, float* xb, const int* enc_len, int B, int T, int V, int blank, int beam, float* rsum, float* rb,
-                     float* psi_prev, cudaStream_t stream) {
+int ctc_prefix_reset(float* x, float* xlin, float* xb, const int* enc_len, int B, int T, int V, int blank, int beam, float* rsum,
+                     float* rb, float* psi_prev, cudaStream_t stream) {
     SBK_REQUIRE(T >= 1 && T * 5 * 4 <= 200 * 1024, "ctc scorer: T=%d out of range", T);
-    ctc_logsoftmax_mask_kernel<<<B * T, 256, 0, stream>>>(x, xb, enc_len, T, V, blank);
+    ctc_logsoftmax_mask_kernel<<<B * T, 256, 0, stream>>>(x, xlin, xb, enc_len, T, V, blank);
     SBK_LAUNCH_CHECK();
     ctc_init_kernel<<<B * beam, 128, T * 4, stream>>>(xb, T, beam, rsum, rb, psi_prev);
     SBK_LAUNCH_CHECK();
@@ -270,28 +310,56 @@ int ctc_prefix_reset(float* x, float* xb, const int* enc_len, int B, int T, int 
 
 static CtcArgs make_args(const CtcStep& p, int step_adj) {
     CtcArgs a;
-    a.x = p.x; a.xb = p.xb; a.rsum_base = p.rsum_base; a.rb_base = p.rb_base; a.psi_base = p.psi_base; a.enc_len = p.enc_len;
+    a.x = p.x; a.xlin = p.xlin; a.xb = p.xb; a.rsum_base = p.rsum_base; a.rb_base = p.rb_base; a.psi_base = p.psi_base; a.enc_len = p.enc_len;
     a.hist_tok = p.hist_tok; a.hist_pred = p.hist_pred; a.step_ptr = p.step_ptr; a.step_adj = step_adj;
     a.n_bh = p.n_bh; a.bos = p.bos; a.T = p.T; a.V = p.V;
     a.beam = p.beam; a.blank = p.blank; a.eos = p.eos; a.weight = p.weight; a.out = p.out; a.accumulate = p.accumulate;
     return a;
 }
 
-int ctc_prefix_score(const CtcStep& p, cudaStream_t stream) {
-    const CtcArgs a = make_args(p, 0);   // runs before the beam kernel advances the step counters
+template <int R>
+static int launch_score(const CtcArgs& a, cudaStream_t stream) {
     static bool attr = false;
     if (!attr) {
-        SBK_CUDA_CHECK(cudaFuncSetAttribute(ctc_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        SBK_CUDA_CHECK(cudaFuncSetAttribute(ctc_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        SBK_CUDA_CHECK(cudaFuncSetAttribute(ctc_score_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr = true;
     }
-    ctc_score_kernel<<<dim3(ceil_div(p.V, CTC_THREADS), p.n_bh), CTC_THREADS, 3 * p.T * 4, stream>>>(a);
+    const int Tp = (a.T + 3) & ~3;
+    ctc_score_kernel<R><<<dim3(ceil_div(a.V, CTC_THREADS), a.n_bh / R), CTC_THREADS, (size_t)2 * R * Tp * 4, stream>>>(a);
     SBK_LAUNCH_CHECK();
     return SBK_OK;
 }
 
+int ctc_prefix_score(const CtcStep& p, cudaStream_t stream) {
+    const CtcArgs a = make_args(p, 0);   // runs before the beam kernel advances the step counters
+    static bool attr = false;
+    if (!attr) {
+        SBK_CUDA_CHECK(cudaFuncSetAttribute(ctc_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr = true;
+    }
+    // hypotheses per CTA: the widest compiled group that divides the beam and whose exponent table fits shared memory
+    const int Tp = (p.T + 3) & ~3;
+    const int fit = (200 * 1024) / (2 * Tp * 4);
+    static const int widths[] = {16, 12, 11, 10, 8, 6, 5, 4, 3, 2, 1};
+    int R = 1;
+    for (int w : widths) if (p.beam % w == 0 && w <= fit) { R = w; break; }
+    switch (R) {
+        case 16: return launch_score<16>(a, stream);
+        case 12: return launch_score<12>(a, stream);
+        case 11: return launch_score<11>(a, stream);
+        case 10: return launch_score<10>(a, stream);
+        case 8: return launch_score<8>(a, stream);
+        case 6: return launch_score<6>(a, stream);
+        case 5: return launch_score<5>(a, stream);
+        case 4: return launch_score<4>(a, stream);
+        case 3: return launch_score<3>(a, stream);
+        case 2: return launch_score<2>(a, stream);
+        default: return launch_score<1>(a, stream);
+    }
+}
+
 int ctc_prefix_update(const CtcStep& p, cudaStream_t stream) {
-    const CtcArgs a = make_args(p, -1);  // runs after it
+    const CtcArgs a = make_args(p, -1);  // runs after it (at the head of the next search step)
     ctc_update_kernel<<<p.n_bh, 128, 5 * p.T * 4, stream>>>(a);
     SBK_LAUNCH_CHECK();
     return SBK_OK;

@@ -314,8 +314,9 @@ __global__ void __launch_bounds__(DA_WARPS * 32, 4) dec_attention_kernel(const D
     const int per = (n_keys + DA_WARPS - 1) / DA_WARPS;
     const int kb = warp * per, ke = min(n_keys, kb + per);
     const int gq = lane >> 3, dl = (lane & 7) * 8;
-    const __half* kbase = a.kbase + static_cast<size_t>(blk) * a.row_stride + h * 64 + dl;
-    const __half* vbase = a.vbase + static_cast<size_t>(blk) * a.row_stride + h * 64 + dl;
+    const int hs = a.head_stride > 0 ? a.head_stride : 64;
+    const __half* kbase = a.kbase + static_cast<size_t>(blk) * a.row_stride + static_cast<size_t>(h) * hs + dl;
+    const __half* vbase = a.vbase + static_cast<size_t>(blk) * a.row_stride + static_cast<size_t>(h) * hs + dl;
     // beam search: position j of hypothesis r lives in the cache row of the ancestor that wrote it
     const int* lin = nullptr;
     if (a.lineage) lin = a.lineage + static_cast<size_t>((n_keys - 1) & 1) * gridDim.y * a.lin_stride + static_cast<size_t>(r) * a.lin_stride;
@@ -696,8 +697,9 @@ __global__ void __launch_bounds__(128) dec_attention_generic_kernel(const DecAtt
     int n_keys;
     if (a.n_keys_ptr) n_keys = *a.n_keys_ptr + 1;
     else n_keys = a.enc_len ? min(a.enc_len[blk], a.n_keys_fixed) : a.n_keys_fixed;
-    const __half* kbase = a.kbase + static_cast<size_t>(blk) * a.row_stride + h * dh;
-    const __half* vbase = a.vbase + static_cast<size_t>(blk) * a.row_stride + h * dh;
+    const int hs = a.head_stride > 0 ? a.head_stride : dh;
+    const __half* kbase = a.kbase + static_cast<size_t>(blk) * a.row_stride + static_cast<size_t>(h) * hs;
+    const __half* vbase = a.vbase + static_cast<size_t>(blk) * a.row_stride + static_cast<size_t>(h) * hs;
     const int* lin = nullptr;
     if (a.lineage) lin = a.lineage + static_cast<size_t>((n_keys - 1) & 1) * gridDim.y * a.lin_stride + static_cast<size_t>(r) * a.lin_stride;
     if (tid < dh) s_q[tid] = __half2float(a.q[static_cast<size_t>(r) * a.ldq + h * dh + tid]);
@@ -939,11 +941,62 @@ layernorm_dual_kernel(float* __restrict__ x, __half* __restrict__ x16, const flo
     }
 }
 
+// Same, the row held in registers (NV float4 per lane, D = 128 * NV): one read of x instead of three dependent passes --
+// this kernel sits 26 times on the critical path of every TransformerLM scorer step.
+template <int NV>
+__global__ void __launch_bounds__(128)
+layernorm_dual_reg_kernel(float* __restrict__ x, __half* __restrict__ x16, const float* __restrict__ gamma,
+                          const float* __restrict__ beta, int M, float eps, int write_f32) {
+    pdl_trigger();
+    pdl_wait();
+    constexpr int D = NV * 128;
+    const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const int lane = threadIdx.x & 31;
+    float4* xr = reinterpret_cast<float4*>(x + static_cast<size_t>(row) * D);
+    float4 v[NV];
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { v[i] = xr[i * 32 + lane]; s += (v[i].x + v[i].y) + (v[i].z + v[i].w); }
+    const float mean = warp_sum(s) / D;
+    float q = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+        q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+    const float rstd = rsqrtf(warp_sum(q) / D + eps);
+    const float4* g4 = reinterpret_cast<const float4*>(gamma);
+    const float4* b4 = reinterpret_cast<const float4*>(beta);
+    uint2* o16 = reinterpret_cast<uint2*>(x16 + static_cast<size_t>(row) * D);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const float4 g = __ldg(g4 + i * 32 + lane), bb = __ldg(b4 + i * 32 + lane);
+        float4 y;
+        y.x = v[i].x * rstd * g.x + bb.x; y.y = v[i].y * rstd * g.y + bb.y;
+        y.z = v[i].z * rstd * g.z + bb.z; y.w = v[i].w * rstd * g.w + bb.w;
+        if (write_f32) xr[i * 32 + lane] = y;
+        const __half2 h0 = floats2half2_sat(y.x, y.y), h1 = floats2half2_sat(y.z, y.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t*>(&h0); pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+        o16[i * 32 + lane] = pk;
+    }
+}
+
 int layernorm_dual(float* x, __half* x16, const float* gamma, const float* beta, int M, int D, float eps, bool write_f32,
                    cudaStream_t stream) {
     if (M == 0) return SBK_OK;
-    SBK_CUDA_CHECK(launch_k(layernorm_dual_kernel, dim3(ceil_div(M, 8)), dim3(256), 0, stream, x, x16, gamma, beta, M, D, eps,
-                            write_f32 ? 1 : 0));
+    const int wf = write_f32 ? 1 : 0;
+    const dim3 grid(ceil_div(M, 4)), block(128);
+    switch (D % 128 == 0 ? D / 128 : 0) {
+        case 2: SBK_CUDA_CHECK(launch_k(layernorm_dual_reg_kernel<2>, grid, block, 0, stream, x, x16, gamma, beta, M, eps, wf)); break;
+        case 4: SBK_CUDA_CHECK(launch_k(layernorm_dual_reg_kernel<4>, grid, block, 0, stream, x, x16, gamma, beta, M, eps, wf)); break;
+        case 6: SBK_CUDA_CHECK(launch_k(layernorm_dual_reg_kernel<6>, grid, block, 0, stream, x, x16, gamma, beta, M, eps, wf)); break;
+        case 8: SBK_CUDA_CHECK(launch_k(layernorm_dual_reg_kernel<8>, grid, block, 0, stream, x, x16, gamma, beta, M, eps, wf)); break;
+        default:
+            SBK_CUDA_CHECK(launch_k(layernorm_dual_kernel, dim3(ceil_div(M, 8)), dim3(256), 0, stream, x, x16, gamma, beta, M, D,
+                                    eps, wf));
+    }
     SBK_LAUNCH_CHECK();
     return SBK_OK;
 }
@@ -1014,27 +1067,33 @@ struct BeamArgs {
     const float* add_row;   // [n_bh] per-hypothesis score added to every token (CoverageScorer), or null
     float attn_weight; int blank; float add_const;
     const float* lm_emb; const float* lm_pe; int lm_d; float lm_sqrt_d; float* lm_x_next; __half* lm_x16_next; int* tok_cache;
+    float* scr_val; int* scr_idx; float* scr_lse;   // beam_rows_kernel -> beam_merge_kernel
 };
 
-__global__ void __launch_bounds__(BS_THREADS) beam_step_kernel(const BeamArgs a) {
+// Two kernels.  beam_rows_kernel, one CTA per hypothesis row (B * beam CTAs instead of B): the row's log-sum-exp, masked eos
+// log-prob and its own top-`beam` candidates under the final score -- the utterance's top-`beam` of beam * V is a subset
+// of the union of the rows' top-`beam` (same order: score descending, candidate index ascending).  beam_merge_kernel, one
+// CTA per utterance: ranks the beam * beam survivors, then does the bookkeeping.  Scratch: [n_bh][BS_MAXB] scores,
+// [n_bh][BS_MAXB] candidate indices (k * V + token), [n_bh] log-sum-exp.
+__global__ void __launch_bounds__(BS_THREADS) beam_rows_kernel(const BeamArgs a) {
     __shared__ float s_red[BS_THREADS / 32];
     __shared__ int s_redi[BS_THREADS / 32];
-    __shared__ float s_lse[BS_MAXB], s_eos[BS_MAXB];
+    __shared__ float s_lse, s_eos;
     __shared__ float s_val[BS_THREADS][BS_MAXB + 1];
     __shared__ int s_idx[BS_THREADS][BS_MAXB + 1];
-    __shared__ int s_wtok[BS_MAXB], s_wpred[BS_MAXB];
     __shared__ int s_redx[BS_THREADS / 32];
     pdl_trigger();
     pdl_wait();
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int beam = a.beam, V = a.V;
-    const int row0 = b * beam;
-    const int step = a.step_arr[row0];
-    const float* seq_in = a.seq_scores + static_cast<size_t>(step & 1) * a.n_bh;
-    float* seq_out = a.seq_scores + static_cast<size_t>((step + 1) & 1) * a.n_bh;
-    // ---- phase 1: per beam row log-sum-exp of logits / T and the (masked) eos log-prob
-    for (int k = 0; k < beam; ++k) {
-        const float* lg = a.logits + static_cast<size_t>(row0 + k) * V;
+    const int k = row % beam;
+    const int step = a.step_arr[row];
+    const float seq = a.seq_scores[static_cast<size_t>(step & 1) * a.n_bh + row];
+    const float* lg = a.logits + static_cast<size_t>(row) * V;
+    const float* add = a.add_scores ? a.add_scores + static_cast<size_t>(row) * V : nullptr;
+    const float add_row = a.add_row ? a.add_row[row] : 0.0f;
+    // ---- phase 1: log-sum-exp of logits / T and the (masked) eos log-prob
+    {
         float mx = -INFINITY;
         for (int j = tid; j < V; j += BS_THREADS) mx = fmaxf(mx, lg[j] * a.inv_temp);
         mx = warp_max(mx);
@@ -1063,11 +1122,11 @@ __global__ void __launch_bounds__(BS_THREADS) beam_step_kernel(const BeamArgs a)
                 const float max_lp = fmaxf(a.attn_weight * (mne - lse), eos_lp);
                 if (!(eos_lp > a.eos_threshold * max_lp)) eos_lp = a.minus_inf;
             }
-            if (a.add_scores) eos_lp += a.add_scores[static_cast<size_t>(row0 + k) * V + a.eos];  // ScorerBuilder.score
-            eos_lp += a.add_const;
-            if (a.add_row) eos_lp += a.add_row[row0 + k];
-            s_lse[k] = lse;
-            s_eos[k] = eos_lp;
+            if (add) eos_lp += add[a.eos];  // ScorerBuilder.score
+            eos_lp += a.add_const + add_row;
+            s_lse = lse;
+            s_eos = eos_lp;
+            a.scr_lse[row] = lse;
         }
         __syncthreads();
     }
@@ -1077,19 +1136,21 @@ __global__ void __launch_bounds__(BS_THREADS) beam_step_kernel(const BeamArgs a)
 #pragma unroll
     for (int i = 0; i < BS_MAXB; ++i) { bv[i] = -INFINITY; bi[i] = 0x7fffffff; }
     const float inv_len = a.length_norm ? 1.0f / static_cast<float>(step + 1) : 1.0f;
-    const int n_cand = beam * V;
-    for (int cidx = tid; cidx < n_cand; cidx += BS_THREADS) {
-        const int k = cidx / V, j = cidx - k * V;
-        float lp = (j == a.eos) ? s_eos[k]
-                                : a.attn_weight * (a.logits[static_cast<size_t>(row0 + k) * V + j] * a.inv_temp - s_lse[k]);
-        if (j == a.blank) lp = a.minus_inf;
-        if (a.add_scores && j != a.eos) lp += a.add_scores[static_cast<size_t>(row0 + k) * V + j];
-        if (j != a.eos) lp += a.add_const;
-        if (a.add_row && j != a.eos) lp += a.add_row[row0 + k];
-        const float sc = (seq_in[row0 + k] + lp) * inv_len;
+    const float lse = s_lse, eos_lp = s_eos;
+    for (int j = tid; j < V; j += BS_THREADS) {
+        float lp;
+        if (j == a.eos) lp = eos_lp;
+        else {
+            lp = a.attn_weight * (lg[j] * a.inv_temp - lse);
+            if (j == a.blank) lp = a.minus_inf;
+            if (add) lp += add[j];
+            lp += a.add_const;
+            if (a.add_row) lp += add_row;
+        }
+        const float sc = (seq + lp) * inv_len;
         if (sc > bv[BS_MAXB - 1] && sc > -INFINITY) {  // insert (list sorted descending; only the first `beam` matter)
             float v = sc;
-            int ix = cidx;
+            int ix = k * V + j;
 #pragma unroll
             for (int i = 0; i < BS_MAXB; ++i) {
                 if (v > bv[i] || (v == bv[i] && ix < bi[i])) {
@@ -1107,7 +1168,7 @@ __global__ void __launch_bounds__(BS_THREADS) beam_step_kernel(const BeamArgs a)
     __syncthreads();
     // ---- phase 3: merge -- `beam` rounds of a block-wide arg-max over the heads of the per-thread lists
     int head = 0;
-    for (int k = 0; k < beam; ++k) {
+    for (int r = 0; r < beam; ++r) {
         float v = s_val[tid][head];
         int ix = s_idx[tid][head];
         int who = tid;
@@ -1116,7 +1177,7 @@ __global__ void __launch_bounds__(BS_THREADS) beam_step_kernel(const BeamArgs a)
             const float ov = __shfl_xor_sync(0xffffffffu, v, o);
             const int oi = __shfl_xor_sync(0xffffffffu, ix, o);
             const int ow = __shfl_xor_sync(0xffffffffu, who, o);
-            if (ov > v || (ov == v && oi < ix)) { v = ov; ix = oi; who = ow; }
+            if (ov > v || (ov == v && (oi < ix || (oi == ix && ow < who)))) { v = ov; ix = oi; who = ow; }
         }
         if (lane == 0) { s_red[warp] = v; s_redi[warp] = who; s_redx[warp] = ix; }
         __syncthreads();
@@ -1126,27 +1187,58 @@ __global__ void __launch_bounds__(BS_THREADS) beam_step_kernel(const BeamArgs a)
             for (int w = 1; w < BS_THREADS / 32; ++w)
                 if (s_red[w] > best || (s_red[w] == best && s_redx[w] < bx)) { best = s_red[w]; bw = s_redi[w]; bx = s_redx[w]; }
             s_redi[0] = bw;
+            a.scr_val[row * BS_MAXB + r] = best;
+            a.scr_idx[row * BS_MAXB + r] = bx;
         }
         __syncthreads();
-        const int winner = s_redi[0];
-        if (tid == winner) {
-            const int cand = s_idx[tid][head];
-            const float sc = s_val[tid][head];
-            int kk = 0, tok = 0;
-            if (cand != 0x7fffffff) { kk = cand / V; tok = cand - kk * V; }
-            const int row = row0 + k, prow = row0 + kk;
-            const float raw_lp = a.attn_weight * (a.logits[static_cast<size_t>(prow) * V + tok] * a.inv_temp - s_lse[kk]);
-            const size_t h = static_cast<size_t>(step) * a.n_bh + row;
-            a.hist_tok[h] = tok; a.hist_pred[h] = prow; a.hist_score[h] = sc; a.hist_lp[h] = raw_lp;
-            float ns = a.length_norm ? sc * static_cast<float>(step + 1) : sc;
-            if (tok == a.eos) ns = -INFINITY;
-            seq_out[row] = ns;
-            s_wtok[k] = tok; s_wpred[k] = prow;
-            ++head;
-        }
+        if (tid == s_redi[0]) ++head;
         __syncthreads();
     }
-    // ---- phase 4: finished counters, lineage of the new beams, next decoder inputs, step counters
+}
+
+__global__ void __launch_bounds__(BS_THREADS) beam_merge_kernel(const BeamArgs a) {
+    __shared__ float s_v[BS_MAXB * BS_MAXB];
+    __shared__ int s_i[BS_MAXB * BS_MAXB];
+    __shared__ int s_wtok[BS_MAXB], s_wpred[BS_MAXB];
+    pdl_trigger();
+    pdl_wait();
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int beam = a.beam, V = a.V;
+    const int row0 = b * beam;
+    const int step = a.step_arr[row0];
+    float* seq_out = a.seq_scores + static_cast<size_t>((step + 1) & 1) * a.n_bh;
+    const int n = beam * beam;
+    float v = -INFINITY;
+    int ix = 0x7fffffff;
+    if (tid < n) {
+        const int r = tid / beam, q = tid - r * beam;
+        v = a.scr_val[(row0 + r) * BS_MAXB + q];
+        ix = a.scr_idx[(row0 + r) * BS_MAXB + q];
+        s_v[tid] = v; s_i[tid] = ix;
+    }
+    __syncthreads();
+    if (tid < n) {
+        int rank = 0;
+        for (int j = 0; j < n; ++j) {
+            const float ov = s_v[j];
+            const int oi = s_i[j];
+            rank += (ov > v || (ov == v && (oi < ix || (oi == ix && j < tid)))) ? 1 : 0;
+        }
+        if (rank < beam) {
+            int kk = 0, tok = 0;
+            if (ix != 0x7fffffff) { kk = ix / V; tok = ix - kk * V; }
+            const int row = row0 + rank, prow = row0 + kk;
+            const float raw_lp = a.attn_weight * (a.logits[static_cast<size_t>(prow) * V + tok] * a.inv_temp - a.scr_lse[prow]);
+            const size_t h = static_cast<size_t>(step) * a.n_bh + row;
+            a.hist_tok[h] = tok; a.hist_pred[h] = prow; a.hist_score[h] = v; a.hist_lp[h] = raw_lp;
+            float ns = a.length_norm ? v * static_cast<float>(step + 1) : v;
+            if (tok == a.eos) ns = -INFINITY;
+            seq_out[row] = ns;
+            s_wtok[rank] = tok; s_wpred[rank] = prow;
+        }
+    }
+    __syncthreads();
+    // ---- finished counters, lineage of the new beams, next decoder inputs, step counters
     if (tid == 0) {
         int n_eos = 0;
         for (int k = 0; k < beam; ++k) n_eos += (s_wtok[k] == a.eos) ? 1 : 0;
@@ -1174,10 +1266,10 @@ __global__ void __launch_bounds__(BS_THREADS) beam_step_kernel(const BeamArgs a)
     if (a.lm_emb) {
         for (int i = tid; i < beam * a.lm_d; i += BS_THREADS) {
             const int k = i / a.lm_d, c = i - k * a.lm_d;
-            const float v = a.lm_emb[static_cast<size_t>(s_wtok[k]) * a.lm_d + c] * a.lm_sqrt_d +
-                            a.lm_pe[static_cast<size_t>(step + 1) * a.lm_d + c];
-            a.lm_x_next[static_cast<size_t>(row0 + k) * a.lm_d + c] = v;
-            a.lm_x16_next[static_cast<size_t>(row0 + k) * a.lm_d + c] = float2half_sat(v);
+            const float v2 = a.lm_emb[static_cast<size_t>(s_wtok[k]) * a.lm_d + c] * a.lm_sqrt_d +
+                             a.lm_pe[static_cast<size_t>(step + 1) * a.lm_d + c];
+            a.lm_x_next[static_cast<size_t>(row0 + k) * a.lm_d + c] = v2;
+            a.lm_x16_next[static_cast<size_t>(row0 + k) * a.lm_d + c] = float2half_sat(v2);
         }
         if (tid < beam) a.tok_cache[static_cast<size_t>(row0 + tid) * a.S_max + step + 1] = s_wtok[tid];
     }
@@ -1196,7 +1288,7 @@ __global__ void __launch_bounds__(BS_THREADS) beam_step_kernel(const BeamArgs a)
 // step parity, like the CTC state), write the row's score.
 struct CoverageArgs {
     const __half* q; int ldq;             // last layer's cross-attention queries [rows, d]
-    const __half* kbase; size_t utt_stride; int key_stride;  // keys of the last layer: kbase + utt * utt_stride + t * key_stride + h * 64
+    const __half* kbase; size_t utt_stride; int key_stride; int head_stride;  // key (utt, h, t) at kbase + utt * utt_stride + h * head_stride + t * key_stride
     const int* enc_len; int rows_per_utt; int T; int H;
     float* cov_base;                      // [2][rows][T]
     const int* hist_pred; const int* step_ptr; int n_bh;
@@ -1222,7 +1314,8 @@ __global__ void __launch_bounds__(256) coverage_score_kernel(const CoverageArgs 
         __syncthreads();
         float mx = -INFINITY;
         for (int t = tid; t < n_keys; t += 256) {
-            const __half* kp = a.kbase + static_cast<size_t>(utt) * a.utt_stride + static_cast<size_t>(t) * a.key_stride + h * 64;
+            const __half* kp = a.kbase + static_cast<size_t>(utt) * a.utt_stride + static_cast<size_t>(t) * a.key_stride +
+                               static_cast<size_t>(h) * a.head_stride;
             float dot = 0.0f;
 #pragma unroll
             for (int e = 0; e < 64; e += 8) {
@@ -1284,6 +1377,7 @@ int coverage_score(const CoverageStep& p, cudaStream_t stream) {
     SBK_REQUIRE(p.T >= 1 && p.T * 8 <= 96 * 1024, "coverage scorer: T=%d out of range", p.T);
     CoverageArgs a;
     a.q = p.q; a.ldq = p.ldq; a.kbase = p.kbase; a.utt_stride = p.utt_stride; a.key_stride = p.key_stride; a.enc_len = p.enc_len;
+    a.head_stride = p.head_stride > 0 ? p.head_stride : 64;
     a.rows_per_utt = p.rows_per_utt; a.T = p.T; a.H = p.H; a.cov_base = p.cov_base; a.hist_pred = p.hist_pred;
     a.step_ptr = p.step_ptr; a.n_bh = p.n_bh; a.threshold = p.threshold; a.weight = p.weight; a.out = p.out;
     static bool attr = false;
@@ -1558,9 +1652,16 @@ int beam_step(const BeamStepArgs& p, int B, cudaStream_t stream) {
     a.add_scores = p.add_scores; a.add_row = p.add_row; a.attn_weight = p.attn_weight; a.blank = p.blank; a.add_const = p.add_const;
     a.lm_emb = p.lm.emb; a.lm_pe = p.lm.pe; a.lm_d = p.lm.d; a.lm_sqrt_d = p.lm.d ? sqrtf(static_cast<float>(p.lm.d)) : 0.f;
     a.lm_x_next = p.lm.x; a.lm_x16_next = p.lm.x16; a.tok_cache = p.lm.tok_cache;
+    a.scr_val = nullptr; a.scr_idx = nullptr; a.scr_lse = nullptr;
     static const bool force_large = getenv("SBK_BEAM_RADIX") != nullptr;  // test hook: radix-select kernel for every width
     if (p.beam > BS_MAXB || force_large) SBK_CUDA_CHECK(launch_k(beam_step_large_kernel, dim3(B), dim3(BS_THREADS), 0, stream, a));
-    else SBK_CUDA_CHECK(launch_k(beam_step_kernel, dim3(B), dim3(BS_THREADS), 0, stream, a));
+    else {
+        SBK_REQUIRE(p.scratch != nullptr, "beam_step: no scratch buffer");
+        a.scr_val = p.scratch; a.scr_idx = reinterpret_cast<int*>(p.scratch + (size_t)a.n_bh * BS_MAXB);
+        a.scr_lse = p.scratch + (size_t)2 * a.n_bh * BS_MAXB;
+        SBK_CUDA_CHECK(launch_k(beam_rows_kernel, dim3(a.n_bh), dim3(BS_THREADS), 0, stream, a));
+        SBK_CUDA_CHECK(launch_k(beam_merge_kernel, dim3(B), dim3(BS_THREADS), 0, stream, a));
+    }
     SBK_LAUNCH_CHECK();
     return SBK_OK;
 }

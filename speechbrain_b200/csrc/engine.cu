@@ -94,12 +94,12 @@ struct AsrModel {
     const __half *lm_wp0, *lm_wp2;
     // CTC prefix scorer state (allocated on the first beam search that uses it): x [B, T, V] masked log-posteriors,
     // xb [B, T], rsum/rb [2][rows, T] and psi [2][rows] ping-pong by step parity, add [rows, V] when there is no LM buffer
-    struct CtcBuf { float* base = nullptr; size_t cap = 0; float *x, *xb, *rsum, *rb, *psi, *add; } ctc;
+    struct CtcBuf { float* base = nullptr; size_t cap = 0; float *x, *xlin, *xb, *rsum, *rb, *psi, *add; } ctc;
     struct CovBuf { float* base = nullptr; size_t cap = 0; } cov;  // CoverageScorer: [2][rows][T] coverage + [rows] scores
     // shapes the workspace is carved for
     int wsB = 0, wsL = 0, ws_rows = 0, ws_steps = 0;
     struct Buf {
-        float *wav, *feats, *x, *glu, *enc_out, *act1_f, *cnn_f, *dx, *logits, *score, *seq_scores, *lnout;
+        float *wav, *feats, *x, *glu, *enc_out, *act1_f, *cnn_f, *dx, *logits, *score, *seq_scores, *lnout, *beam_scr;
         int *utt_max, *enc_len, *tokens, *step, *has_ended, *ended_count, *pred, *lineage, *finished, *hist_tok, *hist_pred;
         float *hist_score, *hist_lp;
         float* rel_len;
@@ -121,12 +121,14 @@ struct AsrModel {
     float* gwav = nullptr; float* grel = nullptr; size_t gwav_cap = 0;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_ready[16] = {};
+    cudaStream_t side_stream = nullptr;     // beam search: the LM scorer's branch of a search step
+    cudaEvent_t ev_bfork = nullptr, ev_bjoin = nullptr;
     struct HostGroupKey { const void *wav[16], *rel[16], *pred[16], *pred_dev[16]; int G, B, L, steps, bos, eos; };
     HostGroupKey hgroup_key{};
     cudaGraphExec_t hgroup_graph = nullptr;
     long long hgroup_nodes = 0;
     // beam search: ONE graph of a whole search step (decoder layers + LM step + CTC scorer + beam kernel), replayed per step
-    struct BeamKey { sbk_beam_params p; int B, T, rows, S_max, fuse_ln, tc_rows; };
+    struct BeamKey { sbk_beam_params p; int B, T, rows, S_max, fuse_ln, tc_rows, fork; };
     BeamKey beam_key{};
     cudaGraphExec_t beam_graph = nullptr;
     long long beam_nodes = 0;
@@ -517,6 +519,9 @@ void asr_destroy(AsrModel* m) {
     cudaFree(m->cov.base);
     if (m->host_flag) cudaFreeHost(m->host_flag);
     if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
+    if (m->side_stream) cudaStreamDestroy(m->side_stream);
+    if (m->ev_bfork) cudaEventDestroy(m->ev_bfork);
+    if (m->ev_bjoin) cudaEventDestroy(m->ev_bjoin);
     delete m;
 }
 
@@ -555,7 +560,7 @@ static int ensure_workspace(AsrModel* m, int B, int L, int rows, int steps) {
     sz(M * d * 2); sz((size_t)T2 * d * 2); sz(Md * d * 2); sz(Md * Ld * 2 * d * 2);
     sz((size_t)Ld * rows * S * d * 2); sz((size_t)Ld * rows * S * d * 2);
     sz((size_t)rows * d * 2); sz((size_t)rows * d * 2); sz((size_t)rows * d * 2); sz((size_t)rows * F * 2);
-    sz((size_t)2 * rows * S * 4); sz(B * 4 + 64); sz((size_t)2 * rows * 4); sz((size_t)rows * d * 4);
+    sz((size_t)2 * rows * S * 4); sz(B * 4 + 64); sz((size_t)2 * rows * 4); sz((size_t)rows * d * 4); sz((size_t)rows * 33 * 4);
     sz((size_t)rows * S * 4); sz((size_t)rows * S * 4); sz((size_t)rows * S * 4); sz((size_t)rows * S * 4);
     const size_t dl = m->has_lm ? c.lm_d_model : 0, Fl = m->has_lm ? c.lm_d_ffn : 0, Ll = m->has_lm ? c.lm_layers : 0;
     if (m->has_lm) {
@@ -590,7 +595,7 @@ static int ensure_workspace(AsrModel* m, int B, int L, int rows, int steps) {
     TAKE(dh16, __half, (size_t)rows * d * 2); TAKE(dq16, __half, (size_t)rows * d * 2); TAKE(datt16, __half, (size_t)rows * d * 2);
     TAKE(df16, __half, (size_t)rows * F * 2);
     TAKE(lineage, int, (size_t)2 * rows * S * 4); TAKE(finished, int, B * 4 + 64); TAKE(seq_scores, float, (size_t)2 * rows * 4);
-    TAKE(lnout, float, (size_t)rows * d * 4);
+    TAKE(lnout, float, (size_t)rows * d * 4); TAKE(beam_scr, float, (size_t)rows * 33 * 4);
     TAKE(hist_tok, int, (size_t)rows * S * 4); TAKE(hist_pred, int, (size_t)rows * S * 4);
     TAKE(hist_score, float, (size_t)rows * S * 4); TAKE(hist_lp, float, (size_t)rows * S * 4);
     if (m->has_lm) {
@@ -701,6 +706,39 @@ static int dec_ln(AsrModel* m, SkinnyArgs& a, const float* g, const float* bta, 
 // Decode step when many hypotheses are live (several batches decoded together, or a wide beam): the projections run on
 // the tcgen05 GEMM (128 x 32/64 tiles, a handful of CTAs each, so concurrent lanes share the GPU) instead of the
 // weight-streaming kernel whose cost grows with every 32 rows.  Same maths: fp16 operands, fp32 accumulate / residual.
+// Cross-attention K/V of every decoder layer, projected once per utterance from the encoder states (b.enc16).  Layout per
+// layer (default): [K | V] parts, each [utt][head][T][64] -- the decode-step attention of (utterance, head) then streams one
+// contiguous T x 128 B block of K and one of V instead of 128-byte pieces 2 KB apart (SBK_XATT_ROWMAJOR=1: the round-1
+// [utt * T][K(d) | V(d)] rows).  Needs head_dim 64.
+static bool xatt_headmajor(const AsrModel* m) {
+    static const bool legacy = getenv("SBK_XATT_ROWMAJOR") != nullptr || getenv("SBK_GEMM_V1") != nullptr;  // (scatter epilogue: 2-CTA kernel only)
+    return !legacy && m->cfg.d_model / m->cfg.nhead == 64 && m->cfg.d_model % 256 == 0;
+}
+static int project_cross_kv(AsrModel* m, int M, int T, cudaStream_t st) {
+    const sbk_asr_config& c = m->cfg;
+    AsrModel::Buf& b = m->b;
+    const int d = c.d_model, Ld = c.num_decoder_layers;
+    RC(cast_f32_f16(b.enc_out, b.enc16, (size_t)M * d, st));
+    for (int l = 0; l < Ld; ++l) {
+        GemmEpilogue e;
+        e.mode = EPI_F16; e.bias = m->b_ckv + (size_t)l * 2 * d; e.out = b.ckv16 + (size_t)l * M * 2 * d; e.ldo = 2 * d;
+        if (xatt_headmajor(m)) { e.kv_heads = c.nhead; e.kv_part_stride = (size_t)M * d; e.T = T; }
+        RC(gemm_f16(b.enc16, d, m->w_ckv + (size_t)l * 2 * d * d, d, e, M, 2 * d, d, st));
+    }
+    return SBK_OK;
+}
+// fills the K/V addressing of a cross-attention call for layer l
+static void cross_kv_args(const AsrModel* m, DecAttnArgs& t, int l, int n_utt, int T) {
+    const int d = m->cfg.d_model;
+    const size_t M = (size_t)n_utt * T;
+    t.kbase = m->b.ckv16 + (size_t)l * M * 2 * d;
+    if (xatt_headmajor(m)) {
+        t.vbase = t.kbase + M * d; t.row_stride = (size_t)T * d; t.head_stride = T * 64; t.key_stride = 64;
+    } else {
+        t.vbase = t.kbase + d; t.row_stride = (size_t)T * 2 * d; t.head_stride = 0; t.key_stride = 2 * d;
+    }
+}
+
 static int enqueue_decode_layers_tc(AsrModel* m, int rows, int rows_per_utt, int T, int S_max, const int* lineage,
                                     cudaStream_t st, bool with_head) {
     const sbk_asr_config& c = m->cfg;
@@ -727,8 +765,7 @@ static int enqueue_decode_layers_tc(AsrModel* m, int rows, int rows_per_utt, int
         e = GemmEpilogue(); e.mode = EPI_F16; e.bias = w.b_cross_q; e.out = b.dq16; e.ldo = d;
         RC(gemm_f16_small(b.dh16, d, w.w_cross_q, d, e, rows, d, d, st));
         t = DecAttnArgs{};
-        t.q = b.dq16; t.ldq = d; t.kbase = b.ckv16 + (size_t)l * n_utt * T * 2 * d; t.vbase = t.kbase + d;
-        t.row_stride = (size_t)T * 2 * d; t.key_stride = 2 * d; t.rows_per_block = rows_per_utt;
+        t.q = b.dq16; t.ldq = d; cross_kv_args(m, t, l, n_utt, T); t.rows_per_block = rows_per_utt;
         t.n_keys_ptr = nullptr; t.enc_len = b.enc_len; t.H = H; t.dh = dh; t.out = b.datt16; t.ldo = d;
         RC(dec_attention(t, rows, T, st));
         e = GemmEpilogue(); e.mode = EPI_RESID; e.bias = w.b_cross_out; e.out = b.dx; e.resid = b.dx; e.ldo = d;
@@ -784,8 +821,7 @@ static int enqueue_decode_layers(AsrModel* m, int rows, int rows_per_utt, int T,
         a.N = d; a.K = d; a.epi = SK_F16; a.out = b.dq16; a.ldo = d;
         RC(skinny_gemm(a, st));
         t = DecAttnArgs{};
-        t.q = b.dq16; t.ldq = d; t.kbase = b.ckv16 + (size_t)l * n_utt * T * 2 * d; t.vbase = t.kbase + d;
-        t.row_stride = (size_t)T * 2 * d; t.key_stride = 2 * d; t.rows_per_block = rows_per_utt;
+        t.q = b.dq16; t.ldq = d; cross_kv_args(m, t, l, n_utt, T); t.rows_per_block = rows_per_utt;
         t.n_keys_ptr = nullptr; t.enc_len = b.enc_len; t.H = H; t.dh = dh; t.out = b.datt16; t.ldo = d;
         RC(dec_attention(t, rows, T, st));
         a = SkinnyArgs{}; a.A = b.datt16; a.lda = d; a.W = w.w_cross_out; a.ldw = d; a.bias = w.b_cross_out; a.n_rows = rows;
@@ -919,12 +955,7 @@ static int run_beam(AsrModel* m, int B, int T, const sbk_beam_params& p, int* hi
     SBK_REQUIRE(p.max_steps <= m->ws_steps && p.max_steps + 1 <= c.max_len, "beam: max_steps=%d too large", p.max_steps);
     *steps_done = 0;
     if (p.max_steps <= 0) return SBK_OK;
-    RC(cast_f32_f16(b.enc_out, b.enc16, (size_t)M * d, st));
-    for (int l = 0; l < Ld; ++l) {
-        GemmEpilogue e;
-        e.mode = EPI_F16; e.bias = m->b_ckv + (size_t)l * 2 * d; e.out = b.ckv16 + (size_t)l * M * 2 * d; e.ldo = 2 * d;
-        RC(gemm_f16(b.enc16, d, m->w_ckv + (size_t)l * 2 * d * d, d, e, M, 2 * d, d, st));
-    }
+    RC(project_cross_kv(m, M, T, st));
     set_pdl(getenv("SBK_PDL") != nullptr);
     const bool use_lm = p.lm_weight != 0.0f;
     SBK_REQUIRE(!use_lm || m->has_lm, "beam: lm_weight != 0 but this handle has no TransformerLM weights");
@@ -938,7 +969,7 @@ static int run_beam(AsrModel* m, int B, int T, const sbk_beam_params& p, int* hi
                     p.bos != p.eos, "Set blank, eos and bos to different indexes for joint ATT/CTC or CTC decoding");
         const size_t V = c.vocab;
         auto al = [](size_t n) { return (n * 4 + 255) & ~size_t(255); };
-        const size_t need = al((size_t)M * V) + al(M) + 2 * al((size_t)2 * rows * T) + al(2 * rows) + (use_lm ? 0 : al(rows * V));
+        const size_t need = 2 * al((size_t)M * V) + al(M) + 2 * al((size_t)2 * rows * T) + al(2 * rows) + (use_lm ? 0 : al(rows * V));
         AsrModel::CtcBuf& cb = m->ctc;
         if (need > cb.cap) {
             if (cb.base) { SBK_CUDA_CHECK(cudaStreamSynchronize(st)); cudaFree(cb.base); cb.base = nullptr; cb.cap = 0; }
@@ -948,6 +979,7 @@ static int run_beam(AsrModel* m, int B, int T, const sbk_beam_params& p, int* hi
         }
         char* q = reinterpret_cast<char*>(cb.base);
         cb.x = reinterpret_cast<float*>(q); q += al((size_t)M * V);
+        cb.xlin = reinterpret_cast<float*>(q); q += al((size_t)M * V);
         cb.xb = reinterpret_cast<float*>(q); q += al(M);
         cb.rsum = reinterpret_cast<float*>(q); q += al((size_t)2 * rows * T);
         cb.rb = reinterpret_cast<float*>(q); q += al((size_t)2 * rows * T);
@@ -956,8 +988,8 @@ static int run_beam(AsrModel* m, int B, int T, const sbk_beam_params& p, int* hi
         GemmEpilogue e;
         e.mode = EPI_F32; e.bias = m->b_ctc; e.out = cb.x; e.ldo = c.vocab;
         RC(gemm_f16(b.enc16, d, m->w_ctc, d, e, M, c.vocab, d, st));
-        RC(ctc_prefix_reset(cb.x, cb.xb, b.enc_len, B, T, c.vocab, p.blank_index, beam, cb.rsum, cb.rb, cb.psi, st));
-        cs.x = cb.x; cs.xb = cb.xb; cs.enc_len = b.enc_len; cs.hist_tok = hist_tok; cs.hist_pred = hist_pred; cs.n_bh = rows;
+        RC(ctc_prefix_reset(cb.x, cb.xlin, cb.xb, b.enc_len, B, T, c.vocab, p.blank_index, beam, cb.rsum, cb.rb, cb.psi, st));
+        cs.x = cb.x; cs.xlin = cb.xlin; cs.xb = cb.xb; cs.enc_len = b.enc_len; cs.hist_tok = hist_tok; cs.hist_pred = hist_pred; cs.n_bh = rows;
         cs.rsum_base = cb.rsum; cs.rb_base = cb.rb; cs.psi_base = cb.psi; cs.step_ptr = b.step;
         cs.bos = p.bos; cs.T = T; cs.V = c.vocab; cs.beam = beam; cs.blank = p.blank_index; cs.eos = p.eos;
         cs.weight = p.ctc_weight; cs.out = cb.add; cs.accumulate = use_lm ? 1 : 0;
@@ -973,8 +1005,10 @@ static int run_beam(AsrModel* m, int B, int T, const sbk_beam_params& p, int* hi
             if (cudaMalloc(&m->cov.base, need) != cudaSuccess) { set_error("beam: coverage scorer cudaMalloc(%zu) failed", need); return SBK_ERR_NOMEM; }
             m->cov.cap = need;
         }
-        cv.q = b.dq16; cv.ldq = d; cv.kbase = b.ckv16 + (size_t)(Ld - 1) * M * 2 * d; cv.utt_stride = (size_t)T * 2 * d;
-        cv.key_stride = 2 * d; cv.enc_len = b.enc_len; cv.rows_per_utt = beam; cv.T = T; cv.H = c.nhead;
+        cv.q = b.dq16; cv.ldq = d; cv.kbase = b.ckv16 + (size_t)(Ld - 1) * M * 2 * d;
+        if (xatt_headmajor(m)) { cv.utt_stride = (size_t)T * d; cv.key_stride = 64; cv.head_stride = T * 64; }
+        else { cv.utt_stride = (size_t)T * 2 * d; cv.key_stride = 2 * d; cv.head_stride = 64; }
+        cv.enc_len = b.enc_len; cv.rows_per_utt = beam; cv.T = T; cv.H = c.nhead;
         cv.cov_base = m->cov.base; cv.hist_pred = hist_pred; cv.step_ptr = b.step; cv.n_bh = rows;
         cv.threshold = p.coverage_threshold; cv.weight = p.coverage_weight; cv.out = m->cov.base + (size_t)2 * rows * T;
     }
@@ -993,23 +1027,41 @@ static int run_beam(AsrModel* m, int B, int T, const sbk_beam_params& p, int* hi
     a.hist_tok = hist_tok; a.hist_pred = hist_pred; a.hist_score = hist_score; a.hist_lp = hist_lp;
     a.temperature = p.temperature; a.eos_threshold = p.eos_threshold; a.minus_inf = p.minus_inf; a.min_steps = p.min_steps;
     a.eos = p.eos; a.use_eos_threshold = p.using_eos_threshold; a.length_norm = p.length_normalization;
-    a.emb = m->emb; a.pe = m->dec_pe; a.d = d; a.x_next = b.dx;
-    // one whole search step; every kernel takes the step index from the device counters, so the sequence is the same
-    // for every step and can be replayed from a graph
+    a.emb = m->emb; a.pe = m->dec_pe; a.d = d; a.x_next = b.dx; a.scratch = b.beam_scr;
+    // One whole search step; every kernel takes the step index from the device counters, so the sequence is the same
+    // for every step and can be replayed from a graph.  The scorers that do not read the decoder's output of this step --
+    // the TransformerLM step and the CTC state update of the PREVIOUS step's survivors -- run as a second branch beside
+    // the decoder layers (both are chains of small kernels that leave most SMs idle) and join before the scores are combined.
+    const bool fork = (use_lm || use_ctc) && getenv("SBK_BEAM_SERIAL") == nullptr;
+    if (fork && !m->side_stream) {
+        SBK_CUDA_CHECK(cudaStreamCreateWithFlags(&m->side_stream, cudaStreamNonBlocking));
+        SBK_CUDA_CHECK(cudaEventCreateWithFlags(&m->ev_bfork, cudaEventDisableTiming));
+        SBK_CUDA_CHECK(cudaEventCreateWithFlags(&m->ev_bjoin, cudaEventDisableTiming));
+    }
     auto enqueue_step = [&](cudaStream_t s_) -> int {
+        cudaStream_t s2 = s_;
+        if (fork) {
+            s2 = m->side_stream;
+            SBK_CUDA_CHECK(cudaEventRecord(m->ev_bfork, s_));
+            SBK_CUDA_CHECK(cudaStreamWaitEvent(s2, m->ev_bfork, 0));
+        }
+        if (use_ctc) RC(ctc_prefix_update(cs, s2));  // permute_scorer_mem on the previous step's survivors (no-op at step 0)
+        if (use_lm) RC(enqueue_lm_step(m, rows, S_max, p.lm_temperature, p.lm_weight, s2));
         RC(enqueue_decode_layers(m, rows, beam, T, S_max, b.lineage, s_));
         if (use_cov) RC(coverage_score(cv, s_));  // reads the last layer's cross-attention query left in b.dq16
-        if (use_lm) RC(enqueue_lm_step(m, rows, S_max, p.lm_temperature, p.lm_weight, s_));
-        if (use_ctc) RC(ctc_prefix_score(cs, s_));  // ScorerBuilder.score (ctc after transformerlm) ...
+        if (fork) {
+            SBK_CUDA_CHECK(cudaEventRecord(m->ev_bjoin, s2));
+            SBK_CUDA_CHECK(cudaStreamWaitEvent(s_, m->ev_bjoin, 0));
+        }
+        if (use_ctc) RC(ctc_prefix_score(cs, s_));  // ScorerBuilder.score (ctc after transformerlm)
         RC(beam_step(a, B, s_));
-        if (use_ctc) RC(ctc_prefix_update(cs, s_));  // ... then permute_scorer_mem on the survivors
         return SBK_OK;
     };
     const bool use_graph = getenv("SBK_NO_GRAPH") == nullptr;
     if (use_graph) {
         AsrModel::BeamKey key;
         memset(&key, 0, sizeof(key));
-        key.p = p; key.B = B; key.T = T; key.rows = rows; key.S_max = S_max; key.fuse_ln = m->fuse_dec_ln; key.tc_rows = m->dec_tc_rows;
+        key.p = p; key.B = B; key.T = T; key.rows = rows; key.S_max = S_max; key.fuse_ln = m->fuse_dec_ln; key.tc_rows = m->dec_tc_rows; key.fork = fork ? 1 : 0;
         if (m->beam_graph == nullptr || memcmp(&key, &m->beam_key, sizeof(key)) != 0) {
             if (m->beam_graph) { cudaGraphExecDestroy(m->beam_graph); m->beam_graph = nullptr; }
             if (!m->cap_stream) SBK_CUDA_CHECK(cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
@@ -1055,19 +1107,12 @@ static int run_greedy(AsrModel* m, int B, int T, int max_steps, int bos, int eos
                       cudaStream_t st, bool in_capture = false) {
     const sbk_asr_config& c = m->cfg;
     AsrModel::Buf& b = m->b;
-    const int d = c.d_model, Ld = c.num_decoder_layers, M = B * T, rows = B, S_max = m->ws_steps + 1;
+    const int d = c.d_model, M = B * T, rows = B, S_max = m->ws_steps + 1;
     SBK_REQUIRE(m->has_dec, "greedy: this handle was created without decoder weights");
     SBK_REQUIRE(max_steps <= m->ws_steps && max_steps + 1 <= c.max_len, "greedy: max_steps=%d too large", max_steps);
     *steps_done = 0;
     if (max_steps <= 0) return SBK_OK;
-    // cross-attention K/V for all layers: one tcgen05 GEMM  [M, d] x [L*2d, d]^T
-    RC(cast_f32_f16(b.enc_out, b.enc16, (size_t)M * d, st));
-    // layout ckv16[layer][B*T][K(d) | V(d)]: one GEMM per layer so each layer's K/V rows are contiguous
-    for (int l = 0; l < Ld; ++l) {
-        GemmEpilogue e;
-        e.mode = EPI_F16; e.bias = m->b_ckv + (size_t)l * 2 * d; e.out = b.ckv16 + (size_t)l * M * 2 * d; e.ldo = 2 * d;
-        RC(gemm_f16(b.enc16, d, m->w_ckv + (size_t)l * 2 * d * d, d, e, M, 2 * d, d, st));
-    }
+    RC(project_cross_kv(m, M, T, st));  // cross-attention K/V of all layers, once per utterance
     RC(greedy_reset(b.tokens, S_max + 1, rows, bos, b.step, b.has_ended, b.ended_count, m->emb, m->dec_pe, d, b.dx, st));
     set_pdl(getenv("SBK_PDL") != nullptr);  // programmatic dependent launch measured slower here: opt-in only
     const bool use_graph = !in_capture && getenv("SBK_NO_GRAPH") == nullptr && log_probs == nullptr;
@@ -1162,15 +1207,10 @@ __global__ void dec_teacher_embed_kernel(const int* __restrict__ tokens, int S, 
 static int run_decode_teacher(AsrModel* m, const int* tokens, int n, int S, int T, float* out, cudaStream_t st) {
     const sbk_asr_config& c = m->cfg;
     AsrModel::Buf& b = m->b;
-    const int d = c.d_model, Ld = c.num_decoder_layers, M = n * T, S_max = m->ws_steps + 1;
+    const int d = c.d_model, M = n * T, S_max = m->ws_steps + 1;
     SBK_REQUIRE(m->has_dec, "decode: this handle was created without decoder weights");
     SBK_REQUIRE(S <= m->ws_steps && S <= c.max_len, "decode: %d target positions exceed the workspace / max_len", S);
-    RC(cast_f32_f16(b.enc_out, b.enc16, (size_t)M * d, st));
-    for (int l = 0; l < Ld; ++l) {
-        GemmEpilogue e;
-        e.mode = EPI_F16; e.bias = m->b_ckv + (size_t)l * 2 * d; e.out = b.ckv16 + (size_t)l * M * 2 * d; e.ldo = 2 * d;
-        RC(gemm_f16(b.enc16, d, m->w_ckv + (size_t)l * 2 * d * d, d, e, M, 2 * d, d, st));
-    }
+    RC(project_cross_kv(m, M, T, st));
     for (int s = 0; s < S; ++s) {
         dec_teacher_embed_kernel<<<n, 128, 0, st>>>(tokens, S, s, m->emb, m->dec_pe, d, sqrtf((float)d), b.dx, b.step);
         SBK_LAUNCH_CHECK();

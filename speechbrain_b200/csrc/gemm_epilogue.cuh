@@ -348,13 +348,31 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmEpilogue& e, 
         // byte offset of this chunk inside a row: fp16 -> col0 * 2 ; GLU fp32 (16 columns) -> (col0 / 2) * 4
         const size_t row_pitch = MODE == EPI_GLU ? static_cast<size_t>(e.ldo) * 4 : static_cast<size_t>(e.ldo) * 2;
         const size_t col_off = static_cast<size_t>(col0) * 2;
+        if (MODE == EPI_F16 && e.kv_heads > 0) {
+            // cross-attention K/V scatter: column c of the [K (d) | V (d)] row goes to part[c / d][utt][head][t][64], so
+            // that the decode-step attention streams one contiguous T x 128 B block per (utterance, head)
+            const int d = e.kv_heads * 64;
+            const int part = col0 / d, cc = col0 - part * d, head = cc >> 6, dcol = cc & 63;
+            __half* pbase = reinterpret_cast<__half*>(e.out) + static_cast<size_t>(part) * e.kv_part_stride;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int r = i * 8 + rsub;
-            const int row = row_base + r;
-            if (row < M)
-                *reinterpret_cast<uint4*>(outp + static_cast<size_t>(row) * row_pitch + col_off + seg * 16) =
-                    lds128(stg_s + r * PITCH + seg * 16);
+            for (int i = 0; i < 4; ++i) {
+                const int r = i * 8 + rsub;
+                const int row = row_base + r;
+                if (row < M) {
+                    const int b = row / e.T, t = row - b * e.T;
+                    __half* dst = pbase + ((static_cast<size_t>(b) * e.kv_heads + head) * e.T + t) * 64 + dcol + seg * 8;
+                    *reinterpret_cast<uint4*>(dst) = lds128(stg_s + r * PITCH + seg * 16);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = i * 8 + rsub;
+                const int row = row_base + r;
+                if (row < M)
+                    *reinterpret_cast<uint4*>(outp + static_cast<size_t>(row) * row_pitch + col_off + seg * 16) =
+                        lds128(stg_s + r * PITCH + seg * 16);
+            }
         }
     }
     __syncwarp();  // staging tile is reused by the next chunk

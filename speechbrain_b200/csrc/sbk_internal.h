@@ -27,6 +27,9 @@ struct GemmEpilogue {
     // EPI_QKV_CACHE (decoder self-attention in_proj, columns [q | k | v] of width qkv_d): q -> out (fp16, ldo), k / v ->
     // cache[(row * S_max + step_ptr[row]) * qkv_d + col]
     __half* kcache = nullptr; __half* vcache = nullptr; const int* step_ptr = nullptr; int S_max = 0; int qkv_d = 0;
+    // EPI_F16 (2-CTA kernel) scatter of the cross-attention [K | V] projection (N = 2 * kv_heads * 64, row = utt * T + t) to
+    // part[K|V][utt][head][t][64]; kv_part_stride = elements between the K part and the V part.  0 = plain row-major store.
+    int kv_heads = 0; size_t kv_part_stride = 0;
 };
 
 // out = epilogue(A[M,K] fp16 x W[N,K]^T fp16), tcgen05 tensor cores. gemm_tc.cu
@@ -109,6 +112,7 @@ struct DecAttnArgs {
     const __half* kbase; const __half* vbase;
     size_t row_stride;
     int key_stride;
+    int head_stride = 0;  // elements between heads inside a row block; 0 = dh (heads side by side in one key row)
     int rows_per_block;
     const int* n_keys_ptr;
     const int* enc_len;
@@ -138,25 +142,27 @@ struct BeamStepArgs {
     int blank = -1;            // CTC blank index, blocked in the log-probs (scorer.py:1248-1250); -1 = no CTC scorer
     float add_const = 0.0f;    // LengthScorer: weight * 1 added to every token (scorer.py:1043-1071)
     const float* add_row = nullptr;  // CoverageScorer: [n_bh] weighted score added to every token of a hypothesis
+    float* scratch = nullptr;        // [n_bh * 33] floats: per-row candidates between the two kernels of a step (beam <= 16)
 };
 // CoverageScorer (decoders/scorer.py:788-955) on the last decoder layer's head-averaged cross-attention
 struct CoverageStep {
     const __half* q; int ldq; const __half* kbase; size_t utt_stride; int key_stride; const int* enc_len;
+    int head_stride = 0;  // 0 = 64 (heads side by side in a key row)
     int rows_per_utt, T, H; float* cov_base; const int* hist_pred; const int* step_ptr; int n_bh;
     float threshold, weight; float* out;
 };
 int coverage_score(const CoverageStep& p, cudaStream_t stream);
 // CTC prefix scorer (ctc_scorer.cu)
 struct CtcStep {
-    const float* x; const float* xb; const int* enc_len;
+    const float* x; const float* xlin; const float* xb; const int* enc_len;   // xlin = exp(x)
     float* rsum_base; float* rb_base; float* psi_base;  // [2][n_bh, T], [2][n_bh, T], [2][n_bh]: ping-pong by step parity
     const int* hist_tok; const int* hist_pred;
     const int* step_ptr;                                // device step counters [n_bh] (same value in every row)
     int n_bh, bos, T, V, beam, blank, eos;
     float weight; float* out; int accumulate;
 };
-int ctc_prefix_reset(float* x, float* xb, const int* enc_len, int B, int T, int V, int blank, int beam, float* rsum, float* rb,
-                     float* psi_prev, cudaStream_t stream);
+int ctc_prefix_reset(float* x, float* xlin, float* xb, const int* enc_len, int B, int T, int V, int blank, int beam, float* rsum,
+                     float* rb, float* psi_prev, cudaStream_t stream);
 int ctc_prefix_score(const CtcStep& p, cudaStream_t stream);
 // x [rows, V] fp32: optional in-place log_softmax per row, arg-max per row -> idx (may be null)
 int rows_logsoftmax_argmax(float* x, int rows, int V, bool do_logsoftmax, int* idx, cudaStream_t stream);
