@@ -122,6 +122,8 @@ struct AsrModel {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_ready[16] = {};
     cudaStream_t side_stream = nullptr;     // beam search: the LM scorer's branch of a search step
+    cudaStream_t dec_stream = nullptr;      // group calls: the decode loop, on a high-priority stream (see transcribe_group_enqueue)
+    cudaEvent_t ev_dfork = nullptr, ev_djoin = nullptr;
     cudaEvent_t ev_bfork = nullptr, ev_bjoin = nullptr;
     struct HostGroupKey { const void *wav[16], *rel[16], *pred[16], *pred_dev[16]; int G, B, L, steps, bos, eos; };
     HostGroupKey hgroup_key{};
@@ -520,6 +522,9 @@ void asr_destroy(AsrModel* m) {
     if (m->host_flag) cudaFreeHost(m->host_flag);
     if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
     if (m->side_stream) cudaStreamDestroy(m->side_stream);
+    if (m->dec_stream) cudaStreamDestroy(m->dec_stream);
+    if (m->ev_dfork) cudaEventDestroy(m->ev_dfork);
+    if (m->ev_djoin) cudaEventDestroy(m->ev_djoin);
     if (m->ev_bfork) cudaEventDestroy(m->ev_bfork);
     if (m->ev_bjoin) cudaEventDestroy(m->ev_bjoin);
     delete m;
@@ -1314,6 +1319,18 @@ int sbk_gemm_f16_test(const void* A_dev, const void* W_dev, const float* bias_de
     return gemm_f16(A_dev, K, W_dev, K, e, M, N, K, static_cast<cudaStream_t>(stream));
 }
 
+int sbk_gemm_f16_resid_test(const void* A_dev, const void* W_dev, const float* bias_dev, float* x_dev, float alpha, int M,
+                            int N, int K, void* stream) {
+    GemmEpilogue e;
+    e.mode = EPI_RESID;
+    e.bias = bias_dev;
+    e.out = x_dev;
+    e.resid = x_dev;
+    e.alpha = alpha;
+    e.ldo = N;
+    return gemm_f16(A_dev, K, W_dev, K, e, M, N, K, static_cast<cudaStream_t>(stream));
+}
+
 int sbk_asr_create(const sbk_asr_config* cfg, const sbk_tensor* weights, int n_weights, sbk_asr** out) {
     return asr_create(cfg, weights, n_weights, reinterpret_cast<AsrModel**>(out));
 }
@@ -1460,16 +1477,38 @@ static int transcribe_group_enqueue(AsrModel* m, int G, const float* const* wav_
         SBK_LAUNCH_CHECK();
         RC(run_encoder(m, b.feats, B, T0, enc_len, nullptr, b.enc_out + (size_t)g * B * T * c.d_model, st));
     }
+    // The decode loop is a chain of ~3300 small, latency-bound kernels; the encoders of the other lanes are machine-filling
+    // ones.  Its kernels go to a stream of the highest priority (under capture: kernel nodes of that priority), so that a ready
+    // decode kernel gets the next free SM slots ahead of the remaining CTAs of an encoder kernel instead of queueing behind
+    // them.  SBK_DEC_PRIORITY=0: same stream as the encoders.
+    static const bool prio = getenv("SBK_DEC_PRIORITY") == nullptr || atoi(getenv("SBK_DEC_PRIORITY")) != 0;
+    cudaStream_t ds = st;
+    if (prio) {
+        if (!m->dec_stream) {
+            int lo = 0, hi = 0;
+            SBK_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // numerically lowest = highest priority
+            SBK_CUDA_CHECK(cudaStreamCreateWithPriority(&m->dec_stream, cudaStreamNonBlocking, hi));
+            SBK_CUDA_CHECK(cudaEventCreateWithFlags(&m->ev_dfork, cudaEventDisableTiming));
+            SBK_CUDA_CHECK(cudaEventCreateWithFlags(&m->ev_djoin, cudaEventDisableTiming));
+        }
+        ds = m->dec_stream;
+        SBK_CUDA_CHECK(cudaEventRecord(m->ev_dfork, st));
+        SBK_CUDA_CHECK(cudaStreamWaitEvent(ds, m->ev_dfork, 0));
+    }
     int done = 0;
-    RC(run_greedy(m, G * B, T, max_steps, bos, eos, nullptr, &done, st, in_capture));
+    RC(run_greedy(m, G * B, T, max_steps, bos, eos, nullptr, &done, ds, in_capture));
     const int S_max = m->ws_steps + 1;
     for (int g = 0; g < G; ++g) {
         if (pred_dev && pred_dev[g])
             SBK_CUDA_CHECK(cudaMemcpy2DAsync(pred_dev[g], (size_t)max_steps * 4, b.pred + (size_t)g * B * S_max, (size_t)S_max * 4,
-                                             (size_t)done * 4, B, cudaMemcpyDeviceToDevice, st));
+                                             (size_t)done * 4, B, cudaMemcpyDeviceToDevice, ds));
         if (pred_host && pred_host[g])
             SBK_CUDA_CHECK(cudaMemcpy2DAsync(pred_host[g], (size_t)max_steps * 4, b.pred + (size_t)g * B * S_max, (size_t)S_max * 4,
-                                             (size_t)done * 4, B, cudaMemcpyDeviceToHost, st));
+                                             (size_t)done * 4, B, cudaMemcpyDeviceToHost, ds));
+    }
+    if (prio) {
+        SBK_CUDA_CHECK(cudaEventRecord(m->ev_djoin, ds));
+        SBK_CUDA_CHECK(cudaStreamWaitEvent(st, m->ev_djoin, 0));
     }
     if (steps_done) *steps_done = done;
     return SBK_OK;

@@ -232,25 +232,47 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             const uint32_t acc_ph = (local_tile >> 1) & 1;
             const int row_base = mt * 2 * G2_BM + static_cast<int>(rank) * G2_BM + q * 32;
             const int n0 = nt * BN + part * PART_COLS;
-            float4 res[8];
+            // residual operands are fetched TWO chunks ahead (two register sets): one chunk of work (~0.3 us) does not cover
+            // an L2 / HBM round trip, and with one tile per pair (N = 512) nothing else hides it
+            float4 res[2][8];
             float4 rcs[4], rsn[4];
-            if constexpr (MODE == EPI_RESID) epilogue_resid_prefetch(epi, res, row_base, n0, M, lane);
+            if constexpr (MODE == EPI_RESID) {
+                epilogue_resid_prefetch(epi, res[0], row_base, n0, M, lane);
+                epilogue_resid_prefetch(epi, res[1], row_base, n0 + 32, M, lane);
+            }
             if constexpr (MODE == EPI_ROPE) epilogue_rope_prefetch(epi, rcs, rsn, row_base, n0, lane);
             mbar_wait_b(&tmem_full_bar[buf], acc_ph, 4);
             tc_fence_after();
             const uint32_t t0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + part * PART_COLS;
-            uint32_t acc[2][32];
-            tmem_ld_32x32(t0, acc[0]);
+            if constexpr (MODE == EPI_RESID) {
+                // one accumulator buffer (a TMEM read is short next to the residual's memory round trip; the registers go to
+                // the second residual set instead)
+                uint32_t acc1[32];
 #pragma unroll 1
-            for (int c = 0; c < CHUNKS; c += 2) {  // two chunks per iteration keep the double buffers statically indexed
-                tmem_ld_wait();
-                tmem_ld_32x32(t0 + (c + 1) * 32, acc[1]);  // next chunk in flight
-                epilogue_chunk_coalesced<MODE, ACT, PITCH>(epi, acc[0], stg, row_base, n0 + c * 32, M, lane, res,
-                                                           n0 + (c + 1) * 32, rcs, rsn);
-                tmem_ld_wait();
-                if (c + 2 < CHUNKS) tmem_ld_32x32(t0 + (c + 2) * 32, acc[0]);
-                epilogue_chunk_coalesced<MODE, ACT, PITCH>(epi, acc[1], stg, row_base, n0 + (c + 1) * 32, M, lane, res,
-                                                           c + 2 < CHUNKS ? n0 + (c + 2) * 32 : -1, rcs, rsn);
+                for (int c = 0; c < CHUNKS; c += 2) {
+                    tmem_ld_32x32(t0 + c * 32, acc1);
+                    tmem_ld_wait();
+                    epilogue_chunk_coalesced<MODE, ACT, PITCH>(epi, acc1, stg, row_base, n0 + c * 32, M, lane, res[0],
+                                                               c + 2 < CHUNKS ? n0 + (c + 2) * 32 : -1, rcs, rsn);
+                    tmem_ld_32x32(t0 + (c + 1) * 32, acc1);
+                    tmem_ld_wait();
+                    epilogue_chunk_coalesced<MODE, ACT, PITCH>(epi, acc1, stg, row_base, n0 + (c + 1) * 32, M, lane, res[1],
+                                                               c + 3 < CHUNKS ? n0 + (c + 3) * 32 : -1, rcs, rsn);
+                }
+            } else {
+                uint32_t acc[2][32];
+                tmem_ld_32x32(t0, acc[0]);
+#pragma unroll 1
+                for (int c = 0; c < CHUNKS; c += 2) {  // two chunks per iteration keep the double buffers statically indexed
+                    tmem_ld_wait();
+                    tmem_ld_32x32(t0 + (c + 1) * 32, acc[1]);  // next chunk in flight
+                    epilogue_chunk_coalesced<MODE, ACT, PITCH>(epi, acc[0], stg, row_base, n0 + c * 32, M, lane, res[0],
+                                                               n0 + (c + 1) * 32, rcs, rsn);
+                    tmem_ld_wait();
+                    if (c + 2 < CHUNKS) tmem_ld_32x32(t0 + (c + 2) * 32, acc[0]);
+                    epilogue_chunk_coalesced<MODE, ACT, PITCH>(epi, acc[1], stg, row_base, n0 + (c + 1) * 32, M, lane, res[0],
+                                                               c + 2 < CHUNKS ? n0 + (c + 2) * 32 : -1, rcs, rsn);
+                }
             }
             tc_fence_before();
             asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");  // all epilogue warps are done with `buf`
@@ -328,7 +350,14 @@ int gemm_f16_2cta(const void* A, int lda, const void* W, int ldw, const GemmEpil
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     }
     const int n_tiles = ceil_div(N, bn), m_tiles = ceil_div(M, 2 * G2_BM);
-    int pairs = std::min(num_sms / 2, n_tiles * m_tiles);
+    // CTA pairs: no more than needed for the wave count the full machine would give (256 tiles: 4 rounds on 64 pairs as on 74;
+    // 96 tiles: 2 rounds on 48) -- the kernel takes the same time, and the SMs it leaves alone run other lanes' decode-step
+    // kernels, which cannot share an SM with a 200 KB GEMM CTA.  SBK_GEMM_PAIRS=n caps the pair count instead (74 = round-1 rule).
+    static const int pairs_env = getenv("SBK_GEMM_PAIRS") ? atoi(getenv("SBK_GEMM_PAIRS")) : 0;
+    const int max_pairs = num_sms / 2, tiles = n_tiles * m_tiles;
+    int pairs = std::min(max_pairs, tiles);
+    if (pairs_env > 0) pairs = std::min(pairs, pairs_env);
+    else pairs = ceil_div(tiles, ceil_div(tiles, max_pairs));
     // SBK_GEMM_CL4=1: clusters of two pairs (needs an even tile count per row of tiles and an even pair count)
     // SBK_GEMM_MC=1 (implies clusters of 4): the A tile is fetched once per cluster, each CTA multicasting half of its rows
     static const bool mc_env = getenv("SBK_GEMM_MC") != nullptr;

@@ -48,6 +48,27 @@ def test_gemm_tc(dev, M, N, K, out_f32, act):
     assert err < tol, f"max abs err {err}"
 
 
+@pytest.mark.parametrize("M,N,K,alpha", [(8032, 512, 512, 1.0), (8032, 512, 2048, 0.5), (300, 512, 512, 1.0), (1000, 256, 64, 0.5)])
+def test_gemm_residual_epilogue(dev, M, N, K, alpha):
+    """x += alpha * (A W^T + b) in place (fp32 residual stream): the epilogue of FFN2 / out-proj / conv pw2."""
+    import ctypes
+
+    from speechbrain_b200._lib import check, lib, ptr, stream_ptr
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).half()
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).half()
+    bias = torch.randn(N, generator=g)
+    x = torch.randn(M, N, generator=g)
+    ref = x + alpha * (A.float() @ W.float().T + bias)
+    Ad, Wd, bd, xd = A.to(dev), W.to(dev), bias.to(dev), x.to(dev)
+    check(lib().sbk_gemm_f16_resid_test(ptr(Ad), ptr(Wd), ptr(bd), ptr(xd), ctypes.c_float(alpha), M, N, K, stream_ptr(dev)),
+          "gemm resid")
+    torch.cuda.synchronize()
+    err = (xd.cpu() - ref).abs().max().item()
+    print(f"gemm resid M={M} N={N} K={K} alpha={alpha}: max abs err {err:.3e}")
+    assert err < 2e-3
+
+
 # ----------------------------------------------------------------------------------------- Fbank
 def _assert_fbank_close(out, ref, name=""):
     """north_star: 'Fbank within 1e-4 rel FP32'.  Outputs are dB values that cross 0, where a pure relative error
