@@ -150,10 +150,16 @@ __global__ void __launch_bounds__(CTC_THREADS) ctc_score_kernel(const CtcArgs a)
 #pragma unroll
     for (int h = 0; h < R; ++h) { base[h] = ((c == s_last[h]) ? R * Tp : 0) + h * Tp; acc[h] = 0.0f; }
     const float* xc = a.xlin + static_cast<size_t>(b) * T * V + c;
-    for (int t = t_lo & ~3; t < T; t += 4) {
+    // (the next 4 frames' posteriors are requested before the current 4 are consumed: the loop is otherwise one exposed
+    // memory round trip per iteration)
+    float xn[4];
+    const int t_first = t_lo & ~3;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) xn[u] = (t_first + u < T) ? xc[static_cast<size_t>(t_first + u) * V] : 0.0f;
+    for (int t = t_first; t < T; t += 4) {
         float xv[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) xv[u] = (t + u < T) ? xc[static_cast<size_t>(t + u) * V] : 0.0f;
+        for (int u = 0; u < 4; ++u) { xv[u] = xn[u]; xn[u] = (t + 4 + u < T) ? xc[static_cast<size_t>(t + 4 + u) * V] : 0.0f; }
 #pragma unroll
         for (int h = 0; h < R; ++h) {
             const float4 av = *reinterpret_cast<const float4*>(smem + base[h] + t);

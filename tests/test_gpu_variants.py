@@ -41,7 +41,8 @@ print(json.dumps({"rel": rel, "finite": bool(torch.isfinite(enc).all()), "tok": 
 VARIANTS = [{}, {"SBK_GEMM_CL4": "1"}, {"SBK_GEMM_MC": "1"}, {"SBK_GEMM_BN128": "1"}, {"SBK_GEMM_V1": "1"}, {"SBK_SILU_EXACT": "1"},
             {"SBK_CNN_UNFUSED": "1"}, {"SBK_FBANK_FR16": "1"}, {"SBK_XATT_ROWMAJOR": "1"},
             {"SBK_XATT_ROWMAJOR": "1", "SBK_DEC_XATT_TMA": "1"}, {"SBK_XATT_ROWMAJOR": "1", "SBK_DEC_XATT_PERSIST": "1"},
-            {"SBK_DEC_SPLITK": "1"}, {"SBK_PDL": "1"}, {"SBK_SKINNY_MT8": "1"}, {"SBK_NO_GRAPH": "1"}, {"SBK_DEC_TC_ROWS": "1"}]
+            {"SBK_DEC_SPLITK": "1"}, {"SBK_PDL": "1"}, {"SBK_SKINNY_MT8": "1"}, {"SBK_NO_GRAPH": "1"}, {"SBK_DEC_TC_ROWS": "1"},
+            {"SBK_GEMM_PAIRS": "74"}, {"SBK_GEMM_PAIRS": "40"}, {"SBK_DEC_PRIORITY": "0"}]
 
 
 @pytest.mark.parametrize("env", VARIANTS, ids=lambda e: "+".join(sorted(e)) or "default")
@@ -56,3 +57,17 @@ def test_kernel_variant_parity(env):
     print(env, r)
     assert r["finite"] and r["rel"] < 1e-3
     assert r["tok"] == g["hyps"] and r["group_tok"] == g["hyps"] and r["rows_equal"] and r["group_equal"]
+
+
+@pytest.mark.parametrize("env", [{"SBK_BEAM_SERIAL": "1"}, {"SBK_NO_GRAPH": "1"}, {"SBK_BEAM_RADIX": "1"}],
+                         ids=lambda e: "+".join(sorted(e)))
+def test_beam_variant_parity(env):
+    """The beam-search goldens (beam 10 with every scorer combination, beam 66, coverage) with the scorer branch serialised,
+    without the per-step CUDA graph, and with the radix-select beam kernel forced for every width."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    p = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_bench_shapes.py"), "-q", "-m", "gpu",
+                        "-k", "beam", "-p", "no:cacheprovider"], env=dict(os.environ, **env), capture_output=True, text=True,
+                       timeout=900, cwd=ROOT)
+    print(p.stdout[-1500:])
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-1000:]
