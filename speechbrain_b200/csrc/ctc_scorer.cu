@@ -106,13 +106,19 @@ struct CtcArgs {
 // the beam width) and 128 tokens.  Shared memory: A[2][R][Tp] -- variant 0 from rsum (Alg.2-10, c != last token), variant 1
 // from r_b (c == last token); A[.][h][t] = exp(phi_h[t-1] - M_h) for t >= max(step, 1), and at step 0 the seed
 // psi_init = x[0, c] (Alg.2-6) is the extra term A[.][h][0] = exp(-M_h) of the same sum.
+// Threads: 128 tokens x CTC_TSPLIT frame groups (group g takes the 4-frame chunks g, g + CTC_TSPLIT, ...): with one thread
+// per token the kernel is a chain of dependent memory round trips at a quarter of the SM's warp slots; the partial sums of the
+// frame groups meet in shared memory.
 constexpr int CTC_THREADS = 128;
+constexpr int CTC_TSPLIT = 4;
 template <int R>
-__global__ void __launch_bounds__(CTC_THREADS) ctc_score_kernel(const CtcArgs a) {
+__global__ void __launch_bounds__(CTC_THREADS * CTC_TSPLIT) ctc_score_kernel(const CtcArgs a) {
     extern __shared__ __align__(16) float smem[];
     __shared__ float s_M[2][R];
     __shared__ int s_last[R];
+    constexpr int NT = CTC_THREADS * CTC_TSPLIT;
     const int T = a.T, V = a.V, Tp = (T + 3) & ~3;
+    float* s_part = smem + 2 * R * Tp;   // [CTC_TSPLIT - 1][R][CTC_THREADS] partial sums of the frame groups 1..
     const int row0 = blockIdx.y * R, b = row0 / a.beam;
     const int step = a.step_ptr[row0] + a.step_adj;
     const size_t half = static_cast<size_t>(step & 1);
@@ -120,9 +126,9 @@ __global__ void __launch_bounds__(CTC_THREADS) ctc_score_kernel(const CtcArgs a)
     const float* rb_in = a.rb_base + half * a.n_bh * T;
     const float* psi_prev = a.psi_base + half * a.n_bh;
     const int t_lo = step == 0 ? 0 : step;   // first term of the sum
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // per (variant, hypothesis): maximum of the exponents, one warp each
-    for (int i = warp; i < 2 * R; i += CTC_THREADS / 32) {
+    for (int i = warp; i < 2 * R; i += NT / 32) {
         const int var = i / R, h = i - var * R;
         const float* phi = (var ? rb_in : rsum_in) + static_cast<size_t>(row0 + h) * T;
         float mx = step == 0 ? 0.0f : -INFINITY;
@@ -130,10 +136,9 @@ __global__ void __launch_bounds__(CTC_THREADS) ctc_score_kernel(const CtcArgs a)
         mx = warp_max(mx);
         if (lane == 0) s_M[var][h] = mx;
     }
-    if (threadIdx.x < R)
-        s_last[threadIdx.x] = step == 0 ? a.bos : a.hist_tok[static_cast<size_t>(step - 1) * a.n_bh + row0 + threadIdx.x];
+    if (tid < R) s_last[tid] = step == 0 ? a.bos : a.hist_tok[static_cast<size_t>(step - 1) * a.n_bh + row0 + tid];
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * R * Tp; i += CTC_THREADS) {
+    for (int i = tid; i < 2 * R * Tp; i += NT) {
         const int vh = i / Tp, t = i - vh * Tp, var = vh / R, h = vh - var * R;
         float v = 0.0f;
         if (t < T && t >= t_lo) {
@@ -143,32 +148,46 @@ __global__ void __launch_bounds__(CTC_THREADS) ctc_score_kernel(const CtcArgs a)
         smem[i] = v;
     }
     __syncthreads();
-    const int c = blockIdx.x * CTC_THREADS + threadIdx.x;
-    if (c >= V) return;
+    const int tx = tid & (CTC_THREADS - 1), grp = tid / CTC_THREADS;
+    const int c = blockIdx.x * CTC_THREADS + tx;
+    const bool live = c < V;
     int base[R];
     float acc[R];
 #pragma unroll
     for (int h = 0; h < R; ++h) { base[h] = ((c == s_last[h]) ? R * Tp : 0) + h * Tp; acc[h] = 0.0f; }
-    const float* xc = a.xlin + static_cast<size_t>(b) * T * V + c;
-    // (the next 4 frames' posteriors are requested before the current 4 are consumed: the loop is otherwise one exposed
-    // memory round trip per iteration)
-    float xn[4];
-    const int t_first = t_lo & ~3;
+    if (live) {
+        const float* xc = a.xlin + static_cast<size_t>(b) * T * V + c;
+        // (the next chunk's posteriors are requested before the current ones are consumed)
+        float xn[4];
+        const int t_first = (t_lo & ~3) + 4 * grp;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) xn[u] = (t_first + u < T) ? xc[static_cast<size_t>(t_first + u) * V] : 0.0f;
-    for (int t = t_first; t < T; t += 4) {
-        float xv[4];
+        for (int u = 0; u < 4; ++u) xn[u] = (t_first + u < T) ? xc[static_cast<size_t>(t_first + u) * V] : 0.0f;
+        for (int t = t_first; t < T; t += 4 * CTC_TSPLIT) {
+            float xv[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { xv[u] = xn[u]; xn[u] = (t + 4 + u < T) ? xc[static_cast<size_t>(t + 4 + u) * V] : 0.0f; }
+            for (int u = 0; u < 4; ++u) {
+                xv[u] = xn[u];
+                const int tn = t + 4 * CTC_TSPLIT + u;
+                xn[u] = (tn < T) ? xc[static_cast<size_t>(tn) * V] : 0.0f;
+            }
 #pragma unroll
-        for (int h = 0; h < R; ++h) {
-            const float4 av = *reinterpret_cast<const float4*>(smem + base[h] + t);
-            acc[h] = fmaf(av.x, xv[0], acc[h]); acc[h] = fmaf(av.y, xv[1], acc[h]);
-            acc[h] = fmaf(av.z, xv[2], acc[h]); acc[h] = fmaf(av.w, xv[3], acc[h]);
+            for (int h = 0; h < R; ++h) {
+                const float4 av = *reinterpret_cast<const float4*>(smem + base[h] + t);
+                acc[h] = fmaf(av.x, xv[0], acc[h]); acc[h] = fmaf(av.y, xv[1], acc[h]);
+                acc[h] = fmaf(av.z, xv[2], acc[h]); acc[h] = fmaf(av.w, xv[3], acc[h]);
+            }
         }
     }
+    if (grp > 0) {
+#pragma unroll
+        for (int h = 0; h < R; ++h) s_part[((grp - 1) * R + h) * CTC_THREADS + tx] = acc[h];
+    }
+    __syncthreads();
+    if (grp > 0 || !live) return;
 #pragma unroll
     for (int h = 0; h < R; ++h) {
+#pragma unroll
+        for (int g = 0; g < CTC_TSPLIT - 1; ++g) acc[h] += s_part[(g * R + h) * CTC_THREADS + tx];
         const int row = row0 + h;
         float psi;
         if (c == a.blank && a.eos != a.blank) {
@@ -331,7 +350,8 @@ static int launch_score(const CtcArgs& a, cudaStream_t stream) {
         attr = true;
     }
     const int Tp = (a.T + 3) & ~3;
-    ctc_score_kernel<R><<<dim3(ceil_div(a.V, CTC_THREADS), a.n_bh / R), CTC_THREADS, (size_t)2 * R * Tp * 4, stream>>>(a);
+    ctc_score_kernel<R><<<dim3(ceil_div(a.V, CTC_THREADS), a.n_bh / R), CTC_THREADS * CTC_TSPLIT,
+                          ((size_t)2 * R * Tp + (size_t)(CTC_TSPLIT - 1) * R * CTC_THREADS) * 4, stream>>>(a);
     SBK_LAUNCH_CHECK();
     return SBK_OK;
 }
@@ -345,7 +365,7 @@ int ctc_prefix_score(const CtcStep& p, cudaStream_t stream) {
     }
     // hypotheses per CTA: the widest compiled group that divides the beam and whose exponent table fits shared memory
     const int Tp = (p.T + 3) & ~3;
-    const int fit = (200 * 1024) / (2 * Tp * 4);
+    const int fit = (200 * 1024) / ((2 * Tp + (CTC_TSPLIT - 1) * CTC_THREADS) * 4);
     static const int widths[] = {16, 12, 11, 10, 8, 6, 5, 4, 3, 2, 1};
     int R = 1;
     for (int w : widths) if (p.beam % w == 0 && w <= fit) { R = w; break; }
