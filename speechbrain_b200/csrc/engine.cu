@@ -94,7 +94,7 @@ struct AsrModel {
     const __half *lm_wp0, *lm_wp2;
     // CTC prefix scorer state (allocated on the first beam search that uses it): x [B, T, V] masked log-posteriors,
     // xb [B, T], rsum/rb [2][rows, T] and psi [2][rows] ping-pong by step parity, add [rows, V] when there is no LM buffer
-    struct CtcBuf { float* base = nullptr; size_t cap = 0; float *x, *xlin, *xb, *rsum, *rb, *psi, *add; } ctc;
+    struct CtcBuf { float* base = nullptr; size_t cap = 0; float *x, *xlin, *xb, *rsum, *rb, *psi, *add, *tab, *tabM; } ctc;
     struct CovBuf { float* base = nullptr; size_t cap = 0; } cov;  // CoverageScorer: [2][rows][T] coverage + [rows] scores
     // shapes the workspace is carved for
     int wsB = 0, wsL = 0, ws_rows = 0, ws_steps = 0;
@@ -974,7 +974,8 @@ static int run_beam(AsrModel* m, int B, int T, const sbk_beam_params& p, int* hi
                     p.bos != p.eos, "Set blank, eos and bos to different indexes for joint ATT/CTC or CTC decoding");
         const size_t V = c.vocab;
         auto al = [](size_t n) { return (n * 4 + 255) & ~size_t(255); };
-        const size_t need = 2 * al((size_t)M * V) + al(M) + 2 * al((size_t)2 * rows * T) + al(2 * rows) + (use_lm ? 0 : al(rows * V));
+        const size_t need = 2 * al((size_t)M * V) + al(M) + 2 * al((size_t)2 * rows * T) + al(2 * rows) + (use_lm ? 0 : al(rows * V)) +
+                            al((size_t)2 * rows * (T + 4)) + al(2 * rows);
         AsrModel::CtcBuf& cb = m->ctc;
         if (need > cb.cap) {
             if (cb.base) { SBK_CUDA_CHECK(cudaStreamSynchronize(st)); cudaFree(cb.base); cb.base = nullptr; cb.cap = 0; }
@@ -989,13 +990,15 @@ static int run_beam(AsrModel* m, int B, int T, const sbk_beam_params& p, int* hi
         cb.rsum = reinterpret_cast<float*>(q); q += al((size_t)2 * rows * T);
         cb.rb = reinterpret_cast<float*>(q); q += al((size_t)2 * rows * T);
         cb.psi = reinterpret_cast<float*>(q); q += al(2 * rows);
+        cb.tab = reinterpret_cast<float*>(q); q += al((size_t)2 * rows * (T + 4));
+        cb.tabM = reinterpret_cast<float*>(q); q += al(2 * rows);
         cb.add = use_lm ? b.lm_extra : reinterpret_cast<float*>(q);
         GemmEpilogue e;
         e.mode = EPI_F32; e.bias = m->b_ctc; e.out = cb.x; e.ldo = c.vocab;
         RC(gemm_f16(b.enc16, d, m->w_ctc, d, e, M, c.vocab, d, st));
-        RC(ctc_prefix_reset(cb.x, cb.xlin, cb.xb, b.enc_len, B, T, c.vocab, p.blank_index, beam, cb.rsum, cb.rb, cb.psi, st));
+        RC(ctc_prefix_reset(cb.x, cb.xlin, cb.xb, b.enc_len, B, T, c.vocab, p.blank_index, beam, cb.rsum, cb.rb, cb.psi, cb.tab, cb.tabM, st));
         cs.x = cb.x; cs.xlin = cb.xlin; cs.xb = cb.xb; cs.enc_len = b.enc_len; cs.hist_tok = hist_tok; cs.hist_pred = hist_pred; cs.n_bh = rows;
-        cs.rsum_base = cb.rsum; cs.rb_base = cb.rb; cs.psi_base = cb.psi; cs.step_ptr = b.step;
+        cs.rsum_base = cb.rsum; cs.rb_base = cb.rb; cs.psi_base = cb.psi; cs.step_ptr = b.step; cs.tab = cb.tab; cs.tabM = cb.tabM;
         cs.bos = p.bos; cs.T = T; cs.V = c.vocab; cs.beam = beam; cs.blank = p.blank_index; cs.eos = p.eos;
         cs.weight = p.ctc_weight; cs.out = cb.add; cs.accumulate = use_lm ? 1 : 0;
     }

@@ -156,13 +156,14 @@ int coverage_score(const CoverageStep& p, cudaStream_t stream);
 struct CtcStep {
     const float* x; const float* xlin; const float* xb; const int* enc_len;   // xlin = exp(x)
     float* rsum_base; float* rb_base; float* psi_base;  // [2][n_bh, T], [2][n_bh, T], [2][n_bh]: ping-pong by step parity
+    float* tab; float* tabM;                            // score-kernel operand tables [n_bh * 2 * (T + 3)], [n_bh * 2]
     const int* hist_tok; const int* hist_pred;
     const int* step_ptr;                                // device step counters [n_bh] (same value in every row)
     int n_bh, bos, T, V, beam, blank, eos;
     float weight; float* out; int accumulate;
 };
 int ctc_prefix_reset(float* x, float* xlin, float* xb, const int* enc_len, int B, int T, int V, int blank, int beam, float* rsum,
-                     float* rb, float* psi_prev, cudaStream_t stream);
+                     float* rb, float* psi_prev, float* tab, float* tabM, cudaStream_t stream);
 int ctc_prefix_score(const CtcStep& p, cudaStream_t stream);
 // x [rows, V] fp32: optional in-place log_softmax per row, arg-max per row -> idx (may be null)
 int rows_logsoftmax_argmax(float* x, int rows, int V, bool do_logsoftmax, int* idx, cudaStream_t stream);
