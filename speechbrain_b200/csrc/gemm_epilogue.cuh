@@ -228,13 +228,21 @@ __device__ __forceinline__ void epilogue_rope_prefetch(const GemmEpilogue& e, fl
 }
 
 template <int MODE, int ACT, int PITCH = EPI_STG_PITCH>
+// sbias: this chunk's 32 bias values in shared memory (staged once per tile by the caller), or null -> read e.bias
 __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmEpilogue& e, const uint32_t (&acc)[32], uint8_t* stg,
                                                          int row_base, int col0, int M, int lane, float4 (&res)[8],
-                                                         int next_col0, float4 (&rc)[4], float4 (&rs)[4]) {
+                                                         int next_col0, float4 (&rc)[4], float4 (&rs)[4],
+                                                         const float* sbias = nullptr) {
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-    if (e.bias != nullptr) {
+    if (sbias != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(sbias + j);   // same address in every lane: broadcast
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+        }
+    } else if (e.bias != nullptr) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
             const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col0 + j));

@@ -43,8 +43,11 @@ struct G2Cfg {
     static_assert(STAGE_BYTES % 1024 == 0, "128B-swizzled stages must stay 1 KB aligned");
     static_assert((2 * ST + 4) * 8 + 4 <= 256, "barrier block");
 };
+// (+ BN floats: the tile's bias vector, staged once per tile by the epilogue warps)
 template <int MODE, int EW, int BN, int ST>
-constexpr int g2_smem() { return G2Cfg<BN, ST>::STG_OFFSET + EW * 32 * epi_stg_pitch<MODE>() + 1024; }
+constexpr int g2_bias_offset() { return G2Cfg<BN, ST>::STG_OFFSET + EW * 32 * epi_stg_pitch<MODE>(); }
+template <int MODE, int EW, int BN, int ST>
+constexpr int g2_smem() { return g2_bias_offset<MODE, EW, BN, ST>() + BN * 4 + 1024; }
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -234,6 +237,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             const int n0 = nt * BN + part * PART_COLS;
             // residual operands are fetched TWO chunks ahead (two register sets): one chunk of work (~0.3 us) does not cover
             // an L2 / HBM round trip, and with one tile per pair (N = 512) nothing else hides it
+            // the tile's bias vector -> shared memory, before the wait for the accumulators (read per chunk from global memory
+            // it was a dependent L2 / HBM round trip in every chunk: ~20 % of the epilogue warps' samples in ncu)
+            constexpr int BIAS_OFF = C::STG_OFFSET + EW * 32 * PITCH;   // = g2_bias_offset<MODE, EW, BN, ST>()
+            float* sbias_tile = reinterpret_cast<float*>(smem + BIAS_OFF);
+            {
+                const int e_tid = (warp - 2) * 32 + lane;
+                for (int j = e_tid; j < BN; j += 32 * EW) sbias_tile[j] = epi.bias ? __ldg(epi.bias + nt * BN + j) : 0.0f;
+                asm volatile("bar.sync 2, %0;" ::"n"(32 * EW) : "memory");
+            }
+            const float* sb = sbias_tile + part * PART_COLS;
             float4 res[2][8];
             float4 rcs[4], rsn[4];
             if constexpr (MODE == EPI_RESID) {
@@ -253,11 +266,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                     tmem_ld_32x32(t0 + c * 32, acc1);
                     tmem_ld_wait();
                     epilogue_chunk_coalesced<MODE, ACT, PITCH>(epi, acc1, stg, row_base, n0 + c * 32, M, lane, res[0],
-                                                               c + 2 < CHUNKS ? n0 + (c + 2) * 32 : -1, rcs, rsn);
+                                                               c + 2 < CHUNKS ? n0 + (c + 2) * 32 : -1, rcs, rsn, sb + c * 32);
                     tmem_ld_32x32(t0 + (c + 1) * 32, acc1);
                     tmem_ld_wait();
                     epilogue_chunk_coalesced<MODE, ACT, PITCH>(epi, acc1, stg, row_base, n0 + (c + 1) * 32, M, lane, res[1],
-                                                               c + 3 < CHUNKS ? n0 + (c + 3) * 32 : -1, rcs, rsn);
+                                                               c + 3 < CHUNKS ? n0 + (c + 3) * 32 : -1, rcs, rsn, sb + (c + 1) * 32);
                 }
             } else {
                 uint32_t acc[2][32];
@@ -267,11 +280,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                     tmem_ld_wait();
                     tmem_ld_32x32(t0 + (c + 1) * 32, acc[1]);  // next chunk in flight
                     epilogue_chunk_coalesced<MODE, ACT, PITCH>(epi, acc[0], stg, row_base, n0 + c * 32, M, lane, res[0],
-                                                               n0 + (c + 1) * 32, rcs, rsn);
+                                                               n0 + (c + 1) * 32, rcs, rsn, sb + c * 32);
                     tmem_ld_wait();
                     if (c + 2 < CHUNKS) tmem_ld_32x32(t0 + (c + 2) * 32, acc[0]);
                     epilogue_chunk_coalesced<MODE, ACT, PITCH>(epi, acc[1], stg, row_base, n0 + (c + 1) * 32, M, lane, res[0],
-                                                               c + 2 < CHUNKS ? n0 + (c + 2) * 32 : -1, rcs, rsn);
+                                                               c + 2 < CHUNKS ? n0 + (c + 2) * 32 : -1, rcs, rsn, sb + (c + 1) * 32);
                 }
             }
             tc_fence_before();
